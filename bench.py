@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py -- Gaussian messages/sec on the batched LGSSM smoothing sweep (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1]): notebook model lifted to d = m = 4,
+T = 1000, batch = 65 536 chains PER GPU (weak scaling), shared (A, B, P, Q, prior), fp32 I/O.
+One "step" = one forward+backward sum-product sweep over the whole batch through the C ABI
+(`rxg_lgssm_smooth_f32`): gain-table kernels + the fused sweep kernel; messages = 6 * T * batch.
+
+  value     device-resident inputs/outputs, CUDA events on the launching stream, max over ranks
+  e2e       same call with HOST (pinned) buffers: H2D of y and D2H of posteriors inside the timed region
+  roofline  dominant kernel (lgssm_shared_kernel): algorithmic 96 B per (chain, step) / its own
+            event-timed duration, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  fp64 C port of the reference's message schedule (oracle/c) on the host cores
+
+`--impl reference` times that CPU port alone (the reference itself is Julia and cannot run here).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D, M, T, BATCH = 4, 4, 1000, 65536
+MSG_PER_STEP = 6                      # rule invocations per (chain, time step), SURVEY.md 8a
+ALGO_BYTES_PER_STEP = 4 * (M + D + D * D)   # 96 B: read y_t, write mu_t and full Sigma_t
+METRIC = "gaussian_messages_per_sec_batched_lgssm_d4_T1000"
+
+
+def notebook_model_f32():
+    def rot(th):
+        return np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    A = np.zeros((4, 4)); A[:2, :2] = rot(np.pi / 15); A[2:, 2:] = rot(np.pi / 35)
+    mod = dict(A=A, B=np.diag([1.3, 0.7, 1.3, 0.7]), P=0.05 * np.eye(4), Q=10.0 * np.eye(4),
+               m0=np.zeros(4), S0=100.0 * np.eye(4))
+    return {k: v.astype(np.float32) for k, v in mod.items()}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(seconds_target=12.0, chunk=2048):
+    """fp64 C port of the reference schedule on all host cores, bounded sample of the same workload."""
+    from oracle import c_twin
+    mod = {k: v.astype(np.float64) for k, v in notebook_model_f32().items()}
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(0)
+    y = (rng.standard_normal((T, M, chunk)) * 3.0).astype(np.float32)
+    c_twin.smooth(y[:, :, :64].copy(), **mod, nthreads=cores)         # warm-up
+    done, t0 = 0, time.perf_counter()
+    while True:
+        c_twin.smooth(y, **mod, nthreads=cores)
+        done += chunk
+        el = time.perf_counter() - t0
+        if el >= seconds_target or done >= BATCH:
+            break
+    return {"value": MSG_PER_STEP * T * done / el, "unit": "messages/s", "cores": cores, "kind": "port",
+            "sample": f"{done} chains x T={T} (d=4) of the same workload, fp64 C port of the reference schedule "
+                      f"(oracle/c/rxg_oracle.c), OpenMP over chains, {el:.1f} s"}
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's CPU path = the fp64 C port (the Julia reference cannot be
+    installed: no julia, no registry packages).  Rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import c_twin
+    mod = {k: v.astype(np.float64) for k, v in notebook_model_f32().items()}
+    cores = os.cpu_count() or 1
+    chunk = 4096                                     # bounded sample per step
+    rng = np.random.default_rng(0)
+    y = (rng.standard_normal((T, M, chunk)) * 3.0).astype(np.float32)
+    for _ in range(max(args.warmup, 1)):
+        c_twin.smooth(y[:, :, :512].copy(), **mod, nthreads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        c_twin.smooth(y, **mod, nthreads=cores)
+    el = time.perf_counter() - t0
+    val = MSG_PER_STEP * T * chunk * args.steps / el
+    sample = f"{chunk} chains x T={T} per step (1/{BATCH // chunk} of the GPU arm's per-GPU batch), fp64, OpenMP x{cores}"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "messages/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "batched LGSSM smoothing d=4 m=4 T=1000, notebook model, shared parameters",
+                   "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "messages/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "messages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH, help="chains per GPU (default = BASELINE config)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--per-chain-path", action="store_true", help="time the per-chain covariance recursion instead")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import rxinfer_jl_b200 as rx
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = rx.Context(local)
+    mod = notebook_model_f32()
+    batch = args.batch
+    kw = dict(A=mod["A"], B=mod["B"], P=mod["P"], Q=mod["Q"], m0=mod["m0"], S0=mod["S0"])
+
+    # synthetic observations of the model's own scale (state O(1), obs noise sd sqrt(10)); generated on device
+    g = torch.Generator(device=dev).manual_seed(42 + rank)
+    y = torch.randn(T, M, batch, device=dev, generator=g) * 3.3
+    mean = torch.empty(T, D, batch, device=dev)
+    cov = torch.empty(T, D, D, batch, device=dev)
+
+    def step():
+        return ctx.lgssm(y, **kw, smooth=True, out_mean=mean, out_cov=cov, asynchronous=True,
+                         force_per_chain_path=args.per_chain_path)
+
+    ctx.set_profiling(True)
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    main_ms, gain_ms = [], []
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = ctx.launches - l0
+    el_ms = ev0.elapsed_time(ev1)
+    # per-kernel timing of the dominant kernel: separate pass so the event syncs do not sit in the timed loop
+    for _ in range(args.steps):
+        step()
+        a, b = ctx.profile_last_ms()
+        main_ms.append(a); gain_ms.append(b)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([el_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    el_ms = float(t.item())
+    ms_per_step = el_ms / args.steps
+    msgs = MSG_PER_STEP * T * batch * world
+    value = msgs / (ms_per_step * 1e-3)
+
+    # ---- all-gather of posterior marginals (north_star: one NCCL all-gather at the end) -- reported separately
+    allgather = None
+    if world > 1:
+        rx.sharding.init_comm(ctx)
+        ctx.allgather_posteriors(mean, cov, world)           # warm-up (allocates the gathered buffers once)
+        torch.cuda.synchronize(); dist.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        g0.record()
+        for _ in range(reps):
+            gm, gc = ctx.allgather_posteriors(mean, cov, world)
+        g1.record(); torch.cuda.synchronize()
+        tg = torch.tensor([g0.elapsed_time(g1) / reps], device=dev, dtype=torch.float64)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        gms = float(tg.item())
+        inbound = (world - 1) * (mean.numel() + cov.numel()) * 4
+        allgather = {"ms": gms, "bytes_in_per_gpu": inbound, "in_GBs_per_gpu": inbound / gms / 1e6,
+                     "value_with_allgather": msgs / ((ms_per_step + gms) * 1e-3)}
+        del gm, gc
+
+    # ---- e2e through the C ABI with host buffers (rank-local; all ranks run it concurrently)
+    e2e = None
+    if not args.no_e2e:
+        yh = torch.empty(T, M, batch, dtype=torch.float32).pin_memory()
+        yh.copy_(y)
+        mh = torch.empty(T, D, batch, dtype=torch.float32).pin_memory()
+        ch = torch.empty(T, D, D, batch, dtype=torch.float32).pin_memory()
+        e_steps = max(2, min(args.steps, 5))
+        ctx.lgssm(yh, **kw, smooth=True, out_mean=mh, out_cov=ch)           # warm-up (staging alloc)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(e_steps):
+            ctx.lgssm(yh, **kw, smooth=True, out_mean=mh, out_cov=ch, asynchronous=True)
+        e1.record(); torch.cuda.synchronize()
+        te = torch.tensor([e0.elapsed_time(e1) / e_steps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": msgs / (float(te.item()) * 1e-3), "unit": "messages/s", "ms_per_step": float(te.item()),
+               "h2d_bytes_per_step": int(yh.numel() * 4), "d2h_bytes_per_step": int((mh.numel() + ch.numel()) * 4),
+               "api": "rxg_lgssm_smooth_f32 with host (pinned) pointers"}
+        del yh, mh, ch
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        k_ms = float(np.mean(main_ms))
+        algo = ALGO_BYTES_PER_STEP * T * batch
+        achieved = algo / (k_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic_bytes.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("per_chain_path" if args.per_chain_path else "shared_path")
+        out = {
+            "metric": METRIC, "value": value, "unit": "messages/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "batched LGSSM smoothing (BASELINE configs[1]): d=4 m=4 T=1000 batch=%d per GPU, "
+                                   "notebook model lifted to d=4, shared (A,B,P,Q,prior)" % batch,
+                       "global_batch": batch * world, "parallelism": f"batch-sharded x{world}, no data-path collective",
+                       "path": "per-chain covariance recursion" if args.per_chain_path else "gain tables + mean sweeps",
+                       "messages_per_chain_step": MSG_PER_STEP, "l2_policy": "inputs+outputs (6.3 GB) larger than L2"},
+            "roofline": {"bound": "hbm", "kernel": "lgssm_chain_kernel" if args.per_chain_path else "lgssm_shared_kernel",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel_ms": k_ms, "gain_kernels_ms": float(np.mean(gain_ms)),
+                         "algorithmic_bytes_per_launch": algo},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if allgather:
+            out["allgather"] = allgather
+        if not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

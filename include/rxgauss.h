@@ -1,0 +1,246 @@
+/* rxgauss.h -- C ABI of librxgauss: B200 (sm_100a) kernels for the Gaussian message-passing hot
+ * path of RxInfer.jl's infer().
+ *
+ * This header is the drop-in boundary.  Every entry point replaces one piece of the reference's
+ * per-message / per-chain machinery; the reference-side interface each one stands in for is cited
+ * as  [ref: file:line]  relative to /root/reference.  Rule bodies marked (upstream) live in the
+ * un-vendored ReactiveMP ~6.0.0 / ExponentialFamily 2.1.0 / BayesBase 1.5.0 / FastCholesky 1.3.0
+ * (Project.toml:43-73); the in-repo citation is the call site that binds or exercises them.
+ *
+ * Conventions
+ *  - plain C, no exceptions, no callbacks.  Every function returns an rxg_status (0 = OK);
+ *    rxg_last_error(ctx) gives a human-readable message for the last failure on that ctx.
+ *  - all arrays are fp32, structure-of-arrays with the batch (message / chain) index INNERMOST:
+ *        vectors  v[k][n]          -> v[k*n_total + i]
+ *        matrices M[r][c][n]       -> M[(r*C + c)*n_total + i]
+ *        series   y[t][k][batch]   -> y[(t*m + k)*batch + b]
+ *    so that a warp reading one component of 32 consecutive chains issues one 128-byte request.
+ *  - (mu, Sigma) = mean / covariance  (MvNormalMeanCovariance),
+ *    (xi, W)     = weighted mean / precision (MvNormalWeightedMeanPrecision), W = inv(Sigma), xi = W mu.
+ *  - pointers are device pointers when RXG_PTR_DEVICE is set in `flags`, host pointers otherwise
+ *    (host buffers are staged through the context's stream; pinned memory from rxg_host_alloc
+ *    makes the copies asynchronous).
+ *  - the caller owns every buffer it passes; the library owns only what hangs off rxg_ctx
+ *    (stream handle, workspace, gain tables, NCCL communicator).
+ *  - a ctx is bound to one device and is not thread-safe: one ctx per host thread and per GPU.
+ *  - calls return after the stream has been synchronised unless RXG_ASYNC is set.
+ *  - there is NO CPU fallback: without a usable CUDA device rxg_create fails with
+ *    RXG_ERR_NO_DEVICE and every compute entry point fails with RXG_ERR_BAD_ARG on a null ctx.
+ */
+#ifndef RXGAUSS_H
+#define RXGAUSS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RXG_VERSION 100 /* 0.1.0 */
+
+typedef struct rxg_ctx rxg_ctx;
+
+typedef enum rxg_status {
+    RXG_OK = 0,
+    RXG_ERR_BAD_ARG = 1,
+    RXG_ERR_CUDA = 2,
+    RXG_ERR_NCCL = 3,
+    RXG_ERR_NOT_SPD = 4,     /* at least one chain/message hit a non-positive Cholesky pivot      */
+    RXG_ERR_NAN = 5,
+    RXG_ERR_UNSUPPORTED = 6, /* shape outside the compiled kernel families (see rxg_supports)   */
+    RXG_ERR_NO_DEVICE = 7
+} rxg_status;
+
+enum rxg_flags {
+    RXG_PTR_DEVICE      = 1u << 0, /* data pointers are device pointers                          */
+    RXG_MODEL_PER_CHAIN = 1u << 1, /* A,B,P,Q,m0,S0 carry a trailing [batch] axis               */
+    RXG_ASYNC           = 1u << 2, /* do not synchronise the stream before returning             */
+    RXG_COV_SHARED_OUT  = 1u << 3, /* shared model only: write post_cov as [T][d][d] (one copy)  */
+    RXG_PATH_PER_CHAIN  = 1u << 4, /* force the per-chain covariance recursion (no gain tables)  */
+    RXG_TRANSITION_FIRST = 1u << 5 /* filter: push the prior through (A, P) before the 1st datum */
+};
+
+/* ------------------------------------------------------------------ context / plumbing ------ */
+int rxg_version(void);
+/* Create a context on CUDA device `device`.  [ref: the reference has no device/ctx notion; this
+ * replaces the per-infer() engine state built at src/inference/batch.jl:177-257]               */
+int rxg_create(rxg_ctx** out, int device, unsigned flags);
+int rxg_destroy(rxg_ctx* ctx);
+const char* rxg_last_error(const rxg_ctx* ctx);
+/* Use an externally owned cudaStream_t (e.g. torch's current stream) for all launches/copies.  */
+int rxg_set_stream(rxg_ctx* ctx, void* cuda_stream);
+int rxg_sync(rxg_ctx* ctx);
+/* Pinned host memory for asynchronous staging of host-pointer calls.                           */
+int rxg_host_alloc(void** out, size_t bytes);
+int rxg_host_free(void* p);
+/* 1 if (d, m) is covered by the thread-per-chain kernel families, 0 otherwise.                 */
+int rxg_supports(int d, int m);
+/* Number of kernels this ctx has launched so far (for bench.py's gpu_launches).               */
+long long rxg_launch_count(const rxg_ctx* ctx);
+/* Per-kernel timing of the most recent fused LGSSM sweep: when enabled, CUDA events are recorded
+ * on the ctx stream around the gain-table kernels and around the dominant sweep kernel.
+ * rxg_profile_last_ms synchronises on those events; *gain_ms is 0 on the per-chain path.        */
+int rxg_set_profiling(rxg_ctx* ctx, int enabled);
+int rxg_profile_last_ms(rxg_ctx* ctx, float* main_kernel_ms, float* gain_kernels_ms);
+
+/* ------------------------------------------------------------------ per-rule kernels --------
+ * Batched twins of the reference's @rule bodies: n independent messages per call, pure
+ * functions.  `M_shared != 0` means the PointMass matrix operand is one d x d (row-major) matrix
+ * shared by all n messages, else it is [r][c][n].
+ * The reference reaches these through ReactiveMP.rule(...) dispatched from the edge pipelines
+ * wired in activate_rmp_factornode! [ref: src/model/plugins/reactivemp_inference.jl:509-540];
+ * callable directly as @call_rule [ref: test/inference/inference_tests.jl:547-585].            */
+
+/* @rule MvNormalMeanCovariance(:out)(m_mu, q_Sigma) -> (mu, S + Sigma)  (upstream
+ * rules/mv_normal_mean_covariance/out.jl)  [ref: alias src/model/graphppl.jl:372-376;
+ * benchmarks/Linear...Benchmark.ipynb:102]                                                      */
+int rxg_rule_mvnormal_meancov_out_f32(rxg_ctx*, int64_t n, int d, const float* mu_in,
+                                      const float* S_in, const float* Sigma, int M_shared,
+                                      float* mu_out, float* S_out, unsigned flags);
+/* @rule MvNormalMeanCovariance(:mu)(m_out, q_Sigma) -> (mu_out, S_out + Sigma)  (upstream
+ * .../mean.jl)  [ref: ipynb:102-103]                                                             */
+int rxg_rule_mvnormal_meancov_mean_f32(rxg_ctx*, int64_t n, int d, const float* mu_in,
+                                       const float* S_in, const float* Sigma, int M_shared,
+                                       float* mu_out, float* S_out, unsigned flags);
+/* same rule with q_out::PointMass (a datum pushed by new_observation!
+ * [ref: src/inference/batch.jl:405-407]) -> (y, Sigma)                                          */
+int rxg_rule_mvnormal_meancov_mean_data_f32(rxg_ctx*, int64_t n, int d, const float* y,
+                                            const float* Sigma, int M_shared, float* mu_out,
+                                            float* S_out, unsigned flags);
+/* @rule typeof(*)(:out)(m_A::PointMass, m_in) -> (A mu, A S A')  (upstream
+ * rules/multiplication/out.jl)  [ref: ipynb:102; src/model/graphppl.jl:58-83]; A is d_out x d_in */
+int rxg_rule_mul_out_f32(rxg_ctx*, int64_t n, int d_out, int d_in, const float* A, int M_shared,
+                         const float* mu_in, const float* S_in, float* mu_out, float* S_out,
+                         unsigned flags);
+/* @rule typeof(*)(:in)(m_out, m_A::PointMass) -> (xi, W) = (A' W_out mu_out, A' W_out A) with
+ * W_out = cholinv(S_out)  (upstream rules/multiplication/in.jl).  status[n] (optional) receives
+ * RXG_ERR_NOT_SPD per message.                                                                  */
+int rxg_rule_mul_in_f32(rxg_ctx*, int64_t n, int d_out, int d_in, const float* A, int M_shared,
+                        const float* mu_out, const float* S_out, float* xi_in, float* W_in,
+                        int32_t* status, unsigned flags);
+/* @rule typeof(+)(:out) -> (mu1 + mu2, S1 + S2); (:in1)/(:in2) -> (mu_out - mu_other, S_out +
+ * S_other)  (upstream rules/addition)  [ref: test/models/statespace/ulgssm_tests.jl:12]         */
+int rxg_rule_add_out_f32(rxg_ctx*, int64_t n, int d, const float* mu1, const float* S1,
+                         const float* mu2, const float* S2, float* mu_out, float* S_out,
+                         unsigned flags);
+int rxg_rule_add_in_f32(rxg_ctx*, int64_t n, int d, const float* mu_out, const float* S_out,
+                        const float* mu_other, const float* S_other, float* mu_in, float* S_in,
+                        unsigned flags);
+/* BayesBase.prod(::MvNormal, ::MvNormal) in (xi, W): (xi1 + xi2, W1 + W2)
+ * [ref: fold at src/model/plugins/reactivemp_inference.jl:365-374]                              */
+int rxg_prod_gaussian_f32(rxg_ctx*, int64_t n, int d, const float* xi1, const float* W1,
+                          const float* xi2, const float* W2, float* xi, float* W, unsigned flags);
+/* weightedmean_precision(::MvNormalMeanCovariance) / mean_cov(::MvNormalWeightedMeanPrecision):
+ * one Cholesky SPD inverse each (FastCholesky.cholinv) [ref: re-export src/RxInfer.jl:6]        */
+int rxg_meancov_to_wmp_f32(rxg_ctx*, int64_t n, int d, const float* mu, const float* S, float* xi,
+                           float* W, int32_t* status, unsigned flags);
+int rxg_wmp_to_meancov_f32(rxg_ctx*, int64_t n, int d, const float* xi, const float* W, float* mu,
+                           float* S, int32_t* status, unsigned flags);
+/* Marginal at a random variable: product of k inbound (xi, W) messages then mean_cov
+ * [ref: src/model/plugins/reactivemp_inference.jl:370-455]; xi_list/W_list are arrays of k
+ * HOST-resident pointers to the message buffers.                                                */
+int rxg_marginal_gaussian_f32(rxg_ctx*, int64_t n, int d, int k, const float* const* xi_list,
+                              const float* const* W_list, float* mu, float* S, int32_t* status,
+                              unsigned flags);
+
+/* Univariate / Gamma-precision VMP rules
+ * @rule NormalMeanPrecision(:tau)(q_out, q_mu) -> GammaShapeRate(3/2, ((m_o-m_m)^2+v_o+v_m)/2)
+ * [ref: test/models/aliases/aliases_gamma_tests.jl:13-18]                                        */
+int rxg_rule_normal_precision_tau_f32(rxg_ctx*, int64_t n, const float* m_out, const float* v_out,
+                                      const float* m_mu, const float* v_mu, float* shape,
+                                      float* rate, unsigned flags);
+/* @rule NormalMeanPrecision(:out)(m_mu, q_tau) -> N(m_mu, v_mu + rate/shape)                    */
+int rxg_rule_normal_precision_out_f32(rxg_ctx*, int64_t n, const float* m_mu, const float* v_mu,
+                                      const float* shape, const float* rate, float* m_out,
+                                      float* v_out, unsigned flags);
+/* prod(GammaShapeRate, GammaShapeRate) = (a1 + a2 - 1, b1 + b2)                                 */
+int rxg_prod_gamma_f32(rxg_ctx*, int64_t n, const float* a1, const float* b1, const float* a2,
+                       const float* b2, float* a, float* b, unsigned flags);
+/* prod of two univariate Normals in (mean, variance) I/O                                        */
+int rxg_prod_normal_f32(rxg_ctx*, int64_t n, const float* m1, const float* v1, const float* m2,
+                        const float* v2, float* m, float* v, unsigned flags);
+
+/* GCV node rules [ref: test/models/statespace/hgf_tests.jl:10-40;
+ * formulas restated at test/inference/inference_tests.jl:587-607]; kappa, omega PointMass.
+ * @rule GCV(:y)(m_x, q_z, ...) -> N(m_x, v_x + 1/(A B))  (and symmetric :x)                     */
+int rxg_rule_gcv_out_f32(rxg_ctx*, int64_t n, const float* m_x, const float* v_x,
+                         const float* m_z, const float* v_z, float kappa, float omega,
+                         float* m_out, float* v_out, unsigned flags);
+/* @marginalrule GCV(:y_x) -> joint (m[2][n], V[2][2][n])                                        */
+int rxg_marginalrule_gcv_yx_f32(rxg_ctx*, int64_t n, const float* m_y, const float* v_y,
+                                const float* m_x, const float* v_x, const float* m_z,
+                                const float* v_z, float kappa, float omega, float* m, float* V,
+                                unsigned flags);
+/* @rule GCV(:z)(q_y_x, ...) -> ExponentialLinearQuadratic(a,b,c,d), then prod(Normal prior, ELQ)
+ * by GaussHermiteCubature(31) moment matching -> q(z) = N(m_z, v_z)                             */
+int rxg_rule_gcv_z_prod_f32(rxg_ctx*, int64_t n, const float* m_yx, const float* V_yx,
+                            const float* m_zprior, const float* v_zprior, float kappa, float omega,
+                            float* m_z, float* v_z, unsigned flags);
+
+/* ------------------------------------------------------------------ fused whole-chain sweeps --
+ * Replace, for the batched case, the Rocket-driven schedule + per-message dispatch that one
+ * infer(model = linear_gaussian_ssm_smoothing(...), data = (y = ...,)) executes
+ * [ref: iteration loop src/inference/batch.jl:391-430; model benchmarks/...ipynb:95-105;
+ *  test/models/statespace/mlgssm_test.jl:8-17].  One launch runs the forward sweep t = 1..T and
+ * the backward sweep t = T..1 for `batch` independent chains: 6 rule messages + 2 products +
+ * 1 marginal per (chain, step).
+ *
+ *   x[1] ~ N(m0, S0);  x[t] ~ N(A x[t-1], P);  y[t] ~ N(B x[t], Q)       (A d x d, B m x d)
+ *
+ * Inputs : y[T][m][batch]; ymask[T][batch] (uint8, 1 = observed) or NULL
+ *          [ref: missing data semantics docs/src/manuals/inference/static.md:98-125];
+ *          A,B,P,Q,m0,S0 row-major, shared (or [..][batch] with RXG_MODEL_PER_CHAIN).
+ * Outputs: post_mean[T][d][batch], post_cov[T][d][d][batch]  (== posteriors[:x], as
+ *          MvNormalMeanCovariance) [ref: src/inference/batch.jl:475-481];
+ *          neg_log_evidence[batch] or NULL (== Bethe free energy on this tree
+ *          [ref: src/model/plugins/reactivemp_free_energy.jl:84-126]);
+ *          status[batch] or NULL (per-chain RXG_OK / RXG_ERR_NOT_SPD / RXG_ERR_NAN).
+ * post_mean / post_cov double as the forward->backward stash (no extra workspace).             */
+int rxg_lgssm_smooth_f32(rxg_ctx*, int d, int m, int T, int64_t batch, const float* A,
+                         const float* B, const float* P, const float* Q, const float* m0,
+                         const float* S0, const float* y, const uint8_t* ymask, float* post_mean,
+                         float* post_cov, float* neg_log_evidence, int32_t* status,
+                         unsigned flags);
+/* Forward half only (filtering) -- what the streaming engine computes per datum with
+ * @autoupdates x_min_t_mean, x_min_t_cov = mean_cov(q(x_t))
+ * [ref: src/inference/streaming.jl:344-388; src/inference/autoupdates.jl:614-659; ipynb:199-216].
+ * With RXG_TRANSITION_FIRST the prior is pushed through (A, P) before the first datum, as the
+ * notebook's one-step model does [ref: ipynb:110-113].                                          */
+int rxg_lgssm_filter_f32(rxg_ctx*, int d, int m, int T, int64_t batch, const float* A,
+                         const float* B, const float* P, const float* Q, const float* m0,
+                         const float* S0, const float* y, const uint8_t* ymask, float* filt_mean,
+                         float* filt_cov, float* neg_log_evidence, int32_t* status,
+                         unsigned flags);
+/* VMP around the smoother with an unknown observation precision shared over time, one per chain
+ * (d = m = 1): y[t] ~ N(x[t], 1/tau), tau ~ Gamma(a0, b0), q(x) q(tau)
+ * [ref: rules of test/models/aliases/aliases_gamma_tests.jl; use case
+ *  test/callbacks/benchmark_tests.jl:8-37].  y[T][batch]; outputs post_mean/var[T][batch],
+ * shape/rate[batch].                                                                            */
+int rxg_lgssm_vmp_gamma_f32(rxg_ctx*, int T, int64_t batch, int iterations, float a, float v_proc,
+                            float m0, float v0, float a0, float b0, float init_E_tau,
+                            const float* y, float* post_mean, float* post_var, float* shape,
+                            float* rate, unsigned flags);
+/* Hierarchical Gaussian Filter, streaming, `iters` VMP iterations per datum
+ * [ref: test/models/statespace/hgf_tests.jl:10-69; loop src/inference/streaming.jl:349-407].
+ * y[T][batch]; init = (m_z, v_z, m_x, v_x); out[T][4][batch] = (m_x, v_x, m_z, v_z).            */
+int rxg_hgf_filter_f32(rxg_ctx*, int T, int64_t batch, int iters, float kappa, float omega,
+                       float z_variance, float y_variance, const float init[4], const float* y,
+                       float* out, unsigned flags);
+
+/* ------------------------------------------------------------------ multi-GPU ----------------
+ * Chains are independent: rank g owns chains [g*batch/G, (g+1)*batch/G); the only collective is
+ * the all-gather of posterior marginals at the end (the reference has no distributed path).
+ * rxg_comm_unique_id fills a 128-byte NCCL id on rank 0; the host broadcasts it out of band.    */
+int rxg_comm_unique_id(void* id128);
+int rxg_comm_init(rxg_ctx*, int nranks, int rank, const void* id128);
+/* Gather each rank's (mean[T][d][b_local], cov[T][d][d][b_local]) slab into
+ * gathered_*[G][...] (rank-major, each slab contiguous).  Device pointers only.                 */
+int rxg_allgather_posteriors(rxg_ctx*, int d, int T, int64_t batch_local, const float* post_mean,
+                             const float* post_cov, float* gathered_mean, float* gathered_cov,
+                             unsigned flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RXGAUSS_H */

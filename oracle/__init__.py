@@ -1,0 +1,26 @@
+"""CPU fp64 restatement of the reference's Gaussian message-passing hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product package (``rxinfer.jl_b200/``)
+may import this; only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` do, and only as the
+checker or as the timed CPU baseline.
+
+The arithmetic of the reference hot path lives in un-vendored Julia packages
+(ReactiveMP ~6.0.0, ExponentialFamily 2.1.0, BayesBase 1.5.0, FastCholesky 1.3.0;
+/root/reference/Project.toml:43-73), so this oracle restates the published
+algorithm of those rules and anchors on the reference's own call sites, tests and
+fixed-data golden values (see ``tests/golden/`` and ``tests/test_oracle_goldens.py``).
+
+Pin status:
+  * Gamma-precision VMP + Addition + Normal rules: PINNED against
+    test/models/aliases/aliases_gamma_tests.jl:43-44 (posterior mean bit-exact,
+    Bethe free energy to 1e-12).
+  * Two-node Gaussian BP + log-evidence: PINNED against
+    test/models/models_tests.jl:242-336 (1.5 / 3.51551, 1.0 / 2.26551).
+  * Normal entropy: PINNED against test/score/diagnostics_tests.jl:24.
+  * LGSSM schedule: cross-checked against textbook Kalman + RTS (1e-12); the
+    reference's own LGSSM goldens need Julia's RNG stream and cannot be
+    regenerated here, so LGSSM parity rests on rule-level pins + that cross-check.
+  * HGF / GCV posteriors: PARITY UNPINNED (formula-level parity only; the
+    reference pins it only through StableRNG-generated data).
+"""

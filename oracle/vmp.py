@@ -1,0 +1,108 @@
+"""fp64 oracle for the Gamma-precision variational (VMP) rules and small fixed-data goldens.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import rules as R
+
+
+def gamma_aliases_golden(iterations=100, y=10.0, n=6):
+    """Replays /root/reference/test/models/aliases/aliases_gamma_tests.jl:2-45:
+
+        gamma[i] ~ Gamma(1, 1); x[i] ~ Normal(mu = 1, tau = gamma[i]), i = 1..6
+        s ~ x[1] + ... + x[6];  y ~ Normal(mu = s, var = 1), y = 10
+        constraints q(x, gamma) = q(x) q(gamma); init vague; 100 iterations.
+
+    One iteration = sum-product over the Gaussian sub-graph (Normal(:out) VMP messages given
+    E[gamma], Addition rules, product at every x[i]) followed by the Gamma update.
+    Returns (mean(q(s)) per iteration, Bethe free energy per iteration).
+    Goldens: mean 9.468846338832027, BFE 4.385584096993327 (test lines 43-44).
+    """
+    q_gamma = [(1.0, R.TINY)] * n            # vague(GammaShapeRate)
+    means, fes = [], []
+    for _ in range(iterations):
+        # VMP message Normal(:out)(q_mu = PointMass(1), q_tau = q(gamma_i)): N(1, 1/E[gamma_i])
+        px = [R.normal_meanprec_out_q_tau((1.0, 0.0), R.gamma_mean(g)) for g in q_gamma]
+        # forward through the addition chain ((x1 + x2) + x3) + ... (rule +(:out))
+        fwd = [px[0]]
+        for i in range(1, n):
+            fwd.append(R.addition_out(fwd[-1], px[i]))
+        # backward: message into s from the observation, then +(:in1)/(:in2)
+        back_s = (y, 1.0)                                   # NormalMeanVariance(:mu) from data
+        q_s = R.prod_normal_mv(fwd[-1], back_s)
+        qx = [None] * n
+        back = back_s
+        for i in range(n - 1, 0, -1):
+            to_xi = R.addition_in2(back, fwd[i - 1])        # message to x[i]
+            qx[i] = R.prod_normal_mv(px[i], to_xi)
+            back = R.addition_in1(back, px[i])              # message to the partial sum
+        qx[0] = R.prod_normal_mv(px[0], back)
+        # Gamma update: prior Gamma(1,1) x NormalMeanPrecision(:tau)(q_out = q(x_i), q_mu = PointMass 1)
+        q_gamma = [R.prod_gamma((1.0, 1.0), R.normal_meanprec_tau(q, (1.0, 0.0))) for q in qx]
+        means.append(q_s[0])
+        fes.append(_gamma_aliases_free_energy(qx, q_gamma, px, y))
+    return np.array(means), np.array(fes)
+
+
+def _gamma_aliases_free_energy(qx, q_gamma, px, y):
+    """Variational free energy F[q] = E_q[log q - log p] of the model above under
+    q(x) q(gamma); q(x) is the exact joint Gaussian given E[gamma] (BP on the addition tree),
+    which is what the Bethe free energy (/root/reference/src/model/plugins/
+    reactivemp_free_energy.jl:84-126, docs/src/manuals/variational/bethe-free-energy.md:45-52)
+    evaluates to for this graph."""
+    n = len(qx)
+    Eg = np.array([R.gamma_mean(g) for g in q_gamma])
+    Elog = np.array([R.gamma_mean_log(g) for g in q_gamma])
+    # joint q(x): prior precision diag(p_i) with the p used for the BP sweep (px), obs y = 1'x + N(0,1)
+    p = np.array([1.0 / v for (_, v) in px])
+    W = np.diag(p) + np.ones((n, n))
+    S = np.linalg.inv(W)
+    m = S @ (p * 1.0 + y * np.ones(n))
+    H_x = R.mvnormal_entropy(S)
+    H_g = sum(R.gamma_entropy(g) for g in q_gamma)
+    # -E log p(y | x)
+    s_m = m.sum(); s_v = S.sum()
+    U_y = 0.5 * (np.log(2 * np.pi) + (y - s_m) ** 2 + s_v)
+    # -E log p(x_i | gamma_i), mu = 1
+    U_x = sum(0.5 * (np.log(2 * np.pi) - Elog[i] + Eg[i] * ((m[i] - 1.0) ** 2 + S[i, i])) for i in range(n))
+    # -E log p(gamma_i), Gamma(1,1): -log p = gamma
+    U_g = Eg.sum()
+    return U_y + U_x + U_g - H_x - H_g
+
+
+def two_node_gaussian(prior_mean=3.0, prior_var=1.0, y=0.0, obs_var=1.0):
+    """x ~ N(prior_mean, prior_var); y ~ N(x, obs_var) with y observed
+    (/root/reference/test/models/models_tests.jl:226-256, 294-336).
+    Returns (posterior mean, posterior var, BFE = -log evidence)."""
+    m, v = R.prod_normal_mv((prior_mean, prior_var), (y, obs_var))
+    s = prior_var + obs_var
+    bfe = 0.5 * (np.log(2 * np.pi * s) + (y - prior_mean) ** 2 / s)
+    return m, v, bfe
+
+
+def lgssm_gamma_precision(y, A_scalar=1.0, prior=(0.0, 100.0), proc_var=1.0,
+                          gamma_prior=(1.0, 1.0), iterations=10, init_Etau=1.0):
+    """Univariate smoother with an unknown SHARED observation precision tau ~ Gamma(a0, b0)
+    (rules row 9): y[t] ~ N(x[t], 1/tau), x[t] ~ N(a x[t-1], v).
+    Mean-field q(x) q(tau).  y[T, batch].  One VMP iteration = BP sweep given E[tau], then
+    tau update with shapes/rates adding over t: Gamma(a0 + T/2, b0 + 1/2 sum E[(y - x)^2])."""
+    from .lgssm import smooth_reference_schedule
+    y = np.asarray(y, dtype=np.float64)
+    T, batch = y.shape
+    Etau = np.full(batch, init_Etau, dtype=np.float64)
+    a0, b0 = gamma_prior
+    hist = []
+    for _ in range(iterations):
+        Q = (1.0 / Etau)[:, None, None]
+        r = smooth_reference_schedule(
+            y[:, None, :], np.array([[A_scalar]]), np.array([[1.0]]), np.array([[proc_var]]), Q,
+            np.array([prior[0]]), np.array([[prior[1]]]))
+        mx = r["mean"][:, 0, :]; vx = r["cov"][:, 0, 0, :]
+        a = a0 + 0.5 * T
+        b = b0 + 0.5 * ((y - mx) ** 2 + vx).sum(0)
+        Etau = a / b
+        hist.append((mx, vx, a, b))
+    return dict(mean=mx, var=vx, shape=np.full(batch, a), rate=b, Etau=Etau)

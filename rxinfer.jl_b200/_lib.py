@@ -1,0 +1,101 @@
+"""ctypes binding of librxgauss.so (include/rxgauss.h).  Fails loudly: there is no CPU fallback.
+
+This is the Python stand-in for the Julia ``ccall`` shim (julia/RxGaussB200.jl) -- Julia is not
+available in the build image, so the host-side mirror of the reference interface is Python.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_longlong, c_size_t, c_uint, c_uint8, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librxgauss.so")
+
+RXG_OK, RXG_ERR_BAD_ARG, RXG_ERR_CUDA, RXG_ERR_NCCL = 0, 1, 2, 3
+RXG_ERR_NOT_SPD, RXG_ERR_NAN, RXG_ERR_UNSUPPORTED, RXG_ERR_NO_DEVICE = 4, 5, 6, 7
+STATUS_NAMES = {0: "OK", 1: "BAD_ARG", 2: "CUDA", 3: "NCCL", 4: "NOT_SPD", 5: "NAN", 6: "UNSUPPORTED", 7: "NO_DEVICE"}
+
+PTR_DEVICE = 1 << 0
+MODEL_PER_CHAIN = 1 << 1
+ASYNC = 1 << 2
+COV_SHARED_OUT = 1 << 3
+PATH_PER_CHAIN = 1 << 4
+TRANSITION_FIRST = 1 << 5
+
+fp = POINTER(c_float)
+u8p = POINTER(c_uint8)
+i32p = POINTER(c_int32)
+
+# name -> (restype, argtypes); the single source of truth checked against include/rxgauss.h by
+# tests/test_abi.py
+SIGNATURES = {
+    "rxg_version": (c_int, []),
+    "rxg_create": (c_int, [POINTER(c_void_p), c_int, c_uint]),
+    "rxg_destroy": (c_int, [c_void_p]),
+    "rxg_last_error": (c_char_p, [c_void_p]),
+    "rxg_set_stream": (c_int, [c_void_p, c_void_p]),
+    "rxg_sync": (c_int, [c_void_p]),
+    "rxg_host_alloc": (c_int, [POINTER(c_void_p), c_size_t]),
+    "rxg_host_free": (c_int, [c_void_p]),
+    "rxg_supports": (c_int, [c_int, c_int]),
+    "rxg_launch_count": (c_longlong, [c_void_p]),
+    "rxg_set_profiling": (c_int, [c_void_p, c_int]),
+    "rxg_profile_last_ms": (c_int, [c_void_p, POINTER(c_float), POINTER(c_float)]),
+    "rxg_rule_mvnormal_meancov_out_f32": (c_int, [c_void_p, c_int64, c_int, fp, fp, fp, c_int, fp, fp, c_uint]),
+    "rxg_rule_mvnormal_meancov_mean_f32": (c_int, [c_void_p, c_int64, c_int, fp, fp, fp, c_int, fp, fp, c_uint]),
+    "rxg_rule_mvnormal_meancov_mean_data_f32": (c_int, [c_void_p, c_int64, c_int, fp, fp, c_int, fp, fp, c_uint]),
+    "rxg_rule_mul_out_f32": (c_int, [c_void_p, c_int64, c_int, c_int, fp, c_int, fp, fp, fp, fp, c_uint]),
+    "rxg_rule_mul_in_f32": (c_int, [c_void_p, c_int64, c_int, c_int, fp, c_int, fp, fp, fp, fp, i32p, c_uint]),
+    "rxg_rule_add_out_f32": (c_int, [c_void_p, c_int64, c_int, fp, fp, fp, fp, fp, fp, c_uint]),
+    "rxg_rule_add_in_f32": (c_int, [c_void_p, c_int64, c_int, fp, fp, fp, fp, fp, fp, c_uint]),
+    "rxg_prod_gaussian_f32": (c_int, [c_void_p, c_int64, c_int, fp, fp, fp, fp, fp, fp, c_uint]),
+    "rxg_meancov_to_wmp_f32": (c_int, [c_void_p, c_int64, c_int, fp, fp, fp, fp, i32p, c_uint]),
+    "rxg_wmp_to_meancov_f32": (c_int, [c_void_p, c_int64, c_int, fp, fp, fp, fp, i32p, c_uint]),
+    "rxg_marginal_gaussian_f32": (c_int, [c_void_p, c_int64, c_int, c_int, POINTER(fp), POINTER(fp), fp, fp, i32p, c_uint]),
+    "rxg_rule_normal_precision_tau_f32": (c_int, [c_void_p, c_int64, fp, fp, fp, fp, fp, fp, c_uint]),
+    "rxg_rule_normal_precision_out_f32": (c_int, [c_void_p, c_int64, fp, fp, fp, fp, fp, fp, c_uint]),
+    "rxg_prod_gamma_f32": (c_int, [c_void_p, c_int64, fp, fp, fp, fp, fp, fp, c_uint]),
+    "rxg_prod_normal_f32": (c_int, [c_void_p, c_int64, fp, fp, fp, fp, fp, fp, c_uint]),
+    "rxg_rule_gcv_out_f32": (c_int, [c_void_p, c_int64, fp, fp, fp, fp, c_float, c_float, fp, fp, c_uint]),
+    "rxg_marginalrule_gcv_yx_f32": (c_int, [c_void_p, c_int64, fp, fp, fp, fp, fp, fp, c_float, c_float, fp, fp, c_uint]),
+    "rxg_rule_gcv_z_prod_f32": (c_int, [c_void_p, c_int64, fp, fp, fp, fp, c_float, c_float, fp, fp, c_uint]),
+    "rxg_lgssm_smooth_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, fp, fp, fp, fp, fp, fp, fp, u8p, fp, fp, fp, i32p, c_uint]),
+    "rxg_lgssm_filter_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, fp, fp, fp, fp, fp, fp, fp, u8p, fp, fp, fp, i32p, c_uint]),
+    "rxg_lgssm_vmp_gamma_f32": (c_int, [c_void_p, c_int, c_int64, c_int, c_float, c_float, c_float, c_float, c_float, c_float, c_float, fp, fp, fp, fp, fp, c_uint]),
+    "rxg_hgf_filter_f32": (c_int, [c_void_p, c_int, c_int64, c_int, c_float, c_float, c_float, c_float, fp, fp, fp, c_uint]),
+    "rxg_comm_unique_id": (c_int, [c_void_p]),
+    "rxg_comm_init": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "rxg_allgather_posteriors": (c_int, [c_void_p, c_int, c_int, c_int64, fp, fp, fp, fp, c_uint]),
+}
+
+
+class RxGaussError(RuntimeError):
+    def __init__(self, code, msg=""):
+        self.code = code
+        super().__init__(f"librxgauss error {code} ({STATUS_NAMES.get(code, '?')}): {msg}")
+
+
+_lib = None
+
+
+def load():
+    """Load the in-tree shared library.  Raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python rxinfer.jl_b200/build.py` "
+            "(nvcc, sm_100a).  There is no CPU fallback for the hot path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the ABI and this table diverge
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def as_fp(ptr_int):
+    return ctypes.cast(c_void_p(int(ptr_int) if ptr_int else None), fp)

@@ -1,0 +1,307 @@
+"""Thin object wrapper over the C ABI: one ``Context`` per GPU / host thread.
+
+PyTorch is used only as plumbing (device memory, the current stream); every computation goes
+through ``librxgauss.so``.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_void_p
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _fp(t):
+    if t is None:
+        return L.as_fp(0)
+    return L.as_fp(t.data_ptr())
+
+
+def _model32(M):
+    """Shared model matrices are small host arrays (row-major fp32)."""
+    a = np.ascontiguousarray(np.asarray(M, dtype=np.float32))
+    return a, a.ctypes.data_as(L.fp)
+
+
+class Context:
+    """``rxg_ctx`` bound to a CUDA device.  Launches go to torch's current stream on that device
+    (so ``torch.cuda.Event`` timing and stream ordering with torch ops are meaningful)."""
+
+    def __init__(self, device: int | None = None, use_torch_stream: bool = True):
+        self.lib = L.load()
+        if not torch.cuda.is_available():
+            raise L.RxGaussError(L.RXG_ERR_NO_DEVICE, "no CUDA device: the hot path has no CPU fallback")
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        h = c_void_p()
+        rc = self.lib.rxg_create(ctypes.byref(h), self.device, 0)
+        if rc != 0:
+            raise L.RxGaussError(rc, "rxg_create failed")
+        self.h = h
+        self._stream = None
+        if use_torch_stream:
+            self.bind_stream()
+
+    # ------------------------------------------------------------------ plumbing
+    def bind_stream(self, stream: torch.cuda.Stream | None = None):
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        self._stream = s
+        self._check(self.lib.rxg_set_stream(self.h, c_void_p(s.cuda_stream)))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise L.RxGaussError(rc, self.lib.rxg_last_error(self.h).decode())
+
+    def sync(self):
+        self._check(self.lib.rxg_sync(self.h))
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.rxg_launch_count(self.h))
+
+    def set_profiling(self, on=True):
+        self._check(self.lib.rxg_set_profiling(self.h, 1 if on else 0))
+
+    def profile_last_ms(self):
+        a, b = ctypes.c_float(), ctypes.c_float()
+        self._check(self.lib.rxg_profile_last_ms(self.h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rxg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _dev(self, *ts):
+        for t in ts:
+            if t is None:
+                continue
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise ValueError("expected contiguous float32 CUDA tensors")
+
+    def empty(self, *shape, dtype=torch.float32):
+        return torch.empty(*shape, dtype=dtype, device=f"cuda:{self.device}")
+
+    # ------------------------------------------------------------------ fused sweeps
+    def lgssm(self, y, A, B, P, Q, m0, S0, *, smooth=True, mask=None, want_cov=True, want_evidence=False,
+              want_status=False, per_chain_model=False, force_per_chain_path=False, cov_shared_out=False,
+              transition_first=False, out_mean=None, out_cov=None, asynchronous=False):
+        """y[T, m, batch] (CUDA fp32, or pinned/pageable CPU fp32 for the host-pointer path)
+        -> dict(mean[T,d,batch], cov[T,d,d,batch] or [T,d,d], neg_log_evidence[batch], status[batch])."""
+        on_dev = y.is_cuda
+        T, m, batch = y.shape
+        flags = L.PTR_DEVICE if on_dev else 0
+        if per_chain_model:
+            flags |= L.MODEL_PER_CHAIN
+            d = A.shape[0]
+            self._dev(A, B, P, Q, m0, S0)
+            ptrs = [_fp(x) for x in (A, B, P, Q, m0, S0)]
+            keep = None
+        else:
+            d = np.asarray(A).shape[-1]
+            keep = [_model32(x) for x in (A, B, P, Q, m0, S0)]
+            ptrs = [k[1] for k in keep]
+        if force_per_chain_path:
+            flags |= L.PATH_PER_CHAIN
+        if cov_shared_out:
+            flags |= L.COV_SHARED_OUT
+        if transition_first:
+            flags |= L.TRANSITION_FIRST
+        if asynchronous:
+            flags |= L.ASYNC
+        mk = lambda *s, dt=torch.float32: (torch.empty(*s, dtype=dt, device=y.device) if on_dev
+                                           else torch.empty(*s, dtype=dt).pin_memory())
+        mean = out_mean if out_mean is not None else mk(T, d, batch)
+        need_cov = want_cov or per_chain_model or force_per_chain_path or mask is not None
+        cov = out_cov
+        if cov is None and need_cov:
+            cov = mk(T, d, d) if cov_shared_out else mk(T, d, d, batch)
+        nle = mk(batch) if want_evidence else None
+        status = mk(batch, dt=torch.int32) if want_status else None
+        fn = self.lib.rxg_lgssm_smooth_f32 if smooth else self.lib.rxg_lgssm_filter_f32
+        mask_p = ctypes.cast(c_void_p(mask.data_ptr()), L.u8p) if mask is not None else ctypes.cast(c_void_p(None), L.u8p)
+        st_p = ctypes.cast(c_void_p(status.data_ptr()), L.i32p) if status is not None else ctypes.cast(c_void_p(None), L.i32p)
+        self._check(fn(self.h, d, m, T, batch, *ptrs, _fp(y), mask_p, _fp(mean), _fp(cov), _fp(nle), st_p, flags))
+        return dict(mean=mean, cov=cov if (want_cov or need_cov) else None, neg_log_evidence=nle, status=status)
+
+    def hgf_filter(self, y, iters=20, kappa=1.0, omega=0.0, z_variance=0.04, y_variance=0.01,
+                   init=(0.0, 5.0, 0.0, 5.0), out=None):
+        self._dev(y)
+        T, batch = y.shape
+        out = out if out is not None else self.empty(T, 4, batch)
+        ini = (ctypes.c_float * 4)(*init)
+        self._check(self.lib.rxg_hgf_filter_f32(self.h, T, batch, iters, kappa, omega, z_variance, y_variance,
+                                                ini, _fp(y), _fp(out), L.PTR_DEVICE))
+        return out
+
+    def lgssm_vmp_gamma(self, y, iterations=10, a=1.0, v_proc=1.0, prior=(0.0, 100.0), gamma_prior=(1.0, 1.0),
+                        init_E_tau=1.0):
+        self._dev(y)
+        T, batch = y.shape
+        pm, pv = self.empty(T, batch), self.empty(T, batch)
+        sh, rt = self.empty(batch), self.empty(batch)
+        self._check(self.lib.rxg_lgssm_vmp_gamma_f32(self.h, T, batch, iterations, a, v_proc, prior[0], prior[1],
+                                                     gamma_prior[0], gamma_prior[1], init_E_tau, _fp(y), _fp(pm),
+                                                     _fp(pv), _fp(sh), _fp(rt), L.PTR_DEVICE))
+        return dict(mean=pm, var=pv, shape=sh, rate=rt)
+
+    # ------------------------------------------------------------------ per-rule kernels
+    def _mat(self, M):
+        """PointMass matrix operand: host array => shared; CUDA tensor [r,c,n] => per message."""
+        if isinstance(M, torch.Tensor) and M.is_cuda:
+            self._dev(M)
+            return M, _fp(M), 0
+        t = torch.as_tensor(np.ascontiguousarray(np.asarray(M, dtype=np.float32)), device=f"cuda:{self.device}")
+        return t, _fp(t), 1
+
+    def rule_add_cov(self, mu, S, Sigma, which="out"):
+        self._dev(mu, S)
+        d, n = mu.shape
+        keep, Sp, shared = self._mat(Sigma)
+        mo, So = torch.empty_like(mu), torch.empty_like(S)
+        fn = self.lib.rxg_rule_mvnormal_meancov_out_f32 if which == "out" else self.lib.rxg_rule_mvnormal_meancov_mean_f32
+        self._check(fn(self.h, n, d, _fp(mu), _fp(S), Sp, shared, _fp(mo), _fp(So), L.PTR_DEVICE))
+        return mo, So
+
+    def rule_mean_from_data(self, y, Sigma):
+        self._dev(y)
+        d, n = y.shape
+        keep, Sp, shared = self._mat(Sigma)
+        mo, So = torch.empty_like(y), self.empty(d, d, n)
+        self._check(self.lib.rxg_rule_mvnormal_meancov_mean_data_f32(self.h, n, d, _fp(y), Sp, shared, _fp(mo), _fp(So), L.PTR_DEVICE))
+        return mo, So
+
+    def rule_mul_out(self, A, mu, S):
+        self._dev(mu, S)
+        di, n = mu.shape
+        keep, Ap, shared = self._mat(A)
+        do = keep.shape[0]
+        mo, So = self.empty(do, n), self.empty(do, do, n)
+        self._check(self.lib.rxg_rule_mul_out_f32(self.h, n, do, di, Ap, shared, _fp(mu), _fp(S), _fp(mo), _fp(So), L.PTR_DEVICE))
+        return mo, So
+
+    def rule_mul_in(self, A, mu_out, S_out):
+        self._dev(mu_out, S_out)
+        do, n = mu_out.shape
+        keep, Ap, shared = self._mat(A)
+        di = keep.shape[1]
+        xi, W = self.empty(di, n), self.empty(di, di, n)
+        st = self.empty(n, dtype=torch.int32)
+        self._check(self.lib.rxg_rule_mul_in_f32(self.h, n, do, di, Ap, shared, _fp(mu_out), _fp(S_out), _fp(xi), _fp(W),
+                                                 ctypes.cast(c_void_p(st.data_ptr()), L.i32p), L.PTR_DEVICE))
+        return xi, W, st
+
+    def _pair(self, fn, a, Sa, b, Sb):
+        self._dev(a, Sa, b, Sb)
+        d, n = a.shape
+        o, So = torch.empty_like(a), torch.empty_like(Sa)
+        self._check(fn(self.h, n, d, _fp(a), _fp(Sa), _fp(b), _fp(Sb), _fp(o), _fp(So), L.PTR_DEVICE))
+        return o, So
+
+    def rule_add_out(self, mu1, S1, mu2, S2):
+        return self._pair(self.lib.rxg_rule_add_out_f32, mu1, S1, mu2, S2)
+
+    def rule_add_in(self, mu_out, S_out, mu_other, S_other):
+        return self._pair(self.lib.rxg_rule_add_in_f32, mu_out, S_out, mu_other, S_other)
+
+    def prod_gaussian(self, xi1, W1, xi2, W2):
+        return self._pair(self.lib.rxg_prod_gaussian_f32, xi1, W1, xi2, W2)
+
+    def _conv(self, fn, v, M):
+        self._dev(v, M)
+        d, n = v.shape
+        vo, Mo = torch.empty_like(v), torch.empty_like(M)
+        st = self.empty(n, dtype=torch.int32)
+        self._check(fn(self.h, n, d, _fp(v), _fp(M), _fp(vo), _fp(Mo), ctypes.cast(c_void_p(st.data_ptr()), L.i32p), L.PTR_DEVICE))
+        return vo, Mo, st
+
+    def meancov_to_wmp(self, mu, S):
+        return self._conv(self.lib.rxg_meancov_to_wmp_f32, mu, S)
+
+    def wmp_to_meancov(self, xi, W):
+        return self._conv(self.lib.rxg_wmp_to_meancov_f32, xi, W)
+
+    def marginal_gaussian(self, msgs):
+        d, n = msgs[0][0].shape
+        k = len(msgs)
+        for xi, W in msgs:
+            self._dev(xi, W)
+        xs = (L.fp * k)(*[_fp(x) for x, _ in msgs])
+        ws = (L.fp * k)(*[_fp(w) for _, w in msgs])
+        mu, S = self.empty(d, n), self.empty(d, d, n)
+        st = self.empty(n, dtype=torch.int32)
+        self._check(self.lib.rxg_marginal_gaussian_f32(self.h, n, d, k, xs, ws, _fp(mu), _fp(S),
+                                                       ctypes.cast(c_void_p(st.data_ptr()), L.i32p), L.PTR_DEVICE))
+        return mu, S, st
+
+    def _six(self, fn, a, b, c, d_):
+        self._dev(a, b, c, d_)
+        n = a.numel()
+        o1, o2 = torch.empty_like(a), torch.empty_like(a)
+        self._check(fn(self.h, n, _fp(a), _fp(b), _fp(c), _fp(d_), _fp(o1), _fp(o2), L.PTR_DEVICE))
+        return o1, o2
+
+    def rule_normal_precision_tau(self, m_out, v_out, m_mu, v_mu):
+        return self._six(self.lib.rxg_rule_normal_precision_tau_f32, m_out, v_out, m_mu, v_mu)
+
+    def rule_normal_precision_out(self, m_mu, v_mu, shape, rate):
+        return self._six(self.lib.rxg_rule_normal_precision_out_f32, m_mu, v_mu, shape, rate)
+
+    def prod_gamma(self, a1, b1, a2, b2):
+        return self._six(self.lib.rxg_prod_gamma_f32, a1, b1, a2, b2)
+
+    def prod_normal(self, m1, v1, m2, v2):
+        return self._six(self.lib.rxg_prod_normal_f32, m1, v1, m2, v2)
+
+    def rule_gcv_out(self, m_x, v_x, m_z, v_z, kappa, omega):
+        self._dev(m_x, v_x, m_z, v_z)
+        n = m_x.numel()
+        mo, vo = torch.empty_like(m_x), torch.empty_like(m_x)
+        self._check(self.lib.rxg_rule_gcv_out_f32(self.h, n, _fp(m_x), _fp(v_x), _fp(m_z), _fp(v_z), kappa, omega, _fp(mo), _fp(vo), L.PTR_DEVICE))
+        return mo, vo
+
+    def marginalrule_gcv_yx(self, m_y, v_y, m_x, v_x, m_z, v_z, kappa, omega):
+        self._dev(m_y, v_y, m_x, v_x, m_z, v_z)
+        n = m_y.numel()
+        m, V = self.empty(2, n), self.empty(2, 2, n)
+        self._check(self.lib.rxg_marginalrule_gcv_yx_f32(self.h, n, _fp(m_y), _fp(v_y), _fp(m_x), _fp(v_x), _fp(m_z), _fp(v_z),
+                                                         kappa, omega, _fp(m), _fp(V), L.PTR_DEVICE))
+        return m, V
+
+    def rule_gcv_z_prod(self, m_yx, V_yx, m_zp, v_zp, kappa, omega):
+        self._dev(m_yx, V_yx, m_zp, v_zp)
+        n = m_zp.numel()
+        mz, vz = torch.empty_like(m_zp), torch.empty_like(m_zp)
+        self._check(self.lib.rxg_rule_gcv_z_prod_f32(self.h, n, _fp(m_yx), _fp(V_yx), _fp(m_zp), _fp(v_zp), kappa, omega,
+                                                     _fp(mz), _fp(vz), L.PTR_DEVICE))
+        return mz, vz
+
+    # ------------------------------------------------------------------ multi-GPU
+    def comm_init(self, nranks, rank, uid: bytes):
+        buf = ctypes.create_string_buffer(uid, 128)
+        self._check(self.lib.rxg_comm_init(self.h, nranks, rank, ctypes.cast(buf, c_void_p)))
+
+    def allgather_posteriors(self, mean, cov, nranks):
+        self._dev(mean, cov)
+        T, d, bl = mean.shape
+        gm = self.empty(nranks, T, d, bl)
+        gc = self.empty(nranks, T, d, d, bl) if cov is not None else None
+        self._check(self.lib.rxg_allgather_posteriors(self.h, d, T, bl, _fp(mean), _fp(cov), _fp(gm), _fp(gc), L.PTR_DEVICE))
+        return gm, gc
+
+
+def comm_unique_id() -> bytes:
+    lib = L.load()
+    buf = ctypes.create_string_buffer(128)
+    rc = lib.rxg_comm_unique_id(ctypes.cast(buf, c_void_p))
+    if rc != 0:
+        raise L.RxGaussError(rc, "rxg_comm_unique_id failed")
+    return buf.raw

@@ -1,0 +1,318 @@
+// C ABI of librxgauss: context, error handling, workspace, the whole-chain LGSSM entry points
+// (device- and host-pointer variants) and the NCCL all-gather of posterior marginals.
+// See include/rxgauss.h for the contract and the reference interfaces each entry replaces.
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "rxg_internal.h"
+
+namespace rxg {
+
+int fail(rxg_ctx* ctx, int code, const char* fmt, ...) {
+    if (ctx) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        ctx->err = buf;
+    }
+    return code;
+}
+
+int check_cuda(rxg_ctx* ctx, cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return RXG_OK;
+    return fail(ctx, RXG_ERR_CUDA, "CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+}
+
+static void* grow(rxg_ctx* ctx, void** buf, size_t* have, size_t want) {
+    if (*have >= want && *buf) return *buf;
+    if (*buf) {
+        // the stream may still be using the old buffer
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(*buf);
+        *buf = nullptr;
+        *have = 0;
+    }
+    size_t sz = (want + ((size_t)1 << 20) - 1) >> 20 << 20;
+    cudaError_t e = cudaMalloc(buf, sz);
+    if (e != cudaSuccess) {
+        check_cuda(ctx, e, "cudaMalloc(workspace)");
+        *buf = nullptr;
+        return nullptr;
+    }
+    *have = sz;
+    return *buf;
+}
+void* workspace(rxg_ctx* ctx, size_t bytes) { return grow(ctx, &ctx->ws, &ctx->ws_bytes, bytes); }
+void* staging(rxg_ctx* ctx, size_t bytes) { return grow(ctx, &ctx->stage, &ctx->stage_bytes, bytes); }
+
+}  // namespace rxg
+
+using namespace rxg;
+
+extern "C" {
+
+int rxg_version(void) { return RXG_VERSION; }
+
+int rxg_create(rxg_ctx** out, int device, unsigned flags) {
+    (void)flags;
+    if (!out) return RXG_ERR_BAD_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) return RXG_ERR_NO_DEVICE;   // no CPU fallback, by design
+    if (device < 0 || device >= n) return RXG_ERR_BAD_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return RXG_ERR_CUDA;
+    rxg_ctx* ctx = new rxg_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return RXG_ERR_CUDA;
+    }
+    ctx->own_stream = true;
+    *out = ctx;
+    return RXG_OK;
+}
+
+int rxg_comm_destroy_internal(rxg_ctx* ctx);
+
+int rxg_destroy(rxg_ctx* ctx) {
+    if (!ctx) return RXG_ERR_BAD_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    rxg_comm_destroy_internal(ctx);
+    if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->stage) cudaFree(ctx->stage);
+    for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return RXG_OK;
+}
+
+const char* rxg_last_error(const rxg_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int rxg_set_stream(rxg_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return RXG_ERR_BAD_ARG;
+    if (ctx->own_stream && ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return RXG_OK;
+}
+
+int rxg_sync(rxg_ctx* ctx) {
+    if (!ctx) return RXG_ERR_BAD_ARG;
+    RXG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RXG_OK;
+}
+
+int rxg_host_alloc(void** out, size_t bytes) {
+    if (!out) return RXG_ERR_BAD_ARG;
+    return cudaMallocHost(out, bytes) == cudaSuccess ? RXG_OK : RXG_ERR_CUDA;
+}
+int rxg_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? RXG_OK : RXG_ERR_CUDA; }
+
+int rxg_supports(int d, int m) { return lgssm_supported(d, m) ? 1 : 0; }
+
+long long rxg_launch_count(const rxg_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int rxg_set_profiling(rxg_ctx* ctx, int enabled) {
+    if (!ctx) return RXG_ERR_BAD_ARG;
+    if (enabled && !ctx->ev[0]) {
+        RXG_CUDA(ctx, cudaSetDevice(ctx->device));
+        for (int i = 0; i < 4; ++i) RXG_CUDA(ctx, cudaEventCreate(&ctx->ev[i]));
+    }
+    ctx->profile = enabled != 0;
+    return RXG_OK;
+}
+int rxg_profile_last_ms(rxg_ctx* ctx, float* main_kernel_ms, float* gain_kernels_ms) {
+    if (!ctx || !ctx->ev[0]) return RXG_ERR_BAD_ARG;
+    RXG_CUDA(ctx, cudaEventSynchronize(ctx->ev[2]));
+    if (main_kernel_ms) RXG_CUDA(ctx, cudaEventElapsedTime(main_kernel_ms, ctx->ev[1], ctx->ev[2]));
+    if (gain_kernels_ms) RXG_CUDA(ctx, cudaEventElapsedTime(gain_kernels_ms, ctx->ev[0], ctx->ev[1]));
+    return RXG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// whole-chain LGSSM sweeps
+// ------------------------------------------------------------------------------------------------
+static int lgssm_entry(rxg_ctx* ctx, bool smooth, int d, int m, int T, int64_t batch, const float* A,
+                       const float* B, const float* P, const float* Q, const float* m0, const float* S0,
+                       const float* y, const uint8_t* ymask, float* mean, float* cov, float* nle,
+                       int32_t* status, unsigned flags) {
+    if (!ctx) return RXG_ERR_BAD_ARG;
+    if (d < 1 || m < 1 || T < 1 || batch < 1) return fail(ctx, RXG_ERR_BAD_ARG, "lgssm: d, m, T, batch must be >= 1");
+    if (!A || !B || !P || !Q || !m0 || !S0 || !y || !mean) return fail(ctx, RXG_ERR_BAD_ARG, "lgssm: null pointer argument");
+    if (!cov && smooth && (flags & (RXG_MODEL_PER_CHAIN | RXG_PATH_PER_CHAIN)))
+        return fail(ctx, RXG_ERR_BAD_ARG, "lgssm: post_cov is required on the per-chain path (it is the stash)");
+    if (!lgssm_supported(d, m))
+        return fail(ctx, RXG_ERR_UNSUPPORTED, "lgssm: (d=%d, m=%d) is outside the thread-per-chain kernel families", d, m);
+    const bool per_chain_model = (flags & RXG_MODEL_PER_CHAIN) != 0;
+    if ((flags & RXG_COV_SHARED_OUT) && (per_chain_model || (flags & RXG_PATH_PER_CHAIN) || ymask))
+        return fail(ctx, RXG_ERR_BAD_ARG, "lgssm: RXG_COV_SHARED_OUT needs the shared-model gain-table path");
+    RXG_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    LgssmCall c;
+    c.d = d; c.m = m; c.T = T; c.batch = batch;
+    c.A = A; c.B = B; c.P = P; c.Q = Q; c.m0 = m0; c.S0 = S0;
+    c.flags = flags; c.smooth = smooth;
+
+    if (flags & RXG_PTR_DEVICE) {
+        if (!cov && (ymask || per_chain_model || (flags & RXG_PATH_PER_CHAIN)))
+            return fail(ctx, RXG_ERR_BAD_ARG, "lgssm: cov output required on the per-chain path");
+        c.y = y; c.ymask = ymask; c.mean = mean; c.cov = cov; c.nle = nle; c.status = status;
+        int rc = lgssm_dispatch(ctx, c);
+        if (rc != RXG_OK) return rc;
+        if (!(flags & RXG_ASYNC)) RXG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return RXG_OK;
+    }
+
+    // ---- host-pointer call: stage through device memory on the context's stream
+    if (per_chain_model)
+        return fail(ctx, RXG_ERR_UNSUPPORTED, "lgssm: per-chain model arrays must be device pointers");
+    const bool cov_shared = (flags & RXG_COV_SHARED_OUT) != 0;
+    const size_t n_y = (size_t)T * m * batch, n_mean = (size_t)T * d * batch;
+    const size_t n_cov_dev = cov ? (cov_shared ? (size_t)T * d * d : (size_t)T * d * d * batch)
+                                 : ((ymask || (flags & RXG_PATH_PER_CHAIN)) ? (size_t)T * d * d * batch : 0);
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t o_y = carve(n_y * 4), o_mean = carve(n_mean * 4), o_cov = carve(n_cov_dev * 4);
+    const size_t o_mask = carve(ymask ? (size_t)T * batch : 0);
+    const size_t o_nle = carve(nle ? (size_t)batch * 4 : 0), o_st = carve(status ? (size_t)batch * 4 : 0);
+    char* base = (char*)staging(ctx, off);
+    if (!base) return RXG_ERR_CUDA;
+    float* d_y = (float*)(base + o_y);
+    c.y = d_y;
+    c.mean = (float*)(base + o_mean);
+    c.cov = n_cov_dev ? (float*)(base + o_cov) : nullptr;
+    c.ymask = ymask ? (const uint8_t*)(base + o_mask) : nullptr;
+    c.nle = nle ? (float*)(base + o_nle) : nullptr;
+    c.status = status ? (int32_t*)(base + o_st) : nullptr;
+    RXG_CUDA(ctx, cudaMemcpyAsync(d_y, y, n_y * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (ymask) RXG_CUDA(ctx, cudaMemcpyAsync((void*)c.ymask, ymask, (size_t)T * batch, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = lgssm_dispatch(ctx, c);
+    if (rc != RXG_OK) return rc;
+    RXG_CUDA(ctx, cudaMemcpyAsync(mean, c.mean, n_mean * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cov) RXG_CUDA(ctx, cudaMemcpyAsync(cov, c.cov, n_cov_dev * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nle) RXG_CUDA(ctx, cudaMemcpyAsync(nle, c.nle, (size_t)batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (status) RXG_CUDA(ctx, cudaMemcpyAsync(status, c.status, (size_t)batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!(flags & RXG_ASYNC)) RXG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RXG_OK;
+}
+
+int rxg_lgssm_smooth_f32(rxg_ctx* ctx, int d, int m, int T, int64_t batch, const float* A, const float* B,
+                         const float* P, const float* Q, const float* m0, const float* S0, const float* y,
+                         const uint8_t* ymask, float* post_mean, float* post_cov, float* neg_log_evidence,
+                         int32_t* status, unsigned flags) {
+    if (ctx && (flags & RXG_TRANSITION_FIRST))
+        return fail(ctx, RXG_ERR_BAD_ARG, "lgssm_smooth: RXG_TRANSITION_FIRST applies to the filter only");
+    return lgssm_entry(ctx, true, d, m, T, batch, A, B, P, Q, m0, S0, y, ymask, post_mean, post_cov,
+                       neg_log_evidence, status, flags);
+}
+
+int rxg_lgssm_filter_f32(rxg_ctx* ctx, int d, int m, int T, int64_t batch, const float* A, const float* B,
+                         const float* P, const float* Q, const float* m0, const float* S0, const float* y,
+                         const uint8_t* ymask, float* filt_mean, float* filt_cov, float* neg_log_evidence,
+                         int32_t* status, unsigned flags) {
+    return lgssm_entry(ctx, false, d, m, T, batch, A, B, P, Q, m0, S0, y, ymask, filt_mean, filt_cov,
+                       neg_log_evidence, status, flags);
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCCL (resolved at run time so that the library loads on hosts without NCCL)
+// ------------------------------------------------------------------------------------------------
+typedef struct { char internal[128]; } nccl_uid_t;
+typedef int (*fn_get_uid)(nccl_uid_t*);
+typedef int (*fn_comm_init)(void**, int, nccl_uid_t, int);
+typedef int (*fn_comm_destroy)(void*);
+typedef int (*fn_allgather)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef const char* (*fn_errstr)(int);
+typedef int (*fn_group)(void);
+
+static void* g_nccl = nullptr;
+static fn_get_uid p_get_uid;
+static fn_comm_init p_comm_init;
+static fn_comm_destroy p_comm_destroy;
+static fn_allgather p_allgather;
+static fn_errstr p_errstr;
+static fn_group p_group_start, p_group_end;
+
+static int nccl_load(rxg_ctx* ctx) {
+    if (g_nccl) return RXG_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+    for (int i = 0; names[i] && !g_nccl; ++i) g_nccl = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!g_nccl) return fail(ctx, RXG_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+    p_get_uid = (fn_get_uid)dlsym(g_nccl, "ncclGetUniqueId");
+    p_comm_init = (fn_comm_init)dlsym(g_nccl, "ncclCommInitRank");
+    p_comm_destroy = (fn_comm_destroy)dlsym(g_nccl, "ncclCommDestroy");
+    p_allgather = (fn_allgather)dlsym(g_nccl, "ncclAllGather");
+    p_errstr = (fn_errstr)dlsym(g_nccl, "ncclGetErrorString");
+    p_group_start = (fn_group)dlsym(g_nccl, "ncclGroupStart");
+    p_group_end = (fn_group)dlsym(g_nccl, "ncclGroupEnd");
+    if (!p_get_uid || !p_comm_init || !p_comm_destroy || !p_allgather || !p_group_start || !p_group_end) {
+        g_nccl = nullptr;
+        return fail(ctx, RXG_ERR_NCCL, "libnccl is missing required symbols");
+    }
+    return RXG_OK;
+}
+
+int rxg_comm_unique_id(void* id128) {
+    if (!id128) return RXG_ERR_BAD_ARG;
+    int rc = nccl_load(nullptr);
+    if (rc != RXG_OK) return rc;
+    nccl_uid_t uid;
+    if (p_get_uid(&uid) != 0) return RXG_ERR_NCCL;
+    memcpy(id128, &uid, sizeof(uid));
+    return RXG_OK;
+}
+
+int rxg_comm_init(rxg_ctx* ctx, int nranks, int rank, const void* id128) {
+    if (!ctx || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return RXG_ERR_BAD_ARG;
+    int rc = nccl_load(ctx);
+    if (rc != RXG_OK) return rc;
+    RXG_CUDA(ctx, cudaSetDevice(ctx->device));
+    nccl_uid_t uid;
+    memcpy(&uid, id128, sizeof(uid));
+    int r = p_comm_init(&ctx->comm, nranks, uid, rank);
+    if (r != 0) return fail(ctx, RXG_ERR_NCCL, "ncclCommInitRank failed: %s", p_errstr ? p_errstr(r) : "?");
+    ctx->nranks = nranks;
+    ctx->rank = rank;
+    return RXG_OK;
+}
+
+int rxg_comm_destroy_internal(rxg_ctx* ctx) {
+    if (ctx->comm && p_comm_destroy) p_comm_destroy(ctx->comm);
+    ctx->comm = nullptr;
+    return RXG_OK;
+}
+
+int rxg_allgather_posteriors(rxg_ctx* ctx, int d, int T, int64_t batch_local, const float* post_mean,
+                             const float* post_cov, float* gathered_mean, float* gathered_cov, unsigned flags) {
+    if (!ctx) return RXG_ERR_BAD_ARG;
+    if (!(flags & RXG_PTR_DEVICE)) return fail(ctx, RXG_ERR_UNSUPPORTED, "allgather takes device pointers");
+    if (!ctx->comm) return fail(ctx, RXG_ERR_NCCL, "allgather: rxg_comm_init has not been called");
+    if (d < 1 || T < 1 || batch_local < 1 || !post_mean || !gathered_mean || (post_cov && !gathered_cov))
+        return fail(ctx, RXG_ERR_BAD_ARG, "allgather: bad argument");
+    const size_t n_mean = (size_t)T * d * batch_local, n_cov = n_mean * d;
+    const int nccl_float = 7;
+    int r = p_group_start();
+    if (r == 0) r = p_allgather(post_mean, gathered_mean, n_mean, nccl_float, ctx->comm, ctx->stream);
+    if (r == 0 && post_cov) r = p_allgather(post_cov, gathered_cov, n_cov, nccl_float, ctx->comm, ctx->stream);
+    int r2 = p_group_end();
+    if (r == 0) r = r2;
+    if (r != 0) return fail(ctx, RXG_ERR_NCCL, "ncclAllGather failed: %s", p_errstr ? p_errstr(r) : "?");
+    ctx->launches += post_cov ? 2 : 1;
+    if (!(flags & RXG_ASYNC)) RXG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RXG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,292 @@
+// Variational (VMP) members of the hot path: the GCV node of the Hierarchical Gaussian Filter
+//  and the Gamma-precision rules around a scalar smoother (row 9).
+//
+// HGF: per datum the reference's streaming engine [ref: /root/reference/src/inference/
+// streaming.jl:349-407] runs `iterations` VMP sweeps over the 5-node graph of
+// test/models/statespace/hgf_tests.jl:10-31 with q(xt, xt_min) q(zt) and GCVMetadata(
+// GaussHermiteCubature(31)) (hgf_tests.jl:33-40), then @autoupdates carry q(zt), q(xt) into the
+// next step's priors (hgf_tests.jl:46-49).  hgf_filter_kernel fuses T steps x iters sweeps per
+// chain into one launch; state lives in registers, the 31 exp(-kappa z_i) factors that do not
+// change across the iterations of a step are hoisted.  This family is SFU/FP32-issue bound
+// (~21 + 31*iters exp per step against 20 bytes of I/O), not HBM bound.
+#include <math.h>
+
+#include "rxg_internal.h"
+
+namespace rxg {
+
+__constant__ float c_gh_t[31];    // Gauss-Hermite nodes (physicists')
+__constant__ float c_gh_lw[31];   // log weights
+
+// Gauss-Hermite nodes/weights by Newton iteration on the orthonormal recurrence (host, fp64).
+static void gauss_hermite_31(double* t, double* w) {
+    const int n = 31;
+    const double pim4 = 0.7511255444649425;
+    double z = 0, z1, pp = 0;
+    const int m = (n + 1) / 2;
+    for (int i = 0; i < m; ++i) {
+        if (i == 0) z = sqrt(2.0 * n + 1.0) - 1.85575 * pow(2.0 * n + 1.0, -0.16667);
+        else if (i == 1) z -= 1.14 * pow((double)n, 0.426) / z;
+        else if (i == 2) z = 1.86 * z - 0.86 * t[0];
+        else if (i == 3) z = 1.91 * z - 0.91 * t[1];
+        else z = 2.0 * z - t[i - 2];
+        for (int its = 0; its < 200; ++its) {
+            double p1 = pim4, p2 = 0.0;
+            for (int j = 0; j < n; ++j) {
+                double p3 = p2; p2 = p1;
+                p1 = z * sqrt(2.0 / (j + 1)) * p2 - sqrt((double)j / (j + 1)) * p3;
+            }
+            pp = sqrt(2.0 * n) * p2;
+            z1 = z; z = z1 - p1 / pp;
+            if (fabs(z - z1) <= 1e-15 * fabs(z) + 1e-300) break;
+        }
+        t[i] = z; t[n - 1 - i] = -z;
+        w[i] = 2.0 / (pp * pp); w[n - 1 - i] = w[i];
+    }
+}
+
+int ensure_gh_tables(rxg_ctx* ctx) {
+    if (ctx->gh_ready) return RXG_OK;
+    double t[31], w[31];
+    gauss_hermite_31(t, w);
+    float tf[31], lw[31];
+    for (int i = 0; i < 31; ++i) { tf[i] = (float)t[i]; lw[i] = (float)log(w[i]); }
+    RXG_CUDA(ctx, cudaMemcpyToSymbol(c_gh_t, tf, sizeof(tf)));
+    RXG_CUDA(ctx, cudaMemcpyToSymbol(c_gh_lw, lw, sizeof(lw)));
+    ctx->gh_ready = true;
+    return RXG_OK;
+}
+
+struct GcvJoint { float m1, m2, V11, V12, V22; };
+
+// @marginalrule GCV(:y_x): W = [[w_y + g, -g], [-g, w_x + g]], xi = [xi_y, xi_x]
+__device__ __forceinline__ GcvJoint gcv_joint(float xiy, float wy, float xix, float wx, float g) {
+    const float a = wy + g, c = wx + g;
+    const float det = __fmaf_rn(a, c, -g * g);
+    const float r = 1.0f / det;
+    GcvJoint j;
+    j.V11 = c * r; j.V12 = g * r; j.V22 = a * r;
+    j.m1 = __fmaf_rn(j.V11, xiy, j.V12 * xix);
+    j.m2 = __fmaf_rn(j.V12, xiy, j.V22 * xix);
+    return j;
+}
+// A * B of the node with PointMass kappa, omega
+__device__ __forceinline__ float gcv_gamma(float mz, float vz, float kappa, float omega) {
+    return expf(-omega - kappa * mz + 0.5f * kappa * kappa * vz);
+}
+
+// prod(Normal(mu0, v0), ELQ(a = kappa, b, c = -kappa, d = 0)) by GH-31 moment matching.
+// ez[i] = exp(-kappa z_i) precomputed; shift = expansion point for the second moment.
+__device__ __forceinline__ void gh_moment_match(const float* ez, float mu0, float s, float kappa, float b,
+                                                float shift, float& mz, float& vz) {
+    float lmax = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 31; ++i) {
+        const float z = __fmaf_rn(s, c_gh_t[i], mu0);
+        const float l = c_gh_lw[i] - 0.5f * __fmaf_rn(b, ez[i], kappa * z);
+        lmax = fmaxf(lmax, l);
+    }
+    float S0 = 0.f, S1 = 0.f, S2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 31; ++i) {
+        const float z = __fmaf_rn(s, c_gh_t[i], mu0);
+        const float l = c_gh_lw[i] - 0.5f * __fmaf_rn(b, ez[i], kappa * z);
+        const float e = __expf(l - lmax);
+        const float u = z - shift;
+        S0 += e;
+        S1 = __fmaf_rn(e, u, S1);
+        S2 = __fmaf_rn(e * u, u, S2);
+    }
+    const float r = 1.0f / S0;
+    const float du = S1 * r;
+    mz = shift + du;
+    vz = __fmaf_rn(-du, du, S2 * r);
+}
+
+__global__ void __launch_bounds__(128)
+hgf_filter_kernel(const float* __restrict__ y, float* __restrict__ out, int T, int64_t batch, int iters,
+                  float kappa, float omega, float zvar, float yvar, float i_mz, float i_vz, float i_mx,
+                  float i_vx) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    float mzp = i_mz, vzp = i_vz, mxp = i_mx, vxp = i_vx;
+    float mz = i_mz, vz = i_vz;                 // q(zt), carried across iterations and steps
+    const float wy = 1.0f / yvar;
+    const float eA = expf(-omega);
+    float ynext = __ldg(y + b);
+    for (int t = 0; t < T; ++t) {
+        const float yt = ynext;
+        if (t + 1 < T) ynext = __ldg(y + (int64_t)(t + 1) * batch + b);
+        // zt ~ Normal(zt_min, z_variance): message into zt from the prior side
+        const float mu0 = mzp, v0 = vzp + zvar;
+        const float s = sqrtf(2.0f * v0);
+        float ez[31];
+#pragma unroll
+        for (int i = 0; i < 31; ++i) ez[i] = expf(-kappa * __fmaf_rn(s, c_gh_t[i], mu0));
+        const float wx = 1.0f / vxp;
+        const float xiy = yt * wy, xix = mxp * wx;
+        GcvJoint j;
+        for (int it = 0; it < iters; ++it) {
+            const float g = gcv_gamma(mz, vz, kappa, omega);
+            j = gcv_joint(xiy, wy, xix, wx, g);
+            const float dm = j.m1 - j.m2;
+            const float psi = __fmaf_rn(dm, dm, j.V11 + j.V22 - 2.0f * j.V12);
+            gh_moment_match(ez, mu0, s, kappa, psi * eA, mz, mz, vz);
+        }
+        out[((int64_t)t * 4 + 0) * batch + b] = j.m1;
+        out[((int64_t)t * 4 + 1) * batch + b] = j.V11;
+        out[((int64_t)t * 4 + 2) * batch + b] = mz;
+        out[((int64_t)t * 4 + 3) * batch + b] = vz;
+        mxp = j.m1; vxp = j.V11; mzp = mz; vzp = vz;
+    }
+}
+
+// ---- per-rule GCV kernels
+__global__ void k_gcv_out(int64_t n, const float* m_x, const float* v_x, const float* m_z, const float* v_z,
+                          float kappa, float omega, float* m_out, float* v_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    m_out[i] = m_x[i];
+    v_out[i] = v_x[i] + 1.0f / gcv_gamma(m_z[i], v_z[i], kappa, omega);
+}
+__global__ void k_gcv_yx(int64_t n, const float* m_y, const float* v_y, const float* m_x, const float* v_x,
+                         const float* m_z, const float* v_z, float kappa, float omega, float* m, float* V) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float wy = 1.0f / v_y[i], wx = 1.0f / v_x[i];
+    GcvJoint j = gcv_joint(m_y[i] * wy, wy, m_x[i] * wx, wx, gcv_gamma(m_z[i], v_z[i], kappa, omega));
+    m[i] = j.m1; m[n + i] = j.m2;
+    V[i] = j.V11; V[n + i] = j.V12; V[2 * n + i] = j.V12; V[3 * n + i] = j.V22;
+}
+__global__ void k_gcv_z_prod(int64_t n, const float* m_yx, const float* V_yx, const float* m_zp, const float* v_zp,
+                             float kappa, float omega, float* m_z, float* v_z) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float dm = m_yx[i] - m_yx[n + i];
+    const float psi = __fmaf_rn(dm, dm, V_yx[i] + V_yx[3 * n + i] - V_yx[n + i] - V_yx[2 * n + i]);
+    const float mu0 = m_zp[i], v0 = v_zp[i];
+    const float s = sqrtf(2.0f * v0);
+    float ez[31];
+#pragma unroll
+    for (int q = 0; q < 31; ++q) ez[q] = expf(-kappa * __fmaf_rn(s, c_gh_t[q], mu0));
+    float mz, vz;
+    gh_moment_match(ez, mu0, s, kappa, psi * expf(-omega), mu0, mz, vz);
+    m_z[i] = mz; v_z[i] = vz;
+}
+
+// ---- Gamma-precision VMP around a scalar smoother (d = m = 1), tau shared over time per chain
+__global__ void __launch_bounds__(128)
+vmp_gamma_kernel(const float* __restrict__ y, float* __restrict__ pm, float* __restrict__ pv,
+                 float* __restrict__ shape, float* __restrict__ rate, int T, int64_t batch, int iterations,
+                 float a, float vproc, float m0, float v0, float a0, float b0, float init_Etau) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    float Etau = init_Etau, sh = a0, rt = b0;
+    for (int it = 0; it < iterations; ++it) {
+        const float q = 1.0f / Etau;       // NormalMeanPrecision(:out)(m_mu, q_tau): variance 1 / E[tau]
+        float m = m0, v = v0;
+        float ynext = __ldg(y + b);
+        for (int t = 0; t < T; ++t) {
+            const float yt = ynext;
+            if (t + 1 < T) ynext = __ldg(y + (int64_t)(t + 1) * batch + b);
+            if (t > 0) { m = a * m; v = __fmaf_rn(a * a, v, vproc); }
+            const float k = v / (v + q);
+            m = __fmaf_rn(k, yt - m, m);
+            v = __fmaf_rn(-k, v, v);
+            pm[(int64_t)t * batch + b] = m;
+            pv[(int64_t)t * batch + b] = v;
+        }
+        float ms = m, vs = v;
+        double res;
+        { const float d = __ldg(y + (int64_t)(T - 1) * batch + b) - ms; res = (double)__fmaf_rn(d, d, vs); }
+        for (int t = T - 2; t >= 0; --t) {
+            const float mf = pm[(int64_t)t * batch + b], vf = pv[(int64_t)t * batch + b];
+            const float vp = __fmaf_rn(a * a, vf, vproc);
+            const float G = a * vf / vp;
+            ms = __fmaf_rn(G, ms - a * mf, mf);
+            vs = __fmaf_rn(G * G, vs - vp, vf);
+            pm[(int64_t)t * batch + b] = ms;
+            pv[(int64_t)t * batch + b] = vs;
+            const float d = __ldg(y + (int64_t)t * batch + b) - ms;
+            res += (double)__fmaf_rn(d, d, vs);
+        }
+        // prod(Gamma(a0, b0), prod_t NormalMeanPrecision(:tau)(q_out = PointMass y_t, q_mu = q(x_t)))
+        sh = a0 + 0.5f * (float)T;
+        rt = b0 + 0.5f * (float)res;
+        Etau = sh / rt;
+    }
+    shape[b] = sh; rate[b] = rt;
+}
+
+}  // namespace rxg
+
+using namespace rxg;
+
+extern "C" {
+
+int rxg_hgf_filter_f32(rxg_ctx* ctx, int T, int64_t batch, int iters, float kappa, float omega, float z_variance,
+                       float y_variance, const float init[4], const float* y, float* out, unsigned flags) {
+    if (!ctx) return RXG_ERR_BAD_ARG;
+    if (T < 1 || batch < 1 || iters < 1 || !y || !out || !init)
+        return rxg::fail(ctx, RXG_ERR_BAD_ARG, "hgf_filter: bad argument");
+    if (!(flags & RXG_PTR_DEVICE)) return rxg::fail(ctx, RXG_ERR_UNSUPPORTED, "hgf_filter takes device pointers");
+    int rc = ensure_gh_tables(ctx);
+    if (rc != RXG_OK) return rc;
+    hgf_filter_kernel<<<(unsigned)((batch + 63) / 64), 64, 0, ctx->stream>>>(
+        y, out, T, batch, iters, kappa, omega, z_variance, y_variance, init[0], init[1], init[2], init[3]);
+    ctx->launches += 1;
+    rc = rxg::check_cuda(ctx, cudaGetLastError(), "hgf_filter_kernel");
+    if (rc != RXG_OK) return rc;
+    if (!(flags & RXG_ASYNC)) RXG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RXG_OK;
+}
+
+#define RXG_GCV_PROLOGUE                                                                          \
+    if (!ctx) return RXG_ERR_BAD_ARG;                                                             \
+    if (!(flags & RXG_PTR_DEVICE)) return rxg::fail(ctx, RXG_ERR_UNSUPPORTED, "GCV rules take device pointers"); \
+    if (n <= 0) return n == 0 ? RXG_OK : rxg::fail(ctx, RXG_ERR_BAD_ARG, "n < 0");                \
+    { int rc0 = ensure_gh_tables(ctx); if (rc0 != RXG_OK) return rc0; }
+#define RXG_GCV_EPILOGUE(what)                                                                    \
+    ctx->launches += 1;                                                                           \
+    { int rc1 = rxg::check_cuda(ctx, cudaGetLastError(), what); if (rc1 != RXG_OK) return rc1; }  \
+    if (!(flags & RXG_ASYNC)) RXG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));                  \
+    return RXG_OK;
+
+int rxg_rule_gcv_out_f32(rxg_ctx* ctx, int64_t n, const float* m_x, const float* v_x, const float* m_z,
+                         const float* v_z, float kappa, float omega, float* m_out, float* v_out, unsigned flags) {
+    RXG_GCV_PROLOGUE
+    k_gcv_out<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, m_x, v_x, m_z, v_z, kappa, omega, m_out, v_out);
+    RXG_GCV_EPILOGUE("k_gcv_out")
+}
+int rxg_marginalrule_gcv_yx_f32(rxg_ctx* ctx, int64_t n, const float* m_y, const float* v_y, const float* m_x,
+                                const float* v_x, const float* m_z, const float* v_z, float kappa, float omega,
+                                float* m, float* V, unsigned flags) {
+    RXG_GCV_PROLOGUE
+    k_gcv_yx<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, m_y, v_y, m_x, v_x, m_z, v_z, kappa, omega, m, V);
+    RXG_GCV_EPILOGUE("k_gcv_yx")
+}
+int rxg_rule_gcv_z_prod_f32(rxg_ctx* ctx, int64_t n, const float* m_yx, const float* V_yx, const float* m_zprior,
+                            const float* v_zprior, float kappa, float omega, float* m_z, float* v_z,
+                            unsigned flags) {
+    RXG_GCV_PROLOGUE
+    k_gcv_z_prod<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(n, m_yx, V_yx, m_zprior, v_zprior, kappa, omega, m_z, v_z);
+    RXG_GCV_EPILOGUE("k_gcv_z_prod")
+}
+
+int rxg_lgssm_vmp_gamma_f32(rxg_ctx* ctx, int T, int64_t batch, int iterations, float a, float v_proc, float m0,
+                            float v0, float a0, float b0, float init_E_tau, const float* y, float* post_mean,
+                            float* post_var, float* shape, float* rate, unsigned flags) {
+    if (!ctx) return RXG_ERR_BAD_ARG;
+    if (T < 1 || batch < 1 || iterations < 1 || !y || !post_mean || !post_var || !shape || !rate)
+        return rxg::fail(ctx, RXG_ERR_BAD_ARG, "lgssm_vmp_gamma: bad argument");
+    if (!(flags & RXG_PTR_DEVICE)) return rxg::fail(ctx, RXG_ERR_UNSUPPORTED, "lgssm_vmp_gamma takes device pointers");
+    vmp_gamma_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, ctx->stream>>>(
+        y, post_mean, post_var, shape, rate, T, batch, iterations, a, v_proc, m0, v0, a0, b0, init_E_tau);
+    ctx->launches += 1;
+    int rc = rxg::check_cuda(ctx, cudaGetLastError(), "vmp_gamma_kernel");
+    if (rc != RXG_OK) return rc;
+    if (!(flags & RXG_ASYNC)) RXG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RXG_OK;
+}
+
+}  // extern "C"

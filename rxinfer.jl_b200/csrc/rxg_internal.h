@@ -1,0 +1,64 @@
+// Internal declarations shared by the translation units of librxgauss (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/rxgauss.h"
+
+struct rxg_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    // grow-only device workspace for gain tables / staging of host-pointer calls
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    void* stage = nullptr;
+    size_t stage_bytes = 0;
+    long long launches = 0;
+    int sm_count = 148;
+    bool gh_ready = false;
+    // optional per-kernel timing of the last fused sweep (bench.py roofline leg)
+    bool profile = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // gain start, main start, main end, (spare)   // Gauss-Hermite tables uploaded to this device's constant memory
+    // NCCL (dlopen'ed lazily; see rxg_comm.cu)
+    void* nccl_dl = nullptr;
+    void* comm = nullptr;
+    int nranks = 1, rank = 0;
+};
+
+namespace rxg {
+
+int fail(rxg_ctx* ctx, int code, const char* fmt, ...);
+int check_cuda(rxg_ctx* ctx, cudaError_t e, const char* what);
+// returns device pointer of >= bytes (grow-only); nullptr on failure (error recorded)
+void* workspace(rxg_ctx* ctx, size_t bytes);
+void* staging(rxg_ctx* ctx, size_t bytes);
+
+#define RXG_CUDA(ctx, call)                                         \
+    do {                                                            \
+        int _rc = ::rxg::check_cuda((ctx), (call), #call);          \
+        if (_rc != RXG_OK) return _rc;                              \
+    } while (0)
+
+struct LgssmCall {
+    int d, m, T;
+    int64_t batch;
+    // shared model: host pointers (row-major); per-chain model: device pointers [..][batch]
+    const float *A, *B, *P, *Q, *m0, *S0;
+    const float* y;          // device
+    const uint8_t* ymask;    // device or null
+    float* mean;             // device
+    float* cov;              // device
+    float* nle;              // device or null
+    int32_t* status;         // device or null
+    unsigned flags;
+    bool smooth;
+};
+
+// rxg_lgssm.cu
+int lgssm_dispatch(rxg_ctx* ctx, const LgssmCall& c);
+bool lgssm_supported(int d, int m);
+
+}  // namespace rxg

@@ -1,0 +1,810 @@
+// Fused forward/backward sum-product sweeps for batched linear-Gaussian state-space models.
+//
+// What this replaces: for `batch` independent chains, the whole per-message schedule that
+// infer(model = linear_gaussian_ssm_smoothing(...), data = (y = ...,)) runs through ReactiveMP
+// and Rocket  [ref: /root/reference/src/inference/batch.jl:391-430 (iteration loop),
+// benchmarks/Linear Multivariate Gaussian State Space Model Benchmark.ipynb:95-105 (model),
+// src/model/plugins/reactivemp_inference.jl:365-374 (left-to-right product fold),
+// src/rocket.jl:51-75 (stack-limited schedule)].  Per (chain, step) the reference evaluates
+//   #1 *(:out)  #2 MvNormalMeanCovariance(:out)  #3 MvNormalMeanCovariance(:mu) from data
+//   #4 *(:in)   #3' MvNormalMeanCovariance(:mu) backward   #4 *(:in) backward
+// plus two outbound products and one 3-way marginal.  The kernels below compute the same
+// messages in Kalman-gain / RTS form (algebraically identical, one SPD solve per direction
+// instead of four cholinv), with (mu, Sigma) resident in registers for the whole sweep and
+// the observation stream read coalesced over the batch axis.
+//
+// Two kernel families:
+//  * lgssm_chain_kernel      one thread = one chain, full covariance recursion per chain
+//                            (per-chain models, missing-data masks, or RXG_PATH_PER_CHAIN).
+//  * lgssm_shared_kernel     shared (A,B,P,Q,S0): the covariance / gain trajectory is
+//                            data-independent and identical across chains, so it is computed
+//                            once into gain tables (fp64, gain_* kernels) and every chain only
+//                            runs the mean recursions; covariances are broadcast-stored.
+// In both, post_mean / post_cov double as the forward->backward stash.
+#include <math.h>
+#include <stdlib.h>
+
+#include "rxg_internal.h"
+#include "rxg_linalg.cuh"
+
+namespace rxg {
+
+template <int D, int M>
+struct ModelF {
+    float A[D * D], B[M * D], P[D * D], Q[M * M], m0[D], S0[D * D];
+};
+
+struct PerChainPtrs {
+    const float *A, *B, *P, *Q, *m0, *S0;
+};
+
+template <typename S, int R, int C>
+__device__ __forceinline__ Mat<S, R, C> load_const(const float* p) {
+    Mat<S, R, C> o;
+#pragma unroll
+    for (int i = 0; i < R * C; ++i) o.a[i] = (S)p[i];
+    return o;
+}
+template <typename S, int R, int C>
+__device__ __forceinline__ Mat<S, R, C> load_strided(const float* p, int64_t stride) {
+    Mat<S, R, C> o;
+#pragma unroll
+    for (int i = 0; i < R * C; ++i) o.a[i] = (S)__ldg(p + i * stride);
+    return o;
+}
+template <typename S, int R, int C>
+__device__ __forceinline__ Mat<S, C, R> transpose(const Mat<S, R, C>& A) {
+    Mat<S, C, R> o;
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int j = 0; j < C; ++j) o(j, i) = A(i, j);
+    return o;
+}
+
+#define RXG_HALF_LOG_2PI 0.91893853320467274178
+
+// ============================================================================================
+// Family 1: one thread per chain, full (mu, Sigma) recursion
+// ============================================================================================
+template <int D, int M, bool PER_CHAIN, bool SMOOTH>
+__global__ void __launch_bounds__(128)
+lgssm_chain_kernel(const __grid_constant__ ModelF<D, M> mdl, PerChainPtrs pc,
+                   const float* __restrict__ y, const uint8_t* __restrict__ mask,
+                   float* __restrict__ mean, float* __restrict__ cov, float* __restrict__ nle,
+                   int32_t* __restrict__ status, int T, int64_t batch, int transition_first) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+
+    Mat<float, D, D> A, P, S0;
+    Mat<float, M, D> B;
+    Mat<float, M, M> Q;
+    Vec<float, D> mu;
+    if (PER_CHAIN) {
+        A = load_strided<float, D, D>(pc.A + b, batch);
+        B = load_strided<float, M, D>(pc.B + b, batch);
+        P = load_strided<float, D, D>(pc.P + b, batch);
+        Q = load_strided<float, M, M>(pc.Q + b, batch);
+        S0 = load_strided<float, D, D>(pc.S0 + b, batch);
+#pragma unroll
+        for (int i = 0; i < D; ++i) mu(i) = __ldg(pc.m0 + i * batch + b);
+    } else {
+        A = load_const<float, D, D>(mdl.A);
+        B = load_const<float, M, D>(mdl.B);
+        P = load_const<float, D, D>(mdl.P);
+        Q = load_const<float, M, M>(mdl.Q);
+        S0 = load_const<float, D, D>(mdl.S0);
+#pragma unroll
+        for (int i = 0; i < D; ++i) mu(i) = mdl.m0[i];
+    }
+    Mat<float, D, D> S = S0;
+    bool bad = false;
+    double acc_nle = 0.0;
+    const bool want_nle = (nle != nullptr);
+
+    // ---------------------------------------------------------------- forward (rules #1-#4)
+    float ynext[M];
+#pragma unroll
+    for (int k = 0; k < M; ++k) ynext[k] = __ldg(y + (int64_t)k * batch + b);
+    uint8_t onext = mask ? mask[b] : (uint8_t)1;
+
+    for (int t = 0; t < T; ++t) {
+        Vec<float, M> yt;
+#pragma unroll
+        for (int k = 0; k < M; ++k) yt(k) = ynext[k];
+        const bool observed = onext != 0;
+        if (t + 1 < T) {   // prefetch next step's datum while this step's arithmetic runs
+#pragma unroll
+            for (int k = 0; k < M; ++k) ynext[k] = __ldg(y + ((int64_t)(t + 1) * M + k) * batch + b);
+            if (mask) onext = mask[(int64_t)(t + 1) * batch + b];
+        }
+        if (t > 0 || transition_first) {
+            // rule #1  *(:out): (A mu, A S A')   rule #2  MvNormalMeanCovariance(:out): + P
+            mu = mulv(A, mu);
+            Mat<float, D, D> AS = mul(A, S);
+            S = sym_mul_nt_add(AS, A, P);
+        }
+        if (observed) {
+            // rules #3,#4 (observation message) folded with the product at x_t, gain form:
+            //   Sinn = B S B' + Q = L L',  V = S B' L^-T,  mu += V L^-1 (y - B mu),  S -= V V'
+            Mat<float, M, D> BS = mul(B, S);
+            Mat<float, M, M> Sinn = sym_mul_nt_add(BS, B, Q);
+            Chol<float, M> ch = want_nle ? cholesky<float, M, true>(Sinn, bad)
+                                         : cholesky<float, M, false>(Sinn, bad);
+            Mat<float, D, M> V = solve_right_Lt(transpose(BS), ch.L);
+            Vec<float, M> e = mulv(B, mu);
+#pragma unroll
+            for (int k = 0; k < M; ++k) e(k) = yt(k) - e(k);
+            Vec<float, M> z = solve_L(ch.L, e);
+            Vec<float, D> dm = mulv(V, z);
+#pragma unroll
+            for (int i = 0; i < D; ++i) mu(i) += dm(i);
+            S = sym_downdate(S, V);
+            if (want_nle) {
+                float q = 0.f;
+#pragma unroll
+                for (int k = 0; k < M; ++k) q = __fmaf_rn(z(k), z(k), q);
+                acc_nle += (double)(0.5f * q - ch.neg_half_logdet) + M * RXG_HALF_LOG_2PI;
+            }
+        }
+        // filtered (mu, Sigma): the filter's output, the smoother's stash (lower triangle only)
+#pragma unroll
+        for (int i = 0; i < D; ++i) mean[((int64_t)t * D + i) * batch + b] = mu(i);
+        const bool full = !SMOOTH || (t == T - 1);
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j < D; ++j)
+                if (full || j <= i) cov[(((int64_t)t * D + i) * D + j) * batch + b] = S(i, j);
+    }
+    if (want_nle) nle[b] = (float)acc_nle;
+
+    // ---------------------------------------------------------------- backward (rules #3',#4 + marginal)
+    if (SMOOTH) {
+        Vec<float, D> mus = mu;          // smoothed at t+1
+        Mat<float, D, D> Ss = S;
+        // prefetch stash of step T-2
+        float pm[D], pS[D * (D + 1) / 2];
+        if (T >= 2) {
+            const int t = T - 2;
+#pragma unroll
+            for (int i = 0; i < D; ++i) pm[i] = mean[((int64_t)t * D + i) * batch + b];
+            int q = 0;
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j) pS[q++] = cov[(((int64_t)t * D + i) * D + j) * batch + b];
+        }
+        for (int t = T - 2; t >= 0; --t) {
+            Vec<float, D> muf;
+            Mat<float, D, D> Sf;
+#pragma unroll
+            for (int i = 0; i < D; ++i) muf(i) = pm[i];
+            {
+                int q = 0;
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+#pragma unroll
+                    for (int j = 0; j <= i; ++j) { Sf(i, j) = pS[q]; Sf(j, i) = pS[q]; ++q; }
+            }
+            if (t > 0) {
+                const int tp = t - 1;
+#pragma unroll
+                for (int i = 0; i < D; ++i) pm[i] = mean[((int64_t)tp * D + i) * batch + b];
+                int q = 0;
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+#pragma unroll
+                    for (int j = 0; j <= i; ++j) pS[q++] = cov[(((int64_t)tp * D + i) * D + j) * batch + b];
+            }
+            // Sp = A Sf A' + P (the forward message into x_{t+1}); RTS gain G = Sf A' Sp^-1
+            Mat<float, D, D> AS = mul(A, Sf);
+            Mat<float, D, D> Sp = sym_mul_nt_add(AS, A, P);
+            Chol<float, D> ch = cholesky<float, D, false>(Sp, bad);
+            Mat<float, D, D> U = solve_right_Lt(transpose(AS), ch.L);   // Sf A' L^-T
+            Mat<float, D, D> G = solve_right_L(U, ch.L);
+            Mat<float, D, D> C = sym_downdate(Sf, U);                   // cov(x_t | x_{t+1})
+            Mat<float, D, D> GS = mul(G, Ss);
+            Ss = sym_mul_nt_add(GS, G, C);
+            Vec<float, D> mup = mulv(A, muf);
+#pragma unroll
+            for (int i = 0; i < D; ++i) mup(i) = mus(i) - mup(i);
+            Vec<float, D> dm = mulv(G, mup);
+#pragma unroll
+            for (int i = 0; i < D; ++i) mus(i) = muf(i) + dm(i);
+#pragma unroll
+            for (int i = 0; i < D; ++i) mean[((int64_t)t * D + i) * batch + b] = mus(i);
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int j = 0; j < D; ++j) cov[(((int64_t)t * D + i) * D + j) * batch + b] = Ss(i, j);
+        }
+        mu = mus;
+    }
+    if (status) {
+        bool nan = false;
+#pragma unroll
+        for (int i = 0; i < D; ++i) nan |= !(mu(i) == mu(i));
+        status[b] = bad ? RXG_ERR_NOT_SPD : (nan ? RXG_ERR_NAN : RXG_OK);
+    }
+}
+
+// ============================================================================================
+// Family 2: shared model -- gain tables (fp64) + mean-only sweeps
+// ============================================================================================
+constexpr int pad4(int n) { return (n + 3) / 4 * 4; }
+
+template <int D, int M>
+struct Tab {
+    // forward record, per t
+    static constexpr int F_OFF = 0;                        // (I - K B) A           D x D
+    static constexpr int K_OFF = F_OFF + pad4(D * D);      // Kalman gain           D x M
+    static constexpr int LI_OFF = K_OFF + pad4(D * M);     // L^-1 of innovation    M x M (lower)
+    static constexpr int C_OFF = LI_OFF + pad4(M * M);     // M/2 log 2pi + 1/2 log det S
+    static constexpr int FWD_REC = C_OFF + 4;
+    // backward record, per t
+    static constexpr int E_OFF = 0;                        // I - G A               D x D
+    static constexpr int G_OFF = E_OFF + pad4(D * D);      // RTS gain              D x D
+    static constexpr int SS_OFF = G_OFF + pad4(D * D);     // smoothed covariance   D x D
+    static constexpr int BWD_REC = SS_OFF + pad4(D * D);
+    static constexpr int SF_REC = pad4(D * D);             // filtered covariance   D x D
+};
+
+struct GainWs {
+    float* fwd;    // [T][FWD_REC]
+    float* bwd;    // [T][BWD_REC]
+    float* sf;     // [T][SF_REC]
+    double* Sp;    // [T][D*D] predicted covariance
+    double* Sf;    // [T][D*D] filtered covariance
+    double* Cc;    // [T][D*D] conditional covariance Sf - U U'
+    double* Gd;    // [T][D*D] RTS gain (fp64)
+};
+
+template <int R, int C>
+__device__ __forceinline__ void store_d(double* p, const Mat<double, R, C>& A) {
+#pragma unroll
+    for (int i = 0; i < R * C; ++i) p[i] = A.a[i];
+}
+template <int R, int C>
+__device__ __forceinline__ Mat<double, R, C> load_d(const double* p) {
+    Mat<double, R, C> o;
+#pragma unroll
+    for (int i = 0; i < R * C; ++i) o.a[i] = p[i];
+    return o;
+}
+template <int R, int C>
+__device__ __forceinline__ void store_f(float* p, const Mat<double, R, C>& A) {
+#pragma unroll
+    for (int i = 0; i < R * C; ++i) p[i] = (float)A.a[i];
+}
+
+// Phase 1 (sequential in t): Riccati recursion for the predicted / filtered covariances.
+template <int D, int M>
+__global__ void gain_riccati_seq(const __grid_constant__ ModelF<D, M> mdl, GainWs ws, int T,
+                                 int transition_first) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const Mat<double, D, D> A = load_const<double, D, D>(mdl.A), P = load_const<double, D, D>(mdl.P);
+    const Mat<double, M, D> B = load_const<double, M, D>(mdl.B);
+    const Mat<double, M, M> Q = load_const<double, M, M>(mdl.Q);
+    Mat<double, D, D> S = load_const<double, D, D>(mdl.S0);
+    bool bad = false;
+    for (int t = 0; t < T; ++t) {
+        if (t > 0 || transition_first) {
+            Mat<double, D, D> AS = mul(A, S);
+            S = sym_mul_nt_add(AS, A, P);
+        }
+        store_d(ws.Sp + (size_t)t * D * D, S);
+        Mat<double, M, D> BS = mul(B, S);
+        Mat<double, M, M> Sinn = sym_mul_nt_add(BS, B, Q);
+        Chol<double, M> ch = cholesky<double, M, false>(Sinn, bad);
+        Mat<double, D, M> V = solve_right_Lt(transpose(BS), ch.L);
+        S = sym_downdate(S, V);
+        store_d(ws.Sf + (size_t)t * D * D, S);
+    }
+}
+
+// Phase 2 (parallel in t): gains, innovation factors, conditional covariances.
+template <int D, int M>
+__global__ void gain_tables(const __grid_constant__ ModelF<D, M> mdl, GainWs ws, int T,
+                            int transition_first) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    using TB = Tab<D, M>;
+    const Mat<double, D, D> A = load_const<double, D, D>(mdl.A);
+    const Mat<double, M, D> B = load_const<double, M, D>(mdl.B);
+    const Mat<double, M, M> Q = load_const<double, M, M>(mdl.Q);
+    bool bad = false;
+    const Mat<double, D, D> Sp = load_d<D, D>(ws.Sp + (size_t)t * D * D);
+    const Mat<double, D, D> Sf = load_d<D, D>(ws.Sf + (size_t)t * D * D);
+    {
+        Mat<double, M, D> BS = mul(B, Sp);
+        Mat<double, M, M> Sinn = sym_mul_nt_add(BS, B, Q);
+        Chol<double, M> ch = cholesky<double, M, true>(Sinn, bad);
+        Mat<double, D, M> V = solve_right_Lt(transpose(BS), ch.L);
+        Mat<double, D, M> K = solve_right_L(V, ch.L);
+        Mat<double, D, D> IKB = identity<double, D>();
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j < D; ++j)
+#pragma unroll
+                for (int k = 0; k < M; ++k) IKB(i, j) -= K(i, k) * B(k, j);
+        Mat<double, D, D> F = (t > 0 || transition_first) ? mul(IKB, A) : IKB;
+        // L^-1 (lower, true diagonal)
+        Mat<double, M, M> Li;
+#pragma unroll
+        for (int i = 0; i < M * M; ++i) Li.a[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            Li(j, j) = ch.L(j, j);
+#pragma unroll
+            for (int i = j + 1; i < M; ++i) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = j; k < i; ++k) s -= ch.L(i, k) * Li(k, j);
+                Li(i, j) = s * ch.L(i, i);
+            }
+        }
+        float* rec = ws.fwd + (size_t)t * TB::FWD_REC;
+        store_f(rec + TB::F_OFF, F);
+        store_f(rec + TB::K_OFF, K);
+        store_f(rec + TB::LI_OFF, Li);
+        rec[TB::C_OFF] = (float)(M * RXG_HALF_LOG_2PI - ch.neg_half_logdet);
+        store_f(ws.sf + (size_t)t * TB::SF_REC, Sf);
+    }
+    float* brec = ws.bwd + (size_t)t * TB::BWD_REC;
+    if (t < T - 1) {
+        const Mat<double, D, D> Sp1 = load_d<D, D>(ws.Sp + (size_t)(t + 1) * D * D);
+        Chol<double, D> ch = cholesky<double, D, false>(Sp1, bad);
+        Mat<double, D, D> AS = mul(A, Sf);
+        Mat<double, D, D> U = solve_right_Lt(transpose(AS), ch.L);
+        Mat<double, D, D> G = solve_right_L(U, ch.L);
+        Mat<double, D, D> C = sym_downdate(Sf, U);
+        Mat<double, D, D> E = identity<double, D>();
+        Mat<double, D, D> GA = mul(G, A);
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) E.a[i] -= GA.a[i];
+        store_f(brec + TB::E_OFF, E);
+        store_f(brec + TB::G_OFF, G);
+        store_d(ws.Cc + (size_t)t * D * D, C);
+        store_d(ws.Gd + (size_t)t * D * D, G);
+    } else {
+        Mat<double, D, D> E = identity<double, D>();
+        Mat<double, D, D> Z;
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) Z.a[i] = 0.0;
+        store_f(brec + TB::E_OFF, E);
+        store_f(brec + TB::G_OFF, Z);
+    }
+}
+
+// Phase 3 (sequential in t): smoothed covariances  Ss[t] = C[t] + G[t] Ss[t+1] G[t]'.
+template <int D, int M>
+__global__ void gain_smooth_seq(GainWs ws, int T, float* cov_shared_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    using TB = Tab<D, M>;
+    Mat<double, D, D> Ss = load_d<D, D>(ws.Sf + (size_t)(T - 1) * D * D);
+    store_f(ws.bwd + (size_t)(T - 1) * TB::BWD_REC + TB::SS_OFF, Ss);
+    if (cov_shared_out) store_f(cov_shared_out + (size_t)(T - 1) * D * D, Ss);
+    for (int t = T - 2; t >= 0; --t) {
+        const Mat<double, D, D> G = load_d<D, D>(ws.Gd + (size_t)t * D * D);
+        const Mat<double, D, D> C = load_d<D, D>(ws.Cc + (size_t)t * D * D);
+        Mat<double, D, D> GS = mul(G, Ss);
+        Ss = sym_mul_nt_add(GS, G, C);
+        store_f(ws.bwd + (size_t)t * TB::BWD_REC + TB::SS_OFF, Ss);
+        if (cov_shared_out) store_f(cov_shared_out + (size_t)t * D * D, Ss);
+    }
+}
+
+// uniform (same address for every lane) loads of a table segment
+template <int N>
+__device__ __forceinline__ void load_uniform(const float* __restrict__ p, float* dst) {
+    if (N % 4 == 0) {
+        const float4* p4 = reinterpret_cast<const float4*>(p);
+#pragma unroll
+        for (int i = 0; i < N / 4; ++i) {
+            float4 v = __ldg(p4 + i);
+            dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) dst[i] = __ldg(p + i);
+    }
+}
+
+template <int CPT> struct Pack;
+template <> struct Pack<1> {
+    static __device__ __forceinline__ void ld(const float* p, float* v) { v[0] = __ldg(p); }
+    static __device__ __forceinline__ void ld_rw(const float* p, float* v) { v[0] = *p; }
+    static __device__ __forceinline__ void st(float* p, const float* v) { *p = v[0]; }
+};
+template <> struct Pack<2> {
+    static __device__ __forceinline__ void ld(const float* p, float* v) {
+        float2 t = __ldg(reinterpret_cast<const float2*>(p)); v[0] = t.x; v[1] = t.y;
+    }
+    static __device__ __forceinline__ void ld_rw(const float* p, float* v) {
+        float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y;
+    }
+    static __device__ __forceinline__ void st(float* p, const float* v) {
+        *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    }
+};
+template <> struct Pack<4> {
+    static __device__ __forceinline__ void ld(const float* p, float* v) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    static __device__ __forceinline__ void ld_rw(const float* p, float* v) {
+        float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    static __device__ __forceinline__ void st(float* p, const float* v) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+
+// One thread = CPT consecutive chains.  PF = prefetch depth in time steps.
+template <int D, int M, int CPT, int PF, bool SMOOTH, bool EVID>
+__global__ void __launch_bounds__(128)
+lgssm_shared_kernel(const __grid_constant__ ModelF<D, M> mdl, const float* __restrict__ fwd_tab,
+                    const float* __restrict__ bwd_tab, const float* __restrict__ sf_tab,
+                    const float* __restrict__ y, float* __restrict__ mean, float* __restrict__ cov,
+                    float* __restrict__ nle, int T, int64_t batch, int transition_first,
+                    int write_cov) {
+    using TB = Tab<D, M>;
+    const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * CPT;
+    if (b >= batch) return;
+
+    float mu[D][CPT];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) mu[i][c] = mdl.m0[i];
+    float ev[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) ev[c] = 0.f;
+    double ev_hi[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) ev_hi[c] = 0.0;
+
+    // ---------------------------------------------------------------- forward
+    float ycur[PF][M][CPT], ynxt[PF][M][CPT];
+#pragma unroll
+    for (int s = 0; s < PF; ++s)
+        if (s < T)
+#pragma unroll
+            for (int k = 0; k < M; ++k) Pack<CPT>::ld(y + ((int64_t)s * M + k) * batch + b, ycur[s][k]);
+
+    for (int t0 = 0; t0 < T; t0 += PF) {
+#pragma unroll
+        for (int s = 0; s < PF; ++s)
+            if (t0 + PF + s < T)
+#pragma unroll
+                for (int k = 0; k < M; ++k)
+                    Pack<CPT>::ld(y + ((int64_t)(t0 + PF + s) * M + k) * batch + b, ynxt[s][k]);
+#pragma unroll
+        for (int s = 0; s < PF; ++s) {
+            const int t = t0 + s;
+            if (t < T) {
+                const float* rec = fwd_tab + (size_t)t * TB::FWD_REC;
+                float Kt[pad4(D * M)];
+                load_uniform<pad4(D * M)>(rec + TB::K_OFF, Kt);
+                float nm[D][CPT];
+                if (!EVID) {
+                    // mu_f[t] = F_t mu_f[t-1] + K_t y_t,  F_t = (I - K_t B) A   (rules #1-#4 + product)
+                    float Ft[pad4(D * D)];
+                    load_uniform<pad4(D * D)>(rec + TB::F_OFF, Ft);
+#pragma unroll
+                    for (int i = 0; i < D; ++i)
+#pragma unroll
+                        for (int c = 0; c < CPT; ++c) {
+                            float a = Ft[i * D] * mu[0][c];
+#pragma unroll
+                            for (int j = 1; j < D; ++j) a = __fmaf_rn(Ft[i * D + j], mu[j][c], a);
+#pragma unroll
+                            for (int k = 0; k < M; ++k) a = __fmaf_rn(Kt[i * M + k], ycur[s][k][c], a);
+                            nm[i][c] = a;
+                        }
+                } else {
+                    // explicit form so that the innovation is available for the evidence
+                    float Li[pad4(M * M)], cc[4];
+                    load_uniform<pad4(M * M)>(rec + TB::LI_OFF, Li);
+                    load_uniform<4>(rec + TB::C_OFF, cc);
+                    const bool pred = (t > 0) || transition_first;
+#pragma unroll
+                    for (int c = 0; c < CPT; ++c) {
+                        float mp[D], e[M], z[M];
+#pragma unroll
+                        for (int i = 0; i < D; ++i) {
+                            if (pred) {
+                                float a = mdl.A[i * D] * mu[0][c];
+#pragma unroll
+                                for (int j = 1; j < D; ++j) a = __fmaf_rn(mdl.A[i * D + j], mu[j][c], a);
+                                mp[i] = a;
+                            } else {
+                                mp[i] = mu[i][c];
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < M; ++k) {
+                            float a = ycur[s][k][c];
+#pragma unroll
+                            for (int j = 0; j < D; ++j) a = __fmaf_rn(-mdl.B[k * D + j], mp[j], a);
+                            e[k] = a;
+                        }
+                        float q = 0.f;
+#pragma unroll
+                        for (int k = 0; k < M; ++k) {
+                            float a = 0.f;
+#pragma unroll
+                            for (int j = 0; j <= k; ++j) a = __fmaf_rn(Li[k * M + j], e[j], a);
+                            z[k] = a;
+                            q = __fmaf_rn(a, a, q);
+                        }
+                        ev[c] += __fmaf_rn(0.5f, q, cc[0]);
+#pragma unroll
+                        for (int i = 0; i < D; ++i) {
+                            float a = mp[i];
+#pragma unroll
+                            for (int k = 0; k < M; ++k) a = __fmaf_rn(Kt[i * M + k], e[k], a);
+                            nm[i][c] = a;
+                        }
+                    }
+                    if ((t & 63) == 63) {   // flush the fp32 partial sum into fp64 every 64 steps
+#pragma unroll
+                        for (int c = 0; c < CPT; ++c) { ev_hi[c] += (double)ev[c]; ev[c] = 0.f; }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+#pragma unroll
+                    for (int c = 0; c < CPT; ++c) mu[i][c] = nm[i][c];
+                    Pack<CPT>::st(mean + ((int64_t)t * D + i) * batch + b, mu[i]);
+                }
+                if (!SMOOTH && write_cov) {
+                    float Sf[pad4(D * D)];
+                    load_uniform<pad4(D * D)>(sf_tab + (size_t)t * TB::SF_REC, Sf);
+#pragma unroll
+                    for (int i = 0; i < D * D; ++i) {
+                        float v[CPT];
+#pragma unroll
+                        for (int c = 0; c < CPT; ++c) v[c] = Sf[i];
+                        Pack<CPT>::st(cov + ((int64_t)t * D * D + i) * batch + b, v);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < PF; ++s)
+#pragma unroll
+            for (int k = 0; k < M; ++k)
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) ycur[s][k][c] = ynxt[s][k][c];
+    }
+    if (EVID && nle) {
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) nle[b + c] = (float)(ev_hi[c] + (double)ev[c]);
+    }
+    if (!SMOOTH) return;
+
+    // ---------------------------------------------------------------- backward
+    // mu_s[t] = E_t mu_f[t] + G_t mu_s[t+1]  (rules #3', #4 backward + 3-way marginal);
+    // record T-1 holds E = I, G = 0.  Sigma_s[t] is chain-independent: broadcast store.
+    float ms[D][CPT];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) ms[i][c] = 0.f;
+    float fcur[PF][D][CPT], fnxt[PF][D][CPT];
+#pragma unroll
+    for (int s = 0; s < PF; ++s)
+        if (T - 1 - s >= 0)
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+                Pack<CPT>::ld_rw(mean + ((int64_t)(T - 1 - s) * D + i) * batch + b, fcur[s][i]);
+
+    for (int t0 = T - 1; t0 >= 0; t0 -= PF) {
+#pragma unroll
+        for (int s = 0; s < PF; ++s)
+            if (t0 - PF - s >= 0)
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+                    Pack<CPT>::ld_rw(mean + ((int64_t)(t0 - PF - s) * D + i) * batch + b, fnxt[s][i]);
+#pragma unroll
+        for (int s = 0; s < PF; ++s) {
+            const int t = t0 - s;
+            if (t >= 0) {
+                const float* rec = bwd_tab + (size_t)t * TB::BWD_REC;
+                float Et[pad4(D * D)], Gt[pad4(D * D)];
+                load_uniform<pad4(D * D)>(rec + TB::E_OFF, Et);
+                load_uniform<pad4(D * D)>(rec + TB::G_OFF, Gt);
+                float nm[D][CPT];
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+#pragma unroll
+                    for (int c = 0; c < CPT; ++c) {
+                        float a = Et[i * D] * fcur[s][0][c];
+#pragma unroll
+                        for (int j = 1; j < D; ++j) a = __fmaf_rn(Et[i * D + j], fcur[s][j][c], a);
+#pragma unroll
+                        for (int j = 0; j < D; ++j) a = __fmaf_rn(Gt[i * D + j], ms[j][c], a);
+                        nm[i][c] = a;
+                    }
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+#pragma unroll
+                    for (int c = 0; c < CPT; ++c) ms[i][c] = nm[i][c];
+                    Pack<CPT>::st(mean + ((int64_t)t * D + i) * batch + b, ms[i]);
+                }
+                if (write_cov) {
+                    float Sst[pad4(D * D)];
+                    load_uniform<pad4(D * D)>(rec + TB::SS_OFF, Sst);
+#pragma unroll
+                    for (int i = 0; i < D * D; ++i) {
+                        float v[CPT];
+#pragma unroll
+                        for (int c = 0; c < CPT; ++c) v[c] = Sst[i];
+                        Pack<CPT>::st(cov + ((int64_t)t * D * D + i) * batch + b, v);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < PF; ++s)
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) fcur[s][i][c] = fnxt[s][i][c];
+    }
+}
+
+// Filter with shared cov output requested: copy the sf table (padded records) to [T][D][D].
+__global__ void copy_table_kernel(const float* __restrict__ tab, int rec, int n, int T, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < T * n) out[i] = tab[(size_t)(i / n) * rec + (i % n)];
+}
+
+// ============================================================================================
+// host-side dispatch
+// ============================================================================================
+template <int D, int M>
+static void fill_model(ModelF<D, M>& mdl, const LgssmCall& c) {
+    for (int i = 0; i < D * D; ++i) { mdl.A[i] = c.A[i]; mdl.P[i] = c.P[i]; mdl.S0[i] = c.S0[i]; }
+    for (int i = 0; i < M * D; ++i) mdl.B[i] = c.B[i];
+    for (int i = 0; i < M * M; ++i) mdl.Q[i] = c.Q[i];
+    for (int i = 0; i < D; ++i) mdl.m0[i] = c.m0[i];
+}
+
+template <int D, int M>
+static int run_chain_family(rxg_ctx* ctx, const LgssmCall& c) {
+    ModelF<D, M> mdl = {};
+    PerChainPtrs pc = {};
+    const bool per_chain = (c.flags & RXG_MODEL_PER_CHAIN) != 0;
+    if (per_chain) pc = PerChainPtrs{c.A, c.B, c.P, c.Q, c.m0, c.S0};
+    else fill_model<D, M>(mdl, c);
+    const int threads = 64;
+    const unsigned blocks = (unsigned)((c.batch + threads - 1) / threads);
+    const int tf = (c.flags & RXG_TRANSITION_FIRST) ? 1 : 0;
+#define RXG_LAUNCH_CHAIN(PC, SM)                                                                   \
+    lgssm_chain_kernel<D, M, PC, SM><<<blocks, threads, 0, ctx->stream>>>(                         \
+        mdl, pc, c.y, c.ymask, c.mean, c.cov, c.nle, c.status, c.T, c.batch, tf)
+    if (ctx->profile) { cudaEventRecord(ctx->ev[0], ctx->stream); cudaEventRecord(ctx->ev[1], ctx->stream); }
+    if (per_chain) { if (c.smooth) RXG_LAUNCH_CHAIN(true, true); else RXG_LAUNCH_CHAIN(true, false); }
+    else           { if (c.smooth) RXG_LAUNCH_CHAIN(false, true); else RXG_LAUNCH_CHAIN(false, false); }
+#undef RXG_LAUNCH_CHAIN
+    if (ctx->profile) cudaEventRecord(ctx->ev[2], ctx->stream);
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "lgssm_chain_kernel launch");
+}
+
+template <int D, int M, int CPT>
+static int launch_shared(rxg_ctx* ctx, const LgssmCall& c, const ModelF<D, M>& mdl, const GainWs& ws,
+                         int write_cov) {
+    constexpr int PF = 4;
+    const int threads = 64;
+    const int64_t nthr = c.batch / CPT;
+    const unsigned blocks = (unsigned)((nthr + threads - 1) / threads);
+    const int tf = (c.flags & RXG_TRANSITION_FIRST) ? 1 : 0;
+    const bool evid = c.nle != nullptr;
+#define RXG_LAUNCH_SHARED(SM, EV)                                                                  \
+    lgssm_shared_kernel<D, M, CPT, PF, SM, EV><<<blocks, threads, 0, ctx->stream>>>(               \
+        mdl, ws.fwd, ws.bwd, ws.sf, c.y, c.mean, c.cov, c.nle, c.T, c.batch, tf, write_cov)
+    if (ctx->profile) cudaEventRecord(ctx->ev[1], ctx->stream);
+    if (c.smooth) { if (evid) RXG_LAUNCH_SHARED(true, true); else RXG_LAUNCH_SHARED(true, false); }
+    else          { if (evid) RXG_LAUNCH_SHARED(false, true); else RXG_LAUNCH_SHARED(false, false); }
+#undef RXG_LAUNCH_SHARED
+    if (ctx->profile) cudaEventRecord(ctx->ev[2], ctx->stream);
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "lgssm_shared_kernel launch");
+}
+
+template <int D, int M>
+static int run_shared_family(rxg_ctx* ctx, const LgssmCall& c) {
+    using TB = Tab<D, M>;
+    ModelF<D, M> mdl = {};
+    fill_model<D, M>(mdl, c);
+    const size_t T = (size_t)c.T;
+    // carve the workspace
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t o_fwd = carve(T * TB::FWD_REC * sizeof(float));
+    const size_t o_bwd = carve(T * TB::BWD_REC * sizeof(float));
+    const size_t o_sf = carve(T * TB::SF_REC * sizeof(float));
+    const size_t o_Sp = carve(T * D * D * sizeof(double));
+    const size_t o_Sf = carve(T * D * D * sizeof(double));
+    const size_t o_Cc = carve(T * D * D * sizeof(double));
+    const size_t o_Gd = carve(T * D * D * sizeof(double));
+    char* base = (char*)workspace(ctx, off);
+    if (!base) return RXG_ERR_CUDA;
+    GainWs ws;
+    ws.fwd = (float*)(base + o_fwd); ws.bwd = (float*)(base + o_bwd); ws.sf = (float*)(base + o_sf);
+    ws.Sp = (double*)(base + o_Sp); ws.Sf = (double*)(base + o_Sf);
+    ws.Cc = (double*)(base + o_Cc); ws.Gd = (double*)(base + o_Gd);
+
+    const int tf = (c.flags & RXG_TRANSITION_FIRST) ? 1 : 0;
+    const bool cov_shared = (c.flags & RXG_COV_SHARED_OUT) != 0;
+    if (ctx->profile) cudaEventRecord(ctx->ev[0], ctx->stream);
+    gain_riccati_seq<D, M><<<1, 32, 0, ctx->stream>>>(mdl, ws, c.T, tf);
+    gain_tables<D, M><<<(c.T + 63) / 64, 64, 0, ctx->stream>>>(mdl, ws, c.T, tf);
+    ctx->launches += 2;
+    if (c.smooth) {
+        gain_smooth_seq<D, M><<<1, 32, 0, ctx->stream>>>(ws, c.T, (cov_shared && c.cov) ? c.cov : nullptr);
+        ctx->launches += 1;
+    } else if (cov_shared && c.cov) {
+        const int n = c.T * D * D;
+        copy_table_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ws.sf, TB::SF_REC, D * D, c.T, c.cov);
+        ctx->launches += 1;
+    }
+    int rc = check_cuda(ctx, cudaGetLastError(), "gain table kernels launch");
+    if (rc != RXG_OK) return rc;
+    const int write_cov = (c.cov != nullptr && !cov_shared) ? 1 : 0;
+    const bool al16 = (((uintptr_t)c.y | (uintptr_t)c.mean | (uintptr_t)c.cov | (uintptr_t)c.nle) & 15) == 0;
+    // chains per thread: keep >= ~2 resident warps per SM sub-partition
+    int cpt = (c.batch >= (int64_t)ctx->sm_count * 2048) ? 2 : 1;
+    if (const char* e = getenv("RXG_FORCE_CPT")) cpt = atoi(e);      // test / tuning override
+    if (cpt == 2 && al16 && c.batch % 2 == 0) return launch_shared<D, M, 2>(ctx, c, mdl, ws, write_cov);
+    return launch_shared<D, M, 1>(ctx, c, mdl, ws, write_cov);
+}
+
+__global__ void fill_status_kernel(int32_t* s, int64_t n, int32_t v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) s[i] = v;
+}
+
+template <int D, int M>
+static int run_dm(rxg_ctx* ctx, const LgssmCall& c) {
+    const bool per_chain = (c.flags & (RXG_MODEL_PER_CHAIN | RXG_PATH_PER_CHAIN)) != 0 || c.ymask != nullptr;
+    if (per_chain) return run_chain_family<D, M>(ctx, c);
+    int rc = run_shared_family<D, M>(ctx, c);
+    if (rc == RXG_OK && c.status) {
+        fill_status_kernel<<<(unsigned)((c.batch + 255) / 256), 256, 0, ctx->stream>>>(c.status, c.batch, RXG_OK);
+        ctx->launches += 1;
+        rc = check_cuda(ctx, cudaGetLastError(), "fill_status launch");
+    }
+    return rc;
+}
+
+bool lgssm_supported(int d, int m) {
+    switch (d * 16 + m) {
+        case 1 * 16 + 1: case 2 * 16 + 1: case 2 * 16 + 2: case 3 * 16 + 3:
+        case 4 * 16 + 1: case 4 * 16 + 2: case 4 * 16 + 4: case 6 * 16 + 6:
+            return true;
+        default: return false;
+    }
+}
+
+int lgssm_dispatch(rxg_ctx* ctx, const LgssmCall& c) {
+    switch (c.d * 16 + c.m) {
+        case 1 * 16 + 1: return run_dm<1, 1>(ctx, c);
+        case 2 * 16 + 1: return run_dm<2, 1>(ctx, c);
+        case 2 * 16 + 2: return run_dm<2, 2>(ctx, c);
+        case 3 * 16 + 3: return run_dm<3, 3>(ctx, c);
+        case 4 * 16 + 1: return run_dm<4, 1>(ctx, c);
+        case 4 * 16 + 2: return run_dm<4, 2>(ctx, c);
+        case 4 * 16 + 4: return run_dm<4, 4>(ctx, c);
+        case 6 * 16 + 6: return run_dm<6, 6>(ctx, c);
+        default:
+            return fail(ctx, RXG_ERR_UNSUPPORTED,
+                        "lgssm: (d=%d, m=%d) is outside the thread-per-chain kernel families", c.d, c.m);
+    }
+}
+
+}  // namespace rxg

@@ -1,0 +1,326 @@
+// Batched twins of the reference's per-message @rule bodies for the Gaussian family
+// (SURVEY.md section 8a rows 1-9).  One thread = one message; structure-of-arrays I/O with the
+// message index innermost, so every global access of a warp is one contiguous 128-byte request.
+// All of these are HBM-bound element-wise kernels (plus a d x d Cholesky where the reference
+// calls cholinv); they exist so that a host-side ReactiveMP.rule / BayesBase.prod method
+// specialised on a batched message type can forward to the GPU one rule at a time
+// [ref: rule binding /root/reference/src/model/plugins/reactivemp_inference.jl:509-540;
+//  direct invocation test/inference/inference_tests.jl:547-585].
+#include "rxg_internal.h"
+#include "rxg_linalg.cuh"
+
+namespace rxg {
+
+template <int R, int C>
+__device__ __forceinline__ Mat<float, R, C> ld_soa(const float* __restrict__ p, int64_t n, int64_t i) {
+    Mat<float, R, C> o;
+#pragma unroll
+    for (int k = 0; k < R * C; ++k) o.a[k] = __ldg(p + (int64_t)k * n + i);
+    return o;
+}
+template <int R, int C>
+__device__ __forceinline__ Mat<float, R, C> ld_mat(const float* __restrict__ p, int shared, int64_t n, int64_t i) {
+    Mat<float, R, C> o;
+    if (shared) {
+#pragma unroll
+        for (int k = 0; k < R * C; ++k) o.a[k] = __ldg(p + k);
+    } else {
+#pragma unroll
+        for (int k = 0; k < R * C; ++k) o.a[k] = __ldg(p + (int64_t)k * n + i);
+    }
+    return o;
+}
+template <int N>
+__device__ __forceinline__ Vec<float, N> ld_vec(const float* __restrict__ p, int64_t n, int64_t i) {
+    Vec<float, N> o;
+#pragma unroll
+    for (int k = 0; k < N; ++k) o.a[k] = __ldg(p + (int64_t)k * n + i);
+    return o;
+}
+template <int R, int C>
+__device__ __forceinline__ void st_soa(float* __restrict__ p, int64_t n, int64_t i, const Mat<float, R, C>& A) {
+#pragma unroll
+    for (int k = 0; k < R * C; ++k) p[(int64_t)k * n + i] = A.a[k];
+}
+template <int N>
+__device__ __forceinline__ void st_vec(float* __restrict__ p, int64_t n, int64_t i, const Vec<float, N>& v) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) p[(int64_t)k * n + i] = v.a[k];
+}
+
+#define RXG_TID                                                            \
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      \
+    if (i >= n) return;
+
+// rules #2 / #3: (mu, S + Sigma)
+template <int D>
+__global__ void k_add_cov(int64_t n, const float* mu_in, const float* S_in, const float* Sigma, int shared,
+                          float* mu_out, float* S_out) {
+    RXG_TID
+    Vec<float, D> mu = ld_vec<D>(mu_in, n, i);
+    Mat<float, D, D> S = ld_soa<D, D>(S_in, n, i);
+    Mat<float, D, D> Sg = ld_mat<D, D>(Sigma, shared, n, i);
+    st_vec<D>(mu_out, n, i, mu);
+    st_soa<D, D>(S_out, n, i, add(S, Sg));
+}
+// rule #3 from data: (y, Sigma)
+template <int D>
+__global__ void k_from_data(int64_t n, const float* y, const float* Sigma, int shared, float* mu_out, float* S_out) {
+    RXG_TID
+    st_vec<D>(mu_out, n, i, ld_vec<D>(y, n, i));
+    st_soa<D, D>(S_out, n, i, ld_mat<D, D>(Sigma, shared, n, i));
+}
+// rule #1: (A mu, A S A')
+template <int DO, int DI>
+__global__ void k_mul_out(int64_t n, const float* A_, int shared, const float* mu_in, const float* S_in,
+                          float* mu_out, float* S_out) {
+    RXG_TID
+    Mat<float, DO, DI> A = ld_mat<DO, DI>(A_, shared, n, i);
+    Vec<float, DI> mu = ld_vec<DI>(mu_in, n, i);
+    Mat<float, DI, DI> S = ld_soa<DI, DI>(S_in, n, i);
+    Mat<float, DO, DI> AS = mul(A, S);
+    Mat<float, DO, DO> Z;
+#pragma unroll
+    for (int k = 0; k < DO * DO; ++k) Z.a[k] = 0.f;
+    st_vec<DO>(mu_out, n, i, mulv(A, mu));
+    st_soa<DO, DO>(S_out, n, i, sym_mul_nt_add(AS, A, Z));
+}
+// rule #4: (A' W mu, A' W A), W = cholinv(S_out)
+template <int DO, int DI>
+__global__ void k_mul_in(int64_t n, const float* A_, int shared, const float* mu_out, const float* S_out,
+                         float* xi_in, float* W_in, int32_t* status) {
+    RXG_TID
+    Mat<float, DO, DI> A = ld_mat<DO, DI>(A_, shared, n, i);
+    Vec<float, DO> mu = ld_vec<DO>(mu_out, n, i);
+    Mat<float, DO, DO> S = ld_soa<DO, DO>(S_out, n, i);
+    bool bad = false;
+    Mat<float, DO, DO> W = cholinv(S, bad);
+    Vec<float, DO> xo = mulv(W, mu);
+    Mat<float, DO, DI> WA = mul(W, A);
+    Mat<float, DI, DI> Win = mul_tn(A, WA);
+    // symmetrise (A' W A is symmetric up to round-off)
+#pragma unroll
+    for (int r = 0; r < DI; ++r)
+#pragma unroll
+        for (int c = 0; c < r; ++c) { float s = 0.5f * (Win(r, c) + Win(c, r)); Win(r, c) = s; Win(c, r) = s; }
+    st_vec<DI>(xi_in, n, i, mulv_t(A, xo));
+    st_soa<DI, DI>(W_in, n, i, Win);
+    if (status) status[i] = bad ? RXG_ERR_NOT_SPD : RXG_OK;
+}
+// rule #5 / prod: c = a + s*b on (vector, matrix) pairs
+template <int D>
+__global__ void k_pair_axpy(int64_t n, const float* v1, const float* M1, const float* v2, const float* M2,
+                            float sv, float* vo, float* Mo) {
+    RXG_TID
+    Vec<float, D> a = ld_vec<D>(v1, n, i), b = ld_vec<D>(v2, n, i);
+#pragma unroll
+    for (int k = 0; k < D; ++k) a.a[k] = __fmaf_rn(sv, b.a[k], a.a[k]);
+    st_vec<D>(vo, n, i, a);
+    st_soa<D, D>(Mo, n, i, add(ld_soa<D, D>(M1, n, i), ld_soa<D, D>(M2, n, i)));
+}
+// conversions: (v, M) -> (inv(M) v, inv(M))
+template <int D>
+__global__ void k_convert(int64_t n, const float* v, const float* M_, float* vo, float* Mo, int32_t* status) {
+    RXG_TID
+    bool bad = false;
+    Mat<float, D, D> Mi = cholinv(ld_soa<D, D>(M_, n, i), bad);
+    st_vec<D>(vo, n, i, mulv(Mi, ld_vec<D>(v, n, i)));
+    st_soa<D, D>(Mo, n, i, Mi);
+    if (status) status[i] = bad ? RXG_ERR_NOT_SPD : RXG_OK;
+}
+struct PtrList { const float* xi[8]; const float* W[8]; };
+template <int D>
+__global__ void k_marginal(int64_t n, int k, PtrList pl, float* mu, float* S, int32_t* status) {
+    RXG_TID
+    Vec<float, D> xi = ld_vec<D>(pl.xi[0], n, i);
+    Mat<float, D, D> W = ld_soa<D, D>(pl.W[0], n, i);
+    for (int q = 1; q < k; ++q) {           // left-to-right fold, as the reference's MessagesProductFromLeftToRight
+        Vec<float, D> x2 = ld_vec<D>(pl.xi[q], n, i);
+#pragma unroll
+        for (int r = 0; r < D; ++r) xi.a[r] += x2.a[r];
+        W = add(W, ld_soa<D, D>(pl.W[q], n, i));
+    }
+    bool bad = false;
+    Mat<float, D, D> Sg = cholinv(W, bad);
+    st_vec<D>(mu, n, i, mulv(Sg, xi));
+    st_soa<D, D>(S, n, i, Sg);
+    if (status) status[i] = bad ? RXG_ERR_NOT_SPD : RXG_OK;
+}
+
+// ---- univariate / Gamma (rows 8-9)
+__global__ void k_normal_precision_tau(int64_t n, const float* mo, const float* vo, const float* mm, const float* vm,
+                                       float* shape, float* rate) {
+    RXG_TID
+    const float d = mo[i] - mm[i];
+    shape[i] = 1.5f;
+    rate[i] = 0.5f * (__fmaf_rn(d, d, vo[i]) + vm[i]);
+}
+__global__ void k_normal_precision_out(int64_t n, const float* mm, const float* vm, const float* shape,
+                                       const float* rate, float* mo, float* vo) {
+    RXG_TID
+    mo[i] = mm[i];
+    vo[i] = vm[i] + rate[i] / shape[i];
+}
+__global__ void k_prod_gamma(int64_t n, const float* a1, const float* b1, const float* a2, const float* b2,
+                             float* a, float* b) {
+    RXG_TID
+    a[i] = a1[i] + a2[i] - 1.0f;
+    b[i] = b1[i] + b2[i];
+}
+__global__ void k_prod_normal(int64_t n, const float* m1, const float* v1, const float* m2, const float* v2,
+                              float* m, float* v) {
+    RXG_TID
+    const float w1 = 1.0f / v1[i], w2 = 1.0f / v2[i];
+    const float w = w1 + w2;
+    const float vv = 1.0f / w;
+    m[i] = (m1[i] * w1 + m2[i] * w2) * vv;
+    v[i] = vv;
+}
+
+}  // namespace rxg
+
+using namespace rxg;
+
+static inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+#define RXG_RULE_PROLOGUE(ctx, n)                                                     \
+    if (!(ctx)) return RXG_ERR_BAD_ARG;                                               \
+    if ((n) < 0) return rxg::fail((ctx), RXG_ERR_BAD_ARG, "n < 0");                   \
+    if (!((flags) & RXG_PTR_DEVICE))                                                  \
+        return rxg::fail((ctx), RXG_ERR_UNSUPPORTED,                                  \
+                         "per-rule kernels take device pointers (set RXG_PTR_DEVICE)"); \
+    if ((n) == 0) return RXG_OK;
+
+#define RXG_RULE_EPILOGUE(ctx, what)                                                  \
+    (ctx)->launches += 1;                                                             \
+    {                                                                                 \
+        int _rc = rxg::check_cuda((ctx), cudaGetLastError(), what);                   \
+        if (_rc != RXG_OK) return _rc;                                                \
+    }                                                                                 \
+    if (!(flags & RXG_ASYNC)) RXG_CUDA((ctx), cudaStreamSynchronize((ctx)->stream));  \
+    return RXG_OK;
+
+#define RXG_DISPATCH_D(d, CALL)                                                        \
+    switch (d) {                                                                       \
+        case 1: { constexpr int D = 1; CALL; } break;                                  \
+        case 2: { constexpr int D = 2; CALL; } break;                                  \
+        case 3: { constexpr int D = 3; CALL; } break;                                  \
+        case 4: { constexpr int D = 4; CALL; } break;                                  \
+        case 5: { constexpr int D = 5; CALL; } break;                                  \
+        case 6: { constexpr int D = 6; CALL; } break;                                  \
+        case 8: { constexpr int D = 8; CALL; } break;                                  \
+        default: return rxg::fail(ctx, RXG_ERR_UNSUPPORTED, "rule kernels: d=%d unsupported (1-6, 8)", d); \
+    }
+
+#define RXG_DISPATCH_DODI(dout, din, CALL)                                             \
+    switch ((dout) * 16 + (din)) {                                                     \
+        case 1 * 16 + 1: { constexpr int DO = 1, DI = 1; CALL; } break;                \
+        case 1 * 16 + 2: { constexpr int DO = 1, DI = 2; CALL; } break;                \
+        case 2 * 16 + 2: { constexpr int DO = 2, DI = 2; CALL; } break;                \
+        case 3 * 16 + 3: { constexpr int DO = 3, DI = 3; CALL; } break;                \
+        case 1 * 16 + 4: { constexpr int DO = 1, DI = 4; CALL; } break;                \
+        case 2 * 16 + 4: { constexpr int DO = 2, DI = 4; CALL; } break;                \
+        case 4 * 16 + 4: { constexpr int DO = 4, DI = 4; CALL; } break;                \
+        case 6 * 16 + 6: { constexpr int DO = 6, DI = 6; CALL; } break;                \
+        case 8 * 16 + 8: { constexpr int DO = 8, DI = 8; CALL; } break;                \
+        default: return rxg::fail(ctx, RXG_ERR_UNSUPPORTED, "rule kernels: A is %dx%d, unsupported", dout, din); \
+    }
+
+extern "C" {
+
+int rxg_rule_mvnormal_meancov_out_f32(rxg_ctx* ctx, int64_t n, int d, const float* mu_in, const float* S_in,
+                                      const float* Sigma, int M_shared, float* mu_out, float* S_out,
+                                      unsigned flags) {
+    RXG_RULE_PROLOGUE(ctx, n)
+    RXG_DISPATCH_D(d, (k_add_cov<D><<<nblk(n, 128), 128, 0, ctx->stream>>>(n, mu_in, S_in, Sigma, M_shared, mu_out, S_out)))
+    RXG_RULE_EPILOGUE(ctx, "k_add_cov")
+}
+int rxg_rule_mvnormal_meancov_mean_f32(rxg_ctx* ctx, int64_t n, int d, const float* mu_in, const float* S_in,
+                                       const float* Sigma, int M_shared, float* mu_out, float* S_out,
+                                       unsigned flags) {
+    return rxg_rule_mvnormal_meancov_out_f32(ctx, n, d, mu_in, S_in, Sigma, M_shared, mu_out, S_out, flags);
+}
+int rxg_rule_mvnormal_meancov_mean_data_f32(rxg_ctx* ctx, int64_t n, int d, const float* y, const float* Sigma,
+                                            int M_shared, float* mu_out, float* S_out, unsigned flags) {
+    RXG_RULE_PROLOGUE(ctx, n)
+    RXG_DISPATCH_D(d, (k_from_data<D><<<nblk(n, 128), 128, 0, ctx->stream>>>(n, y, Sigma, M_shared, mu_out, S_out)))
+    RXG_RULE_EPILOGUE(ctx, "k_from_data")
+}
+int rxg_rule_mul_out_f32(rxg_ctx* ctx, int64_t n, int d_out, int d_in, const float* A, int M_shared,
+                         const float* mu_in, const float* S_in, float* mu_out, float* S_out, unsigned flags) {
+    RXG_RULE_PROLOGUE(ctx, n)
+    RXG_DISPATCH_DODI(d_out, d_in, (k_mul_out<DO, DI><<<nblk(n, 128), 128, 0, ctx->stream>>>(n, A, M_shared, mu_in, S_in, mu_out, S_out)))
+    RXG_RULE_EPILOGUE(ctx, "k_mul_out")
+}
+int rxg_rule_mul_in_f32(rxg_ctx* ctx, int64_t n, int d_out, int d_in, const float* A, int M_shared,
+                        const float* mu_out, const float* S_out, float* xi_in, float* W_in, int32_t* status,
+                        unsigned flags) {
+    RXG_RULE_PROLOGUE(ctx, n)
+    RXG_DISPATCH_DODI(d_out, d_in, (k_mul_in<DO, DI><<<nblk(n, 128), 128, 0, ctx->stream>>>(n, A, M_shared, mu_out, S_out, xi_in, W_in, status)))
+    RXG_RULE_EPILOGUE(ctx, "k_mul_in")
+}
+int rxg_rule_add_out_f32(rxg_ctx* ctx, int64_t n, int d, const float* mu1, const float* S1, const float* mu2,
+                         const float* S2, float* mu_out, float* S_out, unsigned flags) {
+    RXG_RULE_PROLOGUE(ctx, n)
+    RXG_DISPATCH_D(d, (k_pair_axpy<D><<<nblk(n, 128), 128, 0, ctx->stream>>>(n, mu1, S1, mu2, S2, 1.0f, mu_out, S_out)))
+    RXG_RULE_EPILOGUE(ctx, "k_pair_axpy(add_out)")
+}
+int rxg_rule_add_in_f32(rxg_ctx* ctx, int64_t n, int d, const float* mu_out, const float* S_out,
+                        const float* mu_other, const float* S_other, float* mu_in, float* S_in, unsigned flags) {
+    RXG_RULE_PROLOGUE(ctx, n)
+    RXG_DISPATCH_D(d, (k_pair_axpy<D><<<nblk(n, 128), 128, 0, ctx->stream>>>(n, mu_out, S_out, mu_other, S_other, -1.0f, mu_in, S_in)))
+    RXG_RULE_EPILOGUE(ctx, "k_pair_axpy(add_in)")
+}
+int rxg_prod_gaussian_f32(rxg_ctx* ctx, int64_t n, int d, const float* xi1, const float* W1, const float* xi2,
+                          const float* W2, float* xi, float* W, unsigned flags) {
+    RXG_RULE_PROLOGUE(ctx, n)
+    RXG_DISPATCH_D(d, (k_pair_axpy<D><<<nblk(n, 128), 128, 0, ctx->stream>>>(n, xi1, W1, xi2, W2, 1.0f, xi, W)))
+    RXG_RULE_EPILOGUE(ctx, "k_pair_axpy(prod)")
+}
+int rxg_meancov_to_wmp_f32(rxg_ctx* ctx, int64_t n, int d, const float* mu, const float* S, float* xi, float* W,
+                           int32_t* status, unsigned flags) {
+    RXG_RULE_PROLOGUE(ctx, n)
+    RXG_DISPATCH_D(d, (k_convert<D><<<nblk(n, 128), 128, 0, ctx->stream>>>(n, mu, S, xi, W, status)))
+    RXG_RULE_EPILOGUE(ctx, "k_convert")
+}
+int rxg_wmp_to_meancov_f32(rxg_ctx* ctx, int64_t n, int d, const float* xi, const float* W, float* mu, float* S,
+                           int32_t* status, unsigned flags) {
+    return rxg_meancov_to_wmp_f32(ctx, n, d, xi, W, mu, S, status, flags);
+}
+int rxg_marginal_gaussian_f32(rxg_ctx* ctx, int64_t n, int d, int k, const float* const* xi_list,
+                              const float* const* W_list, float* mu, float* S, int32_t* status, unsigned flags) {
+    RXG_RULE_PROLOGUE(ctx, n)
+    if (k < 1 || k > 8) return rxg::fail(ctx, RXG_ERR_BAD_ARG, "marginal: k=%d must be in 1..8", k);
+    PtrList pl = {};
+    for (int q = 0; q < k; ++q) { pl.xi[q] = xi_list[q]; pl.W[q] = W_list[q]; }
+    RXG_DISPATCH_D(d, (k_marginal<D><<<nblk(n, 128), 128, 0, ctx->stream>>>(n, k, pl, mu, S, status)))
+    RXG_RULE_EPILOGUE(ctx, "k_marginal")
+}
+int rxg_rule_normal_precision_tau_f32(rxg_ctx* ctx, int64_t n, const float* m_out, const float* v_out,
+                                      const float* m_mu, const float* v_mu, float* shape, float* rate,
+                                      unsigned flags) {
+    RXG_RULE_PROLOGUE(ctx, n)
+    k_normal_precision_tau<<<nblk(n, 256), 256, 0, ctx->stream>>>(n, m_out, v_out, m_mu, v_mu, shape, rate);
+    RXG_RULE_EPILOGUE(ctx, "k_normal_precision_tau")
+}
+int rxg_rule_normal_precision_out_f32(rxg_ctx* ctx, int64_t n, const float* m_mu, const float* v_mu,
+                                      const float* shape, const float* rate, float* m_out, float* v_out,
+                                      unsigned flags) {
+    RXG_RULE_PROLOGUE(ctx, n)
+    k_normal_precision_out<<<nblk(n, 256), 256, 0, ctx->stream>>>(n, m_mu, v_mu, shape, rate, m_out, v_out);
+    RXG_RULE_EPILOGUE(ctx, "k_normal_precision_out")
+}
+int rxg_prod_gamma_f32(rxg_ctx* ctx, int64_t n, const float* a1, const float* b1, const float* a2, const float* b2,
+                       float* a, float* b, unsigned flags) {
+    RXG_RULE_PROLOGUE(ctx, n)
+    k_prod_gamma<<<nblk(n, 256), 256, 0, ctx->stream>>>(n, a1, b1, a2, b2, a, b);
+    RXG_RULE_EPILOGUE(ctx, "k_prod_gamma")
+}
+int rxg_prod_normal_f32(rxg_ctx* ctx, int64_t n, const float* m1, const float* v1, const float* m2, const float* v2,
+                        float* m, float* v, unsigned flags) {
+    RXG_RULE_PROLOGUE(ctx, n)
+    k_prod_normal<<<nblk(n, 256), 256, 0, ctx->stream>>>(n, m1, v1, m2, v2, m, v);
+    RXG_RULE_EPILOGUE(ctx, "k_prod_normal")
+}
+
+}  // extern "C"

@@ -1,0 +1,143 @@
+"""``infer()``: the entry point of the reference (/root/reference/src/inference/inference.jl:577-733)
+mirrored for the batched Gaussian hot path.
+
+In the reference ``infer`` builds a factor graph from an ``@model`` and lets ReactiveMP/Rocket
+schedule one message at a time (src/inference/batch.jl:103-482, streaming.jl:536-845).  Here the
+``model`` argument is the *recognised pattern* -- what the Julia-side shim (julia/RxGaussB200.jl)
+extracts from the GraphPPL graph -- and ``data`` carries ``batch`` independent series at once.
+The keyword surface, the result object and the error behaviour follow the reference; every
+keyword that would need machinery outside the hot path raises ``NotImplementedError`` instead of
+being silently ignored (those calls must be routed to stock ReactiveMP).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from .context import Context
+from .distributions import GammaShapeRate, MvNormalMeanCovariance, NormalMeanVariance
+
+
+# --------------------------------------------------------------------------- recognised models
+@dataclass
+class linear_gaussian_ssm_smoothing:
+    """``@model linear_gaussian_ssm_smoothing(y, A, B, P, Q)``
+    (/root/reference/benchmarks/Linear Multivariate Gaussian State Space Model Benchmark.ipynb:95-105;
+    same graph as test/models/statespace/mlgssm_test.jl:8-17 with the prior on x[1]).
+    ``x0 = (mean, cov)`` of the prior on x[1]."""
+    A: np.ndarray
+    B: np.ndarray
+    P: np.ndarray
+    Q: np.ndarray
+    x0: tuple
+    per_chain: bool = False     # model matrices carry a trailing [batch] axis (CUDA tensors)
+
+
+@dataclass
+class linear_gaussian_ssm_filtering(linear_gaussian_ssm_smoothing):
+    """One-step model + ``@autoupdates x_min_t_mean, x_min_t_cov = mean_cov(q(x_t))``
+    (ipynb:107-113, 199-216): the prior is pushed through (A, P) before every datum."""
+
+
+@dataclass
+class hgf:
+    """``@model hgf`` with ``hgfconstraints`` / ``hgfmeta`` / autoupdates of
+    /root/reference/test/models/statespace/hgf_tests.jl:10-69."""
+    real_k: float = 1.0
+    real_w: float = 0.0
+    z_variance: float = 0.2 ** 2
+    y_variance: float = 0.1 ** 2
+    init: tuple = (0.0, 5.0, 0.0, 5.0)      # q(zt) = N(0,5), q(xt) = N(0,5)  (hgf_tests.jl:51-54)
+
+
+@dataclass
+class univariate_lgssm_gamma_precision:
+    """Scalar random walk observed with unknown precision tau ~ Gamma(a0, b0), q(x) q(tau)
+    (rules of /root/reference/test/models/aliases/aliases_gamma_tests.jl)."""
+    a: float = 1.0
+    v_proc: float = 1.0
+    x0: tuple = (0.0, 100.0)
+    gamma_prior: tuple = (1.0, 1.0)
+    init_E_tau: float = 1.0
+
+
+@dataclass
+class InferenceResult:
+    """``InferenceResult`` (/root/reference/src/inference/batch.jl:18-24)."""
+    posteriors: dict
+    free_energy: object = None
+    model: object = None
+    error: object = None
+    history: dict = field(default_factory=dict)
+
+
+_UNSUPPORTED = ("constraints", "meta", "callbacks", "annotations", "predictvars", "events", "uselock",
+                "postprocess", "trace", "benchmark", "datastream", "free_energy_diagnostics")
+_ctx_cache: dict = {}
+
+
+def default_context(device=None) -> Context:
+    dev = torch.cuda.current_device() if device is None else device
+    if dev not in _ctx_cache:
+        _ctx_cache[dev] = Context(dev)
+    ctx = _ctx_cache[dev]
+    ctx.bind_stream()
+    return ctx
+
+
+def infer(*, model, data, iterations=None, free_energy=False, returnvars=None, options=None,
+          initialization=None, autoupdates=None, keephistory=None, historyvars=None,
+          catch_exception=False, showprogress=False, session=None, warn=True, allow_node_contraction=False,
+          context: Context | None = None, cov_shared_out=False, **kwargs) -> InferenceResult:
+    """Batched ``infer``.  ``data = {"y": tensor[T, m, batch]}`` (CUDA fp32, or CPU for the
+    host-staged path).  Returns ``posteriors["x"]`` as a batched ``MvNormalMeanCovariance``."""
+    for k in kwargs:
+        if k in _UNSUPPORTED:
+            raise NotImplementedError(
+                f"infer(..., {k}=...) needs per-message machinery outside the batched hot path; "
+                "run this call through stock ReactiveMP")
+        raise TypeError(f"infer() got an unexpected keyword argument '{k}'")
+    if options:
+        bad = set(options) - {"limit_stack_depth", "warn"}   # limit_stack_depth is moot: the schedule is a fused sweep
+        if bad:
+            raise NotImplementedError(f"options {sorted(bad)} are outside the batched hot path")
+    if "y" not in data:
+        raise KeyError("data must contain the observations under key 'y'")   # reference: missing data key error
+    ctx = context or default_context()
+    y = data["y"]
+    mask = data.get("ymask")
+    try:
+        if isinstance(model, linear_gaussian_ssm_filtering):
+            r = ctx.lgssm(y, model.A, model.B, model.P, model.Q, model.x0[0], model.x0[1], smooth=False, mask=mask,
+                          want_evidence=free_energy, per_chain_model=model.per_chain, transition_first=True,
+                          cov_shared_out=cov_shared_out)
+            q = MvNormalMeanCovariance(r["mean"], r["cov"])
+            return InferenceResult(posteriors={}, history={"x_t": q}, free_energy=r["neg_log_evidence"], model=model)
+        if isinstance(model, linear_gaussian_ssm_smoothing):
+            if iterations not in (None, 1):
+                raise NotImplementedError("iterations > 1 on a tree-structured BP model is a no-op in the reference; "
+                                          "KeepEach() results are outside the hot path")
+            r = ctx.lgssm(y, model.A, model.B, model.P, model.Q, model.x0[0], model.x0[1], smooth=True, mask=mask,
+                          want_evidence=free_energy, per_chain_model=model.per_chain, cov_shared_out=cov_shared_out)
+            return InferenceResult(posteriors={"x": MvNormalMeanCovariance(r["mean"], r["cov"])},
+                                   free_energy=r["neg_log_evidence"], model=model)
+        if isinstance(model, hgf):
+            if free_energy:
+                raise NotImplementedError("free_energy for the HGF path is not on the hot path yet")
+            out = ctx.hgf_filter(y, iters=iterations or 1, kappa=model.real_k, omega=model.real_w,
+                                 z_variance=model.z_variance, y_variance=model.y_variance, init=model.init)
+            return InferenceResult(posteriors={}, model=model,
+                                   history={"xt": NormalMeanVariance(out[:, 0], out[:, 1]),
+                                            "zt": NormalMeanVariance(out[:, 2], out[:, 3])})
+        if isinstance(model, univariate_lgssm_gamma_precision):
+            r = ctx.lgssm_vmp_gamma(y, iterations=iterations or 1, a=model.a, v_proc=model.v_proc, prior=model.x0,
+                                    gamma_prior=model.gamma_prior, init_E_tau=model.init_E_tau)
+            return InferenceResult(posteriors={"x": NormalMeanVariance(r["mean"], r["var"]),
+                                               "τ": GammaShapeRate(r["shape"], r["rate"])}, model=model)
+        raise NotImplementedError(f"model pattern {type(model).__name__} is not on the batched hot path")
+    except Exception as e:           # reference: catch_exception=true returns a partial result with .error
+        if catch_exception:
+            return InferenceResult(posteriors={}, model=model, error=e)
+        raise

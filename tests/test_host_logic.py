@@ -1,0 +1,53 @@
+"""Host-side logic that needs no GPU: sharding arithmetic, gathered-slab assembly, the infer()
+keyword surface (unsupported features must raise, never be silently ignored)."""
+import numpy as np
+import pytest
+import torch
+
+
+def test_shard_bounds_cover_and_partition(rx):
+    sh = rx.sharding
+    for batch, world in [(10, 3), (65536, 8), (7, 8), (524288, 8)]:
+        spans = [sh.shard_bounds(batch, world, r) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == batch
+        for (a, b), (c, d) in zip(spans, spans[1:]):
+            assert b == c and b >= a
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_assemble_gathered_layout(rx):
+    G, T, d, b = 3, 4, 2, 5
+    full = torch.arange(T * d * G * b, dtype=torch.float32).reshape(T, d, G * b)
+    slabs = torch.stack([full[..., g * b:(g + 1) * b].contiguous() for g in range(G)])
+    assert torch.equal(rx.sharding.assemble_gathered(slabs), full)
+    fullc = torch.arange(T * d * d * G * b, dtype=torch.float32).reshape(T, d, d, G * b)
+    slabs = torch.stack([fullc[..., g * b:(g + 1) * b].contiguous() for g in range(G)])
+    assert torch.equal(rx.sharding.assemble_gathered(slabs), fullc)
+
+
+def test_infer_rejects_out_of_scope_keywords(rx):
+    model = rx.linear_gaussian_ssm_smoothing(np.eye(2), np.eye(2), np.eye(2), np.eye(2), (np.zeros(2), np.eye(2)))
+    y = torch.zeros(3, 2, 4)
+    for kw in ("callbacks", "constraints", "meta", "predictvars", "annotations"):
+        with pytest.raises(NotImplementedError):
+            rx.infer(model=model, data={"y": y}, **{kw: object()})
+    with pytest.raises(TypeError):
+        rx.infer(model=model, data={"y": y}, not_a_keyword=1)
+    with pytest.raises(NotImplementedError):
+        rx.infer(model=model, data={"y": y}, options={"rulefallback": None})
+    with pytest.raises(KeyError):
+        rx.infer(model=model, data={"z": y})
+
+
+def test_infer_fails_loudly_without_gpu_and_honours_catch_exception(rx):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    model = rx.linear_gaussian_ssm_smoothing(np.eye(2), np.eye(2), np.eye(2), np.eye(2), (np.zeros(2), np.eye(2)))
+    with pytest.raises(Exception):
+        rx.infer(model=model, data={"y": torch.zeros(3, 2, 4)})
+
+
+def test_call_rule_unknown_rule_raises(rx):
+    with pytest.raises(rx.RuleMethodError):
+        rx.call_rule(None, "Bernoulli", "out", m_p=None)

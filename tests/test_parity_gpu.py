@@ -1,0 +1,217 @@
+"""GPU parity tests for the fused LGSSM sweeps: CUDA path (through the C ABI) vs the fp64 oracle
+on the same seeded inputs, against the committed golden fixtures, and -- at BASELINE.json's full
+size -- through size-independent properties.  Tolerances are stated in tests/util.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import lgssm
+from util import TOL_COV, TOL_MEAN, TOL_NLE, f32_model, rel_l2
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def dev(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device="cuda")
+
+
+def check(r, ref, smooth=True, nle=True):
+    km, kc = ("mean", "cov") if smooth else ("filt_mean", "filt_cov")
+    assert rel_l2(r["mean"].cpu().numpy(), ref[km]) < TOL_MEAN
+    if r["cov"] is not None:
+        assert rel_l2(r["cov"].cpu().numpy(), ref[kc]) < TOL_COV
+    if nle and r["neg_log_evidence"] is not None:
+        g = r["neg_log_evidence"].cpu().numpy().astype(np.float64)
+        assert np.max(np.abs(g - ref["neg_log_evidence"]) / np.abs(ref["neg_log_evidence"])) < TOL_NLE
+
+
+@pytest.mark.parametrize("d,T,batch", [(4, 64, 8), (2, 48, 6)])
+def test_golden_fixture(ctx, d, T, batch):
+    z = np.load(os.path.join(GOLD, f"lgssm_d{d}_T{T}_b{batch}.npz"))
+    mod = {k[6:]: z[k] for k in z.files if k.startswith("model_")}
+    ref = {k: z[k] for k in ("mean", "cov", "filt_mean", "filt_cov", "neg_log_evidence")}
+    y = dev(z["y"])
+    for force in (False, True):
+        r = ctx.lgssm(y, **_kw(mod), smooth=True, want_evidence=True, want_status=True, force_per_chain_path=force)
+        check(r, ref)
+        assert int(r["status"].abs().sum()) == 0
+        f = ctx.lgssm(y, **_kw(mod), smooth=False, want_evidence=True, force_per_chain_path=force)
+        check(f, ref, smooth=False)
+
+
+def _kw(mod):
+    return dict(A=mod["A"], B=mod["B"], P=mod["P"], Q=mod["Q"], m0=mod["m0"], S0=mod["S0"])
+
+
+@pytest.mark.parametrize("d", [2, 4])
+@pytest.mark.parametrize("force", [False, True])
+def test_smoothing_T1000_vs_oracle(ctx, d, force):
+    """configs[0] shape (d, T = 1000) on a small batch the oracle finishes in seconds."""
+    mod = f32_model(lgssm.notebook_model(d))
+    _, y = lgssm.generate_data(mod, 1000, 96, seed=42)
+    ref = lgssm.smooth_reference_schedule(y, **mod)
+    r = ctx.lgssm(dev(y), **_kw(mod), smooth=True, want_evidence=True, want_status=True, force_per_chain_path=force)
+    check(r, ref)
+    assert int(r["status"].abs().sum()) == 0
+    # covariances SPD (mlgssm_test.jl:126)
+    cov = r["cov"].permute(0, 3, 1, 2).reshape(-1, d, d).double()
+    assert bool((torch.linalg.eigvalsh(cov) > 0).all())
+
+
+def test_chains_per_thread_2_path(ctx, monkeypatch):
+    mod = f32_model(lgssm.notebook_model(4))
+    _, y = lgssm.generate_data(mod, 200, 64, seed=7)
+    ref = lgssm.smooth_reference_schedule(y, **mod)
+    monkeypatch.setenv("RXG_FORCE_CPT", "2")
+    r = ctx.lgssm(dev(y), **_kw(mod), smooth=True, want_evidence=True)
+    check(r, ref)
+    monkeypatch.setenv("RXG_FORCE_CPT", "1")
+    r1 = ctx.lgssm(dev(y), **_kw(mod), smooth=True, want_evidence=True)
+    check(r1, ref)
+
+
+@pytest.mark.parametrize("d,m", [(1, 1), (2, 1), (3, 3), (4, 1), (4, 2), (6, 6)])
+@pytest.mark.parametrize("force", [False, True])
+def test_other_shapes(ctx, d, m, force):
+    rng = np.random.default_rng(d * 10 + m)
+    Aq, _ = np.linalg.qr(rng.standard_normal((d, d)))
+    mod = f32_model(dict(A=0.95 * Aq, B=rng.standard_normal((m, d)), P=0.1 * np.eye(d), Q=2.0 * np.eye(m),
+                         m0=rng.standard_normal(d), S0=10.0 * np.eye(d)))
+    _, y = lgssm.generate_data(mod, 150, 40, seed=3)
+    ref = lgssm.smooth_reference_schedule(y, **mod)
+    r = ctx.lgssm(dev(y), **_kw(mod), smooth=True, want_evidence=True, force_per_chain_path=force)
+    check(r, ref)
+
+
+def test_edge_T1_and_prior_only(ctx):
+    mod = f32_model(lgssm.notebook_model(4))
+    _, y = lgssm.generate_data(mod, 1, 5, seed=1)
+    ref = lgssm.smooth_reference_schedule(y, **mod)
+    for force in (False, True):
+        check(ctx.lgssm(dev(y), **_kw(mod), smooth=True, want_evidence=True, force_per_chain_path=force), ref)
+    # T = 2 exercises exactly one backward step
+    _, y2 = lgssm.generate_data(mod, 2, 5, seed=2)
+    ref2 = lgssm.smooth_reference_schedule(y2, **mod)
+    for force in (False, True):
+        check(ctx.lgssm(dev(y2), **_kw(mod), smooth=True, want_evidence=True, force_per_chain_path=force), ref2)
+    # all data missing => posterior == prior pushed through the dynamics
+    mask = np.zeros((2, 5), dtype=np.uint8)
+    refm = lgssm.smooth_reference_schedule(y2, **mod, mask=mask)
+    rm = ctx.lgssm(dev(y2), **_kw(mod), smooth=True, mask=dev(mask, torch.uint8))
+    assert rel_l2(rm["cov"].cpu().numpy(), refm["cov"]) < TOL_COV
+    assert np.abs(rm["mean"].cpu().numpy() - refm["mean"]).max() < 1e-6
+
+
+def test_ragged_batch_and_missing_data(ctx):
+    mod = f32_model(lgssm.notebook_model(4))
+    T, batch = 120, 77                                  # not a multiple of the block size
+    _, y = lgssm.generate_data(mod, T, batch, seed=11)
+    rng = np.random.default_rng(5)
+    mask = (rng.random((T, batch)) > 0.25).astype(np.uint8)
+    mask[-5:, 3] = 0
+    ref = lgssm.smooth_reference_schedule(y, **mod, mask=mask)
+    r = ctx.lgssm(dev(y), **_kw(mod), smooth=True, mask=dev(mask, torch.uint8), want_evidence=True, want_status=True)
+    check(r, ref)
+    r0 = ctx.lgssm(dev(y), **_kw(mod), smooth=True)
+    check(r0, lgssm.smooth_reference_schedule(y, **mod), nle=False)
+
+
+def test_per_chain_models(ctx):
+    base = f32_model(lgssm.notebook_model(4))
+    batch, T = 48, 100
+    rng = np.random.default_rng(9)
+    scale = 1.0 + rng.random(batch)
+    mods = {k: np.stack([v * (scale[i] if k in ("P", "Q", "S0") else 1.0) for i in range(batch)]) for k, v in base.items()}
+    mods = {k: v.astype(np.float32).astype(np.float64) for k, v in mods.items()}
+    _, y = lgssm.generate_data(base, T, batch, seed=13)
+    ref = lgssm.smooth_reference_schedule(y, **mods)
+    # ABI layout: [r][c][batch]
+    to_abi = lambda M: dev(np.moveaxis(M, 0, -1))
+    r = ctx.lgssm(dev(y), A=to_abi(mods["A"]), B=to_abi(mods["B"]), P=to_abi(mods["P"]), Q=to_abi(mods["Q"]),
+                  m0=to_abi(mods["m0"]), S0=to_abi(mods["S0"]), smooth=True, want_evidence=True,
+                  per_chain_model=True)
+    check(r, ref)
+
+
+def test_streaming_filter_transition_first(ctx):
+    mod = f32_model(lgssm.notebook_model(2))
+    _, y = lgssm.generate_data(mod, 300, 33, seed=17)
+    ref = lgssm.filter_streaming(y, **mod)
+    for force in (False, True):
+        r = ctx.lgssm(dev(y), **_kw(mod), smooth=False, transition_first=True, force_per_chain_path=force)
+        assert rel_l2(r["mean"].cpu().numpy(), ref["mean"]) < TOL_MEAN
+        assert rel_l2(r["cov"].cpu().numpy(), ref["cov"]) < TOL_COV
+
+
+def test_cov_shared_out_and_host_pointer_path(ctx):
+    mod = f32_model(lgssm.notebook_model(4))
+    _, y = lgssm.generate_data(mod, 80, 24, seed=19)
+    ref = lgssm.smooth_reference_schedule(y, **mod)
+    r = ctx.lgssm(dev(y), **_kw(mod), smooth=True, cov_shared_out=True)
+    assert tuple(r["cov"].shape) == (80, 4, 4)
+    assert rel_l2(r["cov"].cpu().numpy(), ref["cov"][..., 0]) < TOL_COV
+    assert rel_l2(r["mean"].cpu().numpy(), ref["mean"]) < TOL_MEAN
+    # host pointers (pinned) staged by the library
+    yh = torch.from_numpy(y).pin_memory()
+    rh = ctx.lgssm(yh, **_kw(mod), smooth=True, want_evidence=True, want_status=True)
+    assert not rh["mean"].is_cuda
+    check(rh, ref)
+
+
+def test_infer_entry_point(rx, ctx):
+    mod = f32_model(lgssm.notebook_model(4))
+    _, y = lgssm.generate_data(mod, 60, 16, seed=23)
+    ref = lgssm.smooth_reference_schedule(y, **mod)
+    res = rx.infer(model=rx.linear_gaussian_ssm_smoothing(mod["A"], mod["B"], mod["P"], mod["Q"], (mod["m0"], mod["S0"])),
+                   data={"y": dev(y)}, free_energy=True, options={"limit_stack_depth": 500}, context=ctx)
+    q = res.posteriors["x"]
+    assert rel_l2(q.mean().cpu().numpy(), ref["mean"]) < TOL_MEAN
+    assert rel_l2(q.cov().cpu().numpy(), ref["cov"]) < TOL_COV
+    assert rel_l2(res.free_energy.cpu().numpy(), ref["neg_log_evidence"]) < TOL_NLE
+    fil = rx.infer(model=rx.linear_gaussian_ssm_filtering(mod["A"], mod["B"], mod["P"], mod["Q"], (mod["m0"], mod["S0"])),
+                   data={"y": dev(y)}, context=ctx)
+    refs = lgssm.filter_streaming(y, **mod)
+    assert rel_l2(fil.history["x_t"].mean().cpu().numpy(), refs["mean"]) < TOL_MEAN
+
+
+def test_unsupported_shape_errors_loudly(rx, ctx):
+    mod = lgssm.dense_model(8)
+    y = torch.zeros(4, 8, 2, device="cuda")
+    with pytest.raises(rx.RxGaussError) as e:
+        ctx.lgssm(y, **_kw(mod), smooth=True)
+    assert e.value.code == rx._lib.RXG_ERR_UNSUPPORTED
+
+
+def test_full_size_properties(ctx):
+    """BASELINE.json configs[1] (d = 4, T = 1000, batch = 65 536): size-independent properties.
+    (1) chains are independent: a slice re-run alone is bit-identical; (2) linearity of the
+    posterior mean in (y, m0); (3) two chains fed the same series agree bit-exactly; (4) a sample
+    of chains matches the oracle within the parity tolerance; (5) covariances SPD and identical
+    across chains (shared model)."""
+    mod = f32_model(lgssm.notebook_model(4))
+    T, batch = 1000, 65536
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    y = torch.randn(T, 4, batch, device="cuda", generator=g) * 3.0
+    y[:, :, 1] = y[:, :, 0]
+    r = ctx.lgssm(y, **_kw(mod), smooth=True, want_evidence=True)
+    mean, cov = r["mean"], r["cov"]
+    assert torch.equal(mean[:, :, 0], mean[:, :, 1])                                   # (3)
+    sub = ctx.lgssm(y[:, :, 4096:4096 + 512].contiguous(), **_kw(mod), smooth=True)
+    assert torch.equal(sub["mean"], mean[:, :, 4096:4096 + 512])                       # (1)
+    r2 = ctx.lgssm((2.0 * y).contiguous(), A=mod["A"], B=mod["B"], P=mod["P"], Q=mod["Q"], m0=2.0 * mod["m0"],
+                   S0=mod["S0"], smooth=True)
+    assert rel_l2(r2["mean"][:, :, :2048].cpu().numpy(), 2.0 * mean[:, :, :2048].cpu().numpy()) < 1e-6   # (2)
+    idx = [0, 777, 65535]
+    ref = lgssm.smooth_reference_schedule(y[:, :, idx].cpu().numpy(), **mod)
+    assert rel_l2(mean[:, :, idx].cpu().numpy(), ref["mean"]) < TOL_MEAN                # (4)
+    assert rel_l2(cov[:, :, :, idx].cpu().numpy(), ref["cov"]) < TOL_COV
+    nle = r["neg_log_evidence"][idx].cpu().numpy().astype(np.float64)
+    assert np.max(np.abs(nle - ref["neg_log_evidence"]) / np.abs(ref["neg_log_evidence"])) < TOL_NLE
+    assert torch.equal(cov[..., 0], cov[..., 65535])                                    # (5)
+    assert bool((torch.linalg.eigvalsh(cov[..., 0].double()) > 0).all())
+    # the per-chain path at full size agrees with the gain-table path
+    rp = ctx.lgssm(y, **_kw(mod), smooth=True, force_per_chain_path=True)
+    assert rel_l2(rp["mean"][:, :, ::97].cpu().numpy(), mean[:, :, ::97].cpu().numpy()) < 2 * TOL_MEAN

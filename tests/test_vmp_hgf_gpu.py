@@ -1,0 +1,63 @@
+"""GPU parity of the variational members of the path: fused HGF filter (GCV node, GH-31) and the
+Gamma-precision VMP around a scalar smoother.  HGF posteriors are formula-level parity only
+(PARITY UNPINNED against the reference, see oracle/hgf.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hgf, vmp
+from util import rel_l2
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32, device="cuda")
+
+
+def test_hgf_golden_fixture(ctx):
+    z = np.load(os.path.join(GOLD, "hgf_T40_b8.npz"))
+    out = ctx.hgf_filter(dev(z["y"]), iters=10).cpu().numpy()
+    ref = z["out"]
+    for k, tol in ((0, 1e-4), (1, 1e-3), (2, 2e-3), (3, 2e-3)):
+        assert rel_l2(out[:, k], ref[:, k]) < tol, k
+
+
+@pytest.mark.parametrize("iters", [1, 20])
+def test_hgf_vs_oracle(ctx, iters):
+    _, x, y = hgf.generate_data(300, 130, seed=5)
+    ref = hgf.hgf_filter(y, iters=iters)
+    out = ctx.hgf_filter(dev(y), iters=iters).cpu().numpy()
+    assert rel_l2(out[:, 0], ref[:, 0]) < 1e-4          # m_x
+    assert rel_l2(out[:, 1], ref[:, 1]) < 2e-3          # v_x
+    assert np.abs(out[:, 2] - ref[:, 2]).max() < 5e-3   # m_z (O(1) magnitudes)
+    assert rel_l2(out[:, 3], ref[:, 3]) < 5e-3          # v_z
+    assert np.all(out[:, 1] > 0) and np.all(out[:, 3] > 0)      # hgf_tests.jl:131-132
+    inside = np.abs(out[:, 0] - x) < 3 * np.sqrt(out[:, 1])
+    assert inside.mean() > 0.95                                  # hgf_tests.jl:127-130
+
+
+def test_hgf_infer_entry(rx, ctx):
+    _, _, y = hgf.generate_data(50, 64, seed=6)
+    res = rx.infer(model=rx.hgf(), data={"y": dev(y)}, iterations=10, context=ctx)
+    ref = hgf.hgf_filter(y, iters=10)
+    assert rel_l2(res.history["xt"].mean().cpu().numpy(), ref[:, 0]) < 1e-4
+    with pytest.raises(NotImplementedError):
+        rx.infer(model=rx.hgf(), data={"y": dev(y)}, iterations=10, free_energy=True, context=ctx)
+
+
+def test_vmp_gamma_precision(ctx):
+    rng = np.random.default_rng(4)
+    T, batch = 400, 70
+    x = np.cumsum(rng.standard_normal((T, batch)), axis=0)
+    tau = rng.gamma(2.0, 1.0, batch) + 0.2
+    y = (x + rng.standard_normal((T, batch)) / np.sqrt(tau)).astype(np.float32)
+    ref = vmp.lgssm_gamma_precision(y, iterations=8)
+    r = ctx.lgssm_vmp_gamma(dev(y), iterations=8)
+    assert rel_l2(r["mean"].cpu().numpy(), ref["mean"]) < 1e-5
+    assert rel_l2(r["var"].cpu().numpy(), ref["var"]) < 1e-4
+    assert rel_l2(r["rate"].cpu().numpy(), ref["rate"]) < 1e-4
+    assert rel_l2(r["shape"].cpu().numpy(), ref["shape"]) < 1e-6
