@@ -105,14 +105,25 @@ def smooth_reference_schedule(y, A, B, P, Q, m0, S0, mask=None, return_messages=
         if t == 0:
             break
         o_xi, o_W = R.prod_gaussian_wmp((obs_xi[t], obs_W[t]), (b_xi, b_W))
-        # chains with no information from the future (trailing missing data): no message
-        info = np.abs(o_W).reshape(batch, -1).sum(-1) > 0
-        o_W_safe = np.where(info[:, None, None], o_W, np.eye(d))
+        # The reference converts (xi, W) -> (mu, Sigma) here (cholinv), adds P (rule #3'), converts
+        # back (cholinv) and applies rule #4.  That needs W to be invertible.  When it is not --
+        # no information from the future at all (trailing missing data), or m < d so that
+        # B' Q^-1 B is rank deficient -- the reference falls into FastCholesky's
+        # PositiveFactorizations repair (SURVEY.md 8c "not a usable golden"), which is not a
+        # defined result.  The oracle then takes the analytic value of the same two rules,
+        # (W^-1 + P)^-1 = (I + W P)^-1 W, which coincides with the reference form whenever W is SPD.
+        ev = np.linalg.eigvalsh(R.sym(o_W))
+        spd = ev[:, 0] > 1e-10 * np.maximum(ev[:, -1], 1e-300)
+        o_W_safe = np.where(spd[:, None, None], o_W, np.eye(d))
         o_mu, o_S = R.wmp_to_meancov(o_xi, o_W_safe)
         n_mu, n_S = R.mvnormal_meancov_mean((o_mu, o_S), P)
-        nb_xi, nb_W = R.multiplication_in(R.meancov_to_wmp(n_mu, n_S), A)
-        b_xi = np.where(info[:, None], nb_xi, 0.0)
-        b_W = np.where(info[:, None, None], nb_W, 0.0)
+        n_xi, n_W = R.meancov_to_wmp(n_mu, n_S)
+        IWP = np.eye(d) + o_W @ P
+        s_W = R.sym(np.linalg.solve(IWP, o_W))
+        s_xi = np.linalg.solve(IWP, o_xi[..., None])[..., 0]
+        n_xi = np.where(spd[:, None], n_xi, s_xi)
+        n_W = np.where(spd[:, None, None], n_W, s_W)
+        b_xi, b_W = R.multiplication_in((n_xi, n_W), A)
 
     mean, cov = _pack(post_mu, post_S)
     fmean, fcov = _pack(fil_mu, fil_S)
