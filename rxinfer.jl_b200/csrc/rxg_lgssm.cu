@@ -24,45 +24,12 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include "rxg_gain.cuh"
 #include "rxg_internal.h"
 #include "rxg_linalg.cuh"
+#include "rxg_lgssm_common.cuh"
 
 namespace rxg {
-
-template <int D, int M>
-struct ModelF {
-    float A[D * D], B[M * D], P[D * D], Q[M * M], m0[D], S0[D * D];
-};
-
-struct PerChainPtrs {
-    const float *A, *B, *P, *Q, *m0, *S0;
-};
-
-template <typename S, int R, int C>
-__device__ __forceinline__ Mat<S, R, C> load_const(const float* p) {
-    Mat<S, R, C> o;
-#pragma unroll
-    for (int i = 0; i < R * C; ++i) o.a[i] = (S)p[i];
-    return o;
-}
-template <typename S, int R, int C>
-__device__ __forceinline__ Mat<S, R, C> load_strided(const float* p, int64_t stride) {
-    Mat<S, R, C> o;
-#pragma unroll
-    for (int i = 0; i < R * C; ++i) o.a[i] = (S)__ldg(p + i * stride);
-    return o;
-}
-template <typename S, int R, int C>
-__device__ __forceinline__ Mat<S, C, R> transpose(const Mat<S, R, C>& A) {
-    Mat<S, C, R> o;
-#pragma unroll
-    for (int i = 0; i < R; ++i)
-#pragma unroll
-        for (int j = 0; j < C; ++j) o(j, i) = A(i, j);
-    return o;
-}
-
-#define RXG_HALF_LOG_2PI 0.91893853320467274178
 
 // ============================================================================================
 // Family 1: one thread per chain, full (mu, Sigma) recursion
@@ -232,52 +199,6 @@ lgssm_chain_kernel(const __grid_constant__ ModelF<D, M> mdl, PerChainPtrs pc,
 // ============================================================================================
 // Family 2: shared model -- gain tables (fp64) + mean-only sweeps
 // ============================================================================================
-constexpr int pad4(int n) { return (n + 3) / 4 * 4; }
-
-template <int D, int M>
-struct Tab {
-    // forward record, per t
-    static constexpr int F_OFF = 0;                        // (I - K B) A           D x D
-    static constexpr int K_OFF = F_OFF + pad4(D * D);      // Kalman gain           D x M
-    static constexpr int LI_OFF = K_OFF + pad4(D * M);     // L^-1 of innovation    M x M (lower)
-    static constexpr int C_OFF = LI_OFF + pad4(M * M);     // M/2 log 2pi + 1/2 log det S
-    static constexpr int FWD_REC = C_OFF + 4;
-    // backward record, per t
-    static constexpr int E_OFF = 0;                        // I - G A               D x D
-    static constexpr int G_OFF = E_OFF + pad4(D * D);      // RTS gain              D x D
-    static constexpr int SS_OFF = G_OFF + pad4(D * D);     // smoothed covariance   D x D
-    static constexpr int BWD_REC = SS_OFF + pad4(D * D);
-    static constexpr int SF_REC = pad4(D * D);             // filtered covariance   D x D
-};
-
-struct GainWs {
-    float* fwd;    // [T][FWD_REC]
-    float* bwd;    // [T][BWD_REC]
-    float* sf;     // [T][SF_REC]
-    double* Sp;    // [T][D*D] predicted covariance
-    double* Sf;    // [T][D*D] filtered covariance
-    double* Cc;    // [T][D*D] conditional covariance Sf - U U'
-    double* Gd;    // [T][D*D] RTS gain (fp64)
-};
-
-template <int R, int C>
-__device__ __forceinline__ void store_d(double* p, const Mat<double, R, C>& A) {
-#pragma unroll
-    for (int i = 0; i < R * C; ++i) p[i] = A.a[i];
-}
-template <int R, int C>
-__device__ __forceinline__ Mat<double, R, C> load_d(const double* p) {
-    Mat<double, R, C> o;
-#pragma unroll
-    for (int i = 0; i < R * C; ++i) o.a[i] = p[i];
-    return o;
-}
-template <int R, int C>
-__device__ __forceinline__ void store_f(float* p, const Mat<double, R, C>& A) {
-#pragma unroll
-    for (int i = 0; i < R * C; ++i) p[i] = (float)A.a[i];
-}
-
 // Phase 1 (sequential in t): Riccati recursion for the predicted / filtered covariances.
 template <int D, int M>
 __global__ void gain_riccati_seq(const __grid_constant__ ModelF<D, M> mdl, GainWs ws, int T,
@@ -732,23 +653,40 @@ static int run_shared_family(rxg_ctx* ctx, const LgssmCall& c) {
     const size_t o_Sf = carve(T * D * D * sizeof(double));
     const size_t o_Cc = carve(T * D * D * sizeof(double));
     const size_t o_Gd = carve(T * D * D * sizeof(double));
+    const size_t o_fel = carve(T * 3 * D * D * sizeof(double));
+    const size_t o_ftot = carve((size_t)2 * GS_NT * 3 * D * D * sizeof(double));
+    const size_t o_bel = carve(T * 2 * D * D * sizeof(double));
+    const size_t o_btot = carve((size_t)2 * GS_NT * 2 * D * D * sizeof(double));
     char* base = (char*)workspace(ctx, off);
     if (!base) return RXG_ERR_CUDA;
     GainWs ws;
     ws.fwd = (float*)(base + o_fwd); ws.bwd = (float*)(base + o_bwd); ws.sf = (float*)(base + o_sf);
     ws.Sp = (double*)(base + o_Sp); ws.Sf = (double*)(base + o_Sf);
     ws.Cc = (double*)(base + o_Cc); ws.Gd = (double*)(base + o_Gd);
+    ScanWs sw;
+    sw.fel = (double*)(base + o_fel); sw.ftot = (double*)(base + o_ftot);
+    sw.bel = (double*)(base + o_bel); sw.btot = (double*)(base + o_btot);
 
     const int tf = (c.flags & RXG_TRANSITION_FIRST) ? 1 : 0;
     const bool cov_shared = (c.flags & RXG_COV_SHARED_OUT) != 0;
     if (ctx->profile) cudaEventRecord(ctx->ev[0], ctx->stream);
-    gain_riccati_seq<D, M><<<1, 32, 0, ctx->stream>>>(mdl, ws, c.T, tf);
-    gain_tables<D, M><<<(c.T + 63) / 64, 64, 0, ctx->stream>>>(mdl, ws, c.T, tf);
-    ctx->launches += 2;
-    if (c.smooth) {
-        gain_smooth_seq<D, M><<<1, 32, 0, ctx->stream>>>(ws, c.T, (cov_shared && c.cov) ? c.cov : nullptr);
+    float* cov_once = (cov_shared && c.cov && c.smooth) ? c.cov : nullptr;
+    const char* seq_env = getenv("RXG_GAIN_SEQ");
+    if (seq_env && atoi(seq_env) != 0) {
+        // sequential Riccati recursion (cross-check of the scan; ~70x slower at T = 1000)
+        gain_riccati_seq<D, M><<<1, 32, 0, ctx->stream>>>(mdl, ws, c.T, tf);
+        gain_tables<D, M><<<(c.T + 63) / 64, 64, 0, ctx->stream>>>(mdl, ws, c.T, tf);
+        ctx->launches += 2;
+        if (c.smooth) {
+            gain_smooth_seq<D, M><<<1, 32, 0, ctx->stream>>>(ws, c.T, cov_once);
+            ctx->launches += 1;
+        }
+    } else {
+        // time-parallel associative scans in one 8-CTA cluster
+        gain_scan_kernel<D, M><<<GS_CTAS, GS_THREADS, 0, ctx->stream>>>(mdl, ws, sw, c.T, tf, cov_once);
         ctx->launches += 1;
-    } else if (cov_shared && c.cov) {
+    }
+    if (!c.smooth && cov_shared && c.cov) {
         const int n = c.T * D * D;
         copy_table_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ws.sf, TB::SF_REC, D * D, c.T, c.cov);
         ctx->launches += 1;

@@ -215,3 +215,38 @@ def test_full_size_properties(ctx):
     # the per-chain path at full size agrees with the gain-table path
     rp = ctx.lgssm(y, **_kw(mod), smooth=True, force_per_chain_path=True)
     assert rel_l2(rp["mean"][:, :, ::97].cpu().numpy(), mean[:, :, ::97].cpu().numpy()) < 2 * TOL_MEAN
+
+
+@pytest.mark.parametrize("T", [1, 2, 3, 1000, 1024, 1025, 2500, 5000])
+def test_time_parallel_gain_scan_vs_sequential_and_oracle(ctx, monkeypatch, T):
+    """The gain tables come from associative scans over time (rxg_gain.cuh).  They must agree with
+    the sequential Riccati kernels (RXG_GAIN_SEQ=1) and with the fp64 oracle, including T > 1024
+    where every scan thread owns several time steps."""
+    mod = f32_model(lgssm.notebook_model(4))
+    batch = 8
+    _, y = lgssm.generate_data(mod, T, batch, seed=29)
+    yd = dev(y)
+    monkeypatch.setenv("RXG_GAIN_SEQ", "0")
+    a = ctx.lgssm(yd, **_kw(mod), smooth=True, want_evidence=True)
+    f = ctx.lgssm(yd, **_kw(mod), smooth=False, transition_first=True)
+    monkeypatch.setenv("RXG_GAIN_SEQ", "1")
+    b = ctx.lgssm(yd, **_kw(mod), smooth=True, want_evidence=True)
+    fb = ctx.lgssm(yd, **_kw(mod), smooth=False, transition_first=True)
+    assert rel_l2(a["cov"].cpu().numpy(), b["cov"].cpu().numpy()) < 1e-6
+    assert rel_l2(a["mean"].cpu().numpy(), b["mean"].cpu().numpy()) < 1e-6
+    assert rel_l2(f["cov"].cpu().numpy(), fb["cov"].cpu().numpy()) < 1e-6
+    assert rel_l2(f["mean"].cpu().numpy(), fb["mean"].cpu().numpy()) < 1e-6
+    if T <= 2500:
+        ref = lgssm.smooth_reference_schedule(y, **mod)
+        check(a, ref)
+
+
+def test_gain_scan_other_shapes(ctx, monkeypatch):
+    monkeypatch.setenv("RXG_GAIN_SEQ", "0")
+    for d, m in [(1, 1), (2, 1), (3, 3), (4, 2), (6, 6)]:
+        rng = np.random.default_rng(100 + d * 10 + m)
+        Aq, _ = np.linalg.qr(rng.standard_normal((d, d)))
+        mod = f32_model(dict(A=0.9 * Aq, B=rng.standard_normal((m, d)), P=0.2 * np.eye(d), Q=1.5 * np.eye(m),
+                             m0=rng.standard_normal(d), S0=5.0 * np.eye(d)))
+        _, y = lgssm.generate_data(mod, 1300, 6, seed=31)
+        check(ctx.lgssm(dev(y), **_kw(mod), smooth=True, want_evidence=True), lgssm.smooth_reference_schedule(y, **mod))
