@@ -43,6 +43,20 @@ __device__ __forceinline__ Mat<double, R, C> ldcg_d(const double* p) {
     for (int i = 0; i < R * C; ++i) o.a[i] = __ldcg(p + i);
     return o;
 }
+// Scan elements live in global scratch as structure-of-arrays over the element index (component
+// c of element i at p[c * n + i]) so that the 32 lanes of a warp touch consecutive doubles.
+template <int R, int C>
+__device__ __forceinline__ Mat<double, R, C> ld_soa_d(const double* p, size_t n, size_t i) {
+    Mat<double, R, C> o;
+#pragma unroll
+    for (int c = 0; c < R * C; ++c) o.a[c] = __ldcg(p + (size_t)c * n + i);
+    return o;
+}
+template <int R, int C>
+__device__ __forceinline__ void st_soa_d(double* p, size_t n, size_t i, const Mat<double, R, C>& A) {
+#pragma unroll
+    for (int c = 0; c < R * C; ++c) p[(size_t)c * n + i] = A.a[c];
+}
 
 // X = M^-1 R  by Gaussian elimination with partial pivoting (M is I + C J: nonsymmetric).
 template <int N, int K>
@@ -108,14 +122,17 @@ __device__ __forceinline__ FwdEl<D> fwd_identity() {
     return e;
 }
 template <int D>
-__device__ __forceinline__ void fwd_store(double* p, const FwdEl<D>& e) {
-#pragma unroll
-    for (int i = 0; i < D * D; ++i) { p[i] = e.A.a[i]; p[D * D + i] = e.C.a[i]; p[2 * D * D + i] = e.J.a[i]; }
+__device__ __forceinline__ void fwd_store(double* p, size_t n, size_t i, const FwdEl<D>& e) {
+    st_soa_d<D, D>(p, n, i, e.A);
+    st_soa_d<D, D>(p + (size_t)D * D * n, n, i, e.C);
+    st_soa_d<D, D>(p + (size_t)2 * D * D * n, n, i, e.J);
 }
 template <int D>
-__device__ __forceinline__ FwdEl<D> fwd_load(const double* p) {
+__device__ __forceinline__ FwdEl<D> fwd_load(const double* p, size_t n, size_t i) {
     FwdEl<D> e;
-    e.A = ldcg_d<D, D>(p); e.C = ldcg_d<D, D>(p + D * D); e.J = ldcg_d<D, D>(p + 2 * D * D);
+    e.A = ld_soa_d<D, D>(p, n, i);
+    e.C = ld_soa_d<D, D>(p + (size_t)D * D * n, n, i);
+    e.J = ld_soa_d<D, D>(p + (size_t)2 * D * D * n, n, i);
     return e;
 }
 // a_i (x) a_j, i earlier in time
@@ -154,14 +171,15 @@ __device__ __forceinline__ FwdEl<D> fwd_combine(const FwdEl<D>& ei, const FwdEl<
 }
 
 template <int D>
-__device__ __forceinline__ void bwd_store(double* p, const BwdEl<D>& e) {
-#pragma unroll
-    for (int i = 0; i < D * D; ++i) { p[i] = e.E.a[i]; p[D * D + i] = e.L.a[i]; }
+__device__ __forceinline__ void bwd_store(double* p, size_t n, size_t i, const BwdEl<D>& e) {
+    st_soa_d<D, D>(p, n, i, e.E);
+    st_soa_d<D, D>(p + (size_t)D * D * n, n, i, e.L);
 }
 template <int D>
-__device__ __forceinline__ BwdEl<D> bwd_load(const double* p) {
+__device__ __forceinline__ BwdEl<D> bwd_load(const double* p, size_t n, size_t i) {
     BwdEl<D> e;
-    e.E = ldcg_d<D, D>(p); e.L = ldcg_d<D, D>(p + D * D);
+    e.E = ld_soa_d<D, D>(p, n, i);
+    e.L = ld_soa_d<D, D>(p + (size_t)D * D * n, n, i);
     return e;
 }
 // (earlier-in-time element) (x) (accumulated later-in-time element)
@@ -243,10 +261,10 @@ gain_scan_kernel(const __grid_constant__ ModelF<D, M> mdl, GainWs ws, ScanWs sw,
                 } else {
                     acc = (k == k0) ? gen : fwd_combine<D, false>(acc, gen);
                 }
-                if (E > 1) fwd_store<D>(sw.fel + (size_t)k * FE, acc);
+                if (E > 1) fwd_store<D>(sw.fel, T, k, acc);
             }
         }
-        fwd_store<D>(sw.ftot + (size_t)g * FE, acc);
+        fwd_store<D>(sw.ftot, GS_NT, g, acc);
     }
     cluster.sync();
     // ------------------------------------------------------------------ F2: Hillis-Steele over thread totals
@@ -254,12 +272,12 @@ gain_scan_kernel(const __grid_constant__ ModelF<D, M> mdl, GainWs ws, ScanWs sw,
     for (int off = 1; off < GS_NT; off <<= 1) {
         const double* src = sw.ftot + (size_t)cur * GS_NT * FE;
         double* dst = sw.ftot + (size_t)(cur ^ 1) * GS_NT * FE;
-        FwdEl<D> mine = fwd_load<D>(src + (size_t)g * FE);
+        FwdEl<D> mine = fwd_load<D>(src, GS_NT, g);
         if (g >= off && (g - off) * E < T && k0 < T) {
-            FwdEl<D> prev = fwd_load<D>(src + (size_t)(g - off) * FE);
+            FwdEl<D> prev = fwd_load<D>(src, GS_NT, g - off);
             mine = fwd_combine<D, false>(prev, mine);
         }
-        fwd_store<D>(dst + (size_t)g * FE, mine);
+        fwd_store<D>(dst, GS_NT, g, mine);
         cluster.sync();
         cur ^= 1;
     }
@@ -267,15 +285,15 @@ gain_scan_kernel(const __grid_constant__ ModelF<D, M> mdl, GainWs ws, ScanWs sw,
     {
         const double* tot = sw.ftot + (size_t)cur * GS_NT * FE;
         if (E == 1) {
-            if (g < T) store_d(ws.Sf + (size_t)g * D * D, ldcg_d<D, D>(tot + (size_t)g * FE + D * D));
+            if (g < T) store_d(ws.Sf + (size_t)g * D * D, ld_soa_d<D, D>(tot + (size_t)D * D * GS_NT, GS_NT, g));
         } else if (k0 < k1) {
             if (g == 0) {
                 for (int k = k0; k < k1; ++k)
-                    store_d(ws.Sf + (size_t)k * D * D, ldcg_d<D, D>(sw.fel + (size_t)k * FE + D * D));
+                    store_d(ws.Sf + (size_t)k * D * D, ld_soa_d<D, D>(sw.fel + (size_t)D * D * T, T, k));
             } else {
-                const FwdEl<D> excl = fwd_load<D>(tot + (size_t)(g - 1) * FE);
+                const FwdEl<D> excl = fwd_load<D>(tot, GS_NT, g - 1);
                 for (int k = k0; k < k1; ++k) {
-                    const FwdEl<D> pk = fwd_load<D>(sw.fel + (size_t)k * FE);
+                    const FwdEl<D> pk = fwd_load<D>(sw.fel, T, k);
                     store_d(ws.Sf + (size_t)k * D * D, fwd_combine<D, true>(excl, pk).C);
                 }
             }
@@ -351,7 +369,7 @@ gain_scan_kernel(const __grid_constant__ ModelF<D, M> mdl, GainWs ws, ScanWs sw,
             store_f(brec + TB::E_OFF, identity<double, D>());
             store_f(brec + TB::G_OFF, be.E);
         }
-        bwd_store<D>(sw.bel + (size_t)t * BE, be);
+        bwd_store<D>(sw.bel, T, t, be);
     }
     cluster.sync();
     // ------------------------------------------------------------------ B1: local suffix products (r = T-1-t)
@@ -362,37 +380,37 @@ gain_scan_kernel(const __grid_constant__ ModelF<D, M> mdl, GainWs ws, ScanWs sw,
         for (int i = 0; i < D * D; ++i) acc.L.a[i] = 0.0;
         for (int r = k0; r < k1; ++r) {
             const int t = T - 1 - r;
-            const BwdEl<D> el = bwd_load<D>(sw.bel + (size_t)t * BE);
+            const BwdEl<D> el = bwd_load<D>(sw.bel, T, t);
             acc = (r == k0) ? el : bwd_combine<D, false>(el, acc);
-            if (E > 1) bwd_store<D>(sw.bel + (size_t)t * BE, acc);    // in place: element t is consumed
+            if (E > 1) bwd_store<D>(sw.bel, T, t, acc);    // in place: element t is consumed
         }
-        bwd_store<D>(sw.btot + (size_t)g * BE, acc);
+        bwd_store<D>(sw.btot, GS_NT, g, acc);
     }
     cluster.sync();
     cur = 0;
     for (int off = 1; off < GS_NT; off <<= 1) {
         const double* src = sw.btot + (size_t)cur * GS_NT * BE;
         double* dst = sw.btot + (size_t)(cur ^ 1) * GS_NT * BE;
-        BwdEl<D> mine = bwd_load<D>(src + (size_t)g * BE);
+        BwdEl<D> mine = bwd_load<D>(src, GS_NT, g);
         if (g >= off && k0 < T) {
-            BwdEl<D> prev = bwd_load<D>(src + (size_t)(g - off) * BE);    // later in time
+            BwdEl<D> prev = bwd_load<D>(src, GS_NT, g - off);    // later in time
             mine = bwd_combine<D, false>(mine, prev);
         }
-        bwd_store<D>(dst + (size_t)g * BE, mine);
+        bwd_store<D>(dst, GS_NT, g, mine);
         cluster.sync();
         cur ^= 1;
     }
     {
         const double* tot = sw.btot + (size_t)cur * GS_NT * BE;
         BwdEl<D> excl;
-        if (E > 1 && g > 0 && k0 < k1) excl = bwd_load<D>(tot + (size_t)(g - 1) * BE);
+        if (E > 1 && g > 0 && k0 < k1) excl = bwd_load<D>(tot, GS_NT, g - 1);
         for (int r = k0; r < k1; ++r) {
             const int t = T - 1 - r;
             Mat<double, D, D> Ss;
             if (E == 1) {
-                Ss = ldcg_d<D, D>(tot + (size_t)g * BE + D * D);
+                Ss = ld_soa_d<D, D>(tot + (size_t)D * D * GS_NT, GS_NT, g);
             } else {
-                const BwdEl<D> pr = bwd_load<D>(sw.bel + (size_t)t * BE);
+                const BwdEl<D> pr = bwd_load<D>(sw.bel, T, t);
                 Ss = (g == 0) ? pr.L : bwd_combine<D, true>(pr, excl).L;
             }
             store_f(ws.bwd + (size_t)t * TB::BWD_REC + TB::SS_OFF, Ss);

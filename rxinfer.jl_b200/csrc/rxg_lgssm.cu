@@ -28,6 +28,7 @@
 #include "rxg_internal.h"
 #include "rxg_linalg.cuh"
 #include "rxg_lgssm_common.cuh"
+#include "rxg_lgssm_shared.cuh"
 
 namespace rxg {
 
@@ -317,266 +318,6 @@ __global__ void gain_smooth_seq(GainWs ws, int T, float* cov_shared_out) {
     }
 }
 
-// uniform (same address for every lane) loads of a table segment
-template <int N>
-__device__ __forceinline__ void load_uniform(const float* __restrict__ p, float* dst) {
-    if (N % 4 == 0) {
-        const float4* p4 = reinterpret_cast<const float4*>(p);
-#pragma unroll
-        for (int i = 0; i < N / 4; ++i) {
-            float4 v = __ldg(p4 + i);
-            dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < N; ++i) dst[i] = __ldg(p + i);
-    }
-}
-
-template <int CPT> struct Pack;
-template <> struct Pack<1> {
-    static __device__ __forceinline__ void ld(const float* p, float* v) { v[0] = __ldg(p); }
-    static __device__ __forceinline__ void ld_rw(const float* p, float* v) { v[0] = *p; }
-    static __device__ __forceinline__ void st(float* p, const float* v) { *p = v[0]; }
-};
-template <> struct Pack<2> {
-    static __device__ __forceinline__ void ld(const float* p, float* v) {
-        float2 t = __ldg(reinterpret_cast<const float2*>(p)); v[0] = t.x; v[1] = t.y;
-    }
-    static __device__ __forceinline__ void ld_rw(const float* p, float* v) {
-        float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y;
-    }
-    static __device__ __forceinline__ void st(float* p, const float* v) {
-        *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
-    }
-};
-template <> struct Pack<4> {
-    static __device__ __forceinline__ void ld(const float* p, float* v) {
-        float4 t = __ldg(reinterpret_cast<const float4*>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    }
-    static __device__ __forceinline__ void ld_rw(const float* p, float* v) {
-        float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    }
-    static __device__ __forceinline__ void st(float* p, const float* v) {
-        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-    }
-};
-
-// One thread = CPT consecutive chains.  PF = prefetch depth in time steps.
-template <int D, int M, int CPT, int PF, bool SMOOTH, bool EVID>
-__global__ void __launch_bounds__(128)
-lgssm_shared_kernel(const __grid_constant__ ModelF<D, M> mdl, const float* __restrict__ fwd_tab,
-                    const float* __restrict__ bwd_tab, const float* __restrict__ sf_tab,
-                    const float* __restrict__ y, float* __restrict__ mean, float* __restrict__ cov,
-                    float* __restrict__ nle, int T, int64_t batch, int transition_first,
-                    int write_cov) {
-    using TB = Tab<D, M>;
-    const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * CPT;
-    if (b >= batch) return;
-
-    float mu[D][CPT];
-#pragma unroll
-    for (int i = 0; i < D; ++i)
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) mu[i][c] = mdl.m0[i];
-    float ev[CPT];
-#pragma unroll
-    for (int c = 0; c < CPT; ++c) ev[c] = 0.f;
-    double ev_hi[CPT];
-#pragma unroll
-    for (int c = 0; c < CPT; ++c) ev_hi[c] = 0.0;
-
-    // ---------------------------------------------------------------- forward
-    float ycur[PF][M][CPT], ynxt[PF][M][CPT];
-#pragma unroll
-    for (int s = 0; s < PF; ++s)
-        if (s < T)
-#pragma unroll
-            for (int k = 0; k < M; ++k) Pack<CPT>::ld(y + ((int64_t)s * M + k) * batch + b, ycur[s][k]);
-
-    for (int t0 = 0; t0 < T; t0 += PF) {
-#pragma unroll
-        for (int s = 0; s < PF; ++s)
-            if (t0 + PF + s < T)
-#pragma unroll
-                for (int k = 0; k < M; ++k)
-                    Pack<CPT>::ld(y + ((int64_t)(t0 + PF + s) * M + k) * batch + b, ynxt[s][k]);
-#pragma unroll
-        for (int s = 0; s < PF; ++s) {
-            const int t = t0 + s;
-            if (t < T) {
-                const float* rec = fwd_tab + (size_t)t * TB::FWD_REC;
-                float Kt[pad4(D * M)];
-                load_uniform<pad4(D * M)>(rec + TB::K_OFF, Kt);
-                float nm[D][CPT];
-                if (!EVID) {
-                    // mu_f[t] = F_t mu_f[t-1] + K_t y_t,  F_t = (I - K_t B) A   (rules #1-#4 + product)
-                    float Ft[pad4(D * D)];
-                    load_uniform<pad4(D * D)>(rec + TB::F_OFF, Ft);
-#pragma unroll
-                    for (int i = 0; i < D; ++i)
-#pragma unroll
-                        for (int c = 0; c < CPT; ++c) {
-                            float a = Ft[i * D] * mu[0][c];
-#pragma unroll
-                            for (int j = 1; j < D; ++j) a = __fmaf_rn(Ft[i * D + j], mu[j][c], a);
-#pragma unroll
-                            for (int k = 0; k < M; ++k) a = __fmaf_rn(Kt[i * M + k], ycur[s][k][c], a);
-                            nm[i][c] = a;
-                        }
-                } else {
-                    // explicit form so that the innovation is available for the evidence
-                    float Li[pad4(M * M)], cc[4];
-                    load_uniform<pad4(M * M)>(rec + TB::LI_OFF, Li);
-                    load_uniform<4>(rec + TB::C_OFF, cc);
-                    const bool pred = (t > 0) || transition_first;
-#pragma unroll
-                    for (int c = 0; c < CPT; ++c) {
-                        float mp[D], e[M], z[M];
-#pragma unroll
-                        for (int i = 0; i < D; ++i) {
-                            if (pred) {
-                                float a = mdl.A[i * D] * mu[0][c];
-#pragma unroll
-                                for (int j = 1; j < D; ++j) a = __fmaf_rn(mdl.A[i * D + j], mu[j][c], a);
-                                mp[i] = a;
-                            } else {
-                                mp[i] = mu[i][c];
-                            }
-                        }
-#pragma unroll
-                        for (int k = 0; k < M; ++k) {
-                            float a = ycur[s][k][c];
-#pragma unroll
-                            for (int j = 0; j < D; ++j) a = __fmaf_rn(-mdl.B[k * D + j], mp[j], a);
-                            e[k] = a;
-                        }
-                        float q = 0.f;
-#pragma unroll
-                        for (int k = 0; k < M; ++k) {
-                            float a = 0.f;
-#pragma unroll
-                            for (int j = 0; j <= k; ++j) a = __fmaf_rn(Li[k * M + j], e[j], a);
-                            z[k] = a;
-                            q = __fmaf_rn(a, a, q);
-                        }
-                        ev[c] += __fmaf_rn(0.5f, q, cc[0]);
-#pragma unroll
-                        for (int i = 0; i < D; ++i) {
-                            float a = mp[i];
-#pragma unroll
-                            for (int k = 0; k < M; ++k) a = __fmaf_rn(Kt[i * M + k], e[k], a);
-                            nm[i][c] = a;
-                        }
-                    }
-                    if ((t & 63) == 63) {   // flush the fp32 partial sum into fp64 every 64 steps
-#pragma unroll
-                        for (int c = 0; c < CPT; ++c) { ev_hi[c] += (double)ev[c]; ev[c] = 0.f; }
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < D; ++i) {
-#pragma unroll
-                    for (int c = 0; c < CPT; ++c) mu[i][c] = nm[i][c];
-                    Pack<CPT>::st(mean + ((int64_t)t * D + i) * batch + b, mu[i]);
-                }
-                if (!SMOOTH && write_cov) {
-                    float Sf[pad4(D * D)];
-                    load_uniform<pad4(D * D)>(sf_tab + (size_t)t * TB::SF_REC, Sf);
-#pragma unroll
-                    for (int i = 0; i < D * D; ++i) {
-                        float v[CPT];
-#pragma unroll
-                        for (int c = 0; c < CPT; ++c) v[c] = Sf[i];
-                        Pack<CPT>::st(cov + ((int64_t)t * D * D + i) * batch + b, v);
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int s = 0; s < PF; ++s)
-#pragma unroll
-            for (int k = 0; k < M; ++k)
-#pragma unroll
-                for (int c = 0; c < CPT; ++c) ycur[s][k][c] = ynxt[s][k][c];
-    }
-    if (EVID && nle) {
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) nle[b + c] = (float)(ev_hi[c] + (double)ev[c]);
-    }
-    if (!SMOOTH) return;
-
-    // ---------------------------------------------------------------- backward
-    // mu_s[t] = E_t mu_f[t] + G_t mu_s[t+1]  (rules #3', #4 backward + 3-way marginal);
-    // record T-1 holds E = I, G = 0.  Sigma_s[t] is chain-independent: broadcast store.
-    float ms[D][CPT];
-#pragma unroll
-    for (int i = 0; i < D; ++i)
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) ms[i][c] = 0.f;
-    float fcur[PF][D][CPT], fnxt[PF][D][CPT];
-#pragma unroll
-    for (int s = 0; s < PF; ++s)
-        if (T - 1 - s >= 0)
-#pragma unroll
-            for (int i = 0; i < D; ++i)
-                Pack<CPT>::ld_rw(mean + ((int64_t)(T - 1 - s) * D + i) * batch + b, fcur[s][i]);
-
-    for (int t0 = T - 1; t0 >= 0; t0 -= PF) {
-#pragma unroll
-        for (int s = 0; s < PF; ++s)
-            if (t0 - PF - s >= 0)
-#pragma unroll
-                for (int i = 0; i < D; ++i)
-                    Pack<CPT>::ld_rw(mean + ((int64_t)(t0 - PF - s) * D + i) * batch + b, fnxt[s][i]);
-#pragma unroll
-        for (int s = 0; s < PF; ++s) {
-            const int t = t0 - s;
-            if (t >= 0) {
-                const float* rec = bwd_tab + (size_t)t * TB::BWD_REC;
-                float Et[pad4(D * D)], Gt[pad4(D * D)];
-                load_uniform<pad4(D * D)>(rec + TB::E_OFF, Et);
-                load_uniform<pad4(D * D)>(rec + TB::G_OFF, Gt);
-                float nm[D][CPT];
-#pragma unroll
-                for (int i = 0; i < D; ++i)
-#pragma unroll
-                    for (int c = 0; c < CPT; ++c) {
-                        float a = Et[i * D] * fcur[s][0][c];
-#pragma unroll
-                        for (int j = 1; j < D; ++j) a = __fmaf_rn(Et[i * D + j], fcur[s][j][c], a);
-#pragma unroll
-                        for (int j = 0; j < D; ++j) a = __fmaf_rn(Gt[i * D + j], ms[j][c], a);
-                        nm[i][c] = a;
-                    }
-#pragma unroll
-                for (int i = 0; i < D; ++i) {
-#pragma unroll
-                    for (int c = 0; c < CPT; ++c) ms[i][c] = nm[i][c];
-                    Pack<CPT>::st(mean + ((int64_t)t * D + i) * batch + b, ms[i]);
-                }
-                if (write_cov) {
-                    float Sst[pad4(D * D)];
-                    load_uniform<pad4(D * D)>(rec + TB::SS_OFF, Sst);
-#pragma unroll
-                    for (int i = 0; i < D * D; ++i) {
-                        float v[CPT];
-#pragma unroll
-                        for (int c = 0; c < CPT; ++c) v[c] = Sst[i];
-                        Pack<CPT>::st(cov + ((int64_t)t * D * D + i) * batch + b, v);
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int s = 0; s < PF; ++s)
-#pragma unroll
-            for (int i = 0; i < D; ++i)
-#pragma unroll
-                for (int c = 0; c < CPT; ++c) fcur[s][i][c] = fnxt[s][i][c];
-    }
-}
-
 // Filter with shared cov output requested: copy the sf table (padded records) to [T][D][D].
 __global__ void copy_table_kernel(const float* __restrict__ tab, int rec, int n, int T, float* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -620,7 +361,7 @@ template <int D, int M, int CPT>
 static int launch_shared(rxg_ctx* ctx, const LgssmCall& c, const ModelF<D, M>& mdl, const GainWs& ws,
                          int write_cov) {
     constexpr int PF = 4;
-    const int threads = 64;
+    const int threads = 32;                     // one warp per CTA (see rxg_lgssm_shared.cuh)
     const int64_t nthr = c.batch / CPT;
     const unsigned blocks = (unsigned)((nthr + threads - 1) / threads);
     const int tf = (c.flags & RXG_TRANSITION_FIRST) ? 1 : 0;
@@ -696,9 +437,13 @@ static int run_shared_family(rxg_ctx* ctx, const LgssmCall& c) {
     const int write_cov = (c.cov != nullptr && !cov_shared) ? 1 : 0;
     const bool al16 = (((uintptr_t)c.y | (uintptr_t)c.mean | (uintptr_t)c.cov | (uintptr_t)c.nle) & 15) == 0;
     // chains per thread: keep >= ~2 resident warps per SM sub-partition
-    int cpt = (c.batch >= (int64_t)ctx->sm_count * 2048) ? 2 : 1;
+    // Wider per-thread vectors cut the number of (128-byte-per-warp) store instructions per byte;
+    // B200, d = m = 4, T = 1000, batch 65 536: CPT 1 / 2 / 4 = 1.85 / 1.50 / 1.58 ms (262 144: 2 beats 4 too).
+    int cpt = (c.batch >= (int64_t)ctx->sm_count * 64 * 2) ? 2 : 1;
     if (const char* e = getenv("RXG_FORCE_CPT")) cpt = atoi(e);      // test / tuning override
-    if (cpt == 2 && al16 && c.batch % 2 == 0) return launch_shared<D, M, 2>(ctx, c, mdl, ws, write_cov);
+    if (D * M > 16 && cpt > 2) cpt = 2;                              // register budget for d = 6
+    if (cpt == 4 && al16 && c.batch % 4 == 0) return launch_shared<D, M, 4>(ctx, c, mdl, ws, write_cov);
+    if (cpt >= 2 && al16 && c.batch % 2 == 0) return launch_shared<D, M, 2>(ctx, c, mdl, ws, write_cov);
     return launch_shared<D, M, 1>(ctx, c, mdl, ws, write_cov);
 }
 

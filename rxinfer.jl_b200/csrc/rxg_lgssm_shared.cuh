@@ -1,0 +1,335 @@
+// lgssm_shared_kernel: the mean-only forward/backward sweep of the shared-model path.
+//
+// One warp = one CTA = 32 x CPT chains, so CTAs spread over the 148 SMs to within one warp and no
+// block-wide barrier is ever needed.  Per (chain, step) the sweep moves
+//     forward : read y_t (m)            write filtered mean (d)      [stash, in post_mean]
+//     backward: read filtered mean (d)  write smoothed mean (d) + smoothed covariance (d*d)
+// = 4 (m + 3 d + d^2) bytes (128 B at d = m = 4; 96 B of it is the contract's algorithmic I/O).
+//
+// Latency hiding (the kernel is HBM-latency bound, ~3.5 warps per SM sub-partition):
+//   * the data-independent gain tables (F_t, K_t / E_t, G_t, Sigma_s,t) are staged through shared
+//     memory TC steps at a time with cp.async (double buffered), so the per-step table reads are
+//     29-cycle broadcast LDS instead of ~300-cycle L2 hits on the dependent chain;
+//   * the per-chain streams (y forward, stashed means backward) are prefetched PF steps ahead
+//     into registers.
+#pragma once
+#include "rxg_lgssm_common.cuh"
+
+namespace rxg {
+
+// uniform (same address for every lane) loads of a table segment from global memory
+template <int N>
+__device__ __forceinline__ void load_uniform(const float* __restrict__ p, float* dst) {
+    if (N % 4 == 0) {
+        const float4* p4 = reinterpret_cast<const float4*>(p);
+#pragma unroll
+        for (int i = 0; i < N / 4; ++i) {
+            float4 v = __ldg(p4 + i);
+            dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) dst[i] = __ldg(p + i);
+    }
+}
+// broadcast reads of a table segment staged in shared memory (N is a multiple of 4)
+template <int N>
+__device__ __forceinline__ void load_smem(const float* p, float* dst) {
+    const float4* p4 = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) {
+        float4 v = p4[i];
+        dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
+    }
+}
+
+template <int CPT> struct Pack;
+template <> struct Pack<1> {
+    static __device__ __forceinline__ void ld(const float* p, float* v) { v[0] = __ldg(p); }
+    static __device__ __forceinline__ void ld_rw(const float* p, float* v) { v[0] = *p; }
+    static __device__ __forceinline__ void st(float* p, const float* v) { *p = v[0]; }
+};
+template <> struct Pack<2> {
+    static __device__ __forceinline__ void ld(const float* p, float* v) {
+        float2 t = __ldg(reinterpret_cast<const float2*>(p)); v[0] = t.x; v[1] = t.y;
+    }
+    static __device__ __forceinline__ void ld_rw(const float* p, float* v) {
+        float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y;
+    }
+    static __device__ __forceinline__ void st(float* p, const float* v) {
+        *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    }
+};
+template <> struct Pack<4> {
+    static __device__ __forceinline__ void ld(const float* p, float* v) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    static __device__ __forceinline__ void ld_rw(const float* p, float* v) {
+        float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    static __device__ __forceinline__ void st(float* p, const float* v) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// Stage TC consecutive table records (REC floats each, REC % 4 == 0) into shared memory.
+// `first` is the record index of slot 0, `dir` = +1 (forward in t) or -1 (backward in t).
+template <int REC, int TC>
+__device__ __forceinline__ void stage_tables(float* sdst, const float* __restrict__ tab, int first, int dir,
+                                             int T, int lane) {
+    constexpr int PIECES = REC / 4;   // 16-byte pieces per record
+#pragma unroll
+    for (int p = lane; p < TC * PIECES; p += 32) {
+        const int slot = p / PIECES, part = p % PIECES;
+        const int t = first + dir * slot;
+        if (t >= 0 && t < T) cp_async16(sdst + slot * REC + part * 4, tab + (size_t)t * REC + part * 4);
+    }
+    cp_async_commit();
+}
+
+template <int D, int M, int CPT, int PF, bool SMOOTH, bool EVID>
+__global__ void __launch_bounds__(32, 16 / CPT)   // CPT=1: <= 128 regs so ~14 warps/SM stay resident; wider CPT trades warps for ILP
+lgssm_shared_kernel(const __grid_constant__ ModelF<D, M> mdl, const float* __restrict__ fwd_tab,
+                    const float* __restrict__ bwd_tab, const float* __restrict__ sf_tab,
+                    const float* __restrict__ y, float* __restrict__ mean, float* __restrict__ cov,
+                    float* __restrict__ nle, int T, int64_t batch, int transition_first,
+                    int write_cov) {
+    using TB = Tab<D, M>;
+    constexpr int TC = 4 * PF;                                   // table chunk, in time steps
+    constexpr int REC_MAX = TB::FWD_REC > TB::BWD_REC ? TB::FWD_REC : TB::BWD_REC;
+    __shared__ __align__(16) float s_tab[2][TC * REC_MAX];
+
+    const int lane = threadIdx.x;
+    const int64_t b0 = ((int64_t)blockIdx.x * 32 + lane) * CPT;
+    const bool active = b0 < batch;
+    const int64_t b = active ? b0 : 0;      // inactive lanes shadow chain 0 (loads only, no stores)
+
+    float mu[D][CPT];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) mu[i][c] = mdl.m0[i];
+    float ev[CPT];
+    double ev_hi[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) { ev[c] = 0.f; ev_hi[c] = 0.0; }
+
+    // ---------------------------------------------------------------- forward
+    float ycur[PF][M][CPT], ynxt[PF][M][CPT];
+#pragma unroll
+    for (int s = 0; s < PF; ++s)
+        if (s < T)
+#pragma unroll
+            for (int k = 0; k < M; ++k) Pack<CPT>::ld(y + ((int64_t)s * M + k) * batch + b, ycur[s][k]);
+
+    stage_tables<TB::FWD_REC, TC>(s_tab[0], fwd_tab, 0, +1, T, lane);
+    for (int t0 = 0; t0 < T; t0 += PF) {
+        if ((t0 % TC) == 0) {
+            const int c = t0 / TC;
+            __syncwarp();                       // all lanes are done with the buffer about to be refilled
+            stage_tables<TB::FWD_REC, TC>(s_tab[(c + 1) & 1], fwd_tab, (c + 1) * TC, +1, T, lane);
+            cp_async_wait<1>();                 // chunk c has landed (this lane's pieces)
+            __syncwarp();                       // ... and every other lane's
+        }
+#pragma unroll
+        for (int s = 0; s < PF; ++s)
+            if (t0 + PF + s < T)
+#pragma unroll
+                for (int k = 0; k < M; ++k)
+                    Pack<CPT>::ld(y + ((int64_t)(t0 + PF + s) * M + k) * batch + b, ynxt[s][k]);
+#pragma unroll
+        for (int s = 0; s < PF; ++s) {
+            const int t = t0 + s;
+            if (t < T) {
+                const float* rec = s_tab[(t / TC) & 1] + (t % TC) * TB::FWD_REC;
+                float Kt[pad4(D * M)];
+                load_smem<pad4(D * M)>(rec + TB::K_OFF, Kt);
+                float nm[D][CPT];
+                if (!EVID) {
+                    // mu_f[t] = F_t mu_f[t-1] + K_t y_t,  F_t = (I - K_t B) A   (rules #1-#4 + product)
+                    float Ft[pad4(D * D)];
+                    load_smem<pad4(D * D)>(rec + TB::F_OFF, Ft);
+#pragma unroll
+                    for (int i = 0; i < D; ++i)
+#pragma unroll
+                        for (int c = 0; c < CPT; ++c) {
+                            float a = Ft[i * D] * mu[0][c];
+#pragma unroll
+                            for (int j = 1; j < D; ++j) a = __fmaf_rn(Ft[i * D + j], mu[j][c], a);
+#pragma unroll
+                            for (int k = 0; k < M; ++k) a = __fmaf_rn(Kt[i * M + k], ycur[s][k][c], a);
+                            nm[i][c] = a;
+                        }
+                } else {
+                    // explicit form so that the innovation is available for the evidence
+                    float Li[pad4(M * M)], cc[4];
+                    load_smem<pad4(M * M)>(rec + TB::LI_OFF, Li);
+                    load_smem<4>(rec + TB::C_OFF, cc);
+                    const bool pred = (t > 0) || transition_first;
+#pragma unroll
+                    for (int c = 0; c < CPT; ++c) {
+                        float mp[D], e[M];
+#pragma unroll
+                        for (int i = 0; i < D; ++i) {
+                            if (pred) {
+                                float a = mdl.A[i * D] * mu[0][c];
+#pragma unroll
+                                for (int j = 1; j < D; ++j) a = __fmaf_rn(mdl.A[i * D + j], mu[j][c], a);
+                                mp[i] = a;
+                            } else {
+                                mp[i] = mu[i][c];
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < M; ++k) {
+                            float a = ycur[s][k][c];
+#pragma unroll
+                            for (int j = 0; j < D; ++j) a = __fmaf_rn(-mdl.B[k * D + j], mp[j], a);
+                            e[k] = a;
+                        }
+                        float q = 0.f;
+#pragma unroll
+                        for (int k = 0; k < M; ++k) {
+                            float a = 0.f;
+#pragma unroll
+                            for (int j = 0; j <= k; ++j) a = __fmaf_rn(Li[k * M + j], e[j], a);
+                            q = __fmaf_rn(a, a, q);
+                        }
+                        ev[c] += __fmaf_rn(0.5f, q, cc[0]);
+#pragma unroll
+                        for (int i = 0; i < D; ++i) {
+                            float a = mp[i];
+#pragma unroll
+                            for (int k = 0; k < M; ++k) a = __fmaf_rn(Kt[i * M + k], e[k], a);
+                            nm[i][c] = a;
+                        }
+                    }
+                    if ((t & 63) == 63) {   // flush the fp32 partial sum into fp64 every 64 steps
+#pragma unroll
+                        for (int c = 0; c < CPT; ++c) { ev_hi[c] += (double)ev[c]; ev[c] = 0.f; }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+#pragma unroll
+                    for (int c = 0; c < CPT; ++c) mu[i][c] = nm[i][c];
+                    if (active) Pack<CPT>::st(mean + ((int64_t)t * D + i) * batch + b, mu[i]);
+                }
+                if (!SMOOTH && write_cov && active) {
+                    float Sf[pad4(D * D)];
+                    load_uniform<pad4(D * D)>(sf_tab + (size_t)t * TB::SF_REC, Sf);
+#pragma unroll
+                    for (int i = 0; i < D * D; ++i) {
+                        float v[CPT];
+#pragma unroll
+                        for (int c = 0; c < CPT; ++c) v[c] = Sf[i];
+                        Pack<CPT>::st(cov + ((int64_t)t * D * D + i) * batch + b, v);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < PF; ++s)
+#pragma unroll
+            for (int k = 0; k < M; ++k)
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) ycur[s][k][c] = ynxt[s][k][c];
+    }
+    if (EVID && nle && active) {
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) nle[b + c] = (float)(ev_hi[c] + (double)ev[c]);
+    }
+    cp_async_wait<0>();
+    if (!SMOOTH) return;
+
+    // ---------------------------------------------------------------- backward (r = T-1-t ascending)
+    // mu_s[t] = E_t mu_f[t] + G_t mu_s[t+1]  (rules #3', #4 backward + 3-way marginal);
+    // record T-1 holds E = I, G = 0.  Sigma_s[t] is chain-independent: broadcast store.
+    float ms[D][CPT];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) ms[i][c] = 0.f;
+    float fcur[PF][D][CPT], fnxt[PF][D][CPT];
+#pragma unroll
+    for (int s = 0; s < PF; ++s)
+        if (T - 1 - s >= 0)
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+                Pack<CPT>::ld_rw(mean + ((int64_t)(T - 1 - s) * D + i) * batch + b, fcur[s][i]);
+
+    __syncwarp();
+    stage_tables<TB::BWD_REC, TC>(s_tab[0], bwd_tab, T - 1, -1, T, lane);
+    for (int r0 = 0; r0 < T; r0 += PF) {
+        if ((r0 % TC) == 0) {
+            const int c = r0 / TC;
+            __syncwarp();
+            stage_tables<TB::BWD_REC, TC>(s_tab[(c + 1) & 1], bwd_tab, T - 1 - (c + 1) * TC, -1, T, lane);
+            cp_async_wait<1>();
+            __syncwarp();
+        }
+#pragma unroll
+        for (int s = 0; s < PF; ++s)
+            if (T - 1 - (r0 + PF + s) >= 0)
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+                    Pack<CPT>::ld_rw(mean + ((int64_t)(T - 1 - (r0 + PF + s)) * D + i) * batch + b, fnxt[s][i]);
+#pragma unroll
+        for (int s = 0; s < PF; ++s) {
+            const int r = r0 + s;
+            const int t = T - 1 - r;
+            if (t >= 0) {
+                const float* rec = s_tab[(r / TC) & 1] + (r % TC) * TB::BWD_REC;
+                float Et[pad4(D * D)], Gt[pad4(D * D)];
+                load_smem<pad4(D * D)>(rec + TB::E_OFF, Et);
+                load_smem<pad4(D * D)>(rec + TB::G_OFF, Gt);
+                float nm[D][CPT];
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+#pragma unroll
+                    for (int c = 0; c < CPT; ++c) {
+                        float a = Et[i * D] * fcur[s][0][c];
+#pragma unroll
+                        for (int j = 1; j < D; ++j) a = __fmaf_rn(Et[i * D + j], fcur[s][j][c], a);
+#pragma unroll
+                        for (int j = 0; j < D; ++j) a = __fmaf_rn(Gt[i * D + j], ms[j][c], a);
+                        nm[i][c] = a;
+                    }
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+#pragma unroll
+                    for (int c = 0; c < CPT; ++c) ms[i][c] = nm[i][c];
+                    if (active) Pack<CPT>::st(mean + ((int64_t)t * D + i) * batch + b, ms[i]);
+                }
+                if (write_cov && active) {
+                    float Sst[pad4(D * D)];
+                    load_smem<pad4(D * D)>(rec + TB::SS_OFF, Sst);
+#pragma unroll
+                    for (int i = 0; i < D * D; ++i) {
+                        float v[CPT];
+#pragma unroll
+                        for (int c = 0; c < CPT; ++c) v[c] = Sst[i];
+                        Pack<CPT>::st(cov + ((int64_t)t * D * D + i) * batch + b, v);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < PF; ++s)
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) fcur[s][i][c] = fnxt[s][i][c];
+    }
+    cp_async_wait<0>();
+}
+
+}  // namespace rxg

@@ -65,12 +65,15 @@ def test_chains_per_thread_2_path(ctx, monkeypatch):
     mod = f32_model(lgssm.notebook_model(4))
     _, y = lgssm.generate_data(mod, 200, 64, seed=7)
     ref = lgssm.smooth_reference_schedule(y, **mod)
-    monkeypatch.setenv("RXG_FORCE_CPT", "2")
-    r = ctx.lgssm(dev(y), **_kw(mod), smooth=True, want_evidence=True)
-    check(r, ref)
-    monkeypatch.setenv("RXG_FORCE_CPT", "1")
-    r1 = ctx.lgssm(dev(y), **_kw(mod), smooth=True, want_evidence=True)
-    check(r1, ref)
+    for cpt in ("4", "2", "1"):
+        monkeypatch.setenv("RXG_FORCE_CPT", cpt)
+        check(ctx.lgssm(dev(y), **_kw(mod), smooth=True, want_evidence=True), ref)
+        check(ctx.lgssm(dev(y), **_kw(mod), smooth=True), ref, nle=False)
+        check(ctx.lgssm(dev(y), **_kw(mod), smooth=False, want_evidence=True), ref, smooth=False)
+    # ragged: batch not a multiple of 32 * CPT
+    monkeypatch.setenv("RXG_FORCE_CPT", "4")
+    _, y2 = lgssm.generate_data(mod, 90, 100, seed=8)
+    check(ctx.lgssm(dev(y2), **_kw(mod), smooth=True, want_evidence=True), lgssm.smooth_reference_schedule(y2, **mod))
 
 
 @pytest.mark.parametrize("d,m", [(1, 1), (2, 1), (3, 3), (4, 1), (4, 2), (6, 6)])
