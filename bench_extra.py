@@ -1,0 +1,113 @@
+#!/usr/bin/env python
+"""Secondary measurements (not the driver's bench contract): the other BASELINE.json configs and
+the per-rule kernels, one JSON line each.  Device-resident data, CUDA events, >= 3 warm-ups.
+
+  python bench_extra.py [--which per_chain,filter,hgf,rules,vmp,scaling_T]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import rxinfer_jl_b200 as rx  # noqa: E402
+from bench import notebook_model_f32, peaks  # noqa: E402
+
+
+def timed(fn, warm=3, reps=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--which", default="per_chain,filter,hgf,rules,vmp,scaling_T")
+    args = ap.parse_args()
+    which = set(args.which.split(","))
+    ctx = rx.Context(0)
+    peak, _ = peaks()
+    mod = notebook_model_f32()
+    kw = dict(A=mod["A"], B=mod["B"], P=mod["P"], Q=mod["Q"], m0=mod["m0"], S0=mod["S0"])
+    T, batch = 1000, 65536
+    g = torch.Generator(device="cuda").manual_seed(7)
+
+    if which & {"per_chain", "filter"}:
+        y = torch.randn(T, 4, batch, device="cuda", generator=g) * 3.3
+        mean = torch.empty(T, 4, batch, device="cuda"); cov = torch.empty(T, 4, 4, batch, device="cuda")
+        if "per_chain" in which:
+            ms = timed(lambda: ctx.lgssm(y, **kw, smooth=True, out_mean=mean, out_cov=cov, force_per_chain_path=True))
+            print(json.dumps({"what": "lgssm smooth, per-chain covariance recursion (lgssm_chain_kernel)", "d": 4, "T": T,
+                              "batch": batch, "ms": ms, "messages_per_s": 6 * T * batch / ms * 1e3,
+                              "algorithmic_GBs": 96 * T * batch / ms / 1e6, "frac_of_hbm_peak": 96 * T * batch / ms / 1e6 / peak}))
+        if "filter" in which:
+            for tf in (False, True):
+                ms = timed(lambda: ctx.lgssm(y, **kw, smooth=False, out_mean=mean, out_cov=cov, transition_first=tf))
+                print(json.dumps({"what": "lgssm filter (forward half), gain-table path", "transition_first": tf, "d": 4, "T": T,
+                                  "batch": batch, "ms": ms, "messages_per_s": 4 * T * batch / ms * 1e3,
+                                  "algorithmic_GBs": 96 * T * batch / ms / 1e6}))
+        del y, mean, cov
+
+    if "scaling_T" in which:
+        # the notebook's scaling table (ipynb:795-806) at d = 2, batched: T from 50 to 50 000
+        from oracle.lgssm import notebook_model
+        m2 = {k: np.asarray(v, np.float32) for k, v in notebook_model(2).items()}
+        for TT in (50, 1000, 10000, 50000):
+            b = max(1024, min(65536, (1 << 26) // TT))
+            y = torch.randn(TT, 2, b, device="cuda", generator=g) * 3.3
+            ms = timed(lambda: ctx.lgssm(y, **m2, smooth=True), warm=3, reps=3)
+            print(json.dumps({"what": "lgssm smooth d=2 (notebook scaling table shape)", "T": TT, "batch": b, "ms": ms,
+                              "messages_per_s": 6 * TT * b / ms * 1e3, "ms_per_chain_equiv": ms / b}))
+            del y
+
+    if "hgf" in which:
+        Th, bh, iters = 1000, 32768, 20
+        yh = torch.randn(Th, bh, device="cuda", generator=g).cumsum(0) * 0.5
+        out = torch.empty(Th, 4, bh, device="cuda")
+        ms = timed(lambda: ctx.hgf_filter(yh, iters=iters, out=out), warm=3, reps=3)
+        n_exp = (31 + 1 + iters * 32) * Th * bh
+        print(json.dumps({"what": "HGF filter (BASELINE configs[3]): GCV node, GH-31, 20 VMP iterations", "T": Th, "batch": bh,
+                          "iters": iters, "ms": ms, "vmp_iterations_per_s": iters * Th * bh / ms * 1e3,
+                          "messages_per_s": 6 * iters * Th * bh / ms * 1e3, "exp_per_s": n_exp / ms * 1e3,
+                          "io_GBs": 20 * Th * bh / ms / 1e6}))
+
+    if "vmp" in which:
+        yv = torch.randn(1000, 65536, device="cuda", generator=g).cumsum(0)
+        ms = timed(lambda: ctx.lgssm_vmp_gamma(yv, iterations=10), warm=2, reps=3)
+        print(json.dumps({"what": "Gamma-precision VMP around scalar smoother, 10 iterations", "T": 1000, "batch": 65536, "ms": ms,
+                          "sweeps_per_s": 10 / ms * 1e3}))
+
+    if "rules" in which:
+        n, d = 1 << 22, 4
+        mu = torch.randn(d, n, device="cuda", generator=g)
+        X = torch.randn(d, d, n, device="cuda", generator=g)
+        S = torch.einsum("ikn,jkn->ijn", X, X).contiguous() + 4 * torch.eye(d, device="cuda")[:, :, None]
+        S = S.contiguous()
+        A = np.asarray(mod["A"])
+        rows = []
+        rows.append(("MvNormalMeanCovariance(:out)  (mu, S + Sigma)", timed(lambda: ctx.rule_add_cov(mu, S, mod["P"])), 2 * (d + d * d) * 4))
+        rows.append(("*(:out)  (A mu, A S A')", timed(lambda: ctx.rule_mul_out(A, mu, S)), 2 * (d + d * d) * 4))
+        rows.append(("*(:in)   cholinv + A' W A", timed(lambda: ctx.rule_mul_in(A, mu, S)), 2 * (d + d * d) * 4 + 4))
+        rows.append(("prod (xi1 + xi2, W1 + W2)", timed(lambda: ctx.prod_gaussian(mu, S, mu, S)), 3 * (d + d * d) * 4))
+        rows.append(("mean_cov <-> weightedmean_precision (cholinv)", timed(lambda: ctx.meancov_to_wmp(mu, S)), 2 * (d + d * d) * 4 + 4))
+        for name, ms, bytes_per in rows:
+            # note: torch.empty_like allocations are inside the timed call (caching allocator)
+            print(json.dumps({"what": "rule kernel: " + name, "n": n, "d": d, "ms": ms, "messages_per_s": n / ms * 1e3,
+                              "GBs": bytes_per * n / ms / 1e6, "frac_of_hbm_peak": bytes_per * n / ms / 1e6 / peak}))
+
+
+if __name__ == "__main__":
+    main()

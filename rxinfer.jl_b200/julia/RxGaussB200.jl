@@ -1,0 +1,106 @@
+# RxGaussB200.jl -- the Julia-side shim a maintainer would add next to RxInfer to route the batched
+# Gaussian hot path to librxgauss.so (include/rxgauss.h) through plain `ccall`.  No CUDA.jl codegen:
+# the kernels are the hand-written sm_100a ones in csrc/.
+#
+# NOT RUNNABLE IN THE BUILD IMAGE (no Julia there); it is the reference-side binding that
+# INTEGRATION.md describes, kept next to the C ABI it binds.  The Python package in this directory
+# (`_lib.py`, `context.py`, `inference.py`, `rules.py`) is the same binding in the host language
+# that *is* available, and is what the parity tests drive.
+module RxGaussB200
+
+using LinearAlgebra
+# using RxInfer, ReactiveMP, ExponentialFamily, BayesBase    # in a real checkout
+
+const LIB = get(ENV, "RXGAUSS_LIB", joinpath(@__DIR__, "..", "librxgauss.so"))
+
+const RXG_PTR_DEVICE       = UInt32(1) << 0
+const RXG_MODEL_PER_CHAIN  = UInt32(1) << 1
+const RXG_ASYNC            = UInt32(1) << 2
+const RXG_COV_SHARED_OUT   = UInt32(1) << 3
+const RXG_PATH_PER_CHAIN   = UInt32(1) << 4
+const RXG_TRANSITION_FIRST = UInt32(1) << 5
+
+struct RxGaussError <: Exception
+    code::Cint
+    msg::String
+end
+
+mutable struct Context
+    handle::Ptr{Cvoid}
+    function Context(device::Integer = 0)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:rxg_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint, Cuint), h, device, 0)
+        rc == 0 || throw(RxGaussError(rc, "rxg_create failed (no CUDA device? there is no CPU fallback)"))
+        ctx = new(h[])
+        finalizer(c -> ccall((:rxg_destroy, LIB), Cint, (Ptr{Cvoid},), c.handle), ctx)
+        return ctx
+    end
+end
+
+function check(ctx::Context, rc::Cint)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:rxg_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx.handle))
+    throw(RxGaussError(rc, msg))
+end
+
+f32(M) = Matrix{Float32}(M)      # shared model matrices are host constants, row-major on the C side
+rowmajor(M::AbstractMatrix) = collect(transpose(f32(M)))   # Julia is column-major
+
+"""
+    smooth(ctx, y, A, B, P, Q, m0, S0; free_energy = false)
+
+Batched replacement for `infer(model = linear_gaussian_ssm_smoothing(A = A, B = B, P = P, Q = Q),
+data = (y = observations,))` (benchmarks/...Benchmark.ipynb:186-196) over `batch` independent series.
+`y` is `Array{Float32,3}` of size `(batch, m, T)` -- i.e. the C layout `y[T][m][batch]` seen from
+column-major Julia -- so no transposition is needed for the data.
+Returns `(mean[batch, d, T], cov[batch, d, d, T], neg_log_evidence[batch])`.
+"""
+function smooth(ctx::Context, y::Array{Float32,3}, A, B, P, Q, m0, S0; free_energy::Bool = false)
+    batch, m, T = size(y)
+    d = size(A, 1)
+    mean = Array{Float32}(undef, batch, d, T)
+    cov  = Array{Float32}(undef, batch, d, d, T)
+    nle  = free_energy ? Vector{Float32}(undef, batch) : Float32[]
+    Ar, Br, Pr, Qr, S0r = rowmajor(A), rowmajor(B), rowmajor(P), rowmajor(Q), rowmajor(S0)
+    m0r = Vector{Float32}(m0)
+    GC.@preserve y mean cov nle Ar Br Pr Qr S0r m0r begin
+        rc = ccall((:rxg_lgssm_smooth_f32, LIB), Cint,
+            (Ptr{Cvoid}, Cint, Cint, Cint, Int64,
+             Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32},
+             Ptr{Float32}, Ptr{UInt8}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Int32}, Cuint),
+            ctx.handle, d, m, T, batch, Ar, Br, Pr, Qr, m0r, S0r,
+            y, C_NULL, mean, cov, free_energy ? pointer(nle) : C_NULL, C_NULL, 0)   # host pointers: flags = 0
+        check(ctx, rc)
+    end
+    return mean, cov, nle
+end
+
+# --- drop-in for the result object: user code only calls mean./cov./var. on posteriors[:x]
+#     (test/models/statespace/mlgssm_test.jl:121-126), so unpack into MvNormalMeanCovariance:
+#
+# function infer_batched(; model, data, free_energy = false, kwargs...)
+#     pattern = recognise(model)                       # GraphPPL graph -> (A, B, P, Q, prior) or nothing
+#     pattern === nothing && return RxInfer.infer(; model, data, free_energy, kwargs...)   # stock path
+#     isempty(intersect(keys(kwargs), (:callbacks, :constraints, :meta, :predictvars, :annotations))) ||
+#         return RxInfer.infer(; model, data, free_energy, kwargs...)                       # never silently ignore
+#     μ, Σ, F = smooth(CTX[], pack(data.y), pattern...; free_energy)
+#     posteriors = Dict(:x => [MvNormalMeanCovariance(Float64.(μ[b, :, t]), Float64.(Σ[b, :, :, t]))
+#                              for t in axes(μ, 3), b in axes(μ, 1)])
+#     return InferenceResult(posteriors, nothing, free_energy ? F : nothing, model, nothing)
+# end
+#
+# --- per-rule drop-in: ReactiveMP dispatches rules by message type, so a batched message type
+#     makes `@rule` bodies one-liners over the C ABI:
+#
+# struct BatchedMvNormalMeanCovariance{P}; μ::P; Σ::P; n::Int; d::Int; end     # device pointers, SoA
+# @rule typeof(*)(:out, Marginalisation) (m_A::PointMass{<:AbstractMatrix}, m_in::BatchedMvNormalMeanCovariance) = begin
+#     out = similar(m_in)
+#     check(CTX[], ccall((:rxg_rule_mul_out_f32, LIB), Cint,
+#         (Ptr{Cvoid}, Int64, Cint, Cint, Ptr{Float32}, Cint, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Cuint),
+#         CTX[].handle, m_in.n, m_in.d, m_in.d, rowmajor(mean(m_A)), 1, m_in.μ, m_in.Σ, out.μ, out.Σ, RXG_PTR_DEVICE))
+#     return out
+# end
+# BayesBase.prod(::GenericProd, l::BatchedMvNormalWeightedMeanPrecision, r::BatchedMvNormalWeightedMeanPrecision) =
+#     ...ccall((:rxg_prod_gaussian_f32, LIB), ...)
+
+end # module
