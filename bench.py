@@ -219,7 +219,6 @@ def main():
         step()
         a, b = ctx.profile_last_ms()
         main_ms.append(a); gain_ms.append(b)
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([el_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -247,6 +246,18 @@ def main():
         allgather = {"ms": gms, "bytes_in_per_gpu": inbound, "in_GBs_per_gpu": inbound / gms / 1e6,
                      "value_with_allgather": msgs / ((ms_per_step + gms) * 1e-3)}
         del gm, gc
+        # shared model => the covariances are identical on every rank: gathering the means alone is enough
+        ctx.allgather_posteriors(mean, None, world)
+        torch.cuda.synchronize(); dist.barrier()
+        g0.record()
+        for _ in range(reps):
+            gm, _ = ctx.allgather_posteriors(mean, None, world)
+        g1.record(); torch.cuda.synchronize()
+        tg = torch.tensor([g0.elapsed_time(g1) / reps], device=dev, dtype=torch.float64)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        allgather["means_only_ms"] = float(tg.item())
+        allgather["value_with_means_only_allgather"] = msgs / ((ms_per_step + float(tg.item())) * 1e-3)
+        del gm
 
     # ---- e2e through the C ABI with host buffers (rank-local; all ranks run it concurrently)
     e2e = None
@@ -273,6 +284,7 @@ def main():
                "api": "rxg_lgssm_smooth_f32 with host (pinned) pointers"}
         del yh, mh, ch
 
+    clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
         peak, peak_src = peaks()
         k_ms = float(np.mean(main_ms))

@@ -229,23 +229,48 @@ static int smooth_chain(int d, int m, int T, long batch, long b,
     return bad;
 }
 
+/* Chains are processed in blocks of CB: the block's observations are gathered from the
+ * batch-innermost ABI layout into a chain-major scratch copy, every chain runs on that contiguous
+ * copy (so the per-thread working set stays in L2), and the block's posteriors are scattered back
+ * with full-cache-line rows.  Without this the strided 8-byte accesses of the ABI layout make the
+ * port memory-bound and it stops scaling beyond a few cores. */
+#define CB 8
 int rxo_lgssm_smooth_f64(int d, int m, int T, long batch,
                          const double* A, const double* B, const double* P, const double* Q,
                          const double* m0, const double* S0, const float* y,
                          double* mean, double* cov, double* nle, int nthreads) {
     if (d > DMAX || m > DMAX || d < 1 || m < 1 || T < 1 || batch < 1) return -1;
     int bad_total = 0;
+    const long nblk = (batch + CB - 1) / CB;
+    const int dd = d * d;
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #pragma omp parallel reduction(+ : bad_total)
 #endif
     {
         work_t w = work_alloc(T, d, m);
+        float* yl = (float*)malloc(sizeof(float) * (size_t)T * m);          /* one chain, [T][m][1] */
+        double* ml = (double*)malloc(sizeof(double) * (size_t)CB * T * d);   /* [c][T][d]            */
+        double* cl = (double*)malloc(sizeof(double) * (size_t)CB * T * dd);  /* [c][T][d*d]          */
+        double nl[CB];
 #ifdef _OPENMP
-#pragma omp for schedule(static)
+#pragma omp for schedule(dynamic, 1)
 #endif
-        for (long b = 0; b < batch; ++b)
-            bad_total += smooth_chain(d, m, T, batch, b, A, B, P, Q, m0, S0, y, mean, cov, nle, &w);
+        for (long blk = 0; blk < nblk; ++blk) {
+            const long b0 = blk * CB;
+            const int nb = (int)((b0 + CB <= batch) ? CB : (batch - b0));
+            for (int c = 0; c < nb; ++c) {
+                for (long r = 0; r < (long)T * m; ++r) yl[r] = y[r * batch + b0 + c];
+                bad_total += smooth_chain(d, m, T, 1, 0, A, B, P, Q, m0, S0, yl,
+                                          ml + (size_t)c * T * d, cl + (size_t)c * T * dd, nl + c, &w);
+            }
+            for (long r = 0; r < (long)T * d; ++r)
+                for (int c = 0; c < nb; ++c) mean[r * batch + b0 + c] = ml[(size_t)c * T * d + r];
+            for (long r = 0; r < (long)T * dd; ++r)
+                for (int c = 0; c < nb; ++c) cov[r * batch + b0 + c] = cl[(size_t)c * T * dd + r];
+            if (nle) for (int c = 0; c < nb; ++c) nle[b0 + c] = nl[c];
+        }
+        free(yl); free(ml); free(cl);
         work_free(&w);
     }
     return bad_total;

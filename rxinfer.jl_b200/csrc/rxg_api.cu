@@ -4,6 +4,7 @@
 #include <dlfcn.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -91,6 +92,12 @@ int rxg_destroy(rxg_ctx* ctx) {
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->stage) cudaFree(ctx->stage);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->s_in) {
+        cudaStreamSynchronize(ctx->s_in); cudaStreamSynchronize(ctx->s_out);
+        cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_out);
+        for (int q = 0; q < 2; ++q) { cudaEventDestroy(ctx->ev_in[q]); cudaEventDestroy(ctx->ev_comp[q]); cudaEventDestroy(ctx->ev_out[q]); }
+        cudaEventDestroy(ctx->ev_start);
+    }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return RXG_OK;
@@ -176,35 +183,94 @@ static int lgssm_entry(rxg_ctx* ctx, bool smooth, int d, int m, int T, int64_t b
         return RXG_OK;
     }
 
-    // ---- host-pointer call: stage through device memory on the context's stream
+    // ---- host-pointer call: stage through device memory.  The batch is cut into slices that are
+    // pipelined over three streams (H2D of slice s+1 | sweep of slice s | D2H of slice s-1): PCIe is
+    // full duplex, so the 4(m)-byte/step upload hides behind the 4(d + d^2)-byte/step download.
+    // Batch is the innermost axis, so a slice is a pitched 2-D region of every host array.
     if (per_chain_model)
         return fail(ctx, RXG_ERR_UNSUPPORTED, "lgssm: per-chain model arrays must be device pointers");
     const bool cov_shared = (flags & RXG_COV_SHARED_OUT) != 0;
-    const size_t n_y = (size_t)T * m * batch, n_mean = (size_t)T * d * batch;
-    const size_t n_cov_dev = cov ? (cov_shared ? (size_t)T * d * d : (size_t)T * d * d * batch)
-                                 : ((ymask || (flags & RXG_PATH_PER_CHAIN)) ? (size_t)T * d * d * batch : 0);
+    const bool need_cov_dev = cov || ymask || (flags & RXG_PATH_PER_CHAIN);
+    int ns = 1;
+    if (!cov_shared && batch >= 16384) ns = (int)((batch + 8191) / 8192);
+    if (ns > 64) ns = 64;
+    if (const char* e = getenv("RXG_HOST_SLICES")) { int v = atoi(e); if (v >= 1) ns = v; }
+    const int64_t bs = ((batch + ns - 1) / ns + 3) / 4 * 4;          // slice width, multiple of 4 chains
+    ns = (int)((batch + bs - 1) / bs);
+    const int nbuf = ns > 1 ? 2 : 1;
+    const size_t n_y = (size_t)T * m * bs, n_mean = (size_t)T * d * bs;
+    const size_t n_cov = need_cov_dev ? (cov_shared ? (size_t)T * d * d : (size_t)T * d * d * bs) : 0;
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
-    const size_t o_y = carve(n_y * 4), o_mean = carve(n_mean * 4), o_cov = carve(n_cov_dev * 4);
-    const size_t o_mask = carve(ymask ? (size_t)T * batch : 0);
-    const size_t o_nle = carve(nle ? (size_t)batch * 4 : 0), o_st = carve(status ? (size_t)batch * 4 : 0);
+    size_t o_y[2], o_mean[2], o_cov[2], o_mask[2], o_nle[2], o_st[2];
+    for (int q = 0; q < nbuf; ++q) {
+        o_y[q] = carve(n_y * 4); o_mean[q] = carve(n_mean * 4); o_cov[q] = carve(n_cov * 4);
+        o_mask[q] = carve(ymask ? (size_t)T * bs : 0);
+        o_nle[q] = carve(nle ? (size_t)bs * 4 : 0); o_st[q] = carve(status ? (size_t)bs * 4 : 0);
+    }
     char* base = (char*)staging(ctx, off);
     if (!base) return RXG_ERR_CUDA;
-    float* d_y = (float*)(base + o_y);
-    c.y = d_y;
-    c.mean = (float*)(base + o_mean);
-    c.cov = n_cov_dev ? (float*)(base + o_cov) : nullptr;
-    c.ymask = ymask ? (const uint8_t*)(base + o_mask) : nullptr;
-    c.nle = nle ? (float*)(base + o_nle) : nullptr;
-    c.status = status ? (int32_t*)(base + o_st) : nullptr;
-    RXG_CUDA(ctx, cudaMemcpyAsync(d_y, y, n_y * 4, cudaMemcpyHostToDevice, ctx->stream));
-    if (ymask) RXG_CUDA(ctx, cudaMemcpyAsync((void*)c.ymask, ymask, (size_t)T * batch, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = lgssm_dispatch(ctx, c);
-    if (rc != RXG_OK) return rc;
-    RXG_CUDA(ctx, cudaMemcpyAsync(mean, c.mean, n_mean * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (cov) RXG_CUDA(ctx, cudaMemcpyAsync(cov, c.cov, n_cov_dev * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (nle) RXG_CUDA(ctx, cudaMemcpyAsync(nle, c.nle, (size_t)batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (status) RXG_CUDA(ctx, cudaMemcpyAsync(status, c.status, (size_t)batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ns > 1 && !ctx->s_in) {
+        RXG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+        RXG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+        for (int q = 0; q < 2; ++q) {
+            RXG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_in[q], cudaEventDisableTiming));
+            RXG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_comp[q], cudaEventDisableTiming));
+            RXG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_out[q], cudaEventDisableTiming));
+        }
+        RXG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
+    }
+    cudaStream_t s_in = ns > 1 ? ctx->s_in : ctx->stream, s_out = ns > 1 ? ctx->s_out : ctx->stream;
+    if (ns > 1) {   // the side streams start after whatever the caller queued on the ctx stream
+        RXG_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+        RXG_CUDA(ctx, cudaStreamWaitEvent(s_in, ctx->ev_start, 0));
+        RXG_CUDA(ctx, cudaStreamWaitEvent(s_out, ctx->ev_start, 0));
+    }
+    const size_t hp = (size_t)batch * 4;       // host pitch of every fp32 array (bytes)
+    for (int sidx = 0; sidx < ns; ++sidx) {
+        const int q = sidx & (nbuf - 1);
+        const int64_t b0 = (int64_t)sidx * bs;
+        const int64_t nb = (b0 + bs <= batch) ? bs : (batch - b0);
+        const size_t dp = (size_t)nb * 4;      // device pitch = slice width
+        float* d_y = (float*)(base + o_y[q]);
+        c.batch = nb;
+        c.y = d_y;
+        c.mean = (float*)(base + o_mean[q]);
+        c.cov = n_cov ? (float*)(base + o_cov[q]) : nullptr;
+        c.ymask = ymask ? (const uint8_t*)(base + o_mask[q]) : nullptr;
+        c.nle = nle ? (float*)(base + o_nle[q]) : nullptr;
+        c.status = status ? (int32_t*)(base + o_st[q]) : nullptr;
+        // H2D (buffer q was last read by the sweep of slice sidx-2)
+        if (ns > 1 && sidx >= 2) RXG_CUDA(ctx, cudaStreamWaitEvent(s_in, ctx->ev_comp[q], 0));
+        RXG_CUDA(ctx, cudaMemcpy2DAsync(d_y, dp, y + b0, hp, dp, (size_t)T * m, cudaMemcpyHostToDevice, s_in));
+        if (ymask)
+            RXG_CUDA(ctx, cudaMemcpy2DAsync((void*)c.ymask, (size_t)nb, ymask + b0, (size_t)batch, (size_t)nb, (size_t)T,
+                                            cudaMemcpyHostToDevice, s_in));
+        if (ns > 1) {
+            RXG_CUDA(ctx, cudaEventRecord(ctx->ev_in[q], s_in));
+            RXG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[q], 0));
+            if (sidx >= 2) RXG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out[q], 0));   // outputs of sidx-2 drained
+        }
+        int rc = lgssm_dispatch(ctx, c);
+        if (rc != RXG_OK) return rc;
+        if (ns > 1) {
+            RXG_CUDA(ctx, cudaEventRecord(ctx->ev_comp[q], ctx->stream));
+            RXG_CUDA(ctx, cudaStreamWaitEvent(s_out, ctx->ev_comp[q], 0));
+        }
+        // D2H
+        RXG_CUDA(ctx, cudaMemcpy2DAsync(mean + b0, hp, c.mean, dp, dp, (size_t)T * d, cudaMemcpyDeviceToHost, s_out));
+        if (cov) {
+            if (cov_shared)
+                RXG_CUDA(ctx, cudaMemcpyAsync(cov, c.cov, (size_t)T * d * d * 4, cudaMemcpyDeviceToHost, s_out));
+            else
+                RXG_CUDA(ctx, cudaMemcpy2DAsync(cov + b0, hp, c.cov, dp, dp, (size_t)T * d * d, cudaMemcpyDeviceToHost, s_out));
+        }
+        if (nle) RXG_CUDA(ctx, cudaMemcpyAsync(nle + b0, c.nle, (size_t)nb * 4, cudaMemcpyDeviceToHost, s_out));
+        if (status) RXG_CUDA(ctx, cudaMemcpyAsync(status + b0, c.status, (size_t)nb * 4, cudaMemcpyDeviceToHost, s_out));
+        if (ns > 1) RXG_CUDA(ctx, cudaEventRecord(ctx->ev_out[q], s_out));
+    }
+    if (ns > 1)      // completion of the call == completion of the ctx stream
+        for (int q = 0; q < nbuf; ++q) RXG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out[q], 0));
     if (!(flags & RXG_ASYNC)) RXG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return RXG_OK;
 }

@@ -17,6 +17,7 @@ namespace rxg {
 
 __constant__ float c_gh_t[31];    // Gauss-Hermite nodes (physicists')
 __constant__ float c_gh_lw[31];   // log weights
+__constant__ float c_gh_lw2[31];  // log2 weights (for the ex2-based inner loop)
 
 // Gauss-Hermite nodes/weights by Newton iteration on the orthonormal recurrence (host, fp64).
 static void gauss_hermite_31(double* t, double* w) {
@@ -49,10 +50,11 @@ int ensure_gh_tables(rxg_ctx* ctx) {
     if (ctx->gh_ready) return RXG_OK;
     double t[31], w[31];
     gauss_hermite_31(t, w);
-    float tf[31], lw[31];
-    for (int i = 0; i < 31; ++i) { tf[i] = (float)t[i]; lw[i] = (float)log(w[i]); }
+    float tf[31], lw[31], lw2[31];
+    for (int i = 0; i < 31; ++i) { tf[i] = (float)t[i]; lw[i] = (float)log(w[i]); lw2[i] = (float)log2(w[i]); }
     RXG_CUDA(ctx, cudaMemcpyToSymbol(c_gh_t, tf, sizeof(tf)));
     RXG_CUDA(ctx, cudaMemcpyToSymbol(c_gh_lw, lw, sizeof(lw)));
+    RXG_CUDA(ctx, cudaMemcpyToSymbol(c_gh_lw2, lw2, sizeof(lw2)));
     ctx->gh_ready = true;
     return RXG_OK;
 }
@@ -103,16 +105,32 @@ __device__ __forceinline__ void gh_moment_match(const float* ez, float mu0, floa
     vz = __fmaf_rn(-du, du, S2 * r);
 }
 
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Fused HGF filter.  Per step the Gaussian factor of the z-product (prior pushed through the random
+// walk) is fixed across the VMP iterations, so everything that depends only on the 31 quadrature
+// nodes is hoisted out of the iteration loop: z_i - mu0, exp(-kappa z_i) and the log2-domain
+// constant c2_i = log2 w_i - (kappa log2e / 2) z_i.  One iteration then costs, per node,
+//   pass 1:  l_i = fma(b2, ez_i, c2_i); lmax = max(lmax, l_i)                       (2 instr)
+//   pass 2:  e = ex2(l_i - lmax); w = u_i - delta; S0 += e; S1 += e w; S2 += e w w  (8 instr, 1 MUFU)
+// with b2 = -(log2e / 2) psi A and delta = previous iterate minus prior mean (moments are
+// accumulated around the previous iterate, which removes the fp32 cancellation in the variance).
+__global__ void __launch_bounds__(64)
 hgf_filter_kernel(const float* __restrict__ y, float* __restrict__ out, int T, int64_t batch, int iters,
                   float kappa, float omega, float zvar, float yvar, float i_mz, float i_vz, float i_mx,
                   float i_vx) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
+    constexpr float LOG2E = 1.4426950408889634f;
     float mzp = i_mz, vzp = i_vz, mxp = i_mx, vxp = i_vx;
     float mz = i_mz, vz = i_vz;                 // q(zt), carried across iterations and steps
     const float wy = 1.0f / yvar;
     const float eA = expf(-omega);
+    const float hk2 = 0.5f * LOG2E * kappa;
     float ynext = __ldg(y + b);
     for (int t = 0; t < T; ++t) {
         const float yt = ynext;
@@ -120,9 +138,14 @@ hgf_filter_kernel(const float* __restrict__ y, float* __restrict__ out, int T, i
         // zt ~ Normal(zt_min, z_variance): message into zt from the prior side
         const float mu0 = mzp, v0 = vzp + zvar;
         const float s = sqrtf(2.0f * v0);
-        float ez[31];
+        float ez[31], c2[31], u[31];
 #pragma unroll
-        for (int i = 0; i < 31; ++i) ez[i] = expf(-kappa * __fmaf_rn(s, c_gh_t[i], mu0));
+        for (int i = 0; i < 31; ++i) {
+            u[i] = s * c_gh_t[i];
+            const float z = mu0 + u[i];
+            ez[i] = expf(-kappa * z);
+            c2[i] = __fmaf_rn(-hk2, z, c_gh_lw2[i]);
+        }
         const float wx = 1.0f / vxp;
         const float xiy = yt * wy, xix = mxp * wx;
         GcvJoint j;
@@ -131,7 +154,24 @@ hgf_filter_kernel(const float* __restrict__ y, float* __restrict__ out, int T, i
             j = gcv_joint(xiy, wy, xix, wx, g);
             const float dm = j.m1 - j.m2;
             const float psi = __fmaf_rn(dm, dm, j.V11 + j.V22 - 2.0f * j.V12);
-            gh_moment_match(ez, mu0, s, kappa, psi * eA, mz, mz, vz);
+            const float b2 = -0.5f * LOG2E * psi * eA;
+            float lmax = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 31; ++i) lmax = fmaxf(lmax, __fmaf_rn(b2, ez[i], c2[i]));
+            const float delta = mz - mu0;
+            float S0 = 0.f, S1 = 0.f, S2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 31; ++i) {
+                const float e = ex2_approx(__fmaf_rn(b2, ez[i], c2[i]) - lmax);
+                const float w = u[i] - delta;
+                S0 += e;
+                S1 = __fmaf_rn(e, w, S1);
+                S2 = __fmaf_rn(e * w, w, S2);
+            }
+            const float r = 1.0f / S0;
+            const float dw = S1 * r;
+            mz = mz + dw;
+            vz = __fmaf_rn(-dw, dw, S2 * r);
         }
         out[((int64_t)t * 4 + 0) * batch + b] = j.m1;
         out[((int64_t)t * 4 + 1) * batch + b] = j.V11;

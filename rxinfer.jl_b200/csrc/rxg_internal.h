@@ -22,7 +22,11 @@ struct rxg_ctx {
     // optional per-kernel timing of the last fused sweep (bench.py roofline leg)
     bool profile = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // gain start, main start, main end, (spare)   // Gauss-Hermite tables uploaded to this device's constant memory
-    // NCCL (dlopen'ed lazily; see rxg_comm.cu)
+    // host-pointer calls: side streams + events of the sliced H2D | sweep | D2H pipeline
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    cudaEvent_t ev_start = nullptr;
+    // NCCL (dlopen'ed lazily; see rxg_api.cu)
     void* nccl_dl = nullptr;
     void* comm = nullptr;
     int nranks = 1, rank = 0;

@@ -253,3 +253,26 @@ def test_gain_scan_other_shapes(ctx, monkeypatch):
                              m0=rng.standard_normal(d), S0=5.0 * np.eye(d)))
         _, y = lgssm.generate_data(mod, 1300, 6, seed=31)
         check(ctx.lgssm(dev(y), **_kw(mod), smooth=True, want_evidence=True), lgssm.smooth_reference_schedule(y, **mod))
+
+
+def test_host_pointer_path_sliced_pipeline(ctx, monkeypatch):
+    """Host-pointer calls are cut into batch slices pipelined over three streams (H2D | sweep | D2H);
+    force several slices on a ragged batch, with mask, evidence and status outputs."""
+    mod = f32_model(lgssm.notebook_model(4))
+    T, batch = 70, 203
+    _, y = lgssm.generate_data(mod, T, batch, seed=37)
+    rng = np.random.default_rng(11)
+    mask = (rng.random((T, batch)) > 0.2).astype(np.uint8)
+    yh = torch.from_numpy(y).pin_memory()
+    for ns in ("5", "1"):
+        monkeypatch.setenv("RXG_HOST_SLICES", ns)
+        r = ctx.lgssm(yh, **_kw(mod), smooth=True, want_evidence=True, want_status=True)
+        check(r, lgssm.smooth_reference_schedule(y, **mod))
+        assert int(r["status"].abs().sum()) == 0
+        rm = ctx.lgssm(yh, **_kw(mod), smooth=True, mask=torch.from_numpy(mask).pin_memory(), want_evidence=True)
+        check(rm, lgssm.smooth_reference_schedule(y, **mod, mask=mask))
+        f = ctx.lgssm(yh, **_kw(mod), smooth=False, want_evidence=True)
+        check(f, lgssm.smooth_reference_schedule(y, **mod), smooth=False)
+    # pageable (unpinned) host memory is legal too, just slower
+    rp = ctx.lgssm(torch.from_numpy(y.copy()), **_kw(mod), smooth=True)
+    check(rp, lgssm.smooth_reference_schedule(y, **mod), nle=False)
