@@ -95,11 +95,23 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_cores():
+    """Host threads this process can actually use: min(affinity, cgroup CPU quota)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per))))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_baseline(seconds_target=12.0, chunk=2048):
     """fp64 C port of the reference schedule on all host cores, bounded sample of the same workload."""
     from oracle import c_twin
     mod = {k: v.astype(np.float64) for k, v in notebook_model_f32().items()}
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     rng = np.random.default_rng(0)
     y = (rng.standard_normal((T, M, chunk)) * 3.0).astype(np.float32)
     c_twin.smooth(y[:, :, :64].copy(), **mod, nthreads=cores)         # warm-up
@@ -122,7 +134,7 @@ def run_reference_arm(args, rank, world):
         return
     from oracle import c_twin
     mod = {k: v.astype(np.float64) for k, v in notebook_model_f32().items()}
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     chunk = 4096                                     # bounded sample per step
     rng = np.random.default_rng(0)
     y = (rng.standard_normal((T, M, chunk)) * 3.0).astype(np.float32)

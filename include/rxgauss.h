@@ -58,7 +58,7 @@ enum rxg_flags {
     RXG_ASYNC           = 1u << 2, /* do not synchronise the stream before returning             */
     RXG_COV_SHARED_OUT  = 1u << 3, /* shared model only: write post_cov as [T][d][d] (one copy)  */
     RXG_PATH_PER_CHAIN  = 1u << 4, /* force the per-chain covariance recursion (no gain tables)  */
-    RXG_TRANSITION_FIRST = 1u << 5 /* filter: push the prior through (A, P) before the 1st datum */
+    RXG_TRANSITION_FIRST = 1u << 5 /* the prior sits one transition before the first datum       */
 };
 
 /* ------------------------------------------------------------------ context / plumbing ------ */
@@ -186,11 +186,18 @@ int rxg_rule_gcv_z_prod_f32(rxg_ctx*, int64_t n, const float* m_yx, const float*
  * the backward sweep t = T..1 for `batch` independent chains: 6 rule messages + 2 products +
  * 1 marginal per (chain, step).
  *
- *   x[1] ~ N(m0, S0);  x[t] ~ N(A x[t-1], P);  y[t] ~ N(B x[t], Q)       (A d x d, B m x d)
+ *   x[1] ~ N(m0, S0);  x[t] ~ N(A x[t-1] + u, P);  y[t] ~ N(B x[t], Q)     (A d x d, B m x d)
+ *
+ * `u` (d floats, or NULL for none) is a constant transition offset: the `+` rule with a PointMass
+ * operand fused into the sweep [ref: `x[i] ~ x_prev + c`, test/models/statespace/
+ * ulgssm_tests.jl:12].  With RXG_TRANSITION_FIRST the prior sits on the state BEFORE x[1]
+ * (x_prior ~ N(m0, S0); x[1] ~ N(A x_prior + u, P)), as in test/models/statespace/
+ * mlgssm_test.jl:8-17 and the notebook's one-step filtering model (ipynb:110-113).
  *
  * Inputs : y[T][m][batch]; ymask[T][batch] (uint8, 1 = observed) or NULL
  *          [ref: missing data semantics docs/src/manuals/inference/static.md:98-125];
- *          A,B,P,Q,m0,S0 row-major, shared (or [..][batch] with RXG_MODEL_PER_CHAIN).
+ *          A,B,P,Q,m0,S0,u row-major, shared HOST arrays (or device [..][batch] arrays with
+ *          RXG_MODEL_PER_CHAIN).
  * Outputs: post_mean[T][d][batch], post_cov[T][d][d][batch]  (== posteriors[:x], as
  *          MvNormalMeanCovariance) [ref: src/inference/batch.jl:475-481];
  *          neg_log_evidence[batch] or NULL (== Bethe free energy on this tree
@@ -199,19 +206,17 @@ int rxg_rule_gcv_z_prod_f32(rxg_ctx*, int64_t n, const float* m_yx, const float*
  * post_mean / post_cov double as the forward->backward stash (no extra workspace).             */
 int rxg_lgssm_smooth_f32(rxg_ctx*, int d, int m, int T, int64_t batch, const float* A,
                          const float* B, const float* P, const float* Q, const float* m0,
-                         const float* S0, const float* y, const uint8_t* ymask, float* post_mean,
-                         float* post_cov, float* neg_log_evidence, int32_t* status,
-                         unsigned flags);
+                         const float* S0, const float* u, const float* y, const uint8_t* ymask,
+                         float* post_mean, float* post_cov, float* neg_log_evidence,
+                         int32_t* status, unsigned flags);
 /* Forward half only (filtering) -- what the streaming engine computes per datum with
  * @autoupdates x_min_t_mean, x_min_t_cov = mean_cov(q(x_t))
- * [ref: src/inference/streaming.jl:344-388; src/inference/autoupdates.jl:614-659; ipynb:199-216].
- * With RXG_TRANSITION_FIRST the prior is pushed through (A, P) before the first datum, as the
- * notebook's one-step model does [ref: ipynb:110-113].                                          */
+ * [ref: src/inference/streaming.jl:344-388; src/inference/autoupdates.jl:614-659; ipynb:199-216]. */
 int rxg_lgssm_filter_f32(rxg_ctx*, int d, int m, int T, int64_t batch, const float* A,
                          const float* B, const float* P, const float* Q, const float* m0,
-                         const float* S0, const float* y, const uint8_t* ymask, float* filt_mean,
-                         float* filt_cov, float* neg_log_evidence, int32_t* status,
-                         unsigned flags);
+                         const float* S0, const float* u, const float* y, const uint8_t* ymask,
+                         float* filt_mean, float* filt_cov, float* neg_log_evidence,
+                         int32_t* status, unsigned flags);
 /* VMP around the smoother with an unknown observation precision shared over time, one per chain
  * (d = m = 1): y[t] ~ N(x[t], 1/tau), tau ~ Gamma(a0, b0), q(x) q(tau)
  * [ref: rules of test/models/aliases/aliases_gamma_tests.jl; use case

@@ -32,7 +32,7 @@ def _bc(M, batch, shape):
     return M
 
 
-def _unpack(y, A, B, P, Q, m0, S0, mask):
+def _unpack(y, A, B, P, Q, m0, S0, mask, u=None):
     y = np.asarray(y, dtype=np.float64)
     T, m, batch = y.shape
     d = np.asarray(A).shape[-1]
@@ -40,6 +40,7 @@ def _unpack(y, A, B, P, Q, m0, S0, mask):
     A = _bc(A, batch, (d, d)); B = _bc(B, batch, (m, d))
     P = _bc(P, batch, (d, d)); Q = _bc(Q, batch, (m, m))
     m0 = _bc(m0, batch, (d,)); S0 = _bc(S0, batch, (d, d))
+    _unpack.u = _bc(np.zeros(d) if u is None else u, batch, (d,))
     if mask is None:
         mk = np.ones((T, batch), dtype=bool)
     else:
@@ -64,13 +65,23 @@ def observation_message(yt, mk_t, B, Q):
     return xi * keep, W * keep[..., None]
 
 
-def smooth_reference_schedule(y, A, B, P, Q, m0, S0, mask=None, return_messages=False):
+def smooth_reference_schedule(y, A, B, P, Q, m0, S0, mask=None, return_messages=False, u=None,
+                              transition_first=False):
     """Forward/backward sum-product sweep exactly as the reference schedules it.
 
     Returns dict(mean, cov, filt_mean, filt_cov, neg_log_evidence[batch]) in ABI layout.
     Message count: 6 rule calls per (chain, step) (SURVEY.md section 8a accounting).
+
+    ``u``: constant transition offset, ``x[t] ~ MvNormal(A x[t-1] + u, P)`` -- in the reference graph
+    an Addition node with a PointMass operand between ``*`` and the MvNormal node (pure mean shift,
+    rules +(:out) forward and +(:in1) backward; ``x[i] ~ x_prev + c`` at
+    test/models/statespace/ulgssm_tests.jl:12).  ``transition_first``: the prior sits on the state
+    before x[1] (``x_prior ~ MvNormal(mean(x0), cov(x0)); x[1] ~ MvNormal(A x_prior, Q)``,
+    test/models/statespace/mlgssm_test.jl:8-17).
     """
-    yb, A, B, P, Q, m0, S0, mk, T, m, d, batch = _unpack(y, A, B, P, Q, m0, S0, mask)
+    yb, A, B, P, Q, m0, S0, mk, T, m, d, batch = _unpack(y, A, B, P, Q, m0, S0, mask, u)
+    u = _unpack.u
+    shift = lambda msg, sgn: (msg[0] + sgn * u, msg[1])      # +(:out) / +(:in1) with a PointMass operand
 
     fwd_mu = np.zeros((T, batch, d)); fwd_S = np.zeros((T, batch, d, d))
     obs_xi = np.zeros((T, batch, d)); obs_W = np.zeros((T, batch, d, d))
@@ -79,6 +90,8 @@ def smooth_reference_schedule(y, A, B, P, Q, m0, S0, mask=None, return_messages=
 
     # ---- forward: prior, then (#3,#4) observation, product, (#1) A*x, (#2) +P
     f_mu, f_S = R.mvnormal_meancov_out((m0, np.zeros_like(S0)), S0)      # prior, rule #2 with PointMass mean
+    if transition_first:
+        f_mu, f_S = R.mvnormal_meancov_out(shift(R.multiplication_out(A, (f_mu, f_S)), +1.0), P)
     for t in range(T):
         fwd_mu[t], fwd_S[t] = f_mu, f_S
         obs_xi[t], obs_W[t] = observation_message(yb[t], mk[t], B, Q)
@@ -92,7 +105,7 @@ def smooth_reference_schedule(y, A, B, P, Q, m0, S0, mask=None, return_messages=
         # filtered = prod(fwd, obs) in (xi, W); back to (mu, Sigma) for rule #1
         xi_f, W_f = R.prod_gaussian_wmp(R.meancov_to_wmp(f_mu, f_S), (obs_xi[t], obs_W[t]))
         fil_mu[t], fil_S[t] = R.wmp_to_meancov(xi_f, W_f)
-        f_mu, f_S = R.mvnormal_meancov_out(R.multiplication_out(A, (fil_mu[t], fil_S[t])), P)
+        f_mu, f_S = R.mvnormal_meancov_out(shift(R.multiplication_out(A, (fil_mu[t], fil_S[t])), +1.0), P)
 
     # ---- backward: bwd_T = none; out = prod(obs, bwd) -> (#3') +P -> (#4) A' . A
     post_mu = np.zeros((T, batch, d)); post_S = np.zeros((T, batch, d, d))
@@ -123,6 +136,7 @@ def smooth_reference_schedule(y, A, B, P, Q, m0, S0, mask=None, return_messages=
         s_xi = np.linalg.solve(IWP, o_xi[..., None])[..., 0]
         n_xi = np.where(spd[:, None], n_xi, s_xi)
         n_W = np.where(spd[:, None, None], n_W, s_W)
+        n_xi = n_xi - R.mv(n_W, u)                     # +(:in1): mean shifted by -u, in (xi, W) form
         b_xi, b_W = R.multiplication_in((n_xi, n_W), A)
 
     mean, cov = _pack(post_mu, post_S)
@@ -134,7 +148,7 @@ def smooth_reference_schedule(y, A, B, P, Q, m0, S0, mask=None, return_messages=
     return out
 
 
-def filter_reference_schedule(y, A, B, P, Q, m0, S0, mask=None):
+def filter_reference_schedule(y, A, B, P, Q, m0, S0, mask=None, u=None, transition_first=False):
     """Forward half only: what ``rxinfer_inference_filtering`` (ipynb:199-216) produces through
     ``@autoupdates x_min_t_mean, x_min_t_cov = mean_cov(q(x_t))``
     (/root/reference/src/inference/autoupdates.jl:614-659).
@@ -143,18 +157,20 @@ def filter_reference_schedule(y, A, B, P, Q, m0, S0, mask=None):
     x_min_t ~ prior; x_t ~ N(A x_min_t, P); y_t ~ N(B x_t, Q).  ``transition_first=True`` in
     ``filter_streaming`` reproduces that; this function is the forward half of the smoothing
     graph (prior sits on x[1])."""
-    r = smooth_reference_schedule(y, A, B, P, Q, m0, S0, mask)
+    r = smooth_reference_schedule(y, A, B, P, Q, m0, S0, mask, u=u, transition_first=transition_first)
     return dict(mean=r["filt_mean"], cov=r["filt_cov"], neg_log_evidence=r["neg_log_evidence"])
 
 
-def filter_streaming(y, A, B, P, Q, m0, S0, mask=None):
+def filter_streaming(y, A, B, P, Q, m0, S0, mask=None, u=None):
     """Streaming filter as the notebook runs it: the prior (initialised to q(x_t) = N(m0, S0))
     is pushed through the transition before every datum, including the first."""
-    yb, A, B, P, Q, m0, S0, mk, T, m, d, batch = _unpack(y, A, B, P, Q, m0, S0, mask)
+    yb, A, B, P, Q, m0, S0, mk, T, m, d, batch = _unpack(y, A, B, P, Q, m0, S0, mask, u)
+    u = _unpack.u
     mu, S = m0, S0
     out_mu = np.zeros((T, batch, d)); out_S = np.zeros((T, batch, d, d))
     for t in range(T):
-        p_mu, p_S = R.mvnormal_meancov_out(R.multiplication_out(A, (mu, S)), P)
+        p_mu, p_S = R.multiplication_out(A, (mu, S))
+        p_mu, p_S = R.mvnormal_meancov_out((p_mu + u, p_S), P)
         o_xi, o_W = observation_message(yb[t], mk[t], B, Q)
         xi, W = R.prod_gaussian_wmp(R.meancov_to_wmp(p_mu, p_S), (o_xi, o_W))
         mu, S = R.wmp_to_meancov(xi, W)
@@ -163,17 +179,20 @@ def filter_streaming(y, A, B, P, Q, m0, S0, mask=None):
     return dict(mean=mean, cov=cov)
 
 
-def kalman_rts(y, A, B, P, Q, m0, S0, mask=None):
+def kalman_rts(y, A, B, P, Q, m0, S0, mask=None, u=None, transition_first=False):
     """Textbook Kalman filter + Rauch-Tung-Striebel smoother (independent cross-check)."""
-    yb, A, B, P, Q, m0, S0, mk, T, m, d, batch = _unpack(y, A, B, P, Q, m0, S0, mask)
+    yb, A, B, P, Q, m0, S0, mk, T, m, d, batch = _unpack(y, A, B, P, Q, m0, S0, mask, u)
+    u = _unpack.u
     At = np.swapaxes(A, -1, -2); Bt = np.swapaxes(B, -1, -2)
     pm = np.zeros((T, batch, d)); pS = np.zeros((T, batch, d, d))
     fm = np.zeros((T, batch, d)); fS = np.zeros((T, batch, d, d))
     nle = np.zeros(batch)
     mu, S = m0, S0
+    if transition_first:
+        mu, S = R.mv(A, mu) + u, A @ S @ At + P
     for t in range(T):
         if t > 0:
-            mu, S = R.mv(A, fm[t - 1]), A @ fS[t - 1] @ At + P
+            mu, S = R.mv(A, fm[t - 1]) + u, A @ fS[t - 1] @ At + P
         pm[t], pS[t] = mu, S
         Sinn = B @ S @ Bt + Q
         K = S @ Bt @ np.linalg.inv(Sinn)

@@ -91,7 +91,7 @@ class Context:
         return torch.empty(*shape, dtype=dtype, device=f"cuda:{self.device}")
 
     # ------------------------------------------------------------------ fused sweeps
-    def lgssm(self, y, A, B, P, Q, m0, S0, *, smooth=True, mask=None, want_cov=True, want_evidence=False,
+    def lgssm(self, y, A, B, P, Q, m0, S0, *, u=None, smooth=True, mask=None, want_cov=True, want_evidence=False,
               want_status=False, per_chain_model=False, force_per_chain_path=False, cov_shared_out=False,
               transition_first=False, out_mean=None, out_cov=None, asynchronous=False):
         """y[T, m, batch] (CUDA fp32, or pinned/pageable CPU fp32 for the host-pointer path)
@@ -102,13 +102,18 @@ class Context:
         if per_chain_model:
             flags |= L.MODEL_PER_CHAIN
             d = A.shape[0]
-            self._dev(A, B, P, Q, m0, S0)
-            ptrs = [_fp(x) for x in (A, B, P, Q, m0, S0)]
+            self._dev(A, B, P, Q, m0, S0, u)
+            ptrs = [_fp(x) for x in (A, B, P, Q, m0, S0, u)]
             keep = None
         else:
             d = np.asarray(A).shape[-1]
             keep = [_model32(x) for x in (A, B, P, Q, m0, S0)]
             ptrs = [k[1] for k in keep]
+            if u is not None:
+                keep.append(_model32(u))
+                ptrs.append(keep[-1][1])
+            else:
+                ptrs.append(L.as_fp(0))
         if force_per_chain_path:
             flags |= L.PATH_PER_CHAIN
         if cov_shared_out:

@@ -154,7 +154,7 @@ int rxg_profile_last_ms(rxg_ctx* ctx, float* main_kernel_ms, float* gain_kernels
 // ------------------------------------------------------------------------------------------------
 static int lgssm_entry(rxg_ctx* ctx, bool smooth, int d, int m, int T, int64_t batch, const float* A,
                        const float* B, const float* P, const float* Q, const float* m0, const float* S0,
-                       const float* y, const uint8_t* ymask, float* mean, float* cov, float* nle,
+                       const float* u, const float* y, const uint8_t* ymask, float* mean, float* cov, float* nle,
                        int32_t* status, unsigned flags) {
     if (!ctx) return RXG_ERR_BAD_ARG;
     if (d < 1 || m < 1 || T < 1 || batch < 1) return fail(ctx, RXG_ERR_BAD_ARG, "lgssm: d, m, T, batch must be >= 1");
@@ -170,7 +170,7 @@ static int lgssm_entry(rxg_ctx* ctx, bool smooth, int d, int m, int T, int64_t b
 
     LgssmCall c;
     c.d = d; c.m = m; c.T = T; c.batch = batch;
-    c.A = A; c.B = B; c.P = P; c.Q = Q; c.m0 = m0; c.S0 = S0;
+    c.A = A; c.B = B; c.P = P; c.Q = Q; c.m0 = m0; c.S0 = S0; c.u = u;
     c.flags = flags; c.smooth = smooth;
 
     if (flags & RXG_PTR_DEVICE) {
@@ -276,20 +276,18 @@ static int lgssm_entry(rxg_ctx* ctx, bool smooth, int d, int m, int T, int64_t b
 }
 
 int rxg_lgssm_smooth_f32(rxg_ctx* ctx, int d, int m, int T, int64_t batch, const float* A, const float* B,
-                         const float* P, const float* Q, const float* m0, const float* S0, const float* y,
-                         const uint8_t* ymask, float* post_mean, float* post_cov, float* neg_log_evidence,
-                         int32_t* status, unsigned flags) {
-    if (ctx && (flags & RXG_TRANSITION_FIRST))
-        return fail(ctx, RXG_ERR_BAD_ARG, "lgssm_smooth: RXG_TRANSITION_FIRST applies to the filter only");
-    return lgssm_entry(ctx, true, d, m, T, batch, A, B, P, Q, m0, S0, y, ymask, post_mean, post_cov,
+                         const float* P, const float* Q, const float* m0, const float* S0, const float* u,
+                         const float* y, const uint8_t* ymask, float* post_mean, float* post_cov,
+                         float* neg_log_evidence, int32_t* status, unsigned flags) {
+    return lgssm_entry(ctx, true, d, m, T, batch, A, B, P, Q, m0, S0, u, y, ymask, post_mean, post_cov,
                        neg_log_evidence, status, flags);
 }
 
 int rxg_lgssm_filter_f32(rxg_ctx* ctx, int d, int m, int T, int64_t batch, const float* A, const float* B,
-                         const float* P, const float* Q, const float* m0, const float* S0, const float* y,
-                         const uint8_t* ymask, float* filt_mean, float* filt_cov, float* neg_log_evidence,
-                         int32_t* status, unsigned flags) {
-    return lgssm_entry(ctx, false, d, m, T, batch, A, B, P, Q, m0, S0, y, ymask, filt_mean, filt_cov,
+                         const float* P, const float* Q, const float* m0, const float* S0, const float* u,
+                         const float* y, const uint8_t* ymask, float* filt_mean, float* filt_cov,
+                         float* neg_log_evidence, int32_t* status, unsigned flags) {
+    return lgssm_entry(ctx, false, d, m, T, batch, A, B, P, Q, m0, S0, u, y, ymask, filt_mean, filt_cov,
                        neg_log_evidence, status, flags);
 }
 

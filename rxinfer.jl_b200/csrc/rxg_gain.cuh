@@ -345,10 +345,22 @@ gain_scan_kernel(const __grid_constant__ ModelF<D, M> mdl, GainWs ws, ScanWs sw,
             store_f(rec + TB::K_OFF, K);
             store_f(rec + TB::LI_OFF, Li);
             rec[TB::C_OFF] = (float)(M * RXG_HALF_LOG_2PI - ch.neg_half_logdet);
+            Vec<double, D> uu, gf;
+#pragma unroll
+            for (int i = 0; i < D; ++i) uu(i) = (double)mdl.u[i];
+            gf = mulv(IKB, uu);
+            if (!(t > 0 || transition_first)) {
+#pragma unroll
+                for (int i = 0; i < D; ++i) gf(i) = 0.0;
+            }
+            store_fv(rec + TB::GF_OFF, gf);
             store_f(ws.sf + (size_t)t * TB::SF_REC, Sf);
         }
         float* brec = ws.bwd + (size_t)t * TB::BWD_REC;
         BwdEl<D> be;
+        Vec<double, D> gb;
+#pragma unroll
+        for (int i = 0; i < D; ++i) gb(i) = 0.0;
         if (t < T - 1) {
             Mat<double, D, D> AS = mul(A, Sf);
             Mat<double, D, D> Sp1 = sym_mul_nt_add(AS, A, P);
@@ -362,6 +374,10 @@ gain_scan_kernel(const __grid_constant__ ModelF<D, M> mdl, GainWs ws, ScanWs sw,
             for (int i = 0; i < D * D; ++i) Em.a[i] -= GA.a[i];
             store_f(brec + TB::E_OFF, Em);
             store_f(brec + TB::G_OFF, be.E);
+            Vec<double, D> uu;
+#pragma unroll
+            for (int i = 0; i < D; ++i) uu(i) = -(double)mdl.u[i];
+            gb = mulv(be.E, uu);
         } else {
 #pragma unroll
             for (int i = 0; i < D * D; ++i) be.E.a[i] = 0.0;
@@ -369,6 +385,7 @@ gain_scan_kernel(const __grid_constant__ ModelF<D, M> mdl, GainWs ws, ScanWs sw,
             store_f(brec + TB::E_OFF, identity<double, D>());
             store_f(brec + TB::G_OFF, be.E);
         }
+        store_fv(brec + TB::GB_OFF, gb);
         bwd_store<D>(sw.bel, T, t, be);
     }
     cluster.sync();

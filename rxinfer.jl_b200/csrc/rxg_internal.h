@@ -51,6 +51,7 @@ struct LgssmCall {
     int64_t batch;
     // shared model: host pointers (row-major); per-chain model: device pointers [..][batch]
     const float *A, *B, *P, *Q, *m0, *S0;
+    const float* u;          // transition offset (same pointer space as the model) or null
     const float* y;          // device
     const uint8_t* ymask;    // device or null
     float* mean;             // device

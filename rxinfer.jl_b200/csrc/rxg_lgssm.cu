@@ -47,7 +47,7 @@ lgssm_chain_kernel(const __grid_constant__ ModelF<D, M> mdl, PerChainPtrs pc,
     Mat<float, D, D> A, P, S0;
     Mat<float, M, D> B;
     Mat<float, M, M> Q;
-    Vec<float, D> mu;
+    Vec<float, D> mu, u;
     if (PER_CHAIN) {
         A = load_strided<float, D, D>(pc.A + b, batch);
         B = load_strided<float, M, D>(pc.B + b, batch);
@@ -56,6 +56,8 @@ lgssm_chain_kernel(const __grid_constant__ ModelF<D, M> mdl, PerChainPtrs pc,
         S0 = load_strided<float, D, D>(pc.S0 + b, batch);
 #pragma unroll
         for (int i = 0; i < D; ++i) mu(i) = __ldg(pc.m0 + i * batch + b);
+#pragma unroll
+        for (int i = 0; i < D; ++i) u(i) = pc.u ? __ldg(pc.u + i * batch + b) : 0.f;
     } else {
         A = load_const<float, D, D>(mdl.A);
         B = load_const<float, M, D>(mdl.B);
@@ -63,7 +65,7 @@ lgssm_chain_kernel(const __grid_constant__ ModelF<D, M> mdl, PerChainPtrs pc,
         Q = load_const<float, M, M>(mdl.Q);
         S0 = load_const<float, D, D>(mdl.S0);
 #pragma unroll
-        for (int i = 0; i < D; ++i) mu(i) = mdl.m0[i];
+        for (int i = 0; i < D; ++i) { mu(i) = mdl.m0[i]; u(i) = mdl.u[i]; }
     }
     Mat<float, D, D> S = S0;
     bool bad = false;
@@ -88,7 +90,10 @@ lgssm_chain_kernel(const __grid_constant__ ModelF<D, M> mdl, PerChainPtrs pc,
         }
         if (t > 0 || transition_first) {
             // rule #1  *(:out): (A mu, A S A')   rule #2  MvNormalMeanCovariance(:out): + P
+            //          (+ the `+` rule with a PointMass operand: pure mean shift by u)
             mu = mulv(A, mu);
+#pragma unroll
+            for (int i = 0; i < D; ++i) mu(i) += u(i);
             Mat<float, D, D> AS = mul(A, S);
             S = sym_mul_nt_add(AS, A, P);
         }
@@ -176,7 +181,7 @@ lgssm_chain_kernel(const __grid_constant__ ModelF<D, M> mdl, PerChainPtrs pc,
             Ss = sym_mul_nt_add(GS, G, C);
             Vec<float, D> mup = mulv(A, muf);
 #pragma unroll
-            for (int i = 0; i < D; ++i) mup(i) = mus(i) - mup(i);
+            for (int i = 0; i < D; ++i) mup(i) = mus(i) - (mup(i) + u(i));
             Vec<float, D> dm = mulv(G, mup);
 #pragma unroll
             for (int i = 0; i < D; ++i) mus(i) = muf(i) + dm(i);
@@ -272,9 +277,21 @@ __global__ void gain_tables(const __grid_constant__ ModelF<D, M> mdl, GainWs ws,
         store_f(rec + TB::K_OFF, K);
         store_f(rec + TB::LI_OFF, Li);
         rec[TB::C_OFF] = (float)(M * RXG_HALF_LOG_2PI - ch.neg_half_logdet);
+        Vec<double, D> uu, gf;
+#pragma unroll
+        for (int i = 0; i < D; ++i) uu(i) = (double)mdl.u[i];
+        gf = mulv(IKB, uu);
+        if (!(t > 0 || transition_first)) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) gf(i) = 0.0;
+        }
+        store_fv(rec + TB::GF_OFF, gf);
         store_f(ws.sf + (size_t)t * TB::SF_REC, Sf);
     }
     float* brec = ws.bwd + (size_t)t * TB::BWD_REC;
+    Vec<double, D> gb;
+#pragma unroll
+    for (int i = 0; i < D; ++i) gb(i) = 0.0;
     if (t < T - 1) {
         const Mat<double, D, D> Sp1 = load_d<D, D>(ws.Sp + (size_t)(t + 1) * D * D);
         Chol<double, D> ch = cholesky<double, D, false>(Sp1, bad);
@@ -288,6 +305,12 @@ __global__ void gain_tables(const __grid_constant__ ModelF<D, M> mdl, GainWs ws,
         for (int i = 0; i < D * D; ++i) E.a[i] -= GA.a[i];
         store_f(brec + TB::E_OFF, E);
         store_f(brec + TB::G_OFF, G);
+        {
+            Vec<double, D> uu;
+#pragma unroll
+            for (int i = 0; i < D; ++i) uu(i) = -(double)mdl.u[i];
+            gb = mulv(G, uu);
+        }
         store_d(ws.Cc + (size_t)t * D * D, C);
         store_d(ws.Gd + (size_t)t * D * D, G);
     } else {
@@ -298,6 +321,7 @@ __global__ void gain_tables(const __grid_constant__ ModelF<D, M> mdl, GainWs ws,
         store_f(brec + TB::E_OFF, E);
         store_f(brec + TB::G_OFF, Z);
     }
+    store_fv(brec + TB::GB_OFF, gb);
 }
 
 // Phase 3 (sequential in t): smoothed covariances  Ss[t] = C[t] + G[t] Ss[t+1] G[t]'.
@@ -332,7 +356,7 @@ static void fill_model(ModelF<D, M>& mdl, const LgssmCall& c) {
     for (int i = 0; i < D * D; ++i) { mdl.A[i] = c.A[i]; mdl.P[i] = c.P[i]; mdl.S0[i] = c.S0[i]; }
     for (int i = 0; i < M * D; ++i) mdl.B[i] = c.B[i];
     for (int i = 0; i < M * M; ++i) mdl.Q[i] = c.Q[i];
-    for (int i = 0; i < D; ++i) mdl.m0[i] = c.m0[i];
+    for (int i = 0; i < D; ++i) { mdl.m0[i] = c.m0[i]; mdl.u[i] = c.u ? c.u[i] : 0.f; }
 }
 
 template <int D, int M>
@@ -340,7 +364,7 @@ static int run_chain_family(rxg_ctx* ctx, const LgssmCall& c) {
     ModelF<D, M> mdl = {};
     PerChainPtrs pc = {};
     const bool per_chain = (c.flags & RXG_MODEL_PER_CHAIN) != 0;
-    if (per_chain) pc = PerChainPtrs{c.A, c.B, c.P, c.Q, c.m0, c.S0};
+    if (per_chain) pc = PerChainPtrs{c.A, c.B, c.P, c.Q, c.m0, c.S0, c.u};
     else fill_model<D, M>(mdl, c);
     const int threads = 64;
     const unsigned blocks = (unsigned)((c.batch + threads - 1) / threads);
@@ -366,9 +390,17 @@ static int launch_shared(rxg_ctx* ctx, const LgssmCall& c, const ModelF<D, M>& m
     const unsigned blocks = (unsigned)((nthr + threads - 1) / threads);
     const int tf = (c.flags & RXG_TRANSITION_FIRST) ? 1 : 0;
     const bool evid = c.nle != nullptr;
+    bool has_u = false;
+    for (int i = 0; i < D; ++i) has_u |= (mdl.u[i] != 0.f);
 #define RXG_LAUNCH_SHARED(SM, EV)                                                                  \
-    lgssm_shared_kernel<D, M, CPT, PF, SM, EV><<<blocks, threads, 0, ctx->stream>>>(               \
-        mdl, ws.fwd, ws.bwd, ws.sf, c.y, c.mean, c.cov, c.nle, c.T, c.batch, tf, write_cov)
+    do {                                                                                           \
+        if (has_u)                                                                                 \
+            lgssm_shared_kernel<D, M, CPT, PF, SM, EV, true><<<blocks, threads, 0, ctx->stream>>>( \
+                mdl, ws.fwd, ws.bwd, ws.sf, c.y, c.mean, c.cov, c.nle, c.T, c.batch, tf, write_cov); \
+        else                                                                                       \
+            lgssm_shared_kernel<D, M, CPT, PF, SM, EV, false><<<blocks, threads, 0, ctx->stream>>>( \
+                mdl, ws.fwd, ws.bwd, ws.sf, c.y, c.mean, c.cov, c.nle, c.T, c.batch, tf, write_cov); \
+    } while (0)
     if (ctx->profile) cudaEventRecord(ctx->ev[1], ctx->stream);
     if (c.smooth) { if (evid) RXG_LAUNCH_SHARED(true, true); else RXG_LAUNCH_SHARED(true, false); }
     else          { if (evid) RXG_LAUNCH_SHARED(false, true); else RXG_LAUNCH_SHARED(false, false); }
@@ -442,7 +474,6 @@ static int run_shared_family(rxg_ctx* ctx, const LgssmCall& c) {
     int cpt = (c.batch >= (int64_t)ctx->sm_count * 64 * 2) ? 2 : 1;
     if (const char* e = getenv("RXG_FORCE_CPT")) cpt = atoi(e);      // test / tuning override
     if (D * M > 16 && cpt > 2) cpt = 2;                              // register budget for d = 6
-    if (cpt == 4 && al16 && c.batch % 4 == 0) return launch_shared<D, M, 4>(ctx, c, mdl, ws, write_cov);
     if (cpt >= 2 && al16 && c.batch % 2 == 0) return launch_shared<D, M, 2>(ctx, c, mdl, ws, write_cov);
     return launch_shared<D, M, 1>(ctx, c, mdl, ws, write_cov);
 }

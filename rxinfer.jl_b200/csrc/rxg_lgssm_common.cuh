@@ -9,10 +9,11 @@ namespace rxg {
 template <int D, int M>
 struct ModelF {
     float A[D * D], B[M * D], P[D * D], Q[M * M], m0[D], S0[D * D];
+    float u[D];   // constant transition offset: x[t] ~ N(A x[t-1] + u, P)  (the `+` rule with a PointMass operand)
 };
 
 struct PerChainPtrs {
-    const float *A, *B, *P, *Q, *m0, *S0;
+    const float *A, *B, *P, *Q, *m0, *S0, *u;
 };
 
 template <typename S, int R, int C>
@@ -50,12 +51,14 @@ struct Tab {
     static constexpr int K_OFF = F_OFF + pad4(D * D);      // Kalman gain           D x M
     static constexpr int LI_OFF = K_OFF + pad4(D * M);     // L^-1 of innovation    M x M (lower)
     static constexpr int C_OFF = LI_OFF + pad4(M * M);     // M/2 log 2pi + 1/2 log det S
-    static constexpr int FWD_REC = C_OFF + 4;
+    static constexpr int GF_OFF = C_OFF + 4;               // (I - K B) u            D
+    static constexpr int FWD_REC = GF_OFF + pad4(D);
     // backward record, per t
     static constexpr int E_OFF = 0;                        // I - G A               D x D
     static constexpr int G_OFF = E_OFF + pad4(D * D);      // RTS gain              D x D
     static constexpr int SS_OFF = G_OFF + pad4(D * D);     // smoothed covariance   D x D
-    static constexpr int BWD_REC = SS_OFF + pad4(D * D);
+    static constexpr int GB_OFF = SS_OFF + pad4(D * D);    // -G u                   D
+    static constexpr int BWD_REC = GB_OFF + pad4(D);
     static constexpr int SF_REC = pad4(D * D);             // filtered covariance   D x D
 };
 
@@ -80,6 +83,11 @@ __device__ __forceinline__ Mat<double, R, C> load_d(const double* p) {
 #pragma unroll
     for (int i = 0; i < R * C; ++i) o.a[i] = p[i];
     return o;
+}
+template <int N>
+__device__ __forceinline__ void store_fv(float* p, const Vec<double, N>& v) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = (float)v.a[i];
 }
 template <int R, int C>
 __device__ __forceinline__ void store_f(float* p, const Mat<double, R, C>& A) {

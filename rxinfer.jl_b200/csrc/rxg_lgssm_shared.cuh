@@ -95,7 +95,7 @@ __device__ __forceinline__ void stage_tables(float* sdst, const float* __restric
     cp_async_commit();
 }
 
-template <int D, int M, int CPT, int PF, bool SMOOTH, bool EVID>
+template <int D, int M, int CPT, int PF, bool SMOOTH, bool EVID, bool OFFSET>
 __global__ void __launch_bounds__(32, 16 / CPT)   // CPT=1: <= 128 regs so ~14 warps/SM stay resident; wider CPT trades warps for ILP
 lgssm_shared_kernel(const __grid_constant__ ModelF<D, M> mdl, const float* __restrict__ fwd_tab,
                     const float* __restrict__ bwd_tab, const float* __restrict__ sf_tab,
@@ -155,13 +155,14 @@ lgssm_shared_kernel(const __grid_constant__ ModelF<D, M> mdl, const float* __res
                 float nm[D][CPT];
                 if (!EVID) {
                     // mu_f[t] = F_t mu_f[t-1] + K_t y_t,  F_t = (I - K_t B) A   (rules #1-#4 + product)
-                    float Ft[pad4(D * D)];
+                    float Ft[pad4(D * D)], gf[pad4(D)];
                     load_smem<pad4(D * D)>(rec + TB::F_OFF, Ft);
+                    if (OFFSET) load_smem<pad4(D)>(rec + TB::GF_OFF, gf);        // (I - K B) u: the fused `+` rule
 #pragma unroll
                     for (int i = 0; i < D; ++i)
 #pragma unroll
                         for (int c = 0; c < CPT; ++c) {
-                            float a = Ft[i * D] * mu[0][c];
+                            float a = OFFSET ? __fmaf_rn(Ft[i * D], mu[0][c], gf[i]) : Ft[i * D] * mu[0][c];
 #pragma unroll
                             for (int j = 1; j < D; ++j) a = __fmaf_rn(Ft[i * D + j], mu[j][c], a);
 #pragma unroll
@@ -180,7 +181,7 @@ lgssm_shared_kernel(const __grid_constant__ ModelF<D, M> mdl, const float* __res
 #pragma unroll
                         for (int i = 0; i < D; ++i) {
                             if (pred) {
-                                float a = mdl.A[i * D] * mu[0][c];
+                                float a = OFFSET ? __fmaf_rn(mdl.A[i * D], mu[0][c], mdl.u[i]) : mdl.A[i * D] * mu[0][c];
 #pragma unroll
                                 for (int j = 1; j < D; ++j) a = __fmaf_rn(mdl.A[i * D + j], mu[j][c], a);
                                 mp[i] = a;
@@ -288,15 +289,16 @@ lgssm_shared_kernel(const __grid_constant__ ModelF<D, M> mdl, const float* __res
             const int t = T - 1 - r;
             if (t >= 0) {
                 const float* rec = s_tab[(r / TC) & 1] + (r % TC) * TB::BWD_REC;
-                float Et[pad4(D * D)], Gt[pad4(D * D)];
+                float Et[pad4(D * D)], Gt[pad4(D * D)], gb[pad4(D)];
                 load_smem<pad4(D * D)>(rec + TB::E_OFF, Et);
                 load_smem<pad4(D * D)>(rec + TB::G_OFF, Gt);
+                if (OFFSET) load_smem<pad4(D)>(rec + TB::GB_OFF, gb);            // -G u
                 float nm[D][CPT];
 #pragma unroll
                 for (int i = 0; i < D; ++i)
 #pragma unroll
                     for (int c = 0; c < CPT; ++c) {
-                        float a = Et[i * D] * fcur[s][0][c];
+                        float a = OFFSET ? __fmaf_rn(Et[i * D], fcur[s][0][c], gb[i]) : Et[i * D] * fcur[s][0][c];
 #pragma unroll
                         for (int j = 1; j < D; ++j) a = __fmaf_rn(Et[i * D + j], fcur[s][j][c], a);
 #pragma unroll

@@ -33,6 +33,8 @@ class linear_gaussian_ssm_smoothing:
     Q: np.ndarray
     x0: tuple
     per_chain: bool = False     # model matrices carry a trailing [batch] axis (CUDA tensors)
+    u: object = None            # constant offset: x[t] ~ MvNormal(A x[t-1] + u, P)  (`+` with a PointMass)
+    prior_on_previous_state: bool = False   # x_prior ~ x0; x[1] ~ N(A x_prior + u, P)  (mlgssm_test.jl:8-17)
 
 
 @dataclass
@@ -110,7 +112,7 @@ def infer(*, model, data, iterations=None, free_energy=False, returnvars=None, o
     mask = data.get("ymask")
     try:
         if isinstance(model, linear_gaussian_ssm_filtering):
-            r = ctx.lgssm(y, model.A, model.B, model.P, model.Q, model.x0[0], model.x0[1], smooth=False, mask=mask,
+            r = ctx.lgssm(y, model.A, model.B, model.P, model.Q, model.x0[0], model.x0[1], u=model.u, smooth=False, mask=mask,
                           want_evidence=free_energy, per_chain_model=model.per_chain, transition_first=True,
                           cov_shared_out=cov_shared_out)
             q = MvNormalMeanCovariance(r["mean"], r["cov"])
@@ -119,8 +121,9 @@ def infer(*, model, data, iterations=None, free_energy=False, returnvars=None, o
             if iterations not in (None, 1):
                 raise NotImplementedError("iterations > 1 on a tree-structured BP model is a no-op in the reference; "
                                           "KeepEach() results are outside the hot path")
-            r = ctx.lgssm(y, model.A, model.B, model.P, model.Q, model.x0[0], model.x0[1], smooth=True, mask=mask,
-                          want_evidence=free_energy, per_chain_model=model.per_chain, cov_shared_out=cov_shared_out)
+            r = ctx.lgssm(y, model.A, model.B, model.P, model.Q, model.x0[0], model.x0[1], u=model.u, smooth=True, mask=mask,
+                          want_evidence=free_energy, per_chain_model=model.per_chain, cov_shared_out=cov_shared_out,
+                          transition_first=model.prior_on_previous_state)
             return InferenceResult(posteriors={"x": MvNormalMeanCovariance(r["mean"], r["cov"])},
                                    free_energy=r["neg_log_evidence"], model=model)
         if isinstance(model, hgf):

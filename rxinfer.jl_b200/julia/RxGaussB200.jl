@@ -66,9 +66,9 @@ function smooth(ctx::Context, y::Array{Float32,3}, A, B, P, Q, m0, S0; free_ener
     GC.@preserve y mean cov nle Ar Br Pr Qr S0r m0r begin
         rc = ccall((:rxg_lgssm_smooth_f32, LIB), Cint,
             (Ptr{Cvoid}, Cint, Cint, Cint, Int64,
-             Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32},
+             Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32},
              Ptr{Float32}, Ptr{UInt8}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Int32}, Cuint),
-            ctx.handle, d, m, T, batch, Ar, Br, Pr, Qr, m0r, S0r,
+            ctx.handle, d, m, T, batch, Ar, Br, Pr, Qr, m0r, S0r, C_NULL,     # u = NULL: no transition offset
             y, C_NULL, mean, cov, free_energy ? pointer(nle) : C_NULL, C_NULL, 0)   # host pointers: flags = 0
         check(ctx, rc)
     end

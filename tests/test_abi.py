@@ -64,7 +64,7 @@ def test_fails_loudly_without_gpu(rx):
     # every compute entry refuses a null context instead of computing on the CPU
     null = ctypes.c_void_p(None)
     fpn = ctypes.cast(null, rx._lib.fp)
-    rc = lib.rxg_lgssm_smooth_f32(null, 4, 4, 1, 1, fpn, fpn, fpn, fpn, fpn, fpn, fpn,
+    rc = lib.rxg_lgssm_smooth_f32(null, 4, 4, 1, 1, fpn, fpn, fpn, fpn, fpn, fpn, fpn, fpn,
                                   ctypes.cast(null, rx._lib.u8p), fpn, fpn, fpn, ctypes.cast(null, rx._lib.i32p), 0)
     assert rc == rx._lib.RXG_ERR_BAD_ARG
 

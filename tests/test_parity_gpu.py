@@ -65,13 +65,13 @@ def test_chains_per_thread_2_path(ctx, monkeypatch):
     mod = f32_model(lgssm.notebook_model(4))
     _, y = lgssm.generate_data(mod, 200, 64, seed=7)
     ref = lgssm.smooth_reference_schedule(y, **mod)
-    for cpt in ("4", "2", "1"):
+    for cpt in ("2", "1"):
         monkeypatch.setenv("RXG_FORCE_CPT", cpt)
         check(ctx.lgssm(dev(y), **_kw(mod), smooth=True, want_evidence=True), ref)
         check(ctx.lgssm(dev(y), **_kw(mod), smooth=True), ref, nle=False)
         check(ctx.lgssm(dev(y), **_kw(mod), smooth=False, want_evidence=True), ref, smooth=False)
     # ragged: batch not a multiple of 32 * CPT
-    monkeypatch.setenv("RXG_FORCE_CPT", "4")
+    monkeypatch.setenv("RXG_FORCE_CPT", "2")
     _, y2 = lgssm.generate_data(mod, 90, 100, seed=8)
     check(ctx.lgssm(dev(y2), **_kw(mod), smooth=True, want_evidence=True), lgssm.smooth_reference_schedule(y2, **mod))
 
@@ -276,3 +276,30 @@ def test_host_pointer_path_sliced_pipeline(ctx, monkeypatch):
     # pageable (unpinned) host memory is legal too, just slower
     rp = ctx.lgssm(torch.from_numpy(y.copy()), **_kw(mod), smooth=True)
     check(rp, lgssm.smooth_reference_schedule(y, **mod), nle=False)
+
+
+@pytest.mark.parametrize("tf", [False, True])
+def test_transition_offset_and_prior_on_previous_state(ctx, tf):
+    """Fused `+` rule (constant offset u) and RXG_TRANSITION_FIRST, smoothing and filtering, both
+    kernel families, plus per-chain offsets."""
+    rng = np.random.default_rng(77)
+    mod = f32_model(lgssm.notebook_model(4))
+    u = rng.standard_normal(4).astype(np.float32).astype(np.float64)
+    T, batch = 160, 50
+    _, y = lgssm.generate_data(mod, T, batch, seed=41)
+    y = (y + 2.0).astype(np.float32)
+    ref = lgssm.smooth_reference_schedule(y, **mod, u=u, transition_first=tf)
+    for force in (False, True):
+        r = ctx.lgssm(dev(y), **_kw(mod), u=u, smooth=True, want_evidence=True, transition_first=tf, force_per_chain_path=force)
+        check(r, ref)
+        f = ctx.lgssm(dev(y), **_kw(mod), u=u, smooth=False, want_evidence=True, transition_first=tf, force_per_chain_path=force)
+        check(f, ref, smooth=False)
+    # per-chain model with per-chain offsets
+    us = rng.standard_normal((batch, 4)).astype(np.float32).astype(np.float64)
+    mods = {k: np.broadcast_to(v, (batch,) + v.shape).copy() for k, v in mod.items()}
+    refp = lgssm.smooth_reference_schedule(y, **mods, u=us, transition_first=tf)
+    to_abi = lambda M: dev(np.moveaxis(M, 0, -1))
+    rp = ctx.lgssm(dev(y), A=to_abi(mods["A"]), B=to_abi(mods["B"]), P=to_abi(mods["P"]), Q=to_abi(mods["Q"]),
+                   m0=to_abi(mods["m0"]), S0=to_abi(mods["S0"]), u=to_abi(us), smooth=True, want_evidence=True,
+                   per_chain_model=True, transition_first=tf)
+    check(rp, refp)

@@ -1,0 +1,97 @@
+"""The reference's RNG-dependent regression pins, made executable without Julia: the test data of
+test/models/statespace/ulgssm_tests.jl:27-32 and mlgssm_test.jl:70-97 are regenerated with a
+restatement of StableRNGs.jl + Julia's ziggurat randn (oracle/julia_rng.py), and the oracle must
+reproduce the Bethe free energies the reference asserts (1854.297647, 6275.9015944677; the
+reference's own tolerance is 0.01).  The GPU tests then run the CUDA path on exactly that data."""
+import numpy as np
+import pytest
+
+from oracle import lgssm
+from oracle.julia_rng import FI, KI, WI, StableRNG
+
+
+def ulgssm_reference_data():
+    """ulgssm_tests.jl:27-32: data = collect(1:n) + rand(StableRNG(123), Normal(0, sqrt(P)), n)."""
+    rng = StableRNG(123)
+    n, P = 500, 100.0
+    data = np.arange(1, n + 1) + np.array([0.0 + np.sqrt(P) * rng.randn() for _ in range(n)])
+    model = dict(A=np.array([[1.0]]), B=np.array([[1.0]]), P=np.array([[0.0]]), Q=np.array([[P]]),
+                 m0=np.array([0.0]), S0=np.array([[10000.0]]))
+    return data, model, dict(u=np.array([1.0]), transition_first=True)
+
+
+def mlgssm_reference_data():
+    """mlgssm_test.jl:70-97 (StableRNG(1234), theta = pi/35, Q = I (transition), P = 25 I (observation))."""
+    rng = StableRNG(1234)
+    th = np.pi / 35
+    A = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    B = np.eye(2)
+    n = 1000
+    xp = np.array([10.0, -10.0])
+    X, Y = np.zeros((n, 2)), np.zeros((n, 2))
+    for i in range(n):
+        x = A @ xp + np.array([rng.randn(), rng.randn()])          # rand(rng, MvNormal(A x_prev, I))
+        Y[i] = B @ x + 5.0 * np.array([rng.randn(), rng.randn()])  # rand(rng, MvNormal(B x, 25 I))
+        X[i] = x
+        xp = x
+    model = dict(A=A, B=B, P=np.eye(2), Q=25.0 * np.eye(2), m0=np.zeros(2), S0=100.0 * np.eye(2))
+    return X, Y, model, dict(transition_first=True)
+
+
+def test_ziggurat_tables_match_the_stdlib_literals():
+    assert abs(WI[0] / 1.7367254121602630e-15 - 1) < 1e-12 and abs(WI[1] / 9.5586603514556339e-17 - 1) < 1e-12
+    assert abs(FI[1] / 9.7710170126767082e-01 - 1) < 1e-12 and abs(FI[2] / 9.5987909180010600e-01 - 1) < 1e-12
+    assert KI[0] == 0x0007799EC012F7B2 and KI[1] == 0
+
+
+def test_ulgssm_golden_free_energy():
+    data, model, kw = ulgssm_reference_data()
+    r = lgssm.smooth_reference_schedule(data[:, None, None], **model, **kw)
+    assert abs(r["neg_log_evidence"][0] - 1854.297647) < 1e-5          # reference asserts < 0.01
+    m, v = r["mean"][:, 0, 0], r["cov"][:, 0, 0, 0]
+    hidden = np.arange(1, 501)
+    assert np.all(v > 0) and np.all(np.abs(m - hidden) < 3 * np.sqrt(v))   # ulgssm_tests.jl:40-46
+    k = lgssm.kalman_rts(data[:, None, None], **model, **kw)
+    assert np.abs(k["mean"] - r["mean"]).max() < 1e-8
+
+
+def test_mlgssm_golden_free_energy():
+    X, Y, model, kw = mlgssm_reference_data()
+    r = lgssm.smooth_reference_schedule(Y[:, :, None], **model, **kw)
+    assert abs(r["neg_log_evidence"][0] - 6275.9015944677) < 1e-6       # reference asserts < 0.01
+    m = r["mean"][:, :, 0]
+    v = np.stack([r["cov"][:, 0, 0, 0], r["cov"][:, 1, 1, 0]], 1)
+    assert np.all((m - 3 * v < X) & (X < m + 3 * v))                      # mlgssm_test.jl:121-125
+    assert np.all(np.linalg.eigvalsh(np.moveaxis(r["cov"][..., 0], 0, 0)) > 0)   # :126
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_reference_goldens(ctx):
+    import torch
+    dev = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32, device="cuda")
+    # multivariate LGSSM: the reference's own assertions, run against the CUDA path (both families)
+    X, Y, model, kw = mlgssm_reference_data()
+    ref = lgssm.smooth_reference_schedule(Y[:, :, None], **model, **kw)
+    ybatch = np.repeat(Y[:, :, None], 40, axis=2)
+    for force in (False, True):
+        r = ctx.lgssm(dev(ybatch), **model, smooth=True, want_evidence=True, transition_first=True,
+                      force_per_chain_path=force)
+        fe = r["neg_log_evidence"].cpu().numpy().astype(np.float64)
+        assert np.all(np.abs(fe - 6275.9015944677) < 0.01)               # mlgssm_test.jl:128, verbatim tolerance
+        m = r["mean"][:, :, 7].cpu().numpy().astype(np.float64)
+        c = r["cov"][:, :, :, 7].cpu().numpy().astype(np.float64)
+        v = np.stack([c[:, 0, 0], c[:, 1, 1]], 1)
+        assert np.all((m - 3 * v < X) & (X < m + 3 * v))                  # :121-125
+        assert np.all(np.linalg.eigvalsh(c) > 0)                          # :126
+        assert np.linalg.norm(m - ref["mean"][:, :, 0]) / np.linalg.norm(ref["mean"]) < 1e-5
+    # univariate LGSSM with the Addition node (x[i] ~ x_prev + c), zero process noise
+    data, umodel, ukw = ulgssm_reference_data()
+    yb = np.repeat(data[:, None, None], 33, axis=2)
+    uref = lgssm.smooth_reference_schedule(data[:, None, None], **umodel, **ukw)
+    for force in (False, True):
+        r = ctx.lgssm(dev(yb), **umodel, u=ukw["u"], smooth=True, want_evidence=True, transition_first=True,
+                      force_per_chain_path=force)
+        fe = r["neg_log_evidence"].cpu().numpy().astype(np.float64)
+        assert np.all(np.abs(fe - 1854.297647) < 0.01)                    # ulgssm_tests.jl:48
+        m = r["mean"][:, 0, 5].cpu().numpy().astype(np.float64)
+        assert np.linalg.norm(m - uref["mean"][:, 0, 0]) / np.linalg.norm(uref["mean"]) < 1e-5
