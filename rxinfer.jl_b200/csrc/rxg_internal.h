@@ -65,5 +65,8 @@ struct LgssmCall {
 // rxg_lgssm.cu
 int lgssm_dispatch(rxg_ctx* ctx, const LgssmCall& c);
 bool lgssm_supported(int d, int m);
+// rxg_lgssm_large.cu
+int lgssm_large_dispatch(rxg_ctx* ctx, const LgssmCall& c);
+bool lgssm_large_supported(int d, int m);
 
 }  // namespace rxg

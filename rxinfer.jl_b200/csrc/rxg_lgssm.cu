@@ -501,7 +501,7 @@ bool lgssm_supported(int d, int m) {
         case 1 * 16 + 1: case 2 * 16 + 1: case 2 * 16 + 2: case 3 * 16 + 3:
         case 4 * 16 + 1: case 4 * 16 + 2: case 4 * 16 + 4: case 6 * 16 + 6:
             return true;
-        default: return false;
+        default: return lgssm_large_supported(d, m);
     }
 }
 
@@ -516,8 +516,9 @@ int lgssm_dispatch(rxg_ctx* ctx, const LgssmCall& c) {
         case 4 * 16 + 4: return run_dm<4, 4>(ctx, c);
         case 6 * 16 + 6: return run_dm<6, 6>(ctx, c);
         default:
+            if (lgssm_large_supported(c.d, c.m)) return lgssm_large_dispatch(ctx, c);
             return fail(ctx, RXG_ERR_UNSUPPORTED,
-                        "lgssm: (d=%d, m=%d) is outside the thread-per-chain kernel families", c.d, c.m);
+                        "lgssm: (d=%d, m=%d) is outside the compiled kernel families", c.d, c.m);
     }
 }
 

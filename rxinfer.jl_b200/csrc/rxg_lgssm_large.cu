@@ -1,0 +1,490 @@
+// Large-state family of the shared-model LGSSM sweeps (d = m in {8, 16, 32, 64}; BASELINE
+// configs[2] is d = 64, T = 1000, batch = 4096).  Same decomposition as the small-state path
+// (rxg_lgssm_shared.cuh): with shared (A, B, P, Q, S0) every covariance-valued message of the
+// reference schedule [ref: /root/reference/benchmarks/...Benchmark.ipynb:95-105;
+// src/inference/batch.jl:391-430] is chain independent, so
+//   1. the gain tables come from block-cooperative fp64 kernels working on d x d matrices in
+//      shared memory (large_riccati_seq: sequential in t; large_gain_tables: one CTA per t;
+//      large_smooth_seq: sequential in t), and
+//   2. every chain runs only the mean recursions.  Across a tile of NB chains those are small
+//      GEMMs per step,  X <- [F_t | K_t] [X ; Y_t]  and  X <- [E_t | G_t] [mu_f,t ; X],
+//      executed by lgssm_block_sweep with the per-step gain block streamed through shared memory
+//      (cp.async, double buffered) and a 4 x 2 register tile per thread.
+// Round-1 scope of this family: shared model, no missing data, no evidence, no offset; the
+// matrix products run on the FP32 pipe (a tcgen05 variant of the sweep GEMM is the follow-up).
+#include <math.h>
+
+#include "rxg_internal.h"
+
+namespace rxg {
+
+// ------------------------------------------------------------------------------------------------
+// block-cooperative fp64 linear algebra on shared-memory matrices (row-major, leading dim LD)
+// ------------------------------------------------------------------------------------------------
+// C(i,j) = beta * Add(i,j) + sum_k a(i,k) b(k,j); accessors are functors so that transposes are free.
+template <int R, int C, int K, class FA, class FB, class FC>
+__device__ __forceinline__ void bgemm(FA a, FB b, FC store) {
+    constexpr int TR = 4, TC = 4;
+    constexpr int NTR = (R + TR - 1) / TR, NTC = (C + TC - 1) / TC;
+    for (int tile = threadIdx.x; tile < NTR * NTC; tile += blockDim.x) {
+        const int i0 = (tile / NTC) * TR, j0 = (tile % NTC) * TC;
+        double acc[TR][TC];
+#pragma unroll
+        for (int r = 0; r < TR; ++r)
+#pragma unroll
+            for (int c = 0; c < TC; ++c) acc[r][c] = 0.0;
+        for (int k = 0; k < K; ++k) {
+            double av[TR], bv[TC];
+#pragma unroll
+            for (int r = 0; r < TR; ++r) av[r] = (i0 + r < R) ? a(i0 + r, k) : 0.0;
+#pragma unroll
+            for (int c = 0; c < TC; ++c) bv[c] = (j0 + c < C) ? b(k, j0 + c) : 0.0;
+#pragma unroll
+            for (int r = 0; r < TR; ++r)
+#pragma unroll
+                for (int c = 0; c < TC; ++c) acc[r][c] = fma(av[r], bv[c], acc[r][c]);
+        }
+#pragma unroll
+        for (int r = 0; r < TR; ++r)
+#pragma unroll
+            for (int c = 0; c < TC; ++c)
+                if (i0 + r < R && j0 + c < C) store(i0 + r, j0 + c, acc[r][c]);
+    }
+}
+
+// in-place lower Cholesky of the N x N matrix at L (leading dim LD); returns false on a bad pivot
+template <int N, int LD>
+__device__ bool bchol(double* L, int* flag) {
+    for (int j = 0; j < N; ++j) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = L[j * LD + j];
+            if (!(s > 0.0)) { *flag = 1; s = 1e-300; }
+            L[j * LD + j] = sqrt(s);
+        }
+        __syncthreads();
+        const double inv = 1.0 / L[j * LD + j];
+        for (int i = j + 1 + threadIdx.x; i < N; i += blockDim.x) L[i * LD + j] *= inv;
+        __syncthreads();
+        const int n = N - j - 1;
+        for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+            const int i = j + 1 + idx / n, k = j + 1 + idx % n;
+            if (k <= i) L[i * LD + k] = fma(-L[i * LD + j], L[k * LD + j], L[i * LD + k]);
+        }
+    }
+    __syncthreads();
+    return true;
+}
+// X <- L^-1 X  (X is N x C, one thread per column)
+template <int N, int C, int LD>
+__device__ void btrsm_lower(const double* L, double* X) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+        for (int i = 0; i < N; ++i) {
+            double s = X[i * LD + c];
+            for (int k = 0; k < i; ++k) s = fma(-L[i * LD + k], X[k * LD + c], s);
+            X[i * LD + c] = s / L[i * LD + i];
+        }
+    __syncthreads();
+}
+// X <- L^-T X
+template <int N, int C, int LD>
+__device__ void btrsm_lower_t(const double* L, double* X) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+        for (int i = N - 1; i >= 0; --i) {
+            double s = X[i * LD + c];
+            for (int k = i + 1; k < N; ++k) s = fma(-L[k * LD + i], X[k * LD + c], s);
+            X[i * LD + c] = s / L[i * LD + i];
+        }
+    __syncthreads();
+}
+
+struct LargeWs {
+    const double *A, *B, *P, *Q, *S0, *BA;   // fp64 copies of the model (global)
+    double *Sp, *Sf, *Cc, *Gd;               // [T][D*D]
+    float *fwdT;                             // [T][(D+M)][D]   [F_t | K_t] transposed (k-major)
+    float *bwdT;                             // [T][2D][D]      [E_t | G_t] transposed
+    float *ss, *sf;                          // [T][D*D] smoothed / filtered covariance (fp32)
+    int* flag;
+};
+
+template <int D> struct LD_ { static constexpr int v = D + 1; };   // padded leading dim: no bank conflicts on transposed reads
+
+// Phase 1: Riccati recursion, sequential in t, one CTA.
+template <int D, int M>
+__global__ void __launch_bounds__(256) large_riccati_seq(LargeWs w, int T, int transition_first) {
+    constexpr int LD = LD_<D>::v;
+    extern __shared__ double sm[];
+    double* S = sm;                 // D x D   current covariance
+    double* T1 = S + D * LD;        // scratch
+    double* T2 = T1 + D * LD;       // scratch (innovation covariance / its Cholesky factor)
+    for (int i = threadIdx.x; i < D * D; i += blockDim.x) S[(i / D) * LD + i % D] = w.S0[i];
+    __syncthreads();
+    for (int t = 0; t < T; ++t) {
+        if (t > 0 || transition_first) {
+            bgemm<D, D, D>([&](int i, int k) { return w.A[i * D + k]; }, [&](int k, int j) { return S[k * LD + j]; },
+                           [&](int i, int j, double v) { T1[i * LD + j] = v; });
+            __syncthreads();
+            bgemm<D, D, D>([&](int i, int k) { return T1[i * LD + k]; }, [&](int k, int j) { return w.A[j * D + k]; },
+                           [&](int i, int j, double v) { S[i * LD + j] = v + w.P[i * D + j]; });
+            __syncthreads();
+        }
+        for (int i = threadIdx.x; i < D * D; i += blockDim.x) w.Sp[(size_t)t * D * D + i] = S[(i / D) * LD + i % D];
+        // T1 = B S (M x D); T2 = T1 B' + Q (M x M)
+        bgemm<M, D, D>([&](int i, int k) { return w.B[i * D + k]; }, [&](int k, int j) { return S[k * LD + j]; },
+                       [&](int i, int j, double v) { T1[i * LD + j] = v; });
+        __syncthreads();
+        bgemm<M, M, D>([&](int i, int k) { return T1[i * LD + k]; }, [&](int k, int j) { return w.B[j * D + k]; },
+                       [&](int i, int j, double v) { T2[i * LD + j] = v + w.Q[i * M + j]; });
+        bchol<M, LD>(T2, w.flag);
+        btrsm_lower<M, D, LD>(T2, T1);                 // W = L^-1 B S   (M x D)
+        // S <- S - W' W
+        bgemm<D, D, M>([&](int i, int k) { return T1[k * LD + i]; }, [&](int k, int j) { return T1[k * LD + j]; },
+                       [&](int i, int j, double v) { S[i * LD + j] -= v; });
+        __syncthreads();
+        // symmetrise (round-off) and publish
+        for (int idx = threadIdx.x; idx < D * D; idx += blockDim.x) {
+            const int i = idx / D, j = idx % D;
+            if (j < i) { const double s = 0.5 * (S[i * LD + j] + S[j * LD + i]); T2[i * LD + j] = s; }
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < D * D; idx += blockDim.x) {
+            const int i = idx / D, j = idx % D;
+            if (j < i) { S[i * LD + j] = T2[i * LD + j]; S[j * LD + i] = T2[i * LD + j]; }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < D * D; i += blockDim.x) w.Sf[(size_t)t * D * D + i] = S[(i / D) * LD + i % D];
+    }
+}
+
+// Phase 2: one CTA per time step: Kalman gain, F = (I - K B) A, RTS gain, E = I - G A, conditional cov.
+template <int D, int M>
+__global__ void __launch_bounds__(256) large_gain_tables(LargeWs w, int T, int transition_first) {
+    constexpr int LD = LD_<D>::v;
+    extern __shared__ double sm[];
+    double* X0 = sm;
+    double* X1 = X0 + D * LD;
+    double* X2 = X1 + D * LD;
+    const int t = blockIdx.x;
+    const double* Sp = w.Sp + (size_t)t * D * D;
+    const double* Sf = w.Sf + (size_t)t * D * D;
+    // ---- forward gain: X1 = B Sp; X2 = X1 B' + Q = L L'; X1 <- L^-T L^-1 X1 = K'  (M x D)
+    bgemm<M, D, D>([&](int i, int k) { return w.B[i * D + k]; }, [&](int k, int j) { return Sp[k * D + j]; },
+                   [&](int i, int j, double v) { X1[i * LD + j] = v; });
+    __syncthreads();
+    bgemm<M, M, D>([&](int i, int k) { return X1[i * LD + k]; }, [&](int k, int j) { return w.B[j * D + k]; },
+                   [&](int i, int j, double v) { X2[i * LD + j] = v + w.Q[i * M + j]; });
+    bchol<M, LD>(X2, w.flag);
+    btrsm_lower<M, D, LD>(X2, X1);
+    btrsm_lower_t<M, D, LD>(X2, X1);                   // X1 = K' (M x D): K(r, k) = X1[k][r]
+    float* ft = w.fwdT + (size_t)t * (D + M) * D;
+    const bool pred = (t > 0) || transition_first;
+    // F = A - K (B A)   (or I - K B at t = 0 without a leading transition); stored transposed: ft[k][r] = F(r, k)
+    if (pred) {
+        bgemm<D, D, M>([&](int r, int k) { return X1[k * LD + r]; }, [&](int k, int j) { return w.BA[k * D + j]; },
+                       [&](int r, int j, double v) { ft[j * D + r] = (float)(w.A[r * D + j] - v); });
+    } else {
+        bgemm<D, D, M>([&](int r, int k) { return X1[k * LD + r]; }, [&](int k, int j) { return w.B[k * D + j]; },
+                       [&](int r, int j, double v) { ft[j * D + r] = (float)((r == j ? 1.0 : 0.0) - v); });
+    }
+    for (int idx = threadIdx.x; idx < M * D; idx += blockDim.x) {
+        const int k = idx / D, r = idx % D;
+        ft[(D + k) * D + r] = (float)X1[k * LD + r];
+    }
+    for (int i = threadIdx.x; i < D * D; i += blockDim.x) w.sf[(size_t)t * D * D + i] = (float)Sf[i];
+    __syncthreads();
+    // ---- backward gain
+    float* bt = w.bwdT + (size_t)t * 2 * D * D;
+    if (t == T - 1) {
+        for (int idx = threadIdx.x; idx < D * D; idx += blockDim.x) {
+            const int k = idx / D, r = idx % D;
+            bt[k * D + r] = (k == r) ? 1.f : 0.f;
+            bt[(D + k) * D + r] = 0.f;
+        }
+        return;
+    }
+    const double* Sp1 = w.Sp + (size_t)(t + 1) * D * D;
+    for (int i = threadIdx.x; i < D * D; i += blockDim.x) X2[(i / D) * LD + i % D] = Sp1[i];
+    // X0 = A Sf  (= (Sf A')')
+    bgemm<D, D, D>([&](int i, int k) { return w.A[i * D + k]; }, [&](int k, int j) { return Sf[k * D + j]; },
+                   [&](int i, int j, double v) { X0[i * LD + j] = v; });
+    bchol<D, LD>(X2, w.flag);
+    btrsm_lower<D, D, LD>(X2, X0);                     // X0 = U' = Lp^-1 A Sf
+    // C = Sf - U U' = Sf - X0' X0
+    bgemm<D, D, D>([&](int i, int k) { return X0[k * LD + i]; }, [&](int k, int j) { return X0[k * LD + j]; },
+                   [&](int i, int j, double v) { w.Cc[(size_t)t * D * D + i * D + j] = Sf[i * D + j] - v; });
+    __syncthreads();
+    btrsm_lower_t<D, D, LD>(X2, X0);                   // X0 = G' = Lp^-T U'   : G(r, k) = X0[k][r]
+    for (int idx = threadIdx.x; idx < D * D; idx += blockDim.x) {
+        const int k = idx / D, r = idx % D;
+        const double g = X0[k * LD + r];
+        bt[(D + k) * D + r] = (float)g;
+        w.Gd[(size_t)t * D * D + r * D + k] = g;
+    }
+    // E = I - G A: E(r, j) = delta - sum_k G(r,k) A(k,j); stored transposed bt[j][r]
+    bgemm<D, D, D>([&](int r, int k) { return X0[k * LD + r]; }, [&](int k, int j) { return w.A[k * D + j]; },
+                   [&](int r, int j, double v) { bt[j * D + r] = (float)((r == j ? 1.0 : 0.0) - v); });
+}
+
+// Phase 3: smoothed covariances, sequential in t, one CTA:  Ss[t] = C[t] + G[t] Ss[t+1] G[t]'.
+template <int D>
+__global__ void __launch_bounds__(256) large_smooth_seq(LargeWs w, int T) {
+    constexpr int LD = LD_<D>::v;
+    extern __shared__ double sm[];
+    double* S = sm;
+    double* T1 = S + D * LD;
+    for (int i = threadIdx.x; i < D * D; i += blockDim.x) {
+        const double v = w.Sf[(size_t)(T - 1) * D * D + i];
+        S[(i / D) * LD + i % D] = v;
+        w.ss[(size_t)(T - 1) * D * D + i] = (float)v;
+    }
+    __syncthreads();
+    for (int t = T - 2; t >= 0; --t) {
+        const double* G = w.Gd + (size_t)t * D * D;
+        const double* C = w.Cc + (size_t)t * D * D;
+        bgemm<D, D, D>([&](int i, int k) { return G[i * D + k]; }, [&](int k, int j) { return S[k * LD + j]; },
+                       [&](int i, int j, double v) { T1[i * LD + j] = v; });
+        __syncthreads();
+        bgemm<D, D, D>([&](int i, int k) { return T1[i * LD + k]; }, [&](int k, int j) { return G[j * D + k]; },
+                       [&](int i, int j, double v) { S[i * LD + j] = v + C[i * D + j]; });
+        __syncthreads();
+        for (int i = threadIdx.x; i < D * D; i += blockDim.x) w.ss[(size_t)t * D * D + i] = (float)S[(i / D) * LD + i % D];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// mean sweep: a tile of NB chains per CTA, per-step GEMM  out[D x NB] = W_t'[(K2) x D]' * Z[(K2) x NB]
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cpa16(void* s, const void* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(s)), "l"(g));
+}
+__device__ __forceinline__ void cpa4(void* s, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(s)), "l"(g));
+}
+__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// one step of the tile GEMM: thread (rg, cg) owns rows 4 rg .. 4 rg + 3 and columns 2 cg, 2 cg + 1
+template <int D, int K2, int NB>
+__device__ __forceinline__ void tile_step(const float* __restrict__ W, const float* __restrict__ Z, int rg, int cg,
+                                          float (&acc)[4][2]) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; }
+#pragma unroll 8
+    for (int k = 0; k < K2; ++k) {
+        const float4 wv = *reinterpret_cast<const float4*>(W + k * D + 4 * rg);
+        const float2 zv = *reinterpret_cast<const float2*>(Z + k * NB + 2 * cg);
+        acc[0][0] = __fmaf_rn(wv.x, zv.x, acc[0][0]); acc[0][1] = __fmaf_rn(wv.x, zv.y, acc[0][1]);
+        acc[1][0] = __fmaf_rn(wv.y, zv.x, acc[1][0]); acc[1][1] = __fmaf_rn(wv.y, zv.y, acc[1][1]);
+        acc[2][0] = __fmaf_rn(wv.z, zv.x, acc[2][0]); acc[2][1] = __fmaf_rn(wv.z, zv.y, acc[2][1]);
+        acc[3][0] = __fmaf_rn(wv.w, zv.x, acc[3][0]); acc[3][1] = __fmaf_rn(wv.w, zv.y, acc[3][1]);
+    }
+}
+
+template <int D, int M, int NB, bool SMOOTH>
+__global__ void __launch_bounds__((D / 4) * (NB / 2))
+lgssm_block_sweep(const float* __restrict__ fwdT, const float* __restrict__ bwdT, const float* __restrict__ m0,
+                  const float* __restrict__ y, float* __restrict__ mean, int T, int64_t batch) {
+    constexpr int KF = D + M, KB = 2 * D, KMAX = KF > KB ? KF : KB;
+    constexpr int NT = (D / 4) * (NB / 2);
+    extern __shared__ __align__(16) float smf[];
+    float* Wb[2] = {smf, smf + KMAX * D};
+    float* Zb[2] = {smf + 2 * KMAX * D, smf + 2 * KMAX * D + KMAX * NB};
+    const int tid = threadIdx.x;
+    const int cg = tid % (NB / 2), rg = tid / (NB / 2);
+    const int64_t b0 = (int64_t)blockIdx.x * NB;
+    const int nb = (int)((batch - b0) < NB ? (batch - b0) : NB);
+    const bool even = (batch % 2) == 0;         // 8-byte alignment of the paired global stores
+
+    auto load_W = [&](float* dst, const float* src, int K2) {
+        for (int p = tid; p < K2 * D / 4; p += NT) cpa16(dst + 4 * p, src + 4 * p);
+    };
+    auto load_rows = [&](float* dst, const float* src_row0, int rows) {   // rows x NB from a [rows][batch] slab
+        for (int p = tid; p < rows * NB; p += NT) {
+            const int r = p / NB, c = p % NB;
+            if (c < nb) cpa4(dst + r * NB + c, src_row0 + (size_t)r * batch + b0 + c);
+        }
+    };
+    // zero both Z buffers once (inactive columns stay zero), then the initial state
+    for (int p = tid; p < 2 * KMAX * NB; p += NT) Zb[0][p] = 0.f;
+    __syncthreads();
+    for (int p = tid; p < D * NB; p += NT) Zb[0][p] = m0[p / NB];
+    load_W(Wb[0], fwdT, KF);
+    load_rows(Zb[0] + D * NB, y, M);
+    cpa_commit();
+
+    float acc[4][2];
+    // ---------------------------------------------------------------- forward
+    for (int t = 0; t < T; ++t) {
+        const int q = t & 1;
+        if (t + 1 < T) {
+            load_W(Wb[q ^ 1], fwdT + (size_t)(t + 1) * KF * D, KF);
+            load_rows(Zb[q ^ 1] + D * NB, y + (size_t)(t + 1) * M * batch, M);
+        }
+        cpa_commit();
+        cpa_wait<1>();
+        __syncthreads();
+        tile_step<D, KF, NB>(Wb[q], Zb[q], rg, cg, acc);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int row = 4 * rg + r;
+            *reinterpret_cast<float2*>(Zb[q ^ 1] + row * NB + 2 * cg) = make_float2(acc[r][0], acc[r][1]);
+            float* g = mean + ((size_t)t * D + row) * batch + b0 + 2 * cg;
+            if (even && 2 * cg + 1 < nb) *reinterpret_cast<float2*>(g) = make_float2(acc[r][0], acc[r][1]);
+            else { if (2 * cg < nb) g[0] = acc[r][0]; if (2 * cg + 1 < nb) g[1] = acc[r][1]; }
+        }
+        __syncthreads();
+    }
+    cpa_wait<0>();
+    if (!SMOOTH) return;
+    // ---------------------------------------------------------------- backward: Z = [mu_f[t] ; mu_s[t+1]]
+    __syncthreads();
+    for (int p = tid; p < D * NB; p += NT) { Zb[0][D * NB + p] = 0.f; }
+    load_W(Wb[0], bwdT + (size_t)(T - 1) * KB * D, KB);
+    load_rows(Zb[0], mean + (size_t)(T - 1) * D * batch, D);
+    cpa_commit();
+    for (int r = 0; r < T; ++r) {
+        const int t = T - 1 - r, q = r & 1;
+        if (t - 1 >= 0) {
+            load_W(Wb[q ^ 1], bwdT + (size_t)(t - 1) * KB * D, KB);
+            load_rows(Zb[q ^ 1], mean + (size_t)(t - 1) * D * batch, D);
+        }
+        cpa_commit();
+        cpa_wait<1>();
+        __syncthreads();
+        tile_step<D, KB, NB>(Wb[q], Zb[q], rg, cg, acc);
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            const int row = 4 * rg + rr;
+            *reinterpret_cast<float2*>(Zb[q ^ 1] + (D + row) * NB + 2 * cg) = make_float2(acc[rr][0], acc[rr][1]);
+            float* g = mean + ((size_t)t * D + row) * batch + b0 + 2 * cg;
+            if (even && 2 * cg + 1 < nb) *reinterpret_cast<float2*>(g) = make_float2(acc[rr][0], acc[rr][1]);
+            else { if (2 * cg < nb) g[0] = acc[rr][0]; if (2 * cg + 1 < nb) g[1] = acc[rr][1]; }
+        }
+        __syncthreads();
+    }
+    cpa_wait<0>();
+}
+
+// cov[t][i][j][b] = tab[t][i*D + j] for every chain b (the contract's per-chain covariance output)
+__global__ void broadcast_cov_kernel(const float* __restrict__ tab, float* __restrict__ cov, int64_t rows, int64_t batch) {
+    const int64_t row = blockIdx.x;
+    if (row >= rows) return;
+    const float v = __ldg(tab + row);
+    float* dst = cov + row * batch;
+    for (int64_t b = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; b < batch; b += (int64_t)gridDim.y * blockDim.x) dst[b] = v;
+}
+
+__global__ void to_double_kernel(const float* __restrict__ src, double* __restrict__ dst, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (double)src[i];
+}
+template <int D, int M>
+__global__ void ba_kernel(const double* B, const double* A, double* BA) {
+    for (int idx = threadIdx.x; idx < M * D; idx += blockDim.x) {
+        const int i = idx / D, j = idx % D;
+        double s = 0.0;
+        for (int k = 0; k < D; ++k) s = fma(B[i * D + k], A[k * D + j], s);
+        BA[idx] = s;
+    }
+}
+
+template <int D, int M>
+static int run_large(rxg_ctx* ctx, const LgssmCall& c) {
+    if ((c.flags & (RXG_MODEL_PER_CHAIN | RXG_PATH_PER_CHAIN)) || c.ymask || c.nle || c.u)
+        return fail(ctx, RXG_ERR_UNSUPPORTED,
+                    "lgssm (d=%d): the large-state family covers shared models without mask / evidence / offset", D);
+    const size_t T = (size_t)c.T, DD = (size_t)D * D;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t o_model32 = carve((3 * DD + (size_t)M * D + (size_t)M * M + D) * 4);
+    const size_t o_A = carve(DD * 8), o_B = carve((size_t)M * D * 8), o_P = carve(DD * 8), o_Q = carve((size_t)M * M * 8);
+    const size_t o_S0 = carve(DD * 8), o_BA = carve((size_t)M * D * 8);
+    const size_t o_Sp = carve(T * DD * 8), o_Sf = carve(T * DD * 8), o_Cc = carve(T * DD * 8), o_Gd = carve(T * DD * 8);
+    const size_t o_fw = carve(T * (D + M) * D * 4), o_bw = carve(T * 2 * DD * 4), o_ss = carve(T * DD * 4), o_sf = carve(T * DD * 4);
+    const size_t o_flag = carve(4);
+    char* base = (char*)workspace(ctx, off);
+    if (!base) return RXG_ERR_CUDA;
+    // model: host fp32 -> device fp32 -> device fp64
+    float* m32 = (float*)(base + o_model32);
+    float* dA = m32, *dB = dA + DD, *dP = dB + (size_t)M * D, *dQ = dP + DD, *dS0 = dQ + (size_t)M * M, *dm0 = dS0 + DD;
+    RXG_CUDA(ctx, cudaMemcpyAsync(dA, c.A, DD * 4, cudaMemcpyHostToDevice, ctx->stream));
+    RXG_CUDA(ctx, cudaMemcpyAsync(dB, c.B, (size_t)M * D * 4, cudaMemcpyHostToDevice, ctx->stream));
+    RXG_CUDA(ctx, cudaMemcpyAsync(dP, c.P, DD * 4, cudaMemcpyHostToDevice, ctx->stream));
+    RXG_CUDA(ctx, cudaMemcpyAsync(dQ, c.Q, (size_t)M * M * 4, cudaMemcpyHostToDevice, ctx->stream));
+    RXG_CUDA(ctx, cudaMemcpyAsync(dS0, c.S0, DD * 4, cudaMemcpyHostToDevice, ctx->stream));
+    RXG_CUDA(ctx, cudaMemcpyAsync(dm0, c.m0, (size_t)D * 4, cudaMemcpyHostToDevice, ctx->stream));
+    RXG_CUDA(ctx, cudaMemsetAsync(base + o_flag, 0, 4, ctx->stream));
+    LargeWs w;
+    double *A64 = (double*)(base + o_A), *B64 = (double*)(base + o_B), *P64 = (double*)(base + o_P);
+    double *Q64 = (double*)(base + o_Q), *S064 = (double*)(base + o_S0), *BA64 = (double*)(base + o_BA);
+    auto cvt = [&](const float* s, double* d, int n) { to_double_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(s, d, n); };
+    cvt(dA, A64, (int)DD); cvt(dB, B64, M * D); cvt(dP, P64, (int)DD); cvt(dQ, Q64, M * M); cvt(dS0, S064, (int)DD);
+    ba_kernel<D, M><<<1, 256, 0, ctx->stream>>>(B64, A64, BA64);
+    ctx->launches += 6;
+    w.A = A64; w.B = B64; w.P = P64; w.Q = Q64; w.S0 = S064; w.BA = BA64;
+    w.Sp = (double*)(base + o_Sp); w.Sf = (double*)(base + o_Sf); w.Cc = (double*)(base + o_Cc); w.Gd = (double*)(base + o_Gd);
+    w.fwdT = (float*)(base + o_fw); w.bwdT = (float*)(base + o_bw); w.ss = (float*)(base + o_ss); w.sf = (float*)(base + o_sf);
+    w.flag = (int*)(base + o_flag);
+    const int tf = (c.flags & RXG_TRANSITION_FIRST) ? 1 : 0;
+    constexpr int LD = LD_<D>::v;
+    const size_t sm3 = (size_t)3 * D * LD * 8, sm2 = (size_t)2 * D * LD * 8;
+    static bool attr_done = false;
+    if (!attr_done) {
+        RXG_CUDA(ctx, cudaFuncSetAttribute(large_riccati_seq<D, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
+        RXG_CUDA(ctx, cudaFuncSetAttribute(large_gain_tables<D, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
+        RXG_CUDA(ctx, cudaFuncSetAttribute(large_smooth_seq<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+    }
+    if (ctx->profile) cudaEventRecord(ctx->ev[0], ctx->stream);
+    large_riccati_seq<D, M><<<1, 256, sm3, ctx->stream>>>(w, c.T, tf);
+    large_gain_tables<D, M><<<c.T, 256, sm3, ctx->stream>>>(w, c.T, tf);
+    ctx->launches += 2;
+    if (c.smooth) { large_smooth_seq<D><<<1, 256, sm2, ctx->stream>>>(w, c.T); ctx->launches += 1; }
+    int rc = check_cuda(ctx, cudaGetLastError(), "large gain kernels");
+    if (rc != RXG_OK) return rc;
+
+    constexpr int NB = 32;
+    constexpr int KMAX = (D + M) > 2 * D ? (D + M) : 2 * D;
+    const size_t smw = (size_t)(2 * KMAX * D + 2 * KMAX * NB) * 4;
+    if (!attr_done) {
+        RXG_CUDA(ctx, cudaFuncSetAttribute(lgssm_block_sweep<D, M, NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
+        RXG_CUDA(ctx, cudaFuncSetAttribute(lgssm_block_sweep<D, M, NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
+        attr_done = true;
+    }
+    const unsigned blocks = (unsigned)((c.batch + NB - 1) / NB);
+    if (ctx->profile) cudaEventRecord(ctx->ev[1], ctx->stream);
+    if (c.smooth) lgssm_block_sweep<D, M, NB, true><<<blocks, (D / 4) * (NB / 2), smw, ctx->stream>>>(w.fwdT, w.bwdT, dm0, c.y, c.mean, c.T, c.batch);
+    else          lgssm_block_sweep<D, M, NB, false><<<blocks, (D / 4) * (NB / 2), smw, ctx->stream>>>(w.fwdT, w.bwdT, dm0, c.y, c.mean, c.T, c.batch);
+    if (ctx->profile) cudaEventRecord(ctx->ev[2], ctx->stream);
+    ctx->launches += 1;
+    rc = check_cuda(ctx, cudaGetLastError(), "lgssm_block_sweep");
+    if (rc != RXG_OK) return rc;
+    if (c.cov) {
+        const float* tab = c.smooth ? w.ss : w.sf;
+        if (c.flags & RXG_COV_SHARED_OUT) {
+            RXG_CUDA(ctx, cudaMemcpyAsync(c.cov, tab, T * DD * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        } else {
+            const int64_t rows = (int64_t)(T * DD);
+            dim3 grid((unsigned)rows, (unsigned)((c.batch + 4095) / 4096 > 16 ? 16 : (c.batch + 4095) / 4096));
+            broadcast_cov_kernel<<<grid, 256, 0, ctx->stream>>>(tab, c.cov, rows, c.batch);
+            ctx->launches += 1;
+            rc = check_cuda(ctx, cudaGetLastError(), "broadcast_cov_kernel");
+            if (rc != RXG_OK) return rc;
+        }
+    }
+    if (c.status) RXG_CUDA(ctx, cudaMemsetAsync(c.status, 0, (size_t)c.batch * 4, ctx->stream));
+    return RXG_OK;
+}
+
+bool lgssm_large_supported(int d, int m) { return d == m && (d == 8 || d == 16 || d == 32 || d == 64); }
+
+int lgssm_large_dispatch(rxg_ctx* ctx, const LgssmCall& c) {
+    switch (c.d) {
+        case 8: return run_large<8, 8>(ctx, c);
+        case 16: return run_large<16, 16>(ctx, c);
+        case 32: return run_large<32, 32>(ctx, c);
+        case 64: return run_large<64, 64>(ctx, c);
+        default: return fail(ctx, RXG_ERR_UNSUPPORTED, "large-state family: d=%d unsupported", c.d);
+    }
+}
+
+}  // namespace rxg

@@ -181,8 +181,8 @@ def test_infer_entry_point(rx, ctx):
 
 
 def test_unsupported_shape_errors_loudly(rx, ctx):
-    mod = lgssm.dense_model(8)
-    y = torch.zeros(4, 8, 2, device="cuda")
+    mod = lgssm.dense_model(5)
+    y = torch.zeros(4, 5, 2, device="cuda")
     with pytest.raises(rx.RxGaussError) as e:
         ctx.lgssm(y, **_kw(mod), smooth=True)
     assert e.value.code == rx._lib.RXG_ERR_UNSUPPORTED
@@ -303,3 +303,30 @@ def test_transition_offset_and_prior_on_previous_state(ctx, tf):
                    m0=to_abi(mods["m0"]), S0=to_abi(mods["S0"]), u=to_abi(us), smooth=True, want_evidence=True,
                    per_chain_model=True, transition_first=tf)
     check(rp, refp)
+
+
+@pytest.mark.parametrize("d,T,batch", [(8, 120, 37), (16, 200, 70), (32, 150, 64), (64, 300, 96)])
+def test_large_state_family(ctx, d, T, batch):
+    """BASELINE configs[2] family (d = 64 and the smaller block sizes): dense A = 0.99 * Orth, B = I,
+    shared model, gain tables from block-cooperative fp64 kernels, tiled mean sweep."""
+    mod = f32_model(lgssm.dense_model(d, seed=64))
+    _, y = lgssm.generate_data(mod, T, batch, seed=43)
+    ref = lgssm.smooth_reference_schedule(y, **mod)
+    r = ctx.lgssm(dev(y), **_kw(mod), smooth=True, want_status=True)
+    check(r, ref, nle=False)
+    assert int(r["status"].abs().sum()) == 0
+    rs = ctx.lgssm(dev(y), **_kw(mod), smooth=True, cov_shared_out=True)
+    assert tuple(rs["cov"].shape) == (T, d, d)
+    assert rel_l2(rs["cov"].cpu().numpy(), ref["cov"][..., 0]) < TOL_COV
+    f = ctx.lgssm(dev(y), **_kw(mod), smooth=False, transition_first=True)
+    reff = lgssm.filter_streaming(y, **mod)
+    assert rel_l2(f["mean"].cpu().numpy(), reff["mean"]) < TOL_MEAN
+    assert rel_l2(f["cov"].cpu().numpy(), reff["cov"]) < TOL_COV
+
+
+def test_large_state_unsupported_options_fail_loudly(rx, ctx):
+    mod = f32_model(lgssm.dense_model(16))
+    y = torch.zeros(8, 16, 4, device="cuda")
+    with pytest.raises(rx.RxGaussError) as e:
+        ctx.lgssm(y, **_kw(mod), smooth=True, want_evidence=True)
+    assert e.value.code == rx._lib.RXG_ERR_UNSUPPORTED
