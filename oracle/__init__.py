@@ -18,9 +18,10 @@ Pin status:
   * Two-node Gaussian BP + log-evidence: PINNED against
     test/models/models_tests.jl:242-336 (1.5 / 3.51551, 1.0 / 2.26551).
   * Normal entropy: PINNED against test/score/diagnostics_tests.jl:24.
-  * LGSSM schedule: cross-checked against textbook Kalman + RTS (1e-12); the
-    reference's own LGSSM goldens need Julia's RNG stream and cannot be
-    regenerated here, so LGSSM parity rests on rule-level pins + that cross-check.
+  * LGSSM schedule: PINNED against the reference's own regression pins -- the test data of
+    test/models/statespace/mlgssm_test.jl:70-97 (BFE 6275.9015944677) and ulgssm_tests.jl:27-32
+    (BFE 1854.297647) are regenerated with oracle/julia_rng.py (StableRNGs.jl + Julia's ziggurat
+    randn) and reproduced to 4e-9 / 7e-7; also cross-checked against textbook Kalman + RTS (1e-11).
   * HGF / GCV posteriors: PARITY UNPINNED (formula-level parity only; the
     reference pins it only through StableRNG-generated data).
 """

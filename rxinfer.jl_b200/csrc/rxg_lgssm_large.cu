@@ -52,49 +52,62 @@ __device__ __forceinline__ void bgemm(FA a, FB b, FC store) {
     }
 }
 
-// in-place lower Cholesky of the N x N matrix at L (leading dim LD); returns false on a bad pivot
+// in-place lower Cholesky (left-looking), blockDim.x == 256: P = 256 / N threads share the dot
+// product of one row and reduce with shuffles; two barriers per column.  Only the lower triangle
+// is written / meaningful afterwards.
 template <int N, int LD>
-__device__ bool bchol(double* L, int* flag) {
-    for (int j = 0; j < N; ++j) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double s = L[j * LD + j];
-            if (!(s > 0.0)) { *flag = 1; s = 1e-300; }
-            L[j * LD + j] = sqrt(s);
-        }
-        __syncthreads();
-        const double inv = 1.0 / L[j * LD + j];
-        for (int i = j + 1 + threadIdx.x; i < N; i += blockDim.x) L[i * LD + j] *= inv;
-        __syncthreads();
-        const int n = N - j - 1;
-        for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
-            const int i = j + 1 + idx / n, k = j + 1 + idx % n;
-            if (k <= i) L[i * LD + k] = fma(-L[i * LD + j], L[k * LD + j], L[i * LD + k]);
-        }
-    }
+__device__ void bchol(double* A, int* flag) {
+    constexpr int P = (256 / N) > 32 ? 32 : (256 / N);
+    const int row = threadIdx.x / P, part = threadIdx.x % P;
     __syncthreads();
-    return true;
+    for (int j = 0; j < N; ++j) {
+        double s = 0.0;
+        if (row < N && row >= j)
+            for (int k = part; k < j; k += P) s = fma(A[row * LD + k], A[j * LD + k], s);
+#pragma unroll
+        for (int o = P / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (row == j && part == 0) {
+            double d = A[j * LD + j] - s;
+            if (!(d > 0.0)) { *flag = 1; d = 1e-300; }
+            A[j * LD + j] = sqrt(d);
+        }
+        __syncthreads();
+        if (row > j && row < N && part == 0) A[row * LD + j] = (A[row * LD + j] - s) / A[j * LD + j];
+        __syncthreads();
+    }
 }
-// X <- L^-1 X  (X is N x C, one thread per column)
+// X <- L^-1 X  (X is N x C): P = 256 / C threads per column split each dot product
 template <int N, int C, int LD>
 __device__ void btrsm_lower(const double* L, double* X) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x)
+    constexpr int P = (256 / C) > 32 ? 32 : (256 / C);
+    const int col = threadIdx.x / P, part = threadIdx.x % P;
+    if (col < C) {
         for (int i = 0; i < N; ++i) {
-            double s = X[i * LD + c];
-            for (int k = 0; k < i; ++k) s = fma(-L[i * LD + k], X[k * LD + c], s);
-            X[i * LD + c] = s / L[i * LD + i];
+            double s = 0.0;
+            for (int k = part; k < i; k += P) s = fma(L[i * LD + k], X[k * LD + col], s);
+#pragma unroll
+            for (int o = P / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (part == 0) X[i * LD + col] = (X[i * LD + col] - s) / L[i * LD + i];
+            __syncwarp();
         }
+    }
     __syncthreads();
 }
 // X <- L^-T X
 template <int N, int C, int LD>
 __device__ void btrsm_lower_t(const double* L, double* X) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x)
+    constexpr int P = (256 / C) > 32 ? 32 : (256 / C);
+    const int col = threadIdx.x / P, part = threadIdx.x % P;
+    if (col < C) {
         for (int i = N - 1; i >= 0; --i) {
-            double s = X[i * LD + c];
-            for (int k = i + 1; k < N; ++k) s = fma(-L[k * LD + i], X[k * LD + c], s);
-            X[i * LD + c] = s / L[i * LD + i];
+            double s = 0.0;
+            for (int k = i + 1 + part; k < N; k += P) s = fma(L[k * LD + i], X[k * LD + col], s);
+#pragma unroll
+            for (int o = P / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (part == 0) X[i * LD + col] = (X[i * LD + col] - s) / L[i * LD + i];
+            __syncwarp();
         }
+    }
     __syncthreads();
 }
 
@@ -105,6 +118,7 @@ struct LargeWs {
     float *bwdT;                             // [T][2D][D]      [E_t | G_t] transposed
     float *ss, *sf;                          // [T][D*D] smoothed / filtered covariance (fp32)
     int* flag;
+    int b_identity;                          // B == I: skip the two B products
 };
 
 template <int D> struct LD_ { static constexpr int v = D + 1; };   // padded leading dim: no bank conflicts on transposed reads
@@ -117,24 +131,37 @@ __global__ void __launch_bounds__(256) large_riccati_seq(LargeWs w, int T, int t
     double* S = sm;                 // D x D   current covariance
     double* T1 = S + D * LD;        // scratch
     double* T2 = T1 + D * LD;       // scratch (innovation covariance / its Cholesky factor)
-    for (int i = threadIdx.x; i < D * D; i += blockDim.x) S[(i / D) * LD + i % D] = w.S0[i];
+    double* As = T2 + D * LD;       // A staged in shared memory
+    for (int i = threadIdx.x; i < D * D; i += blockDim.x) {
+        S[(i / D) * LD + i % D] = w.S0[i];
+        As[(i / D) * LD + i % D] = w.A[i];
+    }
     __syncthreads();
     for (int t = 0; t < T; ++t) {
         if (t > 0 || transition_first) {
-            bgemm<D, D, D>([&](int i, int k) { return w.A[i * D + k]; }, [&](int k, int j) { return S[k * LD + j]; },
+            bgemm<D, D, D>([&](int i, int k) { return As[i * LD + k]; }, [&](int k, int j) { return S[k * LD + j]; },
                            [&](int i, int j, double v) { T1[i * LD + j] = v; });
             __syncthreads();
-            bgemm<D, D, D>([&](int i, int k) { return T1[i * LD + k]; }, [&](int k, int j) { return w.A[j * D + k]; },
+            bgemm<D, D, D>([&](int i, int k) { return T1[i * LD + k]; }, [&](int k, int j) { return As[j * LD + k]; },
                            [&](int i, int j, double v) { S[i * LD + j] = v + w.P[i * D + j]; });
             __syncthreads();
         }
         for (int i = threadIdx.x; i < D * D; i += blockDim.x) w.Sp[(size_t)t * D * D + i] = S[(i / D) * LD + i % D];
-        // T1 = B S (M x D); T2 = T1 B' + Q (M x M)
-        bgemm<M, D, D>([&](int i, int k) { return w.B[i * D + k]; }, [&](int k, int j) { return S[k * LD + j]; },
-                       [&](int i, int j, double v) { T1[i * LD + j] = v; });
-        __syncthreads();
-        bgemm<M, M, D>([&](int i, int k) { return T1[i * LD + k]; }, [&](int k, int j) { return w.B[j * D + k]; },
-                       [&](int i, int j, double v) { T2[i * LD + j] = v + w.Q[i * M + j]; });
+        if (w.b_identity && M == D) {
+            for (int idx = threadIdx.x; idx < D * D; idx += blockDim.x) {
+                const int i = idx / D, j = idx % D;
+                const double v = S[i * LD + j];
+                T1[i * LD + j] = v;
+                T2[i * LD + j] = v + w.Q[i * M + j];
+            }
+        } else {
+            // T1 = B S (M x D); T2 = T1 B' + Q (M x M)
+            bgemm<M, D, D>([&](int i, int k) { return w.B[i * D + k]; }, [&](int k, int j) { return S[k * LD + j]; },
+                           [&](int i, int j, double v) { T1[i * LD + j] = v; });
+            __syncthreads();
+            bgemm<M, M, D>([&](int i, int k) { return T1[i * LD + k]; }, [&](int k, int j) { return w.B[j * D + k]; },
+                           [&](int i, int j, double v) { T2[i * LD + j] = v + w.Q[i * M + j]; });
+        }
         bchol<M, LD>(T2, w.flag);
         btrsm_lower<M, D, LD>(T2, T1);                 // W = L^-1 B S   (M x D)
         // S <- S - W' W
@@ -164,15 +191,26 @@ __global__ void __launch_bounds__(256) large_gain_tables(LargeWs w, int T, int t
     double* X0 = sm;
     double* X1 = X0 + D * LD;
     double* X2 = X1 + D * LD;
+    double* As = X2 + D * LD;
     const int t = blockIdx.x;
     const double* Sp = w.Sp + (size_t)t * D * D;
     const double* Sf = w.Sf + (size_t)t * D * D;
+    for (int i = threadIdx.x; i < D * D; i += blockDim.x) As[(i / D) * LD + i % D] = w.A[i];
     // ---- forward gain: X1 = B Sp; X2 = X1 B' + Q = L L'; X1 <- L^-T L^-1 X1 = K'  (M x D)
-    bgemm<M, D, D>([&](int i, int k) { return w.B[i * D + k]; }, [&](int k, int j) { return Sp[k * D + j]; },
-                   [&](int i, int j, double v) { X1[i * LD + j] = v; });
-    __syncthreads();
-    bgemm<M, M, D>([&](int i, int k) { return X1[i * LD + k]; }, [&](int k, int j) { return w.B[j * D + k]; },
-                   [&](int i, int j, double v) { X2[i * LD + j] = v + w.Q[i * M + j]; });
+    if (w.b_identity && M == D) {
+        for (int idx = threadIdx.x; idx < D * D; idx += blockDim.x) {
+            const int i = idx / D, j = idx % D;
+            const double v = Sp[idx];
+            X1[i * LD + j] = v;
+            X2[i * LD + j] = v + w.Q[i * M + j];
+        }
+    } else {
+        bgemm<M, D, D>([&](int i, int k) { return w.B[i * D + k]; }, [&](int k, int j) { return Sp[k * D + j]; },
+                       [&](int i, int j, double v) { X1[i * LD + j] = v; });
+        __syncthreads();
+        bgemm<M, M, D>([&](int i, int k) { return X1[i * LD + k]; }, [&](int k, int j) { return w.B[j * D + k]; },
+                       [&](int i, int j, double v) { X2[i * LD + j] = v + w.Q[i * M + j]; });
+    }
     bchol<M, LD>(X2, w.flag);
     btrsm_lower<M, D, LD>(X2, X1);
     btrsm_lower_t<M, D, LD>(X2, X1);                   // X1 = K' (M x D): K(r, k) = X1[k][r]
@@ -181,7 +219,7 @@ __global__ void __launch_bounds__(256) large_gain_tables(LargeWs w, int T, int t
     // F = A - K (B A)   (or I - K B at t = 0 without a leading transition); stored transposed: ft[k][r] = F(r, k)
     if (pred) {
         bgemm<D, D, M>([&](int r, int k) { return X1[k * LD + r]; }, [&](int k, int j) { return w.BA[k * D + j]; },
-                       [&](int r, int j, double v) { ft[j * D + r] = (float)(w.A[r * D + j] - v); });
+                       [&](int r, int j, double v) { ft[j * D + r] = (float)(As[r * LD + j] - v); });
     } else {
         bgemm<D, D, M>([&](int r, int k) { return X1[k * LD + r]; }, [&](int k, int j) { return w.B[k * D + j]; },
                        [&](int r, int j, double v) { ft[j * D + r] = (float)((r == j ? 1.0 : 0.0) - v); });
@@ -205,7 +243,7 @@ __global__ void __launch_bounds__(256) large_gain_tables(LargeWs w, int T, int t
     const double* Sp1 = w.Sp + (size_t)(t + 1) * D * D;
     for (int i = threadIdx.x; i < D * D; i += blockDim.x) X2[(i / D) * LD + i % D] = Sp1[i];
     // X0 = A Sf  (= (Sf A')')
-    bgemm<D, D, D>([&](int i, int k) { return w.A[i * D + k]; }, [&](int k, int j) { return Sf[k * D + j]; },
+    bgemm<D, D, D>([&](int i, int k) { return As[i * LD + k]; }, [&](int k, int j) { return Sf[k * D + j]; },
                    [&](int i, int j, double v) { X0[i * LD + j] = v; });
     bchol<D, LD>(X2, w.flag);
     btrsm_lower<D, D, LD>(X2, X0);                     // X0 = U' = Lp^-1 A Sf
@@ -221,7 +259,7 @@ __global__ void __launch_bounds__(256) large_gain_tables(LargeWs w, int T, int t
         w.Gd[(size_t)t * D * D + r * D + k] = g;
     }
     // E = I - G A: E(r, j) = delta - sum_k G(r,k) A(k,j); stored transposed bt[j][r]
-    bgemm<D, D, D>([&](int r, int k) { return X0[k * LD + r]; }, [&](int k, int j) { return w.A[k * D + j]; },
+    bgemm<D, D, D>([&](int r, int k) { return X0[k * LD + r]; }, [&](int k, int j) { return As[k * LD + j]; },
                    [&](int r, int j, double v) { bt[j * D + r] = (float)((r == j ? 1.0 : 0.0) - v); });
 }
 
@@ -232,6 +270,7 @@ __global__ void __launch_bounds__(256) large_smooth_seq(LargeWs w, int T) {
     extern __shared__ double sm[];
     double* S = sm;
     double* T1 = S + D * LD;
+    double* Gs = T1 + D * LD;
     for (int i = threadIdx.x; i < D * D; i += blockDim.x) {
         const double v = w.Sf[(size_t)(T - 1) * D * D + i];
         S[(i / D) * LD + i % D] = v;
@@ -241,10 +280,12 @@ __global__ void __launch_bounds__(256) large_smooth_seq(LargeWs w, int T) {
     for (int t = T - 2; t >= 0; --t) {
         const double* G = w.Gd + (size_t)t * D * D;
         const double* C = w.Cc + (size_t)t * D * D;
-        bgemm<D, D, D>([&](int i, int k) { return G[i * D + k]; }, [&](int k, int j) { return S[k * LD + j]; },
+        for (int i = threadIdx.x; i < D * D; i += blockDim.x) Gs[(i / D) * LD + i % D] = G[i];
+        __syncthreads();
+        bgemm<D, D, D>([&](int i, int k) { return Gs[i * LD + k]; }, [&](int k, int j) { return S[k * LD + j]; },
                        [&](int i, int j, double v) { T1[i * LD + j] = v; });
         __syncthreads();
-        bgemm<D, D, D>([&](int i, int k) { return T1[i * LD + k]; }, [&](int k, int j) { return G[j * D + k]; },
+        bgemm<D, D, D>([&](int i, int k) { return T1[i * LD + k]; }, [&](int k, int j) { return Gs[j * LD + k]; },
                        [&](int i, int j, double v) { S[i * LD + j] = v + C[i * D + j]; });
         __syncthreads();
         for (int i = threadIdx.x; i < D * D; i += blockDim.x) w.ss[(size_t)t * D * D + i] = (float)S[(i / D) * LD + i % D];
@@ -425,9 +466,11 @@ static int run_large(rxg_ctx* ctx, const LgssmCall& c) {
     w.Sp = (double*)(base + o_Sp); w.Sf = (double*)(base + o_Sf); w.Cc = (double*)(base + o_Cc); w.Gd = (double*)(base + o_Gd);
     w.fwdT = (float*)(base + o_fw); w.bwdT = (float*)(base + o_bw); w.ss = (float*)(base + o_ss); w.sf = (float*)(base + o_sf);
     w.flag = (int*)(base + o_flag);
+    w.b_identity = (M == D) ? 1 : 0;
+    for (int i = 0; i < M * D && w.b_identity; ++i) w.b_identity = (c.B[i] == ((i / D == i % D) ? 1.f : 0.f));
     const int tf = (c.flags & RXG_TRANSITION_FIRST) ? 1 : 0;
     constexpr int LD = LD_<D>::v;
-    const size_t sm3 = (size_t)3 * D * LD * 8, sm2 = (size_t)2 * D * LD * 8;
+    const size_t sm3 = (size_t)4 * D * LD * 8, sm2 = (size_t)3 * D * LD * 8;
     static bool attr_done = false;
     if (!attr_done) {
         RXG_CUDA(ctx, cudaFuncSetAttribute(large_riccati_seq<D, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
