@@ -392,19 +392,22 @@ static int launch_shared(rxg_ctx* ctx, const LgssmCall& c, const ModelF<D, M>& m
     const bool evid = c.nle != nullptr;
     bool has_u = false;
     for (int i = 0; i < D; ++i) has_u |= (mdl.u[i] != 0.f);
+    // checkpoint + recompute instead of the forward->backward stash (RXG_NO_CKPT=1: A/B switch)
+    bool ckpt = c.smooth && (D * D <= 16);
+    if (const char* e = getenv("RXG_NO_CKPT")) ckpt = ckpt && atoi(e) == 0;
+#define RXG_LAUNCH_SHARED2(SM, EV, OF, CK)                                                         \
+    lgssm_shared_kernel<D, M, CPT, PF, SM, EV, OF, CK><<<blocks, threads, 0, ctx->stream>>>(       \
+        mdl, ws.fwd, ws.bwd, ws.sf, c.y, c.mean, c.cov, c.nle, c.T, c.batch, tf, write_cov)
 #define RXG_LAUNCH_SHARED(SM, EV)                                                                  \
     do {                                                                                           \
-        if (has_u)                                                                                 \
-            lgssm_shared_kernel<D, M, CPT, PF, SM, EV, true><<<blocks, threads, 0, ctx->stream>>>( \
-                mdl, ws.fwd, ws.bwd, ws.sf, c.y, c.mean, c.cov, c.nle, c.T, c.batch, tf, write_cov); \
-        else                                                                                       \
-            lgssm_shared_kernel<D, M, CPT, PF, SM, EV, false><<<blocks, threads, 0, ctx->stream>>>( \
-                mdl, ws.fwd, ws.bwd, ws.sf, c.y, c.mean, c.cov, c.nle, c.T, c.batch, tf, write_cov); \
+        if (SM && ckpt) { if (has_u) RXG_LAUNCH_SHARED2(SM, EV, true, true); else RXG_LAUNCH_SHARED2(SM, EV, false, true); } \
+        else            { if (has_u) RXG_LAUNCH_SHARED2(SM, EV, true, false); else RXG_LAUNCH_SHARED2(SM, EV, false, false); } \
     } while (0)
     if (ctx->profile) cudaEventRecord(ctx->ev[1], ctx->stream);
     if (c.smooth) { if (evid) RXG_LAUNCH_SHARED(true, true); else RXG_LAUNCH_SHARED(true, false); }
     else          { if (evid) RXG_LAUNCH_SHARED(false, true); else RXG_LAUNCH_SHARED(false, false); }
 #undef RXG_LAUNCH_SHARED
+#undef RXG_LAUNCH_SHARED2
     if (ctx->profile) cudaEventRecord(ctx->ev[2], ctx->stream);
     ctx->launches += 1;
     return check_cuda(ctx, cudaGetLastError(), "lgssm_shared_kernel launch");

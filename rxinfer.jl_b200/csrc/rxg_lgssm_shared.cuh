@@ -95,7 +95,7 @@ __device__ __forceinline__ void stage_tables(float* sdst, const float* __restric
     cp_async_commit();
 }
 
-template <int D, int M, int CPT, int PF, bool SMOOTH, bool EVID, bool OFFSET>
+template <int D, int M, int CPT, int PF, bool SMOOTH, bool EVID, bool OFFSET, bool CKPT>
 __global__ void __launch_bounds__(32, 16 / CPT)   // CPT=1: <= 128 regs so ~14 warps/SM stay resident; wider CPT trades warps for ILP
 lgssm_shared_kernel(const __grid_constant__ ModelF<D, M> mdl, const float* __restrict__ fwd_tab,
                     const float* __restrict__ bwd_tab, const float* __restrict__ sf_tab,
@@ -105,7 +105,12 @@ lgssm_shared_kernel(const __grid_constant__ ModelF<D, M> mdl, const float* __res
     using TB = Tab<D, M>;
     constexpr int TC = 4 * PF;                                   // table chunk, in time steps
     constexpr int REC_MAX = TB::FWD_REC > TB::BWD_REC ? TB::FWD_REC : TB::BWD_REC;
-    __shared__ __align__(16) float s_tab[2][TC * REC_MAX];
+    // CKPT (smoothing only): the forward pass keeps one filtered mean per TC-step chunk; the backward
+    // pass re-reads y and recomputes the chunk's filtered means into s_f (lane-contiguous, private
+    // to each thread), which replaces the 2 x 4d bytes/step stash by 4m bytes/step of y re-read.
+    constexpr bool CK = SMOOTH && CKPT && (D * D <= 16);   // larger states exceed the static smem budget: stash path
+    __shared__ __align__(16) float s_tab[2][TC * (CK ? (TB::FWD_REC + TB::BWD_REC) : REC_MAX)];
+    __shared__ float s_f[CK ? TC * D * CPT * 32 : 1];
 
     const int lane = threadIdx.x;
     const int64_t b0 = ((int64_t)blockIdx.x * 32 + lane) * CPT;
@@ -222,7 +227,7 @@ lgssm_shared_kernel(const __grid_constant__ ModelF<D, M> mdl, const float* __res
                 for (int i = 0; i < D; ++i) {
 #pragma unroll
                     for (int c = 0; c < CPT; ++c) mu[i][c] = nm[i][c];
-                    if (active) Pack<CPT>::st(mean + ((int64_t)t * D + i) * batch + b, mu[i]);
+                    if (active && (!CK || (t % TC) == TC - 1)) Pack<CPT>::st(mean + ((int64_t)t * D + i) * batch + b, mu[i]);
                 }
                 if (!SMOOTH && write_cov && active) {
                     float Sf[pad4(D * D)];
@@ -250,6 +255,184 @@ lgssm_shared_kernel(const __grid_constant__ ModelF<D, M> mdl, const float* __res
     }
     cp_async_wait<0>();
     if (!SMOOTH) return;
+
+    if (CK) {
+        // ------------------------------------------------------------ backward, chunk by chunk (descending)
+        const int nch = (T + TC - 1) / TC;
+        float ms[D][CPT];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) ms[i][c] = 0.f;
+        auto stage_chunk = [&](int k, int buf) {       // forward + backward records of steps [k TC, k TC + TC)
+            float* dst = s_tab[buf];
+            constexpr int PF_ = TB::FWD_REC / 4, PB_ = TB::BWD_REC / 4;
+            if (k >= 0) {
+#pragma unroll
+                for (int p = lane; p < TC * PF_; p += 32) {
+                    const int slot = p / PF_, part = p % PF_, t = k * TC + slot;
+                    if (t < T) cp_async16(dst + slot * TB::FWD_REC + part * 4, fwd_tab + (size_t)t * TB::FWD_REC + part * 4);
+                }
+#pragma unroll
+                for (int p = lane; p < TC * PB_; p += 32) {
+                    const int slot = p / PB_, part = p % PB_, t = k * TC + slot;
+                    if (t < T) cp_async16(dst + TC * TB::FWD_REC + slot * TB::BWD_REC + part * 4,
+                                          bwd_tab + (size_t)t * TB::BWD_REC + part * 4);
+                }
+            }
+            cp_async_commit();
+        };
+        // y prefetch runs over the recompute order: chunk nch-1, nch-2, ..., each ascending in t
+        auto blk_t0 = [&](int j) { return (nch - 1 - j / (TC / PF)) * TC + (j % (TC / PF)) * PF; };
+        const int nblk = nch * (TC / PF);
+        {
+            const int t0 = blk_t0(0);
+#pragma unroll
+            for (int s = 0; s < PF; ++s)
+                if (t0 + s < T)
+#pragma unroll
+                    for (int k = 0; k < M; ++k) Pack<CPT>::ld(y + ((int64_t)(t0 + s) * M + k) * batch + b, ycur[s][k]);
+        }
+        float ck[D][CPT];                      // checkpoint (filtered mean at the step before the chunk)
+        {
+            const int k = nch - 1;
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                if (k == 0) {
+#pragma unroll
+                    for (int c = 0; c < CPT; ++c) ck[i][c] = mdl.m0[i];
+                } else {
+                    Pack<CPT>::ld_rw(mean + ((int64_t)(k * TC - 1) * D + i) * batch + b, ck[i]);
+                }
+            }
+        }
+        __syncwarp();
+        stage_chunk(nch - 1, 0);
+        int j = 0;
+        for (int k = nch - 1; k >= 0; --k) {
+            const int buf = (nch - 1 - k) & 1;
+            __syncwarp();
+            stage_chunk(k - 1, buf ^ 1);
+            cp_async_wait<1>();
+            __syncwarp();
+            const float* sF = s_tab[buf];
+            const float* sB = s_tab[buf] + TC * TB::FWD_REC;
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) mu[i][c] = ck[i][c];
+            // prefetch the checkpoint of the next (earlier) chunk
+            if (k >= 1) {
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    if (k == 1) {
+#pragma unroll
+                        for (int c = 0; c < CPT; ++c) ck[i][c] = mdl.m0[i];
+                    } else {
+                        Pack<CPT>::ld_rw(mean + ((int64_t)((k - 1) * TC - 1) * D + i) * batch + b, ck[i]);
+                    }
+                }
+            }
+            // ---- recompute the filtered means of the chunk
+            for (int blk = 0; blk < TC / PF; ++blk, ++j) {
+                const int t0 = k * TC + blk * PF;
+                if (j + 1 < nblk) {
+                    const int tn = blk_t0(j + 1);
+#pragma unroll
+                    for (int s = 0; s < PF; ++s)
+                        if (tn + s < T)
+#pragma unroll
+                            for (int kk = 0; kk < M; ++kk)
+                                Pack<CPT>::ld(y + ((int64_t)(tn + s) * M + kk) * batch + b, ynxt[s][kk]);
+                }
+#pragma unroll
+                for (int s = 0; s < PF; ++s) {
+                    const int t = t0 + s;
+                    if (t < T) {
+                        const float* rec = sF + (blk * PF + s) * TB::FWD_REC;
+                        float Kt[pad4(D * M)], Ft[pad4(D * D)], gf[pad4(D)];
+                        load_smem<pad4(D * M)>(rec + TB::K_OFF, Kt);
+                        load_smem<pad4(D * D)>(rec + TB::F_OFF, Ft);
+                        if (OFFSET) load_smem<pad4(D)>(rec + TB::GF_OFF, gf);
+                        float nm[D][CPT];
+                        const bool first_no_pred = (t == 0) && !transition_first && EVID;
+#pragma unroll
+                        for (int i = 0; i < D; ++i)
+#pragma unroll
+                            for (int c = 0; c < CPT; ++c) {
+                                float a = OFFSET ? __fmaf_rn(Ft[i * D], mu[0][c], gf[i]) : Ft[i * D] * mu[0][c];
+#pragma unroll
+                                for (int jj = 1; jj < D; ++jj) a = __fmaf_rn(Ft[i * D + jj], mu[jj][c], a);
+#pragma unroll
+                                for (int kk = 0; kk < M; ++kk) a = __fmaf_rn(Kt[i * M + kk], ycur[s][kk][c], a);
+                                nm[i][c] = a;
+                            }
+                        (void)first_no_pred;
+#pragma unroll
+                        for (int i = 0; i < D; ++i)
+#pragma unroll
+                            for (int c = 0; c < CPT; ++c) {
+                                mu[i][c] = nm[i][c];
+                                s_f[(((blk * PF + s) * D + i) * CPT + c) * 32 + lane] = nm[i][c];
+                            }
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < PF; ++s)
+#pragma unroll
+                    for (int kk = 0; kk < M; ++kk)
+#pragma unroll
+                        for (int c = 0; c < CPT; ++c) ycur[s][kk][c] = ynxt[s][kk][c];
+            }
+            // ---- backward over the chunk
+#pragma unroll 4
+            for (int slot = TC - 1; slot >= 0; --slot) {
+                const int t = k * TC + slot;
+                if (t < T) {
+                    const float* rec = sB + slot * TB::BWD_REC;
+                    float Et[pad4(D * D)], Gt[pad4(D * D)], gb[pad4(D)];
+                    load_smem<pad4(D * D)>(rec + TB::E_OFF, Et);
+                    load_smem<pad4(D * D)>(rec + TB::G_OFF, Gt);
+                    if (OFFSET) load_smem<pad4(D)>(rec + TB::GB_OFF, gb);
+                    float fm[D][CPT], nm[D][CPT];
+#pragma unroll
+                    for (int i = 0; i < D; ++i)
+#pragma unroll
+                        for (int c = 0; c < CPT; ++c) fm[i][c] = s_f[((slot * D + i) * CPT + c) * 32 + lane];
+#pragma unroll
+                    for (int i = 0; i < D; ++i)
+#pragma unroll
+                        for (int c = 0; c < CPT; ++c) {
+                            float a = OFFSET ? __fmaf_rn(Et[i * D], fm[0][c], gb[i]) : Et[i * D] * fm[0][c];
+#pragma unroll
+                            for (int jj = 1; jj < D; ++jj) a = __fmaf_rn(Et[i * D + jj], fm[jj][c], a);
+#pragma unroll
+                            for (int jj = 0; jj < D; ++jj) a = __fmaf_rn(Gt[i * D + jj], ms[jj][c], a);
+                            nm[i][c] = a;
+                        }
+#pragma unroll
+                    for (int i = 0; i < D; ++i) {
+#pragma unroll
+                        for (int c = 0; c < CPT; ++c) ms[i][c] = nm[i][c];
+                        if (active) Pack<CPT>::st(mean + ((int64_t)t * D + i) * batch + b, ms[i]);
+                    }
+                    if (write_cov && active) {
+                        float Sst[pad4(D * D)];
+                        load_smem<pad4(D * D)>(rec + TB::SS_OFF, Sst);
+#pragma unroll
+                        for (int i = 0; i < D * D; ++i) {
+                            float v[CPT];
+#pragma unroll
+                            for (int c = 0; c < CPT; ++c) v[c] = Sst[i];
+                            Pack<CPT>::st(cov + ((int64_t)t * D * D + i) * batch + b, v);
+                        }
+                    }
+                }
+            }
+        }
+        cp_async_wait<0>();
+        return;
+    }
 
     // ---------------------------------------------------------------- backward (r = T-1-t ascending)
     // mu_s[t] = E_t mu_f[t] + G_t mu_s[t+1]  (rules #3', #4 backward + 3-way marginal);
