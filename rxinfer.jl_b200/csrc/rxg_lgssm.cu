@@ -393,7 +393,7 @@ static int launch_shared(rxg_ctx* ctx, const LgssmCall& c, const ModelF<D, M>& m
     bool has_u = false;
     for (int i = 0; i < D; ++i) has_u |= (mdl.u[i] != 0.f);
     // checkpoint + recompute instead of the forward->backward stash (RXG_NO_CKPT=1: A/B switch)
-    bool ckpt = c.smooth && (D * D <= 16);
+    bool ckpt = c.smooth && (D * D <= 16) && (CPT == 2);   // with one chain per thread the stash path is faster (B200: 1.85 vs 2.06 ms)
     if (const char* e = getenv("RXG_NO_CKPT")) ckpt = ckpt && atoi(e) == 0;
 #define RXG_LAUNCH_SHARED2(SM, EV, OF, CK)                                                         \
     lgssm_shared_kernel<D, M, CPT, PF, SM, EV, OF, CK><<<blocks, threads, 0, ctx->stream>>>(       \
