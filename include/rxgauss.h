@@ -233,6 +233,11 @@ int rxg_hgf_filter_f32(rxg_ctx*, int T, int64_t batch, int iters, float kappa, f
                        float z_variance, float y_variance, const float init[4], const float* y,
                        float* out, unsigned flags);
 
+/* Diagnostic: D[128][64] = A[128][128] * B[64][128]' on the tcgen05 tensor pipe (kind::tf32, 3xTF32
+ * split, TMEM accumulator), row-major device arrays.  Validates the hand-written UMMA descriptors
+ * used by the large-state family; no reference counterpart.                                     */
+int rxg_selftest_umma_f32(rxg_ctx*, const float* A, const float* B, float* D, unsigned flags);
+
 /* ------------------------------------------------------------------ multi-GPU ----------------
  * Chains are independent: rank g owns chains [g*batch/G, (g+1)*batch/G); the only collective is
  * the all-gather of posterior marginals at the end (the reference has no distributed path).

@@ -11,8 +11,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librxgauss.so")
-SOURCES = ["rxg_api.cu", "rxg_lgssm.cu", "rxg_lgssm_large.cu", "rxg_rules.cu", "rxg_hgf.cu"]
-HEADERS = ["rxg_internal.h", "rxg_linalg.cuh", "rxg_gain.cuh", "rxg_lgssm_common.cuh", "rxg_lgssm_shared.cuh", os.path.join("..", "..", "include", "rxgauss.h")]
+SOURCES = ["rxg_api.cu", "rxg_lgssm.cu", "rxg_lgssm_large.cu", "rxg_umma_sweep.cu", "rxg_rules.cu", "rxg_hgf.cu"]
+HEADERS = ["rxg_internal.h", "rxg_linalg.cuh", "rxg_gain.cuh", "rxg_lgssm_common.cuh", "rxg_lgssm_shared.cuh", "rxg_umma.cuh", os.path.join("..", "..", "include", "rxgauss.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

@@ -289,6 +289,13 @@ class Context:
                                                      _fp(mz), _fp(vz), L.PTR_DEVICE))
         return mz, vz
 
+    def selftest_umma(self, A, B):
+        """D[128, 64] = A[128, 128] @ B[64, 128].T on the tcgen05 tensor pipe (3xTF32)."""
+        self._dev(A, B)
+        D = self.empty(128, 64)
+        self._check(self.lib.rxg_selftest_umma_f32(self.h, _fp(A), _fp(B), _fp(D), L.PTR_DEVICE))
+        return D
+
     # ------------------------------------------------------------------ multi-GPU
     def comm_init(self, nranks, rank, uid: bytes):
         buf = ctypes.create_string_buffer(uid, 128)
