@@ -14,7 +14,10 @@
 // matrix products run on the FP32 pipe (a tcgen05 variant of the sweep GEMM is the follow-up).
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "rxg_internal.h"
+#include "rxg_umma.cuh"
 
 namespace rxg {
 
@@ -119,6 +122,7 @@ struct LargeWs {
     float *ss, *sf;                          // [T][D*D] smoothed / filtered covariance (fp32)
     int* flag;
     int b_identity;                          // B == I: skip the two B products
+    float *fwdU, *bwdU;                      // d = 64 only: [T][2][64 x 128] tf32 hi/lo gain blocks in UMMA canonical layout (or null)
 };
 
 template <int D> struct LD_ { static constexpr int v = D + 1; };   // padded leading dim: no bank conflicts on transposed reads
@@ -216,6 +220,19 @@ __global__ void __launch_bounds__(256) large_gain_tables(LargeWs w, int T, int t
     btrsm_lower_t<M, D, LD>(X2, X1);                   // X1 = K' (M x D): K(r, k) = X1[k][r]
     float* ft = w.fwdT + (size_t)t * (D + M) * D;
     const bool pred = (t > 0) || transition_first;
+    // d = 64: additionally emit W[r][k] (r = state row, k over the stacked K axis) split into tf32 hi / lo parts
+    // in the canonical K-major UMMA layout (rxg_umma.cuh) for lgssm_umma_sweep
+    auto emit_umma = [&](float* rec, const float* srcT, int K2) {        // srcT[k][r] (the transposed fp32 block)
+        if (!rec) return;
+        for (int idx = threadIdx.x; idx < D * K2; idx += blockDim.x) {
+            const int k = idx / D, r = idx % D;
+            float hi, lo;
+            umma::split_tf32(srcT[k * D + r], hi, lo);
+            const uint32_t off = umma::elem_off(r, k, 128) / 4;
+            rec[off] = hi;
+            rec[D * 128 + off] = lo;
+        }
+    };
     // F = A - K (B A)   (or I - K B at t = 0 without a leading transition); stored transposed: ft[k][r] = F(r, k)
     if (pred) {
         bgemm<D, D, M>([&](int r, int k) { return X1[k * LD + r]; }, [&](int k, int j) { return w.BA[k * D + j]; },
@@ -230,6 +247,7 @@ __global__ void __launch_bounds__(256) large_gain_tables(LargeWs w, int T, int t
     }
     for (int i = threadIdx.x; i < D * D; i += blockDim.x) w.sf[(size_t)t * D * D + i] = (float)Sf[i];
     __syncthreads();
+    if (D == 64 && M == 64 && w.fwdU) emit_umma(w.fwdU + (size_t)t * 2 * D * 128, ft, D + M);
     // ---- backward gain
     float* bt = w.bwdT + (size_t)t * 2 * D * D;
     if (t == T - 1) {
@@ -238,6 +256,8 @@ __global__ void __launch_bounds__(256) large_gain_tables(LargeWs w, int T, int t
             bt[k * D + r] = (k == r) ? 1.f : 0.f;
             bt[(D + k) * D + r] = 0.f;
         }
+        __syncthreads();
+        if (D == 64 && M == 64 && w.bwdU) emit_umma(w.bwdU + (size_t)t * 2 * D * 128, bt, 2 * D);
         return;
     }
     const double* Sp1 = w.Sp + (size_t)(t + 1) * D * D;
@@ -261,6 +281,8 @@ __global__ void __launch_bounds__(256) large_gain_tables(LargeWs w, int T, int t
     // E = I - G A: E(r, j) = delta - sum_k G(r,k) A(k,j); stored transposed bt[j][r]
     bgemm<D, D, D>([&](int r, int k) { return X0[k * LD + r]; }, [&](int k, int j) { return As[k * LD + j]; },
                    [&](int r, int j, double v) { bt[j * D + r] = (float)((r == j ? 1.0 : 0.0) - v); });
+    __syncthreads();
+    if (D == 64 && M == 64 && w.bwdU) emit_umma(w.bwdU + (size_t)t * 2 * D * 128, bt, 2 * D);
 }
 
 // Phase 3: smoothed covariances, sequential in t, one CTA:  Ss[t] = C[t] + G[t] Ss[t+1] G[t]'.
@@ -442,6 +464,8 @@ static int run_large(rxg_ctx* ctx, const LgssmCall& c) {
     const size_t o_S0 = carve(DD * 8), o_BA = carve((size_t)M * D * 8);
     const size_t o_Sp = carve(T * DD * 8), o_Sf = carve(T * DD * 8), o_Cc = carve(T * DD * 8), o_Gd = carve(T * DD * 8);
     const size_t o_fw = carve(T * (D + M) * D * 4), o_bw = carve(T * 2 * DD * 4), o_ss = carve(T * DD * 4), o_sf = carve(T * DD * 4);
+    const bool use_umma = (D == 64 && M == 64) && !(getenv("RXG_NO_UMMA") && atoi(getenv("RXG_NO_UMMA")) != 0);
+    const size_t o_fu = carve(use_umma ? T * 2 * 64 * 128 * 4 : 0), o_bu = carve(use_umma ? T * 2 * 64 * 128 * 4 : 0);
     const size_t o_flag = carve(4);
     char* base = (char*)workspace(ctx, off);
     if (!base) return RXG_ERR_CUDA;
@@ -466,6 +490,8 @@ static int run_large(rxg_ctx* ctx, const LgssmCall& c) {
     w.Sp = (double*)(base + o_Sp); w.Sf = (double*)(base + o_Sf); w.Cc = (double*)(base + o_Cc); w.Gd = (double*)(base + o_Gd);
     w.fwdT = (float*)(base + o_fw); w.bwdT = (float*)(base + o_bw); w.ss = (float*)(base + o_ss); w.sf = (float*)(base + o_sf);
     w.flag = (int*)(base + o_flag);
+    w.fwdU = use_umma ? (float*)(base + o_fu) : nullptr;
+    w.bwdU = use_umma ? (float*)(base + o_bu) : nullptr;
     w.b_identity = (M == D) ? 1 : 0;
     for (int i = 0; i < M * D && w.b_identity; ++i) w.b_identity = (c.B[i] == ((i / D == i % D) ? 1.f : 0.f));
     const int tf = (c.flags & RXG_TRANSITION_FIRST) ? 1 : 0;
@@ -495,12 +521,18 @@ static int run_large(rxg_ctx* ctx, const LgssmCall& c) {
     }
     const unsigned blocks = (unsigned)((c.batch + NB - 1) / NB);
     if (ctx->profile) cudaEventRecord(ctx->ev[1], ctx->stream);
-    if (c.smooth) lgssm_block_sweep<D, M, NB, true><<<blocks, (D / 4) * (NB / 2), smw, ctx->stream>>>(w.fwdT, w.bwdT, dm0, c.y, c.mean, c.T, c.batch);
-    else          lgssm_block_sweep<D, M, NB, false><<<blocks, (D / 4) * (NB / 2), smw, ctx->stream>>>(w.fwdT, w.bwdT, dm0, c.y, c.mean, c.T, c.batch);
+    if (use_umma) {
+        // tensor-pipe sweep (tcgen05 kind::tf32, 3xTF32): 128 chains per CTA
+        rc = launch_umma_sweep(ctx, c.smooth, w.fwdU, w.bwdU, dm0, c.y, c.mean, c.T, c.batch);
+        if (rc != RXG_OK) return rc;
+    } else {
+        if (c.smooth) lgssm_block_sweep<D, M, NB, true><<<blocks, (D / 4) * (NB / 2), smw, ctx->stream>>>(w.fwdT, w.bwdT, dm0, c.y, c.mean, c.T, c.batch);
+        else          lgssm_block_sweep<D, M, NB, false><<<blocks, (D / 4) * (NB / 2), smw, ctx->stream>>>(w.fwdT, w.bwdT, dm0, c.y, c.mean, c.T, c.batch);
+        ctx->launches += 1;
+        rc = check_cuda(ctx, cudaGetLastError(), "lgssm_block_sweep");
+        if (rc != RXG_OK) return rc;
+    }
     if (ctx->profile) cudaEventRecord(ctx->ev[2], ctx->stream);
-    ctx->launches += 1;
-    rc = check_cuda(ctx, cudaGetLastError(), "lgssm_block_sweep");
-    if (rc != RXG_OK) return rc;
     if (c.cov) {
         const float* tab = c.smooth ? w.ss : w.sf;
         if (c.flags & RXG_COV_SHARED_OUT) {
