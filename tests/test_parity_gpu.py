@@ -188,7 +188,7 @@ def test_unsupported_shape_errors_loudly(rx, ctx):
     assert e.value.code == rx._lib.RXG_ERR_UNSUPPORTED
 
 
-def test_full_size_properties(ctx):
+def test_full_size_properties(ctx, monkeypatch):
     """BASELINE.json configs[1] (d = 4, T = 1000, batch = 65 536): size-independent properties.
     (1) chains are independent: a slice re-run alone is bit-identical; (2) linearity of the
     posterior mean in (y, m0); (3) two chains fed the same series agree bit-exactly; (4) a sample
@@ -202,7 +202,9 @@ def test_full_size_properties(ctx):
     r = ctx.lgssm(y, **_kw(mod), smooth=True, want_evidence=True)
     mean, cov = r["mean"], r["cov"]
     assert torch.equal(mean[:, :, 0], mean[:, :, 1])                                   # (3)
+    monkeypatch.setenv("RXG_FORCE_CPT", "2")     # same kernel variant as the full batch (2 chains / thread, checkpoint mode)
     sub = ctx.lgssm(y[:, :, 4096:4096 + 512].contiguous(), **_kw(mod), smooth=True, want_evidence=True)
+    monkeypatch.delenv("RXG_FORCE_CPT")
     assert torch.equal(sub["mean"], mean[:, :, 4096:4096 + 512])                       # (1)
     r2 = ctx.lgssm((2.0 * y).contiguous(), A=mod["A"], B=mod["B"], P=mod["P"], Q=mod["Q"], m0=2.0 * mod["m0"],
                    S0=mod["S0"], smooth=True)
