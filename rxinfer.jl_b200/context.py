@@ -301,11 +301,14 @@ class Context:
         buf = ctypes.create_string_buffer(uid, 128)
         self._check(self.lib.rxg_comm_init(self.h, nranks, rank, ctypes.cast(buf, c_void_p)))
 
-    def allgather_posteriors(self, mean, cov, nranks):
+    def allgather_posteriors(self, mean, cov, nranks, out_mean=None, out_cov=None):
+        """Rank-major gathered slabs ([G, T, d, b], [G, T, d, d, b]); pass out_* to reuse buffers."""
         self._dev(mean, cov)
         T, d, bl = mean.shape
-        gm = self.empty(nranks, T, d, bl)
-        gc = self.empty(nranks, T, d, d, bl) if cov is not None else None
+        gm = out_mean if out_mean is not None else self.empty(nranks, T, d, bl)
+        gc = None
+        if cov is not None:
+            gc = out_cov if out_cov is not None else self.empty(nranks, T, d, d, bl)
         self._check(self.lib.rxg_allgather_posteriors(self.h, d, T, bl, _fp(mean), _fp(cov), _fp(gm), _fp(gc), L.PTR_DEVICE))
         return gm, gc
 
