@@ -127,7 +127,7 @@ def cpu_baseline(seconds_target=12.0, chunk=2048):
                       f"(oracle/c/rxg_oracle.c), OpenMP over chains, {el:.1f} s"}
 
 
-def run_reference_arm(args, rank, world):
+def run_reference_arm(args, rank, world, emit=lambda o: print(json.dumps(o))):
     """--impl reference: the reference's CPU path = the fp64 C port (the Julia reference cannot be
     installed: no julia, no registry packages).  Rank 0 only."""
     if rank != 0:
@@ -146,7 +146,7 @@ def run_reference_arm(args, rank, world):
     el = time.perf_counter() - t0
     val = MSG_PER_STEP * T * chunk * args.steps / el
     sample = f"{chunk} chains x T={T} per step (1/{BATCH // chunk} of the GPU arm's per-GPU batch), fp64, OpenMP x{cores}"
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "messages/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -159,6 +159,14 @@ def run_reference_arm(args, rank, world):
 
 
 def main():
+    # keep stdout clean for the ONE JSON line: libraries (NCCL's version banner, torchrun notes) print to
+    # fd 1 as well, so everything else is routed to stderr and the result goes to the saved descriptor
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -175,7 +183,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference_arm(args, rank, world)
+        run_reference_arm(args, rank, world, emit)
         return
 
     import torch
@@ -338,7 +346,7 @@ def main():
             out["allgather"] = allgather
         if not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
