@@ -255,6 +255,8 @@ __global__ void __launch_bounds__(256) large_gain_tables(LargeWs w, int T, int t
             const int k = idx / D, r = idx % D;
             bt[k * D + r] = (k == r) ? 1.f : 0.f;
             bt[(D + k) * D + r] = 0.f;
+            w.Gd[(size_t)t * D * D + idx] = 0.0;                 // suffix-scan element of the last step: (0, Sf)
+            w.Cc[(size_t)t * D * D + idx] = Sf[idx];
         }
         __syncthreads();
         if (D == 64 && M == 64 && w.bwdU) emit_umma(w.bwdU + (size_t)t * 2 * D * 128, bt, 2 * D);
@@ -312,6 +314,214 @@ __global__ void __launch_bounds__(256) large_smooth_seq(LargeWs w, int T) {
         __syncthreads();
         for (int i = threadIdx.x; i < D * D; i += blockDim.x) w.ss[(size_t)t * D * D + i] = (float)S[(i / D) * LD + i % D];
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Time-parallel replacement of the two sequential phases (RXG_LARGE_SEQ=1 keeps the sequential ones).
+//
+// Forward, by DOUBLING: the model is time invariant, so the covariance parts (A, C, J) of the
+// filtering scan element (Sarkka & Garcia-Fernandez 2021) are the same "gen" for every step >= 1.
+// With G_r = gen (x) ... (x) gen (2^r factors) the filtered covariances satisfy
+//     Sigma_f[k] = C( P[k - 2^r] (x) G_r ),   2^r <= k < 2^(r+1),      G_(r+1) = G_r (x) G_r,
+// i.e. round r applies 2^r Riccati steps at once to 2^r already-known covariances, one CTA each:
+// ceil(log2 T) launches instead of T dependent steps.  Prefixes have A = 0, J = 0, so only
+//     C_new = A_G (I + C_i J_G)^-1 C_i A_G' + C_G
+// is needed; with C_i = L L' and I + L' J_G L = R R' this is Z' Z + C_G, Z = R^-1 L' A_G'
+// (two Cholesky factorisations, one triangular solve, four products; symmetric PSD by construction).
+// ------------------------------------------------------------------------------------------------
+struct ScanG { double *A, *C, *J; };
+
+template <int D, int LD>
+__device__ __forceinline__ void load_mat(double* dst, const double* src) {
+    for (int i = threadIdx.x; i < D * D; i += blockDim.x) dst[(i / D) * LD + i % D] = src[i];
+}
+
+// first element (C_0 -> Sf[0]) and the generic element gen -> G0
+template <int D, int M>
+__global__ void __launch_bounds__(256) large_fwd_init(LargeWs w, ScanG g0, int transition_first) {
+    constexpr int LD = LD_<D>::v;
+    extern __shared__ double sm[];
+    double* X0 = sm; double* X1 = X0 + D * LD; double* X2 = X1 + D * LD; double* X3 = X2 + D * LD;
+    if (blockIdx.x == 0) {
+        // S' = S0 (or A S0 A' + P); C_0 = S' - W' W, W = L^-1 B S', L L' = B S' B' + Q
+        load_mat<D, LD>(X0, w.S0);
+        __syncthreads();
+        if (transition_first) {
+            bgemm<D, D, D>([&](int i, int k) { return w.A[i * D + k]; }, [&](int k, int j) { return X0[k * LD + j]; },
+                           [&](int i, int j, double v) { X1[i * LD + j] = v; });
+            __syncthreads();
+            bgemm<D, D, D>([&](int i, int k) { return X1[i * LD + k]; }, [&](int k, int j) { return w.A[j * D + k]; },
+                           [&](int i, int j, double v) { X0[i * LD + j] = v + w.P[i * D + j]; });
+            __syncthreads();
+        }
+        bgemm<M, D, D>([&](int i, int k) { return w.B[i * D + k]; }, [&](int k, int j) { return X0[k * LD + j]; },
+                       [&](int i, int j, double v) { X1[i * LD + j] = v; });
+        __syncthreads();
+        bgemm<M, M, D>([&](int i, int k) { return X1[i * LD + k]; }, [&](int k, int j) { return w.B[j * D + k]; },
+                       [&](int i, int j, double v) { X2[i * LD + j] = v + w.Q[i * M + j]; });
+        bchol<M, LD>(X2, w.flag);
+        btrsm_lower<M, D, LD>(X2, X1);
+        bgemm<D, D, M>([&](int i, int k) { return X1[k * LD + i]; }, [&](int k, int j) { return X1[k * LD + j]; },
+                       [&](int i, int j, double v) { w.Sf[i * D + j] = X0[i * LD + j] - v; });
+    } else {
+        // gen: L L' = B P B' + Q; W1 = L^-1 B P, W2 = L^-1 B, W3 = L^-1 B A
+        //      A_gen = (I - W1' W2) A,  C_gen = P - W1' W1,  J_gen = W3' W3
+        bgemm<M, D, D>([&](int i, int k) { return w.B[i * D + k]; }, [&](int k, int j) { return w.P[k * D + j]; },
+                       [&](int i, int j, double v) { X0[i * LD + j] = v; });              // B P
+        __syncthreads();
+        bgemm<M, M, D>([&](int i, int k) { return X0[i * LD + k]; }, [&](int k, int j) { return w.B[j * D + k]; },
+                       [&](int i, int j, double v) { X3[i * LD + j] = v + w.Q[i * M + j]; });
+        for (int i = threadIdx.x; i < M * D; i += blockDim.x) {
+            X1[(i / D) * LD + i % D] = w.B[i];
+            X2[(i / D) * LD + i % D] = w.BA[i];
+        }
+        bchol<M, LD>(X3, w.flag);
+        btrsm_lower<M, D, LD>(X3, X0);     // W1
+        btrsm_lower<M, D, LD>(X3, X1);     // W2
+        btrsm_lower<M, D, LD>(X3, X2);     // W3
+        bgemm<D, D, M>([&](int i, int k) { return X0[k * LD + i]; }, [&](int k, int j) { return X0[k * LD + j]; },
+                       [&](int i, int j, double v) { g0.C[i * D + j] = w.P[i * D + j] - v; });
+        bgemm<D, D, M>([&](int i, int k) { return X2[k * LD + i]; }, [&](int k, int j) { return X2[k * LD + j]; },
+                       [&](int i, int j, double v) { g0.J[i * D + j] = v; });
+        // X3 <- I - W1' W2 (the Cholesky factor is no longer needed)
+        __syncthreads();
+        bgemm<D, D, M>([&](int i, int k) { return X0[k * LD + i]; }, [&](int k, int j) { return X1[k * LD + j]; },
+                       [&](int i, int j, double v) { X3[i * LD + j] = (i == j ? 1.0 : 0.0) - v; });
+        __syncthreads();
+        bgemm<D, D, D>([&](int i, int k) { return X3[i * LD + k]; }, [&](int k, int j) { return w.A[k * D + j]; },
+                       [&](int i, int j, double v) { g0.A[i * D + j] = v; });
+    }
+}
+
+// shared core of a combine: given C_i (in X0) and J_j (staged in X2), leaves
+//   X0 = L (lower Cholesky factor of C_i),  X1 = Y = R^-1 L'  with R R' = I + L' J_j L
+template <int D, int LD>
+__device__ __forceinline__ void combine_core(double* X0, double* X1, double* X2, int* flag) {
+    bchol<D, LD>(X0, flag);
+    auto Lf = [&](int i, int k) { return k <= i ? X0[i * LD + k] : 0.0; };
+    bgemm<D, D, D>([&](int i, int k) { return X2[i * LD + k]; }, [&](int k, int j) { return Lf(k, j); },
+                   [&](int i, int j, double v) { X1[i * LD + j] = v; });                 // J L
+    __syncthreads();
+    bgemm<D, D, D>([&](int i, int k) { return Lf(k, i); }, [&](int k, int j) { return X1[k * LD + j]; },
+                   [&](int i, int j, double v) { X2[i * LD + j] = v + (i == j ? 1.0 : 0.0); });   // I + L' J L
+    bchol<D, LD>(X2, flag);
+    for (int idx = threadIdx.x; idx < D * D; idx += blockDim.x) {
+        const int i = idx / D, j = idx % D;
+        X1[i * LD + j] = Lf(j, i);                                                       // L'
+    }
+    __syncthreads();
+    btrsm_lower<D, D, LD>(X2, X1);                                                       // Y = R^-1 L'
+}
+
+// round r: CTAs 0 .. n-1 advance prefixes by 2^r steps; the last CTA squares G
+template <int D>
+__global__ void __launch_bounds__(256) large_fwd_doubling(LargeWs w, ScanG gc, ScanG gn, int r, int T) {
+    constexpr int LD = LD_<D>::v;
+    extern __shared__ double sm[];
+    double* X0 = sm; double* X1 = X0 + D * LD; double* X2 = X1 + D * LD; double* X3 = X2 + D * LD;
+    const int step = 1 << r;
+    const int n = min(step, T - step);           // prefixes produced this round: k = step .. step + n - 1
+    if ((int)blockIdx.x < n) {
+        const int k = step + blockIdx.x, i = k - step;
+        load_mat<D, LD>(X0, w.Sf + (size_t)i * D * D);
+        load_mat<D, LD>(X2, gc.J);
+        load_mat<D, LD>(X3, gc.A);
+        combine_core<D, LD>(X0, X1, X2, w.flag);
+        // Z = Y A_G' ; Sf[k] = Z' Z + C_G
+        bgemm<D, D, D>([&](int a, int kk) { return X1[a * LD + kk]; }, [&](int kk, int b) { return X3[b * LD + kk]; },
+                       [&](int a, int b, double v) { X0[a * LD + b] = v; });
+        __syncthreads();
+        bgemm<D, D, D>([&](int a, int kk) { return X0[kk * LD + a]; }, [&](int kk, int b) { return X0[kk * LD + b]; },
+                       [&](int a, int b, double v) { w.Sf[(size_t)k * D * D + a * D + b] = v + gc.C[a * D + b]; });
+    } else {
+        // G_next = G (x) G (full combine):  X2m = Y' Y = (I + C J)^-1 C;  X1m = A - X2m (J A);
+        //   A_n = A X1m;  C_n = A X2m A' + C = Z' Z + C (Z = Y A');  J_n = sym(A' J X1m) + J
+        double* X4 = X3 + D * LD; double* X5 = X4 + D * LD;
+        load_mat<D, LD>(X0, gc.C);
+        load_mat<D, LD>(X2, gc.J);
+        load_mat<D, LD>(X3, gc.A);
+        combine_core<D, LD>(X0, X1, X2, w.flag);                                          // X1 = Y
+        bgemm<D, D, D>([&](int a, int kk) { return X1[kk * LD + a]; }, [&](int kk, int b) { return X1[kk * LD + b]; },
+                       [&](int a, int b, double v) { X4[a * LD + b] = v; });              // X4 = X2m
+        bgemm<D, D, D>([&](int a, int kk) { return gc.J[a * D + kk]; }, [&](int kk, int b) { return X3[kk * LD + b]; },
+                       [&](int a, int b, double v) { X5[a * LD + b] = v; });              // X5 = J A
+        __syncthreads();
+        bgemm<D, D, D>([&](int a, int kk) { return X4[a * LD + kk]; }, [&](int kk, int b) { return X5[kk * LD + b]; },
+                       [&](int a, int b, double v) { X0[a * LD + b] = X3[a * LD + b] - v; });   // X0 = X1m
+        bgemm<D, D, D>([&](int a, int kk) { return X1[a * LD + kk]; }, [&](int kk, int b) { return X3[b * LD + kk]; },
+                       [&](int a, int b, double v) { X2[a * LD + b] = v; });              // X2 = Z = Y A'
+        __syncthreads();
+        bgemm<D, D, D>([&](int a, int kk) { return X3[a * LD + kk]; }, [&](int kk, int b) { return X0[kk * LD + b]; },
+                       [&](int a, int b, double v) { gn.A[a * D + b] = v; });
+        bgemm<D, D, D>([&](int a, int kk) { return X2[kk * LD + a]; }, [&](int kk, int b) { return X2[kk * LD + b]; },
+                       [&](int a, int b, double v) { gn.C[a * D + b] = v + gc.C[a * D + b]; });
+        bgemm<D, D, D>([&](int a, int kk) { return gc.J[a * D + kk]; }, [&](int kk, int b) { return X0[kk * LD + b]; },
+                       [&](int a, int b, double v) { X5[a * LD + b] = v; });              // X5 = J X1m
+        __syncthreads();
+        bgemm<D, D, D>([&](int a, int kk) { return X3[kk * LD + a]; }, [&](int kk, int b) { return X5[kk * LD + b]; },
+                       [&](int a, int b, double v) { X4[a * LD + b] = v; });              // A' J X1m
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < D * D; idx += blockDim.x) {
+            const int a = idx / D, b = idx % D;
+            gn.J[idx] = 0.5 * (X4[a * LD + b] + X4[b * LD + a]) + gc.J[idx];
+        }
+    }
+}
+
+// predicted covariances from the filtered ones (parallel over t): Sp[t] = A Sf[t-1] A' + P
+template <int D>
+__global__ void __launch_bounds__(256) large_predict(LargeWs w, int T, int transition_first) {
+    constexpr int LD = LD_<D>::v;
+    extern __shared__ double sm[];
+    double* X0 = sm; double* X1 = X0 + D * LD;
+    const int t = blockIdx.x;
+    double* out = w.Sp + (size_t)t * D * D;
+    if (t == 0 && !transition_first) {
+        for (int i = threadIdx.x; i < D * D; i += blockDim.x) out[i] = w.S0[i];
+        return;
+    }
+    load_mat<D, LD>(X0, t == 0 ? w.S0 : w.Sf + (size_t)(t - 1) * D * D);
+    __syncthreads();
+    bgemm<D, D, D>([&](int i, int k) { return w.A[i * D + k]; }, [&](int k, int j) { return X0[k * LD + j]; },
+                   [&](int i, int j, double v) { X1[i * LD + j] = v; });
+    __syncthreads();
+    bgemm<D, D, D>([&](int i, int k) { return X1[i * LD + k]; }, [&](int k, int j) { return w.A[j * D + k]; },
+                   [&](int i, int j, double v) { out[i * D + j] = v + w.P[i * D + j]; });
+}
+
+// backward Hillis-Steele round over the suffix elements (E, L): new[t] = old[t] (x) old[t + off]
+template <int D>
+__global__ void __launch_bounds__(256)
+large_bwd_scan_round(const double* __restrict__ Es, const double* __restrict__ Ls, double* __restrict__ Ed,
+                     double* __restrict__ Ld, float* __restrict__ ss_out, int off, int T) {
+    constexpr int LD = LD_<D>::v;
+    extern __shared__ double sm[];
+    double* X0 = sm; double* X1 = X0 + D * LD; double* X2 = X1 + D * LD;
+    const int t = blockIdx.x;
+    const size_t o = (size_t)t * D * D;
+    if (t + off >= T) {
+        for (int i = threadIdx.x; i < D * D; i += blockDim.x) {
+            const double l = Ls[o + i];
+            Ed[o + i] = Es[o + i]; Ld[o + i] = l;
+            if (ss_out) ss_out[o + i] = (float)l;
+        }
+        return;
+    }
+    const size_t o2 = (size_t)(t + off) * D * D;
+    load_mat<D, LD>(X0, Es + o);
+    load_mat<D, LD>(X1, Ls + o2);
+    __syncthreads();
+    bgemm<D, D, D>([&](int i, int k) { return X0[i * LD + k]; }, [&](int k, int j) { return X1[k * LD + j]; },
+                   [&](int i, int j, double v) { X2[i * LD + j] = v; });                   // E_t L_late
+    __syncthreads();
+    bgemm<D, D, D>([&](int i, int k) { return X2[i * LD + k]; }, [&](int k, int j) { return X0[j * LD + k]; },
+                   [&](int i, int j, double v) {
+                       const double l = v + Ls[o + i * D + j];
+                       Ld[o + i * D + j] = l;
+                       if (ss_out) ss_out[o + i * D + j] = (float)l;
+                   });
+    bgemm<D, D, D>([&](int i, int k) { return X0[i * LD + k]; }, [&](int k, int j) { return Es[o2 + k * D + j]; },
+                   [&](int i, int j, double v) { Ed[o + i * D + j] = v; });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -466,6 +676,8 @@ static int run_large(rxg_ctx* ctx, const LgssmCall& c) {
     const size_t o_fw = carve(T * (D + M) * D * 4), o_bw = carve(T * 2 * DD * 4), o_ss = carve(T * DD * 4), o_sf = carve(T * DD * 4);
     const bool use_umma = (D == 64 && M == 64) && !(getenv("RXG_NO_UMMA") && atoi(getenv("RXG_NO_UMMA")) != 0);
     const size_t o_fu = carve(use_umma ? T * 2 * 64 * 128 * 4 : 0), o_bu = carve(use_umma ? T * 2 * 64 * 128 * 4 : 0);
+    const size_t o_scan = carve(6 * DD * 8);                                  // G_r ping-pong (A, C, J) x 2
+    const size_t o_E2 = carve(T * DD * 8), o_L2 = carve(T * DD * 8);           // backward scan ping-pong
     const size_t o_flag = carve(4);
     char* base = (char*)workspace(ctx, off);
     if (!base) return RXG_ERR_CUDA;
@@ -503,11 +715,61 @@ static int run_large(rxg_ctx* ctx, const LgssmCall& c) {
         RXG_CUDA(ctx, cudaFuncSetAttribute(large_gain_tables<D, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
         RXG_CUDA(ctx, cudaFuncSetAttribute(large_smooth_seq<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
     }
+    const size_t sm4 = (size_t)4 * D * LD * 8, sm6 = (size_t)6 * D * LD * 8;
+    static bool attr2_done = false;
+    if (!attr2_done) {
+        RXG_CUDA(ctx, cudaFuncSetAttribute(large_fwd_init<D, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4));
+        RXG_CUDA(ctx, cudaFuncSetAttribute(large_fwd_doubling<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm6));
+        RXG_CUDA(ctx, cudaFuncSetAttribute(large_predict<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+        RXG_CUDA(ctx, cudaFuncSetAttribute(large_bwd_scan_round<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+        attr2_done = true;
+    }
+    const bool seq = getenv("RXG_LARGE_SEQ") && atoi(getenv("RXG_LARGE_SEQ")) != 0;
     if (ctx->profile) cudaEventRecord(ctx->ev[0], ctx->stream);
-    large_riccati_seq<D, M><<<1, 256, sm3, ctx->stream>>>(w, c.T, tf);
+    if (seq) {
+        large_riccati_seq<D, M><<<1, 256, sm3, ctx->stream>>>(w, c.T, tf);
+        ctx->launches += 1;
+    } else {
+        // forward by doubling: ceil(log2 T) rounds, round r advances 2^r prefixes by 2^r steps
+        double* gb = (double*)(base + o_scan);
+        ScanG g[2] = {{gb, gb + DD, gb + 2 * DD}, {gb + 3 * DD, gb + 4 * DD, gb + 5 * DD}};
+        large_fwd_init<D, M><<<2, 256, sm4, ctx->stream>>>(w, g[0], tf);
+        ctx->launches += 1;
+        int cur = 0;
+        for (int r = 0; (1 << r) < c.T; ++r) {
+            const int step = 1 << r;
+            const int n = step < c.T - step ? step : c.T - step;
+            large_fwd_doubling<D><<<n + 1, 256, sm6, ctx->stream>>>(w, g[cur], g[cur ^ 1], r, c.T);
+            ctx->launches += 1;
+            cur ^= 1;
+        }
+        large_predict<D><<<c.T, 256, sm2, ctx->stream>>>(w, c.T, tf);
+        ctx->launches += 1;
+    }
     large_gain_tables<D, M><<<c.T, 256, sm3, ctx->stream>>>(w, c.T, tf);
-    ctx->launches += 2;
-    if (c.smooth) { large_smooth_seq<D><<<1, 256, sm2, ctx->stream>>>(w, c.T); ctx->launches += 1; }
+    ctx->launches += 1;
+    if (c.smooth) {
+        if (seq) {
+            large_smooth_seq<D><<<1, 256, sm2, ctx->stream>>>(w, c.T);
+            ctx->launches += 1;
+        } else {
+            // backward suffix scan over (E, L) = (G_t, C_t): ceil(log2 T) Hillis-Steele rounds, one CTA per step
+            double* Eb[2] = {w.Gd, (double*)(base + o_E2)};
+            double* Lb[2] = {w.Cc, (double*)(base + o_L2)};
+            int cur = 0, nr = 0;
+            for (int off = 1; off < c.T; off <<= 1) ++nr;
+            if (nr == 0) {      // T == 1
+                large_bwd_scan_round<D><<<c.T, 256, sm2, ctx->stream>>>(Eb[0], Lb[0], Eb[1], Lb[1], w.ss, c.T, c.T);
+                ctx->launches += 1;
+            }
+            for (int off = 1, i = 0; off < c.T; off <<= 1, ++i) {
+                large_bwd_scan_round<D><<<c.T, 256, sm2, ctx->stream>>>(Eb[cur], Lb[cur], Eb[cur ^ 1], Lb[cur ^ 1],
+                                                                        (i == nr - 1) ? w.ss : nullptr, off, c.T);
+                ctx->launches += 1;
+                cur ^= 1;
+            }
+        }
+    }
     int rc = check_cuda(ctx, cudaGetLastError(), "large gain kernels");
     if (rc != RXG_OK) return rc;
 

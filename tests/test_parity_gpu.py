@@ -332,3 +332,22 @@ def test_large_state_unsupported_options_fail_loudly(rx, ctx):
     with pytest.raises(rx.RxGaussError) as e:
         ctx.lgssm(y, **_kw(mod), smooth=True, want_evidence=True)
     assert e.value.code == rx._lib.RXG_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("d,T", [(16, 1), (16, 2), (16, 37), (32, 130), (64, 257)])
+def test_large_state_doubling_vs_sequential(ctx, monkeypatch, d, T):
+    """Large-state gain tables: forward by doubling + backward suffix scan (default) must agree with the
+    sequential Riccati kernels (RXG_LARGE_SEQ=1) and the oracle, including T = 1, 2 and non powers of two."""
+    mod = f32_model(lgssm.dense_model(d, seed=11))
+    _, y = lgssm.generate_data(mod, T, 8, seed=47)
+    yd = dev(y)
+    monkeypatch.setenv("RXG_LARGE_SEQ", "0")
+    a = ctx.lgssm(yd, **_kw(mod), smooth=True)
+    fa = ctx.lgssm(yd, **_kw(mod), smooth=False, transition_first=True)
+    monkeypatch.setenv("RXG_LARGE_SEQ", "1")
+    b = ctx.lgssm(yd, **_kw(mod), smooth=True)
+    fb = ctx.lgssm(yd, **_kw(mod), smooth=False, transition_first=True)
+    for k in ("mean", "cov"):
+        assert rel_l2(a[k].cpu().numpy(), b[k].cpu().numpy()) < 2e-6
+        assert rel_l2(fa[k].cpu().numpy(), fb[k].cpu().numpy()) < 2e-6
+    check(a, lgssm.smooth_reference_schedule(y, **mod), nle=False)
