@@ -269,19 +269,25 @@ def main():
                      "value_with_allgather": msgs / ((ms_per_step + gms) * 1e-3)}
         # spot check of the gathered layout: slab r must equal what rank r computed (rank 0's own slab here)
         assert torch.equal(gm[rank], mean) and torch.equal(gc[rank][:8], cov[:8])
-        del gc
-        # shared model => the covariances are identical on every rank: gathering the means alone is enough
-        ctx.allgather_posteriors(mean, None, world, out_mean=gm)
+        # shared model => the covariances do not depend on the chain (nor on the rank): gather the means over
+        # NVLink and replicate the covariance slabs locally (RXG_COV_REPLICATE) -- same gathered buffers,
+        # bit-identical contents, 1/5 of the NVLink traffic
+        ref_rows = [gc[r][:4].clone() for r in range(world)]
+        gc.zero_(); gm.zero_()
+        ctx.allgather_posteriors(mean, cov, world, out_mean=gm, out_cov=gc, replicate_cov=True)
         torch.cuda.synchronize(); dist.barrier()
+        assert torch.equal(gm[rank], mean) and all(torch.equal(gc[r][:4], ref_rows[r]) for r in range(world))
+        assert torch.equal(gc[world - 1][-1], cov[-1])
         g0.record()
         for _ in range(reps):
-            ctx.allgather_posteriors(mean, None, world, out_mean=gm)
+            ctx.allgather_posteriors(mean, cov, world, out_mean=gm, out_cov=gc, replicate_cov=True)
         g1.record(); torch.cuda.synchronize()
         tg = torch.tensor([g0.elapsed_time(g1) / reps], device=dev, dtype=torch.float64)
         dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-        allgather["means_only_ms"] = float(tg.item())
-        allgather["value_with_means_only_allgather"] = msgs / ((ms_per_step + float(tg.item())) * 1e-3)
-        del gm
+        allgather["replicated_cov_ms"] = float(tg.item())
+        allgather["replicated_cov_bytes_in_per_gpu"] = (world - 1) * mean.numel() * 4
+        allgather["value_with_replicated_cov_allgather"] = msgs / ((ms_per_step + float(tg.item())) * 1e-3)
+        del gc, gm, ref_rows
         torch.cuda.empty_cache()
 
     # ---- e2e through the C ABI with host buffers (rank-local; all ranks run it concurrently)
@@ -312,7 +318,25 @@ def main():
             e2e = {"value": msgs / (float(te.item()) * 1e-3), "unit": "messages/s", "ms_per_step": float(te.item()),
                    "h2d_bytes_per_step": int(yh.numel() * 4), "d2h_bytes_per_step": int((mh.numel() + ch.numel()) * 4),
                    "api": "rxg_lgssm_smooth_f32 with host (pinned) pointers, sliced 3-stream pipeline"}
-            del yh, mh, ch
+            # same call with RXG_COV_SHARED_OUT: the chain-independent covariances come back once ([T][d][d])
+            # instead of per chain -- what a host binding that aliases one matrix per time step would request
+            del ch
+            cs = torch.empty(T, D, D, dtype=torch.float32).pin_memory()
+            ctx.lgssm(yh, **kw, smooth=True, out_mean=mh, out_cov=cs, cov_shared_out=True)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            e0.record()
+            for _ in range(e_steps):
+                ctx.lgssm(yh, **kw, smooth=True, out_mean=mh, out_cov=cs, cov_shared_out=True, asynchronous=True)
+            e1.record(); torch.cuda.synchronize()
+            ts = torch.tensor([e0.elapsed_time(e1) / e_steps], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+            e2e["shared_cov_out"] = {"value": msgs / (float(ts.item()) * 1e-3), "ms_per_step": float(ts.item()),
+                                     "d2h_bytes_per_step": int((mh.numel() + cs.numel()) * 4),
+                                     "note": "RXG_COV_SHARED_OUT: posterior covariances de-duplicated over chains (not the contract output)"}
+            del yh, mh, cs
         elif world > 1:
             dist.barrier()
 

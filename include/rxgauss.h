@@ -58,7 +58,9 @@ enum rxg_flags {
     RXG_ASYNC           = 1u << 2, /* do not synchronise the stream before returning             */
     RXG_COV_SHARED_OUT  = 1u << 3, /* shared model only: write post_cov as [T][d][d] (one copy)  */
     RXG_PATH_PER_CHAIN  = 1u << 4, /* force the per-chain covariance recursion (no gain tables)  */
-    RXG_TRANSITION_FIRST = 1u << 5 /* the prior sits one transition before the first datum       */
+    RXG_TRANSITION_FIRST = 1u << 5, /* the prior sits one transition before the first datum      */
+    RXG_COV_REPLICATE   = 1u << 6  /* all-gather: covariances are chain independent (shared model,
+                                      no missing data) -- replicate them locally, gather only means */
 };
 
 /* ------------------------------------------------------------------ context / plumbing ------ */
@@ -233,6 +235,31 @@ int rxg_hgf_filter_f32(rxg_ctx*, int T, int64_t batch, int iters, float kappa, f
                        float z_variance, float y_variance, const float init[4], const float* y,
                        float* out, unsigned flags);
 
+/* ------------------------------------------------------------------ streaming engine ----------
+ * The reference's second entry point: infer(..., autoupdates = ..., keephistory = ...) builds an
+ * RxInferenceEngine that re-triggers a ONE-step graph per datum and feeds q(x_t) back as the next
+ * prior [ref: executor src/inference/streaming.jl:344-430; @autoupdates x_min_t_mean, x_min_t_cov =
+ * mean_cov(q(x_t)) src/inference/autoupdates.jl:614-659; model ipynb:107-113, run ipynb:199-216].
+ * Here the datastream is consumed in time-chunks: one call = one fused filtering sweep over Tc data
+ * for all chains, with the autoupdate carry made explicit (no hidden state in the ctx):
+ *   prev_mean[d][batch]  (device)  in : means of q(x_{t0-1}) -- for the first chunk the broadcast
+ *                                       initialisation; afterwards filt_mean[Tc-1] of the last chunk
+ *   carry_cov[d][d]      (HOST)    in : covariance of q(x_{t0-1}) (chain independent for a shared
+ *                                       model);  out: covariance of q(x_{t0+Tc-1})
+ * Model per datum: x_t ~ N(A x_{t-1} + u, P), y_t ~ N(B x_t, Q) (transition first).  Chunking is
+ * exact: any split of the stream gives the same posteriors as one call (up to the fp32 rounding of
+ * the carried covariance).  Shared model, no mask; device pointers; always synchronous.          */
+int rxg_lgssm_filter_chunk_f32(rxg_ctx*, int d, int m, int Tc, int64_t batch, const float* A,
+                               const float* B, const float* P, const float* Q, const float* u,
+                               const float* prev_mean, float* carry_cov, const float* y,
+                               float* filt_mean, float* filt_cov, float* neg_log_evidence,
+                               unsigned flags);
+/* HGF datastream in time-chunks: prev[4][batch] = out[Tc-1] of the previous chunk (rows m_x, v_x,
+ * m_z, v_z: the @autoupdates of hgf_tests.jl:46-49).  First chunk: rxg_hgf_filter_f32 with init.  */
+int rxg_hgf_filter_chunk_f32(rxg_ctx*, int Tc, int64_t batch, int iters, float kappa, float omega,
+                             float z_variance, float y_variance, const float* prev, const float* y,
+                             float* out, unsigned flags);
+
 /* Diagnostic: D[128][64] = A[128][128] * B[64][128]' on the tcgen05 tensor pipe (kind::tf32, 3xTF32
  * split, TMEM accumulator), row-major device arrays.  Validates the hand-written UMMA descriptors
  * used by the large-state family; no reference counterpart.                                     */
@@ -245,7 +272,12 @@ int rxg_selftest_umma_f32(rxg_ctx*, const float* A, const float* B, float* D, un
 int rxg_comm_unique_id(void* id128);
 int rxg_comm_init(rxg_ctx*, int nranks, int rank, const void* id128);
 /* Gather each rank's (mean[T][d][b_local], cov[T][d][d][b_local]) slab into
- * gathered_*[G][...] (rank-major, each slab contiguous).  Device pointers only.                 */
+ * gathered_*[G][...] (rank-major, each slab contiguous).  Device pointers only.
+ * With RXG_COV_REPLICATE (shared model on every rank, no ymask: the covariances do not depend on
+ * the chain) only the means cross NVLink; gathered_cov[G][T][d][d][b_local]
+ * is filled locally from post_cov (its first chain column, or the [T][d][d] table when
+ * RXG_COV_SHARED_OUT is also set) at HBM write speed, concurrently with the gather.  Results are
+ * bit-identical to the full gather.                                                              */
 int rxg_allgather_posteriors(rxg_ctx*, int d, int T, int64_t batch_local, const float* post_mean,
                              const float* post_cov, float* gathered_mean, float* gathered_cov,
                              unsigned flags);

@@ -23,6 +23,9 @@ def __getattr__(name):   # lazy: these import torch
     if name in ("call_rule", "prod", "RuleMethodError"):
         from . import rules
         return getattr(rules, name)
+    if name == "RxInferenceEngine":
+        from . import streaming
+        return streaming.RxInferenceEngine
     if name == "sharding":
         import importlib
         return importlib.import_module(".sharding", __name__)

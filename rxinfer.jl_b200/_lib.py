@@ -22,6 +22,7 @@ ASYNC = 1 << 2
 COV_SHARED_OUT = 1 << 3
 PATH_PER_CHAIN = 1 << 4
 TRANSITION_FIRST = 1 << 5
+COV_REPLICATE = 1 << 6
 
 fp = POINTER(c_float)
 u8p = POINTER(c_uint8)
@@ -64,6 +65,8 @@ SIGNATURES = {
     "rxg_lgssm_filter_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, fp, fp, fp, fp, fp, fp, fp, fp, u8p, fp, fp, fp, i32p, c_uint]),
     "rxg_lgssm_vmp_gamma_f32": (c_int, [c_void_p, c_int, c_int64, c_int, c_float, c_float, c_float, c_float, c_float, c_float, c_float, fp, fp, fp, fp, fp, c_uint]),
     "rxg_hgf_filter_f32": (c_int, [c_void_p, c_int, c_int64, c_int, c_float, c_float, c_float, c_float, fp, fp, fp, c_uint]),
+    "rxg_lgssm_filter_chunk_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, c_uint]),
+    "rxg_hgf_filter_chunk_f32": (c_int, [c_void_p, c_int, c_int64, c_int, c_float, c_float, c_float, c_float, fp, fp, fp, c_uint]),
     "rxg_selftest_umma_f32": (c_int, [c_void_p, fp, fp, fp, c_uint]),
     "rxg_comm_unique_id": (c_int, [c_void_p]),
     "rxg_comm_init": (c_int, [c_void_p, c_int, c_int, c_void_p]),

@@ -137,6 +137,41 @@ class Context:
         self._check(fn(self.h, d, m, T, batch, *ptrs, _fp(y), mask_p, _fp(mean), _fp(cov), _fp(nle), st_p, flags))
         return dict(mean=mean, cov=cov if (want_cov or need_cov) else None, neg_log_evidence=nle, status=status)
 
+    def lgssm_filter_chunk(self, y, A, B, P, Q, prev_mean, carry_cov, *, u=None, want_evidence=False,
+                           cov_shared_out=False, out_mean=None, out_cov=None):
+        """One time-chunk of the streaming engine (``rxg_lgssm_filter_chunk_f32``).  ``prev_mean[d, batch]``
+        (CUDA) and ``carry_cov[d, d]`` (host fp32 numpy, updated IN PLACE) are the autoupdate carry."""
+        self._dev(y, prev_mean)
+        T, m, batch = y.shape
+        d = prev_mean.shape[0]
+        if not (isinstance(carry_cov, np.ndarray) and carry_cov.dtype == np.float32 and carry_cov.shape == (d, d)
+                and carry_cov.flags.c_contiguous):
+            raise ValueError("carry_cov must be a C-contiguous float32 numpy array of shape (d, d)")
+        keep = [_model32(x) for x in (A, B, P, Q)]
+        ptrs = [k[1] for k in keep]
+        if u is not None:
+            keep.append(_model32(u))
+            ptrs.append(keep[-1][1])
+        else:
+            ptrs.append(L.as_fp(0))
+        mean = out_mean if out_mean is not None else self.empty(T, d, batch)
+        cov = out_cov if out_cov is not None else (self.empty(T, d, d) if cov_shared_out else self.empty(T, d, d, batch))
+        nle = self.empty(batch) if want_evidence else None
+        flags = L.PTR_DEVICE | (L.COV_SHARED_OUT if cov_shared_out else 0)
+        cc = carry_cov.ctypes.data_as(L.fp)
+        self._check(self.lib.rxg_lgssm_filter_chunk_f32(self.h, d, m, T, batch, *ptrs, _fp(prev_mean), cc, _fp(y),
+                                                        _fp(mean), _fp(cov), _fp(nle), flags))
+        return dict(mean=mean, cov=cov, neg_log_evidence=nle)
+
+    def hgf_filter_chunk(self, y, prev, iters=20, kappa=1.0, omega=0.0, z_variance=0.04, y_variance=0.01, out=None):
+        """HGF datastream chunk; ``prev[4, batch]`` = ``out[-1]`` of the previous chunk."""
+        self._dev(y, prev)
+        T, batch = y.shape
+        out = out if out is not None else self.empty(T, 4, batch)
+        self._check(self.lib.rxg_hgf_filter_chunk_f32(self.h, T, batch, iters, kappa, omega, z_variance, y_variance,
+                                                      _fp(prev), _fp(y), _fp(out), L.PTR_DEVICE))
+        return out
+
     def hgf_filter(self, y, iters=20, kappa=1.0, omega=0.0, z_variance=0.04, y_variance=0.01,
                    init=(0.0, 5.0, 0.0, 5.0), out=None):
         self._dev(y)
@@ -301,15 +336,25 @@ class Context:
         buf = ctypes.create_string_buffer(uid, 128)
         self._check(self.lib.rxg_comm_init(self.h, nranks, rank, ctypes.cast(buf, c_void_p)))
 
-    def allgather_posteriors(self, mean, cov, nranks, out_mean=None, out_cov=None):
-        """Rank-major gathered slabs ([G, T, d, b], [G, T, d, d, b]); pass out_* to reuse buffers."""
+    def allgather_posteriors(self, mean, cov, nranks, out_mean=None, out_cov=None, replicate_cov=False):
+        """Rank-major gathered slabs ([G, T, d, b], [G, T, d, d, b]); pass out_* to reuse buffers.
+        ``replicate_cov=True`` (shared model on every rank, no missing data: chain-independent
+        covariances): only the means cross NVLink, the covariance slabs are filled locally;
+        ``cov`` may then also be the de-duplicated [T, d, d] table of ``cov_shared_out=True``."""
         self._dev(mean, cov)
         T, d, bl = mean.shape
         gm = out_mean if out_mean is not None else self.empty(nranks, T, d, bl)
         gc = None
+        flags = L.PTR_DEVICE
         if cov is not None:
             gc = out_cov if out_cov is not None else self.empty(nranks, T, d, d, bl)
-        self._check(self.lib.rxg_allgather_posteriors(self.h, d, T, bl, _fp(mean), _fp(cov), _fp(gm), _fp(gc), L.PTR_DEVICE))
+            if replicate_cov:
+                flags |= L.COV_REPLICATE
+                if cov.dim() == 3:
+                    flags |= L.COV_SHARED_OUT
+            elif cov.dim() == 3:
+                raise ValueError("a [T, d, d] covariance table can only be replicated (replicate_cov=True)")
+        self._check(self.lib.rxg_allgather_posteriors(self.h, d, T, bl, _fp(mean), _fp(cov), _fp(gm), _fp(gc), flags))
         return gm, gc
 
 

@@ -98,6 +98,11 @@ int rxg_destroy(rxg_ctx* ctx) {
         for (int q = 0; q < 2; ++q) { cudaEventDestroy(ctx->ev_in[q]); cudaEventDestroy(ctx->ev_comp[q]); cudaEventDestroy(ctx->ev_out[q]); }
         cudaEventDestroy(ctx->ev_start);
     }
+    if (ctx->s_aux) {
+        cudaStreamSynchronize(ctx->s_aux);
+        cudaStreamDestroy(ctx->s_aux);
+        cudaEventDestroy(ctx->ev_aux[0]); cudaEventDestroy(ctx->ev_aux[1]);
+    }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return RXG_OK;
@@ -192,7 +197,7 @@ static int lgssm_entry(rxg_ctx* ctx, bool smooth, int d, int m, int T, int64_t b
     const bool cov_shared = (flags & RXG_COV_SHARED_OUT) != 0;
     const bool need_cov_dev = cov || ymask || (flags & RXG_PATH_PER_CHAIN);
     int ns = 1;
-    if (!cov_shared && batch >= 16384) ns = (int)((batch + 8191) / 8192);
+    if (batch >= 16384) ns = (int)((batch + 8191) / 8192);
     if (ns > 64) ns = 64;
     if (const char* e = getenv("RXG_HOST_SLICES")) { int v = atoi(e); if (v >= 1) ns = v; }
     const int64_t bs = ((batch + ns - 1) / ns + 3) / 4 * 4;          // slice width, multiple of 4 chains
@@ -291,6 +296,47 @@ int rxg_lgssm_filter_f32(rxg_ctx* ctx, int d, int m, int T, int64_t batch, const
                        neg_log_evidence, status, flags);
 }
 
+// Streaming engine, one time-chunk.  The reference's streaming executor re-triggers a one-step graph per
+// datum and carries q(x_t) into the next step's prior through @autoupdates; here a chunk of Tc data is
+// one fused filtering sweep, and the carry is explicit: per-chain means (device) + the chain-independent
+// covariance (host, d x d) in, the same pair for the last step of the chunk out.
+int rxg_lgssm_filter_chunk_f32(rxg_ctx* ctx, int d, int m, int T, int64_t batch, const float* A, const float* B,
+                               const float* P, const float* Q, const float* u, const float* prev_mean,
+                               float* carry_cov, const float* y, float* filt_mean, float* filt_cov,
+                               float* neg_log_evidence, unsigned flags) {
+    if (!ctx) return RXG_ERR_BAD_ARG;
+    if (!(flags & RXG_PTR_DEVICE)) return fail(ctx, RXG_ERR_UNSUPPORTED, "lgssm_filter_chunk takes device pointers");
+    if (flags & (RXG_MODEL_PER_CHAIN | RXG_PATH_PER_CHAIN))
+        return fail(ctx, RXG_ERR_UNSUPPORTED, "lgssm_filter_chunk: shared-model gain-table path only");
+    if (d < 1 || m < 1 || T < 1 || batch < 1) return fail(ctx, RXG_ERR_BAD_ARG, "lgssm_filter_chunk: d, m, T, batch must be >= 1");
+    if (!A || !B || !P || !Q || !prev_mean || !carry_cov || !y || !filt_mean || !filt_cov)
+        return fail(ctx, RXG_ERR_BAD_ARG, "lgssm_filter_chunk: null pointer argument");
+    if (!lgssm_supported(d, m))
+        return fail(ctx, RXG_ERR_UNSUPPORTED, "lgssm_filter_chunk: (d=%d, m=%d) is outside the compiled kernel families", d, m);
+    if (lgssm_large_supported(d, m) && (neg_log_evidence || u))
+        return fail(ctx, RXG_ERR_UNSUPPORTED, "lgssm_filter_chunk (d=%d): the large-state family has no evidence / offset", d);
+    RXG_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<float> zero((size_t)d, 0.f);
+    LgssmCall c;
+    c.d = d; c.m = m; c.T = T; c.batch = batch;
+    c.A = A; c.B = B; c.P = P; c.Q = Q; c.m0 = zero.data(); c.S0 = carry_cov; c.u = u;
+    c.mean0_chain = prev_mean;
+    c.y = y; c.ymask = nullptr; c.mean = filt_mean; c.cov = filt_cov; c.nle = neg_log_evidence; c.status = nullptr;
+    c.flags = (flags | RXG_TRANSITION_FIRST) & ~(unsigned)RXG_ASYNC;
+    c.smooth = false;
+    int rc = lgssm_dispatch(ctx, c);
+    if (rc != RXG_OK) return rc;
+    // carry out: the filtered covariance of the last step (chain independent)
+    const size_t dd = (size_t)d * d;
+    if (flags & RXG_COV_SHARED_OUT)
+        RXG_CUDA(ctx, cudaMemcpyAsync(carry_cov, filt_cov + (size_t)(T - 1) * dd, dd * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    else
+        RXG_CUDA(ctx, cudaMemcpy2DAsync(carry_cov, 4, filt_cov + (size_t)(T - 1) * dd * batch, (size_t)batch * 4, 4, dd,
+                                        cudaMemcpyDeviceToHost, ctx->stream));
+    RXG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // carry_cov is a host output: always synchronous
+    return RXG_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // NCCL (resolved at run time so that the library loads on hosts without NCCL)
 // ------------------------------------------------------------------------------------------------
@@ -359,6 +405,33 @@ int rxg_comm_destroy_internal(rxg_ctx* ctx) {
     return RXG_OK;
 }
 
+}  // extern "C"
+
+// Replicates the chain-independent covariances of a shared model into the rank-major gathered layout
+// [G][rows][b] without moving them over NVLink: every rank holds the same rows = T*d*d values (the
+// gain tables depend on the model only), so the gather of 4 d^2 of the 4 (d + d^2) bytes per
+// (chain, step) degenerates into a broadcast fill at HBM write speed.  src_stride = b (value taken
+// from the first chain of the local slab) or 1 (RXG_COV_SHARED_OUT table).
+__global__ void __launch_bounds__(256) replicate_cov_kernel(const float* __restrict__ src, int64_t src_stride,
+                                                            float* __restrict__ dst, int64_t rows, int64_t b, int G) {
+    const int64_t row = blockIdx.x;
+    const float v = __ldg(src + row * src_stride);
+    for (int g = blockIdx.y; g < G; g += gridDim.y) {
+        float* out = dst + ((int64_t)g * rows + row) * b;
+        const int64_t head = (4 - ((reinterpret_cast<uintptr_t>(out) >> 2) & 3)) & 3;   // floats to 16-byte alignment
+        const int64_t h = head < b ? head : b;
+        if (threadIdx.x < h) out[threadIdx.x] = v;
+        const int64_t n4 = (b - h) / 4;
+        float4* o4 = reinterpret_cast<float4*>(out + h);
+        const float4 v4 = make_float4(v, v, v, v);
+        for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) __stcs(o4 + i, v4);     // streaming: never re-read here
+        const int64_t tail = h + 4 * n4;
+        if (tail + threadIdx.x < b) out[tail + threadIdx.x] = v;
+    }
+}
+
+extern "C" {
+
 int rxg_allgather_posteriors(rxg_ctx* ctx, int d, int T, int64_t batch_local, const float* post_mean,
                              const float* post_cov, float* gathered_mean, float* gathered_cov, unsigned flags) {
     if (!ctx) return RXG_ERR_BAD_ARG;
@@ -368,13 +441,35 @@ int rxg_allgather_posteriors(rxg_ctx* ctx, int d, int T, int64_t batch_local, co
         return fail(ctx, RXG_ERR_BAD_ARG, "allgather: bad argument");
     const size_t n_mean = (size_t)T * d * batch_local, n_cov = n_mean * d;
     const int nccl_float = 7;
+    const bool replicate = post_cov && (flags & RXG_COV_REPLICATE);
+    if ((flags & RXG_COV_SHARED_OUT) && post_cov && !replicate)
+        return fail(ctx, RXG_ERR_BAD_ARG, "allgather: a [T][d][d] covariance table can only be replicated (RXG_COV_REPLICATE)");
+    RXG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (replicate) {
+        // local broadcast fill on a side stream, concurrent with the NVLink gather of the means
+        if (!ctx->s_aux) {
+            RXG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking));
+            RXG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_aux[0], cudaEventDisableTiming));
+            RXG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_aux[1], cudaEventDisableTiming));
+        }
+        RXG_CUDA(ctx, cudaEventRecord(ctx->ev_aux[0], ctx->stream));
+        RXG_CUDA(ctx, cudaStreamWaitEvent(ctx->s_aux, ctx->ev_aux[0], 0));
+        const int64_t rows = (int64_t)T * d * d;
+        const int gy = ctx->nranks < 8 ? ctx->nranks : 8;
+        replicate_cov_kernel<<<dim3((unsigned)rows, (unsigned)gy), 256, 0, ctx->s_aux>>>(
+            post_cov, (flags & RXG_COV_SHARED_OUT) ? 1 : batch_local, gathered_cov, rows, batch_local, ctx->nranks);
+        RXG_CUDA(ctx, cudaGetLastError());
+        RXG_CUDA(ctx, cudaEventRecord(ctx->ev_aux[1], ctx->s_aux));
+        ctx->launches += 1;
+    }
     int r = p_group_start();
     if (r == 0) r = p_allgather(post_mean, gathered_mean, n_mean, nccl_float, ctx->comm, ctx->stream);
-    if (r == 0 && post_cov) r = p_allgather(post_cov, gathered_cov, n_cov, nccl_float, ctx->comm, ctx->stream);
+    if (r == 0 && post_cov && !replicate) r = p_allgather(post_cov, gathered_cov, n_cov, nccl_float, ctx->comm, ctx->stream);
     int r2 = p_group_end();
     if (r == 0) r = r2;
+    if (replicate) RXG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_aux[1], 0));
     if (r != 0) return fail(ctx, RXG_ERR_NCCL, "ncclAllGather failed: %s", p_errstr ? p_errstr(r) : "?");
-    ctx->launches += post_cov ? 2 : 1;
+    ctx->launches += (post_cov && !replicate) ? 2 : 1;
     if (!(flags & RXG_ASYNC)) RXG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return RXG_OK;
 }

@@ -122,10 +122,14 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __global__ void __launch_bounds__(64)
 hgf_filter_kernel(const float* __restrict__ y, float* __restrict__ out, int T, int64_t batch, int iters,
                   float kappa, float omega, float zvar, float yvar, float i_mz, float i_vz, float i_mx,
-                  float i_vx) {
+                  float i_vx, const float* __restrict__ prev) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
     constexpr float LOG2E = 1.4426950408889634f;
+    if (prev) {   // streaming carry: out[T-1] of the previous chunk, rows (m_x, v_x, m_z, v_z)
+        i_mx = __ldg(prev + b); i_vx = __ldg(prev + batch + b);
+        i_mz = __ldg(prev + 2 * batch + b); i_vz = __ldg(prev + 3 * batch + b);
+    }
     float mzp = i_mz, vzp = i_vz, mxp = i_mx, vxp = i_vx;
     float mz = i_mz, vz = i_vz;                 // q(zt), carried across iterations and steps
     const float wy = 1.0f / yvar;
@@ -273,9 +277,26 @@ int rxg_hgf_filter_f32(rxg_ctx* ctx, int T, int64_t batch, int iters, float kapp
     int rc = ensure_gh_tables(ctx);
     if (rc != RXG_OK) return rc;
     hgf_filter_kernel<<<(unsigned)((batch + 63) / 64), 64, 0, ctx->stream>>>(
-        y, out, T, batch, iters, kappa, omega, z_variance, y_variance, init[0], init[1], init[2], init[3]);
+        y, out, T, batch, iters, kappa, omega, z_variance, y_variance, init[0], init[1], init[2], init[3], nullptr);
     ctx->launches += 1;
     rc = rxg::check_cuda(ctx, cudaGetLastError(), "hgf_filter_kernel");
+    if (rc != RXG_OK) return rc;
+    if (!(flags & RXG_ASYNC)) RXG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RXG_OK;
+}
+
+int rxg_hgf_filter_chunk_f32(rxg_ctx* ctx, int T, int64_t batch, int iters, float kappa, float omega, float z_variance,
+                             float y_variance, const float* prev, const float* y, float* out, unsigned flags) {
+    if (!ctx) return RXG_ERR_BAD_ARG;
+    if (T < 1 || batch < 1 || iters < 1 || !y || !out || !prev)
+        return rxg::fail(ctx, RXG_ERR_BAD_ARG, "hgf_filter_chunk: bad argument");
+    if (!(flags & RXG_PTR_DEVICE)) return rxg::fail(ctx, RXG_ERR_UNSUPPORTED, "hgf_filter_chunk takes device pointers");
+    int rc = ensure_gh_tables(ctx);
+    if (rc != RXG_OK) return rc;
+    hgf_filter_kernel<<<(unsigned)((batch + 63) / 64), 64, 0, ctx->stream>>>(
+        y, out, T, batch, iters, kappa, omega, z_variance, y_variance, 0.f, 1.f, 0.f, 1.f, prev);
+    ctx->launches += 1;
+    rc = rxg::check_cuda(ctx, cudaGetLastError(), "hgf_filter_kernel (chunk)");
     if (rc != RXG_OK) return rc;
     if (!(flags & RXG_ASYNC)) RXG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return RXG_OK;

@@ -26,6 +26,9 @@ struct rxg_ctx {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     cudaEvent_t ev_start = nullptr;
+    // side stream for work that overlaps a collective (covariance replication next to the all-gather)
+    cudaStream_t s_aux = nullptr;
+    cudaEvent_t ev_aux[2] = {nullptr, nullptr};
     // NCCL (dlopen'ed lazily; see rxg_api.cu)
     void* nccl_dl = nullptr;
     void* comm = nullptr;
@@ -52,6 +55,7 @@ struct LgssmCall {
     // shared model: host pointers (row-major); per-chain model: device pointers [..][batch]
     const float *A, *B, *P, *Q, *m0, *S0;
     const float* u;          // transition offset (same pointer space as the model) or null
+    const float* mean0_chain = nullptr;   // device [d][batch]: per-chain prior mean (streaming carry) or null
     const float* y;          // device
     const uint8_t* ymask;    // device or null
     float* mean;             // device
@@ -69,7 +73,7 @@ bool lgssm_supported(int d, int m);
 int lgssm_large_dispatch(rxg_ctx* ctx, const LgssmCall& c);
 bool lgssm_large_supported(int d, int m);
 // rxg_umma_sweep.cu (d = 64 mean sweep on tcgen05)
-int launch_umma_sweep(rxg_ctx* ctx, bool smooth, const float* fwdU, const float* bwdU, const float* m0, const float* y,
-                      float* mean, int T, int64_t batch);
+int launch_umma_sweep(rxg_ctx* ctx, bool smooth, const float* fwdU, const float* bwdU, const float* m0, const float* m0c,
+                      const float* y, float* mean, int T, int64_t batch);
 
 }  // namespace rxg

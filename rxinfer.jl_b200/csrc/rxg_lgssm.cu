@@ -397,7 +397,7 @@ static int launch_shared(rxg_ctx* ctx, const LgssmCall& c, const ModelF<D, M>& m
     if (const char* e = getenv("RXG_NO_CKPT")) ckpt = ckpt && atoi(e) == 0;
 #define RXG_LAUNCH_SHARED2(SM, EV, OF, CK)                                                         \
     lgssm_shared_kernel<D, M, CPT, PF, SM, EV, OF, CK><<<blocks, threads, 0, ctx->stream>>>(       \
-        mdl, ws.fwd, ws.bwd, ws.sf, c.y, c.mean, c.cov, c.nle, c.T, c.batch, tf, write_cov)
+        mdl, ws.fwd, ws.bwd, ws.sf, c.y, c.mean, c.cov, c.nle, c.T, c.batch, tf, write_cov, c.mean0_chain)
 #define RXG_LAUNCH_SHARED(SM, EV)                                                                  \
     do {                                                                                           \
         if (SM && ckpt) { if (has_u) RXG_LAUNCH_SHARED2(SM, EV, true, true); else RXG_LAUNCH_SHARED2(SM, EV, false, true); } \
@@ -470,7 +470,7 @@ static int run_shared_family(rxg_ctx* ctx, const LgssmCall& c) {
     int rc = check_cuda(ctx, cudaGetLastError(), "gain table kernels launch");
     if (rc != RXG_OK) return rc;
     const int write_cov = (c.cov != nullptr && !cov_shared) ? 1 : 0;
-    const bool al16 = (((uintptr_t)c.y | (uintptr_t)c.mean | (uintptr_t)c.cov | (uintptr_t)c.nle) & 15) == 0;
+    const bool al16 = (((uintptr_t)c.y | (uintptr_t)c.mean | (uintptr_t)c.cov | (uintptr_t)c.nle | (uintptr_t)c.mean0_chain) & 15) == 0;
     // chains per thread: keep >= ~2 resident warps per SM sub-partition
     // Wider per-thread vectors cut the number of (128-byte-per-warp) store instructions per byte;
     // B200, d = m = 4, T = 1000, batch 65 536: CPT 1 / 2 / 4 = 1.85 / 1.50 / 1.58 ms (262 144: 2 beats 4 too).

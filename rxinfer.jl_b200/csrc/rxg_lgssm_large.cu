@@ -556,7 +556,8 @@ __device__ __forceinline__ void tile_step(const float* __restrict__ W, const flo
 template <int D, int M, int NB, bool SMOOTH>
 __global__ void __launch_bounds__((D / 4) * (NB / 2))
 lgssm_block_sweep(const float* __restrict__ fwdT, const float* __restrict__ bwdT, const float* __restrict__ m0,
-                  const float* __restrict__ y, float* __restrict__ mean, int T, int64_t batch) {
+                  const float* __restrict__ m0c, const float* __restrict__ y, float* __restrict__ mean, int T,
+                  int64_t batch) {
     constexpr int KF = D + M, KB = 2 * D, KMAX = KF > KB ? KF : KB;
     constexpr int NT = (D / 4) * (NB / 2);
     extern __shared__ __align__(16) float smf[];
@@ -580,7 +581,8 @@ lgssm_block_sweep(const float* __restrict__ fwdT, const float* __restrict__ bwdT
     // zero both Z buffers once (inactive columns stay zero), then the initial state
     for (int p = tid; p < 2 * KMAX * NB; p += NT) Zb[0][p] = 0.f;
     __syncthreads();
-    for (int p = tid; p < D * NB; p += NT) Zb[0][p] = m0[p / NB];
+    for (int p = tid; p < D * NB; p += NT)     // prior mean: shared, or per chain (streaming carry) for the active columns
+        Zb[0][p] = m0c ? ((p % NB) < nb ? m0c[(size_t)(p / NB) * batch + b0 + (p % NB)] : 0.f) : m0[p / NB];
     load_W(Wb[0], fwdT, KF);
     load_rows(Zb[0] + D * NB, y, M);
     cpa_commit();
@@ -785,11 +787,11 @@ static int run_large(rxg_ctx* ctx, const LgssmCall& c) {
     if (ctx->profile) cudaEventRecord(ctx->ev[1], ctx->stream);
     if (use_umma) {
         // tensor-pipe sweep (tcgen05 kind::tf32, 3xTF32): 128 chains per CTA
-        rc = launch_umma_sweep(ctx, c.smooth, w.fwdU, w.bwdU, dm0, c.y, c.mean, c.T, c.batch);
+        rc = launch_umma_sweep(ctx, c.smooth, w.fwdU, w.bwdU, dm0, c.mean0_chain, c.y, c.mean, c.T, c.batch);
         if (rc != RXG_OK) return rc;
     } else {
-        if (c.smooth) lgssm_block_sweep<D, M, NB, true><<<blocks, (D / 4) * (NB / 2), smw, ctx->stream>>>(w.fwdT, w.bwdT, dm0, c.y, c.mean, c.T, c.batch);
-        else          lgssm_block_sweep<D, M, NB, false><<<blocks, (D / 4) * (NB / 2), smw, ctx->stream>>>(w.fwdT, w.bwdT, dm0, c.y, c.mean, c.T, c.batch);
+        if (c.smooth) lgssm_block_sweep<D, M, NB, true><<<blocks, (D / 4) * (NB / 2), smw, ctx->stream>>>(w.fwdT, w.bwdT, dm0, c.mean0_chain, c.y, c.mean, c.T, c.batch);
+        else          lgssm_block_sweep<D, M, NB, false><<<blocks, (D / 4) * (NB / 2), smw, ctx->stream>>>(w.fwdT, w.bwdT, dm0, c.mean0_chain, c.y, c.mean, c.T, c.batch);
         ctx->launches += 1;
         rc = check_cuda(ctx, cudaGetLastError(), "lgssm_block_sweep");
         if (rc != RXG_OK) return rc;

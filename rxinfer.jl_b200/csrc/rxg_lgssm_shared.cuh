@@ -101,7 +101,7 @@ lgssm_shared_kernel(const __grid_constant__ ModelF<D, M> mdl, const float* __res
                     const float* __restrict__ bwd_tab, const float* __restrict__ sf_tab,
                     const float* __restrict__ y, float* __restrict__ mean, float* __restrict__ cov,
                     float* __restrict__ nle, int T, int64_t batch, int transition_first,
-                    int write_cov) {
+                    int write_cov, const float* __restrict__ mu0c) {
     using TB = Tab<D, M>;
     constexpr int TC = 4 * PF;                                   // table chunk, in time steps
     constexpr int REC_MAX = TB::FWD_REC > TB::BWD_REC ? TB::FWD_REC : TB::BWD_REC;
@@ -117,11 +117,16 @@ lgssm_shared_kernel(const __grid_constant__ ModelF<D, M> mdl, const float* __res
     const bool active = b0 < batch;
     const int64_t b = active ? b0 : 0;      // inactive lanes shadow chain 0 (loads only, no stores)
 
+    // prior mean: shared (parameter block) or per chain (mu0c[d][batch]: the streaming engine's carry,
+    // @autoupdates x_min_t_mean = mean(q(x_t)), /root/reference/src/inference/autoupdates.jl:614-659)
     float mu[D][CPT];
 #pragma unroll
-    for (int i = 0; i < D; ++i)
+    for (int i = 0; i < D; ++i) {
+        if (mu0c) Pack<CPT>::ld(mu0c + (int64_t)i * batch + b, mu[i]);
+        else
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) mu[i][c] = mdl.m0[i];
+            for (int c = 0; c < CPT; ++c) mu[i][c] = mdl.m0[i];
+    }
     float ev[CPT];
     double ev_hi[CPT];
 #pragma unroll
@@ -299,8 +304,10 @@ lgssm_shared_kernel(const __grid_constant__ ModelF<D, M> mdl, const float* __res
 #pragma unroll
             for (int i = 0; i < D; ++i) {
                 if (k == 0) {
+                    if (mu0c) Pack<CPT>::ld(mu0c + (int64_t)i * batch + b, ck[i]);
+                    else
 #pragma unroll
-                    for (int c = 0; c < CPT; ++c) ck[i][c] = mdl.m0[i];
+                        for (int c = 0; c < CPT; ++c) ck[i][c] = mdl.m0[i];
                 } else {
                     Pack<CPT>::ld_rw(mean + ((int64_t)(k * TC - 1) * D + i) * batch + b, ck[i]);
                 }
@@ -326,8 +333,10 @@ lgssm_shared_kernel(const __grid_constant__ ModelF<D, M> mdl, const float* __res
 #pragma unroll
                 for (int i = 0; i < D; ++i) {
                     if (k == 1) {
+                        if (mu0c) Pack<CPT>::ld(mu0c + (int64_t)i * batch + b, ck[i]);
+                        else
 #pragma unroll
-                        for (int c = 0; c < CPT; ++c) ck[i][c] = mdl.m0[i];
+                            for (int c = 0; c < CPT; ++c) ck[i][c] = mdl.m0[i];
                     } else {
                         Pack<CPT>::ld_rw(mean + ((int64_t)((k - 1) * TC - 1) * D + i) * batch + b, ck[i]);
                     }

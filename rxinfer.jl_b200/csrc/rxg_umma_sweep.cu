@@ -93,7 +93,8 @@ __device__ __forceinline__ void cpa16u(void* s, const void* g) {
 template <bool SMOOTH>
 __global__ void __launch_bounds__(128, 1)
 lgssm_umma_sweep(const float* __restrict__ fwdU, const float* __restrict__ bwdU, const float* __restrict__ m0,
-                 const float* __restrict__ y, float* __restrict__ mean, int T, int64_t batch) {
+                 const float* __restrict__ m0c, const float* __restrict__ y, float* __restrict__ mean, int T,
+                 int64_t batch) {
     constexpr int D = 64;
     extern __shared__ __align__(1024) uint8_t sm[];
     uint8_t* sZhi = sm;
@@ -136,7 +137,7 @@ lgssm_umma_sweep(const float* __restrict__ fwdU, const float* __restrict__ bwdU,
     load_W(fwdU);
     float x[D], nxt[D];
 #pragma unroll
-    for (int k = 0; k < D; ++k) { x[k] = m0[k]; nxt[k] = __ldg(y + (int64_t)k * batch + bc); }
+    for (int k = 0; k < D; ++k) { x[k] = m0c ? __ldg(m0c + (int64_t)k * batch + bc) : m0[k]; nxt[k] = __ldg(y + (int64_t)k * batch + bc); }
 #pragma unroll
     for (int k = 0; k < D; k += 4) { put4(k, x[k], x[k + 1], x[k + 2], x[k + 3]); put4(D + k, nxt[k], nxt[k + 1], nxt[k + 2], nxt[k + 3]); }
     umma::fence_before();
@@ -235,8 +236,8 @@ lgssm_umma_sweep(const float* __restrict__ fwdU, const float* __restrict__ bwdU,
     if (warp == 0) umma::tmem_dealloc(tmem, TCOLS);
 }
 
-int launch_umma_sweep(rxg_ctx* ctx, bool smooth, const float* fwdU, const float* bwdU, const float* m0, const float* y,
-                      float* mean, int T, int64_t batch) {
+int launch_umma_sweep(rxg_ctx* ctx, bool smooth, const float* fwdU, const float* bwdU, const float* m0, const float* m0c,
+                      const float* y, float* mean, int T, int64_t batch) {
     const size_t smem = 2 * UM_A_BYTES + 2 * UM_B_BYTES + 64;
     static bool done = false;
     if (!done) {
@@ -245,8 +246,8 @@ int launch_umma_sweep(rxg_ctx* ctx, bool smooth, const float* fwdU, const float*
         done = true;
     }
     const unsigned blocks = (unsigned)((batch + UM_M - 1) / UM_M);
-    if (smooth) lgssm_umma_sweep<true><<<blocks, 128, smem, ctx->stream>>>(fwdU, bwdU, m0, y, mean, T, batch);
-    else        lgssm_umma_sweep<false><<<blocks, 128, smem, ctx->stream>>>(fwdU, bwdU, m0, y, mean, T, batch);
+    if (smooth) lgssm_umma_sweep<true><<<blocks, 128, smem, ctx->stream>>>(fwdU, bwdU, m0, m0c, y, mean, T, batch);
+    else        lgssm_umma_sweep<false><<<blocks, 128, smem, ctx->stream>>>(fwdU, bwdU, m0, m0c, y, mean, T, batch);
     ctx->launches += 1;
     return check_cuda(ctx, cudaGetLastError(), "lgssm_umma_sweep");
 }

@@ -76,7 +76,7 @@ class InferenceResult:
 
 
 _UNSUPPORTED = ("constraints", "meta", "callbacks", "annotations", "predictvars", "events", "uselock",
-                "postprocess", "trace", "benchmark", "datastream", "free_energy_diagnostics")
+                "postprocess", "trace", "benchmark", "free_energy_diagnostics")
 _ctx_cache: dict = {}
 
 
@@ -89,12 +89,17 @@ def default_context(device=None) -> Context:
     return ctx
 
 
-def infer(*, model, data, iterations=None, free_energy=False, returnvars=None, options=None,
+def infer(*, model, iterations=None, free_energy=False, returnvars=None, options=None,
           initialization=None, autoupdates=None, keephistory=None, historyvars=None,
           catch_exception=False, showprogress=False, session=None, warn=True, allow_node_contraction=False,
-          context: Context | None = None, cov_shared_out=False, **kwargs) -> InferenceResult:
+          context: Context | None = None, cov_shared_out=False, data=None, datastream=None, autostart=True,
+          batch=None, **kwargs):
     """Batched ``infer``.  ``data = {"y": tensor[T, m, batch]}`` (CUDA fp32, or CPU for the
-    host-staged path).  Returns ``posteriors["x"]`` as a batched ``MvNormalMeanCovariance``."""
+    host-staged path).  Returns ``posteriors["x"]`` as a batched ``MvNormalMeanCovariance``.
+
+    With ``datastream=`` (an iterable of time-chunks, or ``None`` + ``autoupdates`` for a push-driven
+    engine) the call returns an ``RxInferenceEngine`` (streaming.py), as the reference does when
+    ``autoupdates`` is given (/root/reference/src/inference/inference.jl:577-733 dispatch)."""
     for k in kwargs:
         if k in _UNSUPPORTED:
             raise NotImplementedError(
@@ -105,6 +110,17 @@ def infer(*, model, data, iterations=None, free_energy=False, returnvars=None, o
         bad = set(options) - {"limit_stack_depth", "warn"}   # limit_stack_depth is moot: the schedule is a fused sweep
         if bad:
             raise NotImplementedError(f"options {sorted(bad)} are outside the batched hot path")
+    if data is not None and datastream is not None:
+        raise ValueError("`data` and `datastream` are mutually exclusive")    # reference: inference.jl argument check
+    if data is None:
+        if datastream is None and autoupdates is None:
+            raise ValueError("either `data` or `datastream` (or `autoupdates` for a push-driven engine) is required")
+        if batch is None:
+            raise ValueError("streaming inference needs `batch` (number of lock-step datastreams)")
+        from .streaming import RxInferenceEngine
+        return RxInferenceEngine(context or default_context(), model, batch=batch, iterations=iterations,
+                                 keephistory=keephistory, historyvars=historyvars, free_energy=free_energy,
+                                 datastream=datastream, autostart=autostart, cov_shared_out=cov_shared_out)
     if "y" not in data:
         raise KeyError("data must contain the observations under key 'y'")   # reference: missing data key error
     ctx = context or default_context()
