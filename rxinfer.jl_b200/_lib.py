@@ -10,7 +10,8 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_longlong, c_size_t, c_uint, c_uint8, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librxgauss.so")
+# RXG_LIB selects an A/B build of the same library (tuning experiments); the product is librxgauss.so
+LIB_PATH = os.environ.get("RXG_LIB") or os.path.join(HERE, "librxgauss.so")
 
 RXG_OK, RXG_ERR_BAD_ARG, RXG_ERR_CUDA, RXG_ERR_NCCL = 0, 1, 2, 3
 RXG_ERR_NOT_SPD, RXG_ERR_NAN, RXG_ERR_UNSUPPORTED, RXG_ERR_NO_DEVICE = 4, 5, 6, 7

@@ -34,16 +34,18 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), lib: str = LIB, objdir_name: str = "build") -> str:
+    """``extra_flags`` / ``lib`` / ``objdir_name`` build an A/B variant next to the product library (tuning
+    experiments, e.g. ``extra_flags=("-DSOME_SWITCH=1",), lib=".../librxgauss_b.so"``, selected at run time with RXG_LIB=<path>)."""
+    if not force and lib == LIB and not _stale():
         return LIB
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, objdir_name)
     os.makedirs(objdir, exist_ok=True)
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = os.path.join(objdir, src.replace(".cu", ".ptxas.log"))
         with open(log, "w") as f:
@@ -56,11 +58,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-ldl", "-Xcompiler", "-fPIC"]
+    cmd = [nvcc, "-shared", "-o", lib, *objs, "-ldl", "-Xcompiler", "-fPIC"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
