@@ -35,7 +35,7 @@ def timed(fn, warm=3, reps=5):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--which", default="per_chain,filter,hgf,rules,vmp,scaling_T")
+    ap.add_argument("--which", default="per_chain,filter,hgf,rules,vmp,scaling_T,large")
     args = ap.parse_args()
     which = set(args.which.split(","))
     ctx = rx.Context(0)
@@ -72,6 +72,31 @@ def main():
             print(json.dumps({"what": "lgssm smooth d=2 (notebook scaling table shape)", "T": TT, "batch": b, "ms": ms,
                               "messages_per_s": 6 * TT * b / ms * 1e3, "ms_per_chain_equiv": ms / b}))
             del y
+
+    if "large" in which:
+        # BASELINE configs[2] (d = 64, T = 1000, batch = 4096) and the smaller tensor-core sizes; shared model.
+        # flops: textbook Kalman + RTS mean recursions only = 2 * (2 d^2 [F x + K y] + 2 d^2 [E x + G x]) per (chain, step)
+        from oracle.lgssm import dense_model
+        ctx.set_profiling(True)
+        for d, b in ((64, 4096), (64, 18944), (32, 16384), (16, 65536)):
+            md = {k: np.asarray(v, np.float32) for k, v in dense_model(d).items()}
+            y = torch.randn(T, d, b, device="cuda", generator=g) * 3.3
+            mean = torch.empty(T, d, b, device="cuda")
+            for no_umma in ("0", "1"):
+                os.environ["RXG_NO_UMMA"] = no_umma
+                sw, gn = [], []
+                def run():
+                    ctx.lgssm(y, **md, smooth=True, out_mean=mean, cov_shared_out=True)
+                    a, bb = ctx.profile_last_ms(); sw.append(a); gn.append(bb)
+                ms = timed(run, warm=2, reps=3)
+                print(json.dumps({"what": "lgssm smooth, large-state family (shared model, cov de-duplicated)", "d": d, "T": T, "batch": b,
+                                  "sweep": "tcgen05 3xTF32 (umma_ky + lgssm_umma_sweep)" if no_umma == "0" else "FP32 pipe (lgssm_block_sweep)",
+                                  "ms": ms, "sweep_ms": float(np.mean(sw[-3:])), "gain_tables_ms": float(np.mean(gn[-3:])),
+                                  "messages_per_s": 6 * T * b / ms * 1e3,
+                                  "sweep_TFLOPs": 8 * d * d * T * b / (float(np.mean(sw[-3:])) * 1e-3) / 1e12}))
+            os.environ.pop("RXG_NO_UMMA", None)
+            del y, mean
+        ctx.set_profiling(False)
 
     if "hgf" in which:
         Th, bh, iters = 1000, 32768, 20

@@ -264,6 +264,10 @@ int rxg_hgf_filter_chunk_f32(rxg_ctx*, int Tc, int64_t batch, int iters, float k
  * split, TMEM accumulator), row-major device arrays.  Validates the hand-written UMMA descriptors
  * used by the large-state family; no reference counterpart.                                     */
 int rxg_selftest_umma_f32(rxg_ctx*, const float* A, const float* B, float* D, unsigned flags);
+/* Same for every operand shape the sweeps issue: D[128][n] = A[128][k] * B[n][k]' with
+ * (n, k) in {(64,128), (128,64), (64,64), (64,32), (32,32), (32,16), (16,16)}.                    */
+int rxg_selftest_umma_shape_f32(rxg_ctx*, int n, int k, const float* A, const float* B, float* D,
+                                unsigned flags);
 
 /* ------------------------------------------------------------------ multi-GPU ----------------
  * Chains are independent: rank g owns chains [g*batch/G, (g+1)*batch/G); the only collective is

@@ -325,10 +325,11 @@ class Context:
         return mz, vz
 
     def selftest_umma(self, A, B):
-        """D[128, 64] = A[128, 128] @ B[64, 128].T on the tcgen05 tensor pipe (3xTF32)."""
+        """D[128, n] = A[128, k] @ B[n, k].T on the tcgen05 tensor pipe (3xTF32), for the sweeps' operand shapes."""
         self._dev(A, B)
-        D = self.empty(128, 64)
-        self._check(self.lib.rxg_selftest_umma_f32(self.h, _fp(A), _fp(B), _fp(D), L.PTR_DEVICE))
+        n, k = B.shape
+        D = self.empty(128, n)
+        self._check(self.lib.rxg_selftest_umma_shape_f32(self.h, n, k, _fp(A), _fp(B), _fp(D), L.PTR_DEVICE))
         return D
 
     # ------------------------------------------------------------------ multi-GPU

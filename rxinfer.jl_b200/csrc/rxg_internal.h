@@ -72,8 +72,8 @@ bool lgssm_supported(int d, int m);
 // rxg_lgssm_large.cu
 int lgssm_large_dispatch(rxg_ctx* ctx, const LgssmCall& c);
 bool lgssm_large_supported(int d, int m);
-// rxg_umma_sweep.cu (d = 64 mean sweep on tcgen05)
-int launch_umma_sweep(rxg_ctx* ctx, bool smooth, const float* fwdU, const float* bwdU, const float* m0, const float* m0c,
-                      const float* y, float* mean, int T, int64_t batch);
+// rxg_umma_sweep.cu (d = 16 / 32 / 64 mean recursions on tcgen05)
+int launch_umma_sweep(rxg_ctx* ctx, int d, bool smooth, const float* recFE, const float* recG, const float* recK,
+                      const float* m0, const float* m0c, const float* y, float* mean, int T, int64_t batch);
 
 }  // namespace rxg

@@ -122,7 +122,9 @@ struct LargeWs {
     float *ss, *sf;                          // [T][D*D] smoothed / filtered covariance (fp32)
     int* flag;
     int b_identity;                          // B == I: skip the two B products
-    float *fwdU, *bwdU;                      // d = 64 only: [T][2][64 x 128] tf32 hi/lo gain blocks in UMMA canonical layout (or null)
+    // tensor-core sweep (rxg_umma_sweep.cu): per-step gain blocks split tf32 hi | lo in the canonical UMMA
+    // K-major layout (K = D), or null:  recFE[t] = [F_t ; E_{t-1}] (2D x D),  recG[t] = G_t,  recK[t] = K_t (D x D)
+    float *recFE, *recG, *recK;
 };
 
 template <int D> struct LD_ { static constexpr int v = D + 1; };   // padded leading dim: no bank conflicts on transposed reads
@@ -220,19 +222,19 @@ __global__ void __launch_bounds__(256) large_gain_tables(LargeWs w, int T, int t
     btrsm_lower_t<M, D, LD>(X2, X1);                   // X1 = K' (M x D): K(r, k) = X1[k][r]
     float* ft = w.fwdT + (size_t)t * (D + M) * D;
     const bool pred = (t > 0) || transition_first;
-    // d = 64: additionally emit W[r][k] (r = state row, k over the stacked K axis) split into tf32 hi / lo parts
-    // in the canonical K-major UMMA layout (rxg_umma.cuh) for lgssm_umma_sweep
-    auto emit_umma = [&](float* rec, const float* srcT, int K2) {        // srcT[k][r] (the transposed fp32 block)
-        if (!rec) return;
-        for (int idx = threadIdx.x; idx < D * K2; idx += blockDim.x) {
+    // tensor-core sweep: emit a D x D block W(r, k) = srcT[k][r] into rows [row0, row0 + D) of a record whose hi part
+    // starts at rec_hi and lo part at rec_lo (canonical K-major UMMA layout with K = D, rxg_umma.cuh)
+    auto emit_umma = [&](float* rec_hi, float* rec_lo, const float* srcT, int row0) {
+        for (int idx = threadIdx.x; idx < D * D; idx += blockDim.x) {
             const int k = idx / D, r = idx % D;
             float hi, lo;
             umma::split_tf32(srcT[k * D + r], hi, lo);
-            const uint32_t off = umma::elem_off(r, k, 128) / 4;
-            rec[off] = hi;
-            rec[D * 128 + off] = lo;
+            const uint32_t off = umma::elem_off(row0 + r, k, D) / 4;
+            rec_hi[off] = hi;
+            rec_lo[off] = lo;
         }
     };
+    constexpr size_t FE_REC = (size_t)4 * D * D, G_REC = (size_t)2 * D * D;
     // F = A - K (B A)   (or I - K B at t = 0 without a leading transition); stored transposed: ft[k][r] = F(r, k)
     if (pred) {
         bgemm<D, D, M>([&](int r, int k) { return X1[k * LD + r]; }, [&](int k, int j) { return w.BA[k * D + j]; },
@@ -247,7 +249,17 @@ __global__ void __launch_bounds__(256) large_gain_tables(LargeWs w, int T, int t
     }
     for (int i = threadIdx.x; i < D * D; i += blockDim.x) w.sf[(size_t)t * D * D + i] = (float)Sf[i];
     __syncthreads();
-    if (D == 64 && M == 64 && w.fwdU) emit_umma(w.fwdU + (size_t)t * 2 * D * 128, ft, D + M);
+    if (M == D && w.recFE) {
+        float* fe = w.recFE + (size_t)t * FE_REC;
+        emit_umma(fe, fe + 2 * D * D, ft, 0);                                   // F_t -> rows [0, D) of record t
+        float* kr = w.recK + (size_t)t * G_REC;
+        emit_umma(kr, kr + D * D, ft + D * D, 0);                               // K_t
+        if (t == 0)                                                              // record 0 has no E_{-1}: zero rows [D, 2D)
+            for (int idx = threadIdx.x; idx < D * D; idx += blockDim.x) {
+                const uint32_t off = umma::elem_off(D + idx % D, idx / D, D) / 4;
+                fe[off] = 0.f; fe[2 * D * D + off] = 0.f;
+            }
+    }
     // ---- backward gain
     float* bt = w.bwdT + (size_t)t * 2 * D * D;
     if (t == T - 1) {
@@ -258,9 +270,7 @@ __global__ void __launch_bounds__(256) large_gain_tables(LargeWs w, int T, int t
             w.Gd[(size_t)t * D * D + idx] = 0.0;                 // suffix-scan element of the last step: (0, Sf)
             w.Cc[(size_t)t * D * D + idx] = Sf[idx];
         }
-        __syncthreads();
-        if (D == 64 && M == 64 && w.bwdU) emit_umma(w.bwdU + (size_t)t * 2 * D * 128, bt, 2 * D);
-        return;
+        return;                  // E_{T-1} = I, G_{T-1} = 0: the tensor-core sweep sets mu_s[T-1] = x_{T-1} directly
     }
     const double* Sp1 = w.Sp + (size_t)(t + 1) * D * D;
     for (int i = threadIdx.x; i < D * D; i += blockDim.x) X2[(i / D) * LD + i % D] = Sp1[i];
@@ -284,7 +294,12 @@ __global__ void __launch_bounds__(256) large_gain_tables(LargeWs w, int T, int t
     bgemm<D, D, D>([&](int r, int k) { return X0[k * LD + r]; }, [&](int k, int j) { return As[k * LD + j]; },
                    [&](int r, int j, double v) { bt[j * D + r] = (float)((r == j ? 1.0 : 0.0) - v); });
     __syncthreads();
-    if (D == 64 && M == 64 && w.bwdU) emit_umma(w.bwdU + (size_t)t * 2 * D * 128, bt, 2 * D);
+    if (M == D && w.recFE) {
+        float* fe = w.recFE + (size_t)(t + 1) * FE_REC;                          // t + 1 <= T - 1 here
+        emit_umma(fe, fe + 2 * D * D, bt, D);                                    // E_t -> rows [D, 2D) of record t + 1
+        float* gr = w.recG + (size_t)t * G_REC;
+        emit_umma(gr, gr + D * D, bt + D * D, 0);                                // G_t
+    }
 }
 
 // Phase 3: smoothed covariances, sequential in t, one CTA:  Ss[t] = C[t] + G[t] Ss[t+1] G[t]'.
@@ -676,8 +691,10 @@ static int run_large(rxg_ctx* ctx, const LgssmCall& c) {
     const size_t o_S0 = carve(DD * 8), o_BA = carve((size_t)M * D * 8);
     const size_t o_Sp = carve(T * DD * 8), o_Sf = carve(T * DD * 8), o_Cc = carve(T * DD * 8), o_Gd = carve(T * DD * 8);
     const size_t o_fw = carve(T * (D + M) * D * 4), o_bw = carve(T * 2 * DD * 4), o_ss = carve(T * DD * 4), o_sf = carve(T * DD * 4);
-    const bool use_umma = (D == 64 && M == 64) && !(getenv("RXG_NO_UMMA") && atoi(getenv("RXG_NO_UMMA")) != 0);
-    const size_t o_fu = carve(use_umma ? T * 2 * 64 * 128 * 4 : 0), o_bu = carve(use_umma ? T * 2 * 64 * 128 * 4 : 0);
+    // d >= 16: the mean recursions run on the tensor cores (RXG_NO_UMMA=1: FP32-pipe block sweep, the cross-check)
+    const bool use_umma = (D >= 16 && M == D) && !(getenv("RXG_NO_UMMA") && atoi(getenv("RXG_NO_UMMA")) != 0);
+    const size_t o_fe = carve(use_umma ? T * 4 * DD * 4 : 0), o_gu = carve(use_umma ? T * 2 * DD * 4 : 0);
+    const size_t o_ku = carve(use_umma ? T * 2 * DD * 4 : 0);
     const size_t o_scan = carve(6 * DD * 8);                                  // G_r ping-pong (A, C, J) x 2
     const size_t o_E2 = carve(T * DD * 8), o_L2 = carve(T * DD * 8);           // backward scan ping-pong
     const size_t o_flag = carve(4);
@@ -704,8 +721,9 @@ static int run_large(rxg_ctx* ctx, const LgssmCall& c) {
     w.Sp = (double*)(base + o_Sp); w.Sf = (double*)(base + o_Sf); w.Cc = (double*)(base + o_Cc); w.Gd = (double*)(base + o_Gd);
     w.fwdT = (float*)(base + o_fw); w.bwdT = (float*)(base + o_bw); w.ss = (float*)(base + o_ss); w.sf = (float*)(base + o_sf);
     w.flag = (int*)(base + o_flag);
-    w.fwdU = use_umma ? (float*)(base + o_fu) : nullptr;
-    w.bwdU = use_umma ? (float*)(base + o_bu) : nullptr;
+    w.recFE = use_umma ? (float*)(base + o_fe) : nullptr;
+    w.recG = use_umma ? (float*)(base + o_gu) : nullptr;
+    w.recK = use_umma ? (float*)(base + o_ku) : nullptr;
     w.b_identity = (M == D) ? 1 : 0;
     for (int i = 0; i < M * D && w.b_identity; ++i) w.b_identity = (c.B[i] == ((i / D == i % D) ? 1.f : 0.f));
     const int tf = (c.flags & RXG_TRANSITION_FIRST) ? 1 : 0;
@@ -786,8 +804,8 @@ static int run_large(rxg_ctx* ctx, const LgssmCall& c) {
     const unsigned blocks = (unsigned)((c.batch + NB - 1) / NB);
     if (ctx->profile) cudaEventRecord(ctx->ev[1], ctx->stream);
     if (use_umma) {
-        // tensor-pipe sweep (tcgen05 kind::tf32, 3xTF32): 128 chains per CTA
-        rc = launch_umma_sweep(ctx, c.smooth, w.fwdU, w.bwdU, dm0, c.mean0_chain, c.y, c.mean, c.T, c.batch);
+        // tensor-pipe sweep (tcgen05 kind::tf32, 3xTF32): 128 chains per CTA; u_t = K_t y_t pre-pass + recursion
+        rc = launch_umma_sweep(ctx, D, c.smooth, w.recFE, w.recG, w.recK, dm0, c.mean0_chain, c.y, c.mean, c.T, c.batch);
         if (rc != RXG_OK) return rc;
     } else {
         if (c.smooth) lgssm_block_sweep<D, M, NB, true><<<blocks, (D / 4) * (NB / 2), smw, ctx->stream>>>(w.fwdT, w.bwdT, dm0, c.mean0_chain, c.y, c.mean, c.T, c.batch);

@@ -97,6 +97,57 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// NC = 16 or 32 columns
+template <int NC>
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, float* v) {
+    if (NC == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+}
+
+// ---- TMA bulk copy (1-D, no tensor map): global -> shared, completion on an mbarrier (complete_tx)
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(mbar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(mbar))
+                 : "memory");
+}
+// bounded spin on an mbarrier phase: a mis-programmed pipeline traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* mbar, uint32_t parity) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(mbar);
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < (1u << 27); ++spin) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+
 // split an fp32 value into a tf32-representable high part and the (tf32-rounded) remainder:
 // x ~= hi + lo with ~21 bits, so A B ~= Ahi Bhi + Ahi Blo + Alo Bhi to fp32-level accuracy ("3xTF32")
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {

@@ -1,40 +1,71 @@
-// tcgen05 (UMMA) kernels of the large-state family.
-//   umma_selftest_kernel : D[128 x 64] = A[128 x 128] * B[64 x 128]' with the 3xTF32 split -- validates the
-//                          hand-written descriptors / TMEM plumbing against an fp64 product (tests/).
+// tcgen05 (UMMA) kernels of the large-state family (d = 16 / 32 / 64): the mean recursions of the shared-model
+// LGSSM sweep on the 5th-generation tensor cores, hand-written PTX (rxg_umma.cuh).
+//
+//   umma_selftest_kernel<N, K> : D[128 x N] = A[128 x K] * B[N x K]' with the 3xTF32 split -- validates the
+//                                descriptors / TMEM plumbing of every shape the sweep uses against an fp64 product.
+//   umma_ky_kernel<D>          : u_t = K_t y_t for all (t, chain): no dependency along t, so it is a plain batched
+//                                GEMM, parallel over time and chain tiles (off the recursion's critical path).
+//   lgssm_umma_sweep<D, SMOOTH>: the dependent chain  x_t = F_t x_{t-1} + u_t  (forward) and
+//                                mu_s[t] = v_t + G_t mu_s[t+1],  v_t = E_t x_t  (backward).  One CTA = 128 chains =
+//                                the M rows of the A operand X[128 x D] (K-major); the forward B operand is the
+//                                stacked block [F_t ; E_{t-1}] (N = 2D), so one MMA group yields both x_t and the
+//                                backward pass's v_{t-1} from the same A operand.
+// Operands are split tf32 hi / lo and combined as hi*hi + hi*lo + lo*hi (3xTF32), accumulated in several TMEM
+// accumulators that are summed in fp32 registers (the tensor pipe's adder truncates).
+// Per-step gain records are pre-arranged in the canonical UMMA layout by large_gain_tables and arrive with one
+// TMA bulk copy (cp.async.bulk ... mbarrier::complete_tx) per step, double buffered.
 #include "rxg_internal.h"
 #include "rxg_umma.cuh"
 
 namespace rxg {
 
-constexpr int UM_M = 128, UM_N = 64, UM_K = 128;
-constexpr uint32_t UM_A_BYTES = UM_M * UM_K * 4, UM_B_BYTES = UM_N * UM_K * 4;
+template <int D>
+struct US {
+    static constexpr int KS = D / 8;                       // MMAs (K = 8) per pass over the K axis
+    static constexpr int NHH = (KS + 3) / 4;               // hi*hi accumulators: at most 4 MMAs each
+    static constexpr int NACC = NHH + 1;                   // + one for the two cross terms
+    static constexpr uint32_t X_BYTES = 128u * D * 4u;     // one part (hi or lo) of the A operand
+    static constexpr uint32_t G_BYTES = (uint32_t)D * D * 4u;       // one part of a D x D gain block
+    static constexpr uint32_t FE_BYTES = 2u * G_BYTES;              // one part of [F ; E] (2D x D)
+    static constexpr uint32_t SBO = umma::sbo_bytes(D);
+    static constexpr int NC = D >= 32 ? 32 : 16;           // TMEM load width (columns)
+    static constexpr uint32_t tcols(int n) {               // power of two >= NACC * n, >= 32
+        uint32_t c = 32;
+        while (c < (uint32_t)(NACC * n)) c <<= 1;
+        return c;
+    }
+};
 
+// ------------------------------------------------------------------------------------------------ self-test
+template <int N, int K>
 __global__ void __launch_bounds__(128, 1)
 umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ Dout) {
+    constexpr uint32_t A_BYTES = 128u * K * 4u, B_BYTES = (uint32_t)N * K * 4u;
+    constexpr uint32_t TC = N < 32 ? 32 : N;
     extern __shared__ __align__(1024) uint8_t sm[];
     uint8_t* sAhi = sm;
-    uint8_t* sAlo = sAhi + UM_A_BYTES;
-    uint8_t* sBhi = sAlo + UM_A_BYTES;
-    uint8_t* sBlo = sBhi + UM_B_BYTES;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(sBlo + UM_B_BYTES);
+    uint8_t* sAlo = sAhi + A_BYTES;
+    uint8_t* sBhi = sAlo + A_BYTES;
+    uint8_t* sBlo = sBhi + B_BYTES;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(sBlo + B_BYTES);
     uint32_t* tptr = reinterpret_cast<uint32_t*>(mbar + 1);
-    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+    const int tid = threadIdx.x, warp = tid / 32;
 
-    for (int idx = tid; idx < UM_M * UM_K; idx += 128) {
-        const int r = idx / UM_K, k = idx % UM_K;
+    for (int idx = tid; idx < 128 * K; idx += 128) {
+        const int r = idx / K, k = idx % K;
         float hi, lo;
         umma::split_tf32(A[idx], hi, lo);
-        *reinterpret_cast<float*>(sAhi + umma::elem_off(r, k, UM_K)) = hi;
-        *reinterpret_cast<float*>(sAlo + umma::elem_off(r, k, UM_K)) = lo;
+        *reinterpret_cast<float*>(sAhi + umma::elem_off(r, k, K)) = hi;
+        *reinterpret_cast<float*>(sAlo + umma::elem_off(r, k, K)) = lo;
     }
-    for (int idx = tid; idx < UM_N * UM_K; idx += 128) {
-        const int r = idx / UM_K, k = idx % UM_K;
+    for (int idx = tid; idx < N * K; idx += 128) {
+        const int r = idx / K, k = idx % K;
         float hi, lo;
         umma::split_tf32(B[idx], hi, lo);
-        *reinterpret_cast<float*>(sBhi + umma::elem_off(r, k, UM_K)) = hi;
-        *reinterpret_cast<float*>(sBlo + umma::elem_off(r, k, UM_K)) = lo;
+        *reinterpret_cast<float*>(sBhi + umma::elem_off(r, k, K)) = hi;
+        *reinterpret_cast<float*>(sBlo + umma::elem_off(r, k, K)) = lo;
     }
-    if (warp == 0) umma::tmem_alloc(tptr, 64);
+    if (warp == 0) umma::tmem_alloc(tptr, TC);
     if (tid == 0) {
         umma::mbar_init(mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -45,14 +76,14 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, f
     umma::fence_after();
     const uint32_t tmem = *tptr;
     if (tid == 0) {
-        const uint32_t idesc = umma::idesc_tf32(UM_M, UM_N);
-        const uint32_t sbo = umma::sbo_bytes(UM_K);
+        const uint32_t idesc = umma::idesc_tf32(128, N);
+        const uint32_t sbo = umma::sbo_bytes(K);
         const uint32_t a_hi = (uint32_t)__cvta_generic_to_shared(sAhi), a_lo = (uint32_t)__cvta_generic_to_shared(sAlo);
         const uint32_t b_hi = (uint32_t)__cvta_generic_to_shared(sBhi), b_lo = (uint32_t)__cvta_generic_to_shared(sBlo);
         uint32_t acc = 0;
         for (int pass = 0; pass < 3; ++pass) {
             const uint32_t a0 = pass == 2 ? a_lo : a_hi, b0 = pass == 1 ? b_lo : b_hi;
-            for (int kk = 0; kk < UM_K / 8; ++kk) {
+            for (int kk = 0; kk < K / 8; ++kk) {
                 umma::mma_tf32(tmem, umma::smem_desc(a0 + kk * 2 * umma::LBO, umma::LBO, sbo),
                                umma::smem_desc(b0 + kk * 2 * umma::LBO, umma::LBO, sbo), idesc, acc);
                 acc = 1;
@@ -60,211 +91,377 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, f
         }
         umma::commit(mbar);
     }
-    umma::mbar_wait(mbar, 0);
+    umma::mbar_wait_bounded(mbar, 0);
     umma::fence_after();
-    float v[32];
-    const int row = warp * 32 + lane;
+    constexpr int NC = N >= 32 ? 32 : 16;
+    float v[NC];
+    const int row = tid;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + half * 32, v);
+    for (int c = 0; c < N / NC; ++c) {
+        umma::tmem_ldn<NC>(tmem + ((uint32_t)(warp * 32) << 16) + c * NC, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) Dout[row * UM_N + half * 32 + j] = v[j];
+        for (int j = 0; j < NC; ++j) Dout[row * N + c * NC + j] = v[j];
     }
     umma::fence_before();
     __syncthreads();
-    if (warp == 0) umma::tmem_dealloc(tmem, 64);
+    if (warp == 0) umma::tmem_dealloc(tmem, TC);
 }
 
-
-// ------------------------------------------------------------------------------------------------
-// lgssm_umma_sweep: the d = 64 mean sweep on the tensor pipe.  One CTA = 128 chains = the M rows of
-// the UMMA A operand Z[128 x 128] = [x ; y_t] (forward) or [mu_f,t ; x_next] (backward), K-major;
-// the B operand is the per-step gain block W_t[64 x 128] = [F_t | K_t] or [E_t | G_t], pre-split
-// into tf32 hi / lo parts and pre-arranged in the canonical layout by large_gain_tables, so one
-// cp.async stream brings it in.  D[128 x 64] (fp32, TMEM) is the new state: every thread owns one
-// chain, reads its 64 new components with tcgen05.ld, stores them to HBM (coalesced over chains) and
-// writes them back, hi/lo split, as next step's A operand.  Z = Zhi + Zlo, W = Whi + Wlo, and the
-// product is Zhi Whi + Zhi Wlo + Zlo Whi (3xTF32) so the recursion keeps fp32-level accuracy.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cpa16u(void* s, const void* g) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(s)), "l"(g));
-}
-
-template <bool SMOOTH>
-__global__ void __launch_bounds__(128, 1)
-lgssm_umma_sweep(const float* __restrict__ fwdU, const float* __restrict__ bwdU, const float* __restrict__ m0,
-                 const float* __restrict__ m0c, const float* __restrict__ y, float* __restrict__ mean, int T,
-                 int64_t batch) {
-    constexpr int D = 64;
-    extern __shared__ __align__(1024) uint8_t sm[];
-    uint8_t* sZhi = sm;
-    uint8_t* sZlo = sZhi + UM_A_BYTES;
-    uint8_t* sWhi = sZlo + UM_A_BYTES;            // Whi and Wlo are contiguous (one 64 KB record per step)
-    uint8_t* sWlo = sWhi + UM_B_BYTES;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(sWlo + UM_B_BYTES);
-    uint32_t* tptr = reinterpret_cast<uint32_t*>(mbar + 1);
-    const int tid = threadIdx.x, warp = tid / 32;
-    const int64_t b0 = (int64_t)blockIdx.x * UM_M;
-    const bool active = (b0 + tid) < batch;
-    const int64_t bc = active ? b0 + tid : b0;    // inactive rows shadow the first chain (never stored)
-    constexpr size_t REC = (size_t)2 * UM_N * UM_K;   // floats per per-step record (hi then lo)
-
-    auto load_W = [&](const float* rec) {
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(rec);
-        for (int p = tid; p < (int)(2 * UM_B_BYTES / 16); p += 128) cpa16u(sWhi + 16 * p, src + 16 * p);
-        asm volatile("cp.async.commit_group;\n" ::);
-    };
-    // write 4 consecutive k of row `tid` (one 16-byte chunk of a core matrix), hi and lo parts
-    auto put4 = [&](int k0, float a, float b, float c, float d) {
+// ------------------------------------------------------------------------------------------------ shared pieces
+// write this thread's row (chain) of the A operand: D values, split hi / lo, 16-byte pieces of the core matrices
+template <int D>
+__device__ __forceinline__ void put_row(uint8_t* sHi, uint8_t* sLo, int row, const float* x) {
+#pragma unroll
+    for (int k0 = 0; k0 < D; k0 += 4) {
         float4 hi, lo;
-        umma::split_tf32(a, hi.x, lo.x); umma::split_tf32(b, hi.y, lo.y);
-        umma::split_tf32(c, hi.z, lo.z); umma::split_tf32(d, hi.w, lo.w);
-        const uint32_t off = umma::elem_off(tid, k0, UM_K);
-        *reinterpret_cast<float4*>(sZhi + off) = hi;
-        *reinterpret_cast<float4*>(sZlo + off) = lo;
-    };
+        umma::split_tf32(x[k0], hi.x, lo.x); umma::split_tf32(x[k0 + 1], hi.y, lo.y);
+        umma::split_tf32(x[k0 + 2], hi.z, lo.z); umma::split_tf32(x[k0 + 3], hi.w, lo.w);
+        const uint32_t off = umma::elem_off(row, k0, D);
+        *reinterpret_cast<float4*>(sHi + off) = hi;
+        *reinterpret_cast<float4*>(sLo + off) = lo;
+    }
+}
+// one thread: D_acc[128 x N] = X * W'  as hi*hi (NHH accumulators, <= 4 MMAs each) + hi*lo + lo*hi (one accumulator)
+template <int D>
+__device__ __forceinline__ void issue_3xtf32(uint32_t tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                             int N, uint64_t* mbar) {
+    using S = US<D>;
+    const uint32_t idesc = umma::idesc_tf32(128, N);
+#pragma unroll
+    for (int kk = 0; kk < S::KS; ++kk)
+        umma::mma_tf32(tmem + (uint32_t)N * (kk / 4), umma::smem_desc(a_hi + kk * 2 * umma::LBO, umma::LBO, S::SBO),
+                       umma::smem_desc(b_hi + kk * 2 * umma::LBO, umma::LBO, S::SBO), idesc, (kk % 4) != 0);
+#pragma unroll
+    for (int kk = 0; kk < S::KS; ++kk)
+        umma::mma_tf32(tmem + (uint32_t)N * S::NHH, umma::smem_desc(a_hi + kk * 2 * umma::LBO, umma::LBO, S::SBO),
+                       umma::smem_desc(b_lo + kk * 2 * umma::LBO, umma::LBO, S::SBO), idesc, kk != 0);
+#pragma unroll
+    for (int kk = 0; kk < S::KS; ++kk)
+        umma::mma_tf32(tmem + (uint32_t)N * S::NHH, umma::smem_desc(a_lo + kk * 2 * umma::LBO, umma::LBO, S::SBO),
+                       umma::smem_desc(b_hi + kk * 2 * umma::LBO, umma::LBO, S::SBO), idesc, 1u);
+    umma::commit(mbar);
+}
+// this thread's row of columns [c0, c0 + D) summed over the NACC accumulators (cross terms first: smallest)
+template <int D>
+__device__ __forceinline__ void read_acc(uint32_t lane_base, int N, int c0, float* out) {
+    using S = US<D>;
+    float v[S::NC];
+#pragma unroll
+    for (int c = 0; c < D / S::NC; ++c) {
+        umma::tmem_ldn<S::NC>(lane_base + (uint32_t)N * S::NHH + c0 + c * S::NC, out + c * S::NC);
+#pragma unroll
+        for (int a = 0; a < S::NHH; ++a) {
+            umma::tmem_ldn<S::NC>(lane_base + (uint32_t)N * a + c0 + c * S::NC, v);
+#pragma unroll
+            for (int k = 0; k < S::NC; ++k) out[c * S::NC + k] += v[k];
+        }
+    }
+}
 
-    // Five fp32 accumulators of 64 columns each: the tensor pipe's adder truncates, so a single
-    // accumulator over 48 MMAs drifts by ~3e-6 per step (measured: 2e-5 after the recursion).  The
-    // hi*hi product is accumulated in four K-chunks (4 MMAs each) and the two cross terms in a
-    // fifth; the five partial sums are added in fp32 registers (round-to-nearest).
-    constexpr uint32_t NACC = 5, TCOLS = 512;
+// ------------------------------------------------------------------------------------------------ u_t = K_t y_t
+// grid = (chain tiles, time slices).  recK[t] = K_t (D x D) hi | lo in the canonical layout.  u is written in the
+// [T][D][batch] layout of the posterior means (the sweep consumes u_t from mean[t] before it overwrites that row).
+template <int D>
+__global__ void __launch_bounds__(128)
+umma_ky_kernel(const float* __restrict__ recK, const float* __restrict__ y, float* __restrict__ u, int T, int64_t batch) {
+    using S = US<D>;
+    constexpr uint32_t REC_BYTES = 2 * S::G_BYTES;
+    extern __shared__ __align__(1024) uint8_t sm[];
+    uint8_t* sYhi = sm;
+    uint8_t* sYlo = sYhi + S::X_BYTES;
+    uint8_t* sK[2] = {sYlo + S::X_BYTES, sYlo + S::X_BYTES + REC_BYTES};
+    uint64_t* mma_bar = reinterpret_cast<uint64_t*>(sK[1] + REC_BYTES);
+    uint64_t* full = mma_bar + 1;                 // [2]
+    uint32_t* tptr = reinterpret_cast<uint32_t*>(full + 2);
+    const int tid = threadIdx.x, warp = tid / 32;
+    const int64_t b0 = (int64_t)blockIdx.x * 128;
+    const bool active = (b0 + tid) < batch;
+    const int64_t bc = active ? b0 + tid : b0;
+    const int t_lo = (int)(((int64_t)T * blockIdx.y) / gridDim.y), t_hi = (int)(((int64_t)T * (blockIdx.y + 1)) / gridDim.y);
+    if (t_lo >= t_hi) return;
+    constexpr uint32_t TCOLS = S::tcols(D);
     if (warp == 0) umma::tmem_alloc(tptr, TCOLS);
     if (tid == 0) {
-        umma::mbar_init(mbar, 1);
+        umma::mbar_init(mma_bar, 1); umma::mbar_init(full, 1); umma::mbar_init(full + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    load_W(fwdU);
-    float x[D], nxt[D];
+    float yv[D], yn[D];
 #pragma unroll
-    for (int k = 0; k < D; ++k) { x[k] = m0c ? __ldg(m0c + (int64_t)k * batch + bc) : m0[k]; nxt[k] = __ldg(y + (int64_t)k * batch + bc); }
-#pragma unroll
-    for (int k = 0; k < D; k += 4) { put4(k, x[k], x[k + 1], x[k + 2], x[k + 3]); put4(D + k, nxt[k], nxt[k + 1], nxt[k + 2], nxt[k + 3]); }
+    for (int k = 0; k < D; ++k) yv[k] = __ldg(y + ((int64_t)t_lo * D + k) * batch + bc);
     umma::fence_before();
     __syncthreads();
     umma::fence_after();
     const uint32_t tmem = *tptr;
-    const uint32_t idesc = umma::idesc_tf32(UM_M, UM_N), sbo = umma::sbo_bytes(UM_K);
-    const uint32_t a_hi = (uint32_t)__cvta_generic_to_shared(sZhi), a_lo = (uint32_t)__cvta_generic_to_shared(sZlo);
-    const uint32_t b_hi = (uint32_t)__cvta_generic_to_shared(sWhi), b_lo = (uint32_t)__cvta_generic_to_shared(sWlo);
-    uint32_t phase = 0;
-
-    auto step_mma = [&]() {     // operands are in place (generic writes + cp.async): publish, issue, commit
-        asm volatile("cp.async.wait_all;\n" ::: "memory");
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t a_hi = (uint32_t)__cvta_generic_to_shared(sYhi), a_lo = (uint32_t)__cvta_generic_to_shared(sYlo);
+    constexpr size_t REC = (size_t)2 * D * D;
+    if (tid == 0) {
+        for (int j = 0; j < 2; ++j)
+            if (t_lo + j < t_hi) {
+                umma::mbar_expect_tx(full + j, REC_BYTES);
+                umma::bulk_g2s(sK[j], recK + (size_t)(t_lo + j) * REC, REC_BYTES, full + j);
+            }
+    }
+    uint32_t use[2] = {0, 0}, mstep = 0;
+    for (int t = t_lo; t < t_hi; ++t) {
+        const int buf = (t - t_lo) & 1;
+        put_row<D>(sYhi, sYlo, tid, yv);
         umma::fence_async_smem();
         umma::fence_before();
         __syncthreads();
         umma::fence_after();
         if (tid == 0) {
-#pragma unroll
-            for (int kk = 0; kk < UM_K / 8; ++kk)          // hi * hi, accumulator kk / 4
-                umma::mma_tf32(tmem + 64 * (kk / 4), umma::smem_desc(a_hi + kk * 2 * umma::LBO, umma::LBO, sbo),
-                               umma::smem_desc(b_hi + kk * 2 * umma::LBO, umma::LBO, sbo), idesc, (kk % 4) != 0);
-#pragma unroll
-            for (int kk = 0; kk < UM_K / 8; ++kk)          // hi * lo
-                umma::mma_tf32(tmem + 64 * 4, umma::smem_desc(a_hi + kk * 2 * umma::LBO, umma::LBO, sbo),
-                               umma::smem_desc(b_lo + kk * 2 * umma::LBO, umma::LBO, sbo), idesc, kk != 0);
-#pragma unroll
-            for (int kk = 0; kk < UM_K / 8; ++kk)          // lo * hi
-                umma::mma_tf32(tmem + 64 * 4, umma::smem_desc(a_lo + kk * 2 * umma::LBO, umma::LBO, sbo),
-                               umma::smem_desc(b_hi + kk * 2 * umma::LBO, umma::LBO, sbo), idesc, 1u);
-            umma::commit(mbar);
+            umma::mbar_wait_bounded(full + buf, use[buf] & 1);
+            ++use[buf];
+            const uint32_t b_hi = (uint32_t)__cvta_generic_to_shared(sK[buf]);
+            issue_3xtf32<D>(tmem, a_hi, a_lo, b_hi, b_hi + S::G_BYTES, D, mma_bar);
         }
-    };
-    auto read_state = [&]() {   // sum of the five accumulators, row of this thread's chain -> x[0..63]
-        umma::mbar_wait(mbar, phase);
-        phase ^= 1;
+        if (t + 1 < t_hi) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) yn[k] = __ldg(y + ((int64_t)(t + 1) * D + k) * batch + bc);
+        }
+        umma::mbar_wait_bounded(mma_bar, mstep & 1);
+        ++mstep;
         umma::fence_after();
-        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-        float v[32];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            umma::tmem_ld32(lane_base + 64 * 4 + 32 * half, x + 32 * half);          // cross terms first (smallest)
-#pragma unroll
-            for (uint32_t a = 0; a < NACC - 1; ++a) {
-                umma::tmem_ld32(lane_base + 64 * a + 32 * half, v);
-#pragma unroll
-                for (int k = 0; k < 32; ++k) x[32 * half + k] += v[k];
-            }
+        if (tid == 0 && t + 2 < t_hi) {          // the MMAs that read sK[buf] are complete
+            umma::mbar_expect_tx(full + buf, REC_BYTES);
+            umma::bulk_g2s(sK[buf], recK + (size_t)(t + 2) * REC, REC_BYTES, full + buf);
         }
-        umma::fence_before();
-    };
-
-    // ---------------------------------------------------------------- forward: Z = [x ; y_t], W = [F_t | K_t]
-    for (int t = 0; t < T; ++t) {
-        step_mma();
-        if (t + 1 < T) {
+        float out[D];
+        read_acc<D>(lane_base, D, 0, out);
+        if (active) {
 #pragma unroll
-            for (int k = 0; k < D; ++k) nxt[k] = __ldg(y + ((int64_t)(t + 1) * D + k) * batch + bc);
+            for (int k = 0; k < D; ++k) u[((int64_t)t * D + k) * batch + bc] = out[k];
         }
-        read_state();
-        if (t + 1 < T) load_W(fwdU + (size_t)(t + 1) * REC);
 #pragma unroll
-        for (int k = 0; k < D; ++k)
-            if (active) mean[((int64_t)t * D + k) * batch + bc] = x[k];
-        if (t + 1 < T) {
-#pragma unroll
-            for (int k = 0; k < D; k += 4) { put4(k, x[k], x[k + 1], x[k + 2], x[k + 3]); put4(D + k, nxt[k], nxt[k + 1], nxt[k + 2], nxt[k + 3]); }
-        }
+        for (int k = 0; k < D; ++k) yv[k] = yn[k];
     }
-    if (SMOOTH) {
-        // ------------------------------------------------------------ backward: Z = [mu_f,t ; x_next], W = [E_t | G_t]
-        // x currently holds mu_f[T-1]; record T-1 is E = I, G = 0
-        load_W(bwdU + (size_t)(T - 1) * REC);
-#pragma unroll
-        for (int k = 0; k < D; k += 4) { put4(k, x[k], x[k + 1], x[k + 2], x[k + 3]); put4(D + k, 0.f, 0.f, 0.f, 0.f); }
-        for (int t = T - 1; t >= 0; --t) {
-            step_mma();
-            if (t - 1 >= 0) {
-#pragma unroll
-                for (int k = 0; k < D; ++k) nxt[k] = mean[((int64_t)(t - 1) * D + k) * batch + bc];
-            }
-            read_state();
-            if (t - 1 >= 0) load_W(bwdU + (size_t)(t - 1) * REC);
-#pragma unroll
-            for (int k = 0; k < D; ++k)
-                if (active) mean[((int64_t)t * D + k) * batch + bc] = x[k];
-            if (t - 1 >= 0) {
-#pragma unroll
-                for (int k = 0; k < D; k += 4) { put4(k, nxt[k], nxt[k + 1], nxt[k + 2], nxt[k + 3]); put4(D + k, x[k], x[k + 1], x[k + 2], x[k + 3]); }
-            }
-        }
-    }
-    asm volatile("cp.async.wait_all;\n" ::: "memory");
     umma::fence_before();
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem, TCOLS);
 }
 
-int launch_umma_sweep(rxg_ctx* ctx, bool smooth, const float* fwdU, const float* bwdU, const float* m0, const float* m0c,
-                      const float* y, float* mean, int T, int64_t batch) {
-    const size_t smem = 2 * UM_A_BYTES + 2 * UM_B_BYTES + 64;
+// ------------------------------------------------------------------------------------------------ the recursion
+// mean[t] holds u_t on entry.  Forward step t: D = X_{t-1} [F_t ; E_{t-1}]'  ->  x_t = D[:, :D] + u_t (next A
+// operand; stored as the filtered mean when !SMOOTH), v_{t-1} = D[:, D:] (stored into mean[t-1]).  Backward step t:
+// mu_s[t] = v_t + mu_s[t+1] G_t' (stored into mean[t]; next A operand).  mu_s[T-1] = x_{T-1}.
+template <int D, bool SMOOTH>
+__global__ void __launch_bounds__(128)
+lgssm_umma_sweep(const float* __restrict__ recFE, const float* __restrict__ recG, const float* __restrict__ m0,
+                 const float* __restrict__ m0c, float* mean, int T, int64_t batch) {
+    using S = US<D>;
+    constexpr int NF = SMOOTH ? 2 * D : D;                       // forward N
+    constexpr uint32_t FE_REC_BYTES = 2 * S::FE_BYTES, G_REC_BYTES = 2 * S::G_BYTES;
+    constexpr size_t FE_REC = (size_t)4 * D * D, G_REC = (size_t)2 * D * D;   // floats per record
+    extern __shared__ __align__(1024) uint8_t sm[];
+    uint8_t* sXhi = sm;
+    uint8_t* sXlo = sXhi + S::X_BYTES;
+    uint8_t* sB[2] = {sXlo + S::X_BYTES, sXlo + S::X_BYTES + FE_REC_BYTES};
+    uint64_t* mma_bar = reinterpret_cast<uint64_t*>(sB[1] + FE_REC_BYTES);
+    uint64_t* full = mma_bar + 1;                 // [2]
+    uint32_t* tptr = reinterpret_cast<uint32_t*>(full + 2);
+    const int tid = threadIdx.x, warp = tid / 32;
+    const int64_t b0 = (int64_t)blockIdx.x * 128;
+    const bool active = (b0 + tid) < batch;
+    const int64_t bc = active ? b0 + tid : b0;    // inactive rows shadow the tile's first chain (never stored)
+    constexpr uint32_t TCOLS = S::tcols(NF);
+    if (warp == 0) umma::tmem_alloc(tptr, TCOLS);
+    if (tid == 0) {
+        umma::mbar_init(mma_bar, 1); umma::mbar_init(full, 1); umma::mbar_init(full + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    float x[D], cur[D], nxt[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        x[k] = m0c ? __ldg(m0c + (int64_t)k * batch + bc) : m0[k];
+        cur[k] = mean[(int64_t)k * batch + bc];                  // u_0
+    }
+    put_row<D>(sXhi, sXlo, tid, x);
+    umma::fence_before();
+    __syncthreads();
+    umma::fence_after();
+    const uint32_t tmem = *tptr;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t a_hi = (uint32_t)__cvta_generic_to_shared(sXhi), a_lo = (uint32_t)__cvta_generic_to_shared(sXlo);
+    if (tid == 0) {
+        for (int j = 0; j < 2; ++j)
+            if (j < T) {
+                umma::mbar_expect_tx(full + j, FE_REC_BYTES);
+                umma::bulk_g2s(sB[j], recFE + (size_t)j * FE_REC, FE_REC_BYTES, full + j);
+            }
+    }
+    uint32_t use[2] = {0, 0}, mstep = 0;
+    // ---------------------------------------------------------------- forward
+    for (int t = 0; t < T; ++t) {
+        const int buf = t & 1;
+        umma::fence_async_smem();                  // this thread's A-operand row -> visible to the tensor (async) proxy
+        umma::fence_before();
+        __syncthreads();
+        umma::fence_after();
+        if (tid == 0) {
+            umma::mbar_wait_bounded(full + buf, use[buf] & 1);
+            ++use[buf];
+            const uint32_t b_hi = (uint32_t)__cvta_generic_to_shared(sB[buf]);
+            issue_3xtf32<D>(tmem, a_hi, a_lo, b_hi, b_hi + S::FE_BYTES, NF, mma_bar);
+        }
+        if (t + 1 < T) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) nxt[k] = mean[((int64_t)(t + 1) * D + k) * batch + bc];   // u_{t+1}
+        }
+        umma::mbar_wait_bounded(mma_bar, mstep & 1);
+        ++mstep;
+        umma::fence_after();
+        if (tid == 0 && t + 2 < T) {               // sB[buf] is free again: the MMAs of step t are complete
+            umma::mbar_expect_tx(full + buf, FE_REC_BYTES);
+            umma::bulk_g2s(sB[buf], recFE + (size_t)(t + 2) * FE_REC, FE_REC_BYTES, full + buf);
+        }
+        read_acc<D>(lane_base, NF, 0, x);
+#pragma unroll
+        for (int k = 0; k < D; ++k) x[k] += cur[k];
+        put_row<D>(sXhi, sXlo, tid, x);            // next step's A operand (and the backward pass's first one)
+        if (!SMOOTH) {
+            if (active) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) mean[((int64_t)t * D + k) * batch + bc] = x[k];
+            }
+        } else if (t >= 1) {
+            float v[D];
+            read_acc<D>(lane_base, NF, D, v);      // v_{t-1} = E_{t-1} x_{t-1}
+            if (active) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) mean[((int64_t)(t - 1) * D + k) * batch + bc] = v[k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) cur[k] = nxt[k];
+        umma::fence_before();
+    }
+    if (SMOOTH) {
+        // ------------------------------------------------------------ backward
+        if (active) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) mean[((int64_t)(T - 1) * D + k) * batch + bc] = x[k];      // mu_s[T-1] = x_{T-1}
+        }
+        if (tid == 0) {
+            for (int j = 0; j < 2; ++j)
+                if (T - 2 - j >= 0) {
+                    umma::mbar_expect_tx(full + j, G_REC_BYTES);
+                    umma::bulk_g2s(sB[j], recG + (size_t)(T - 2 - j) * G_REC, G_REC_BYTES, full + j);
+                }
+        }
+        if (T >= 2) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) cur[k] = mean[((int64_t)(T - 2) * D + k) * batch + bc];    // v_{T-2}
+        }
+        for (int r = 0; T - 2 - r >= 0; ++r) {
+            const int t = T - 2 - r, buf = r & 1;
+            umma::fence_async_smem();
+            umma::fence_before();
+            __syncthreads();
+            umma::fence_after();
+            if (tid == 0) {
+                umma::mbar_wait_bounded(full + buf, use[buf] & 1);
+                ++use[buf];
+                const uint32_t b_hi = (uint32_t)__cvta_generic_to_shared(sB[buf]);
+                issue_3xtf32<D>(tmem, a_hi, a_lo, b_hi, b_hi + S::G_BYTES, D, mma_bar);
+            }
+            if (t - 1 >= 0) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) nxt[k] = mean[((int64_t)(t - 1) * D + k) * batch + bc];   // v_{t-1}
+            }
+            umma::mbar_wait_bounded(mma_bar, mstep & 1);
+            ++mstep;
+            umma::fence_after();
+            if (tid == 0 && t - 2 >= 0) {
+                umma::mbar_expect_tx(full + buf, G_REC_BYTES);
+                umma::bulk_g2s(sB[buf], recG + (size_t)(t - 2) * G_REC, G_REC_BYTES, full + buf);
+            }
+            read_acc<D>(lane_base, D, 0, x);
+#pragma unroll
+            for (int k = 0; k < D; ++k) x[k] += cur[k];
+            if (t > 0) put_row<D>(sXhi, sXlo, tid, x);
+            if (active) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) mean[((int64_t)t * D + k) * batch + bc] = x[k];
+            }
+#pragma unroll
+            for (int k = 0; k < D; ++k) cur[k] = nxt[k];
+            umma::fence_before();
+        }
+    }
+    umma::fence_before();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, TCOLS);
+}
+
+template <int D>
+static int launch_umma_sweep_d(rxg_ctx* ctx, bool smooth, const float* recFE, const float* recG, const float* recK,
+                               const float* m0, const float* m0c, const float* y, float* mean, int T, int64_t batch) {
+    using S = US<D>;
+    const size_t smem_ky = 2 * S::X_BYTES + 4 * S::G_BYTES + 64;
+    const size_t smem_sw = 2 * S::X_BYTES + 4 * S::FE_BYTES + 64;
     static bool done = false;
     if (!done) {
-        RXG_CUDA(ctx, cudaFuncSetAttribute(lgssm_umma_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RXG_CUDA(ctx, cudaFuncSetAttribute(lgssm_umma_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RXG_CUDA(ctx, cudaFuncSetAttribute(umma_ky_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ky));
+        RXG_CUDA(ctx, cudaFuncSetAttribute(lgssm_umma_sweep<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sw));
+        RXG_CUDA(ctx, cudaFuncSetAttribute(lgssm_umma_sweep<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sw));
         done = true;
     }
-    const unsigned blocks = (unsigned)((batch + UM_M - 1) / UM_M);
-    if (smooth) lgssm_umma_sweep<true><<<blocks, 128, smem, ctx->stream>>>(fwdU, bwdU, m0, m0c, y, mean, T, batch);
-    else        lgssm_umma_sweep<false><<<blocks, 128, smem, ctx->stream>>>(fwdU, bwdU, m0, m0c, y, mean, T, batch);
-    ctx->launches += 1;
+    const unsigned tiles = (unsigned)((batch + 127) / 128);
+    // time slices of the K y pre-pass: about two CTAs per SM in flight overall
+    int tsplit = (int)((2 * (unsigned)ctx->sm_count + tiles - 1) / tiles);
+    if (tsplit < 1) tsplit = 1;
+    if (tsplit > T) tsplit = T;
+    umma_ky_kernel<D><<<dim3(tiles, (unsigned)tsplit), 128, smem_ky, ctx->stream>>>(recK, y, mean, T, batch);
+    if (smooth) lgssm_umma_sweep<D, true><<<tiles, 128, smem_sw, ctx->stream>>>(recFE, recG, m0, m0c, mean, T, batch);
+    else        lgssm_umma_sweep<D, false><<<tiles, 128, smem_sw, ctx->stream>>>(recFE, recG, m0, m0c, mean, T, batch);
+    ctx->launches += 2;
     return check_cuda(ctx, cudaGetLastError(), "lgssm_umma_sweep");
+}
+
+int launch_umma_sweep(rxg_ctx* ctx, int d, bool smooth, const float* recFE, const float* recG, const float* recK,
+                      const float* m0, const float* m0c, const float* y, float* mean, int T, int64_t batch) {
+    switch (d) {
+        case 16: return launch_umma_sweep_d<16>(ctx, smooth, recFE, recG, recK, m0, m0c, y, mean, T, batch);
+        case 32: return launch_umma_sweep_d<32>(ctx, smooth, recFE, recG, recK, m0, m0c, y, mean, T, batch);
+        case 64: return launch_umma_sweep_d<64>(ctx, smooth, recFE, recG, recK, m0, m0c, y, mean, T, batch);
+        default: return fail(ctx, RXG_ERR_UNSUPPORTED, "umma sweep: d=%d", d);
+    }
+}
+
+template <int N, int K>
+static int run_selftest(rxg_ctx* ctx, const float* A, const float* B, float* D) {
+    const size_t smem = 2 * (size_t)128 * K * 4 + 2 * (size_t)N * K * 4 + 64;
+    RXG_CUDA(ctx, cudaFuncSetAttribute(umma_selftest_kernel<N, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_selftest_kernel<N, K><<<1, 128, smem, ctx->stream>>>(A, B, D);
+    ctx->launches += 1;
+    int rc = check_cuda(ctx, cudaGetLastError(), "umma_selftest_kernel");
+    if (rc != RXG_OK) return rc;
+    RXG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RXG_OK;
 }
 
 }  // namespace rxg
 
 using namespace rxg;
 
-extern "C" int rxg_selftest_umma_f32(rxg_ctx* ctx, const float* A, const float* B, float* D, unsigned flags) {
+extern "C" int rxg_selftest_umma_shape_f32(rxg_ctx* ctx, int n, int k, const float* A, const float* B, float* D,
+                                           unsigned flags) {
     if (!ctx) return RXG_ERR_BAD_ARG;
     if (!(flags & RXG_PTR_DEVICE) || !A || !B || !D) return fail(ctx, RXG_ERR_BAD_ARG, "selftest_umma: device pointers required");
-    const size_t smem = 2 * UM_A_BYTES + 2 * UM_B_BYTES + 64;
-    RXG_CUDA(ctx, cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    umma_selftest_kernel<<<1, 128, smem, ctx->stream>>>(A, B, D);
-    ctx->launches += 1;
-    int rc = check_cuda(ctx, cudaGetLastError(), "umma_selftest_kernel");
-    if (rc != RXG_OK) return rc;
-    RXG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return RXG_OK;
+    RXG_CUDA(ctx, cudaSetDevice(ctx->device));
+    switch (n * 1000 + k) {
+        case 64 * 1000 + 128: return run_selftest<64, 128>(ctx, A, B, D);
+        case 128 * 1000 + 64: return run_selftest<128, 64>(ctx, A, B, D);
+        case 64 * 1000 + 64: return run_selftest<64, 64>(ctx, A, B, D);
+        case 64 * 1000 + 32: return run_selftest<64, 32>(ctx, A, B, D);
+        case 32 * 1000 + 32: return run_selftest<32, 32>(ctx, A, B, D);
+        case 32 * 1000 + 16: return run_selftest<32, 16>(ctx, A, B, D);
+        case 16 * 1000 + 16: return run_selftest<16, 16>(ctx, A, B, D);
+        default: return fail(ctx, RXG_ERR_UNSUPPORTED, "selftest_umma: shape (N=%d, K=%d) is not one the sweeps use", n, k);
+    }
+}
+
+extern "C" int rxg_selftest_umma_f32(rxg_ctx* ctx, const float* A, const float* B, float* D, unsigned flags) {
+    return rxg_selftest_umma_shape_f32(ctx, 64, 128, A, B, D, flags);
 }

@@ -351,3 +351,24 @@ def test_large_state_doubling_vs_sequential(ctx, monkeypatch, d, T):
         assert rel_l2(a[k].cpu().numpy(), b[k].cpu().numpy()) < 2e-6
         assert rel_l2(fa[k].cpu().numpy(), fb[k].cpu().numpy()) < 2e-6
     check(a, lgssm.smooth_reference_schedule(y, **mod), nle=False)
+
+
+@pytest.mark.parametrize("d,T,batch", [(16, 90, 300), (32, 70, 129), (64, 50, 257)])
+def test_large_state_tensor_core_vs_fp32_pipe(ctx, monkeypatch, d, T, batch):
+    """d >= 16: the mean recursions run on tcgen05 (u_t = K_t y_t pre-pass + [F;E] / G recursion, 3xTF32);
+    RXG_NO_UMMA=1 runs the same tables through the FP32-pipe block sweep.  Ragged last chain tile, several
+    time slices in the pre-pass; smoothing and filtering; both against each other and the oracle."""
+    mod = f32_model(lgssm.dense_model(d, seed=5))
+    _, y = lgssm.generate_data(mod, T, batch, seed=48)
+    yd = dev(y)
+    monkeypatch.setenv("RXG_NO_UMMA", "0")
+    a = ctx.lgssm(yd, **_kw(mod), smooth=True, cov_shared_out=True)
+    fa = ctx.lgssm(yd, **_kw(mod), smooth=False, transition_first=True, cov_shared_out=True)
+    monkeypatch.setenv("RXG_NO_UMMA", "1")
+    b = ctx.lgssm(yd, **_kw(mod), smooth=True, cov_shared_out=True)
+    fb = ctx.lgssm(yd, **_kw(mod), smooth=False, transition_first=True, cov_shared_out=True)
+    assert rel_l2(a["mean"].cpu().numpy(), b["mean"].cpu().numpy()) < 5e-6
+    assert rel_l2(fa["mean"].cpu().numpy(), fb["mean"].cpu().numpy()) < 5e-6
+    ref = lgssm.smooth_reference_schedule(y, **mod)
+    assert rel_l2(a["mean"].cpu().numpy(), ref["mean"]) < TOL_MEAN
+    assert rel_l2(fa["mean"].cpu().numpy(), lgssm.filter_streaming(y, **mod)["mean"]) < TOL_MEAN
