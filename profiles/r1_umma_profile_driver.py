@@ -1,9 +1,12 @@
-import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import torch, numpy as np, rxinfer_jl_b200 as rx
-from oracle import lgssm
+import sys, os, numpy as np, torch
+sys.path.insert(0, os.getcwd())
+import rxinfer_jl_b200 as rx
+from oracle.lgssm import dense_model
+d, b, T = 64, int(os.environ.get("B", "4096")), 1000
 ctx = rx.Context(0)
-mod = {k: np.asarray(v, np.float32) for k, v in lgssm.dense_model(64).items()}
-y = torch.randn(1000, 64, 18944, device="cuda") * 3.3
-for i in range(2):
-    r = ctx.lgssm(y, **mod, smooth=True, cov_shared_out=True)
+md = {k: np.asarray(v, np.float32) for k, v in dense_model(d).items()}
+y = torch.randn(T, d, b, device="cuda") * 3.3
+mean = torch.empty(T, d, b, device="cuda")
+for _ in range(3):
+    ctx.lgssm(y, **md, smooth=True, out_mean=mean, cov_shared_out=True)
 torch.cuda.synchronize()
