@@ -313,8 +313,8 @@ int rxg_lgssm_filter_chunk_f32(rxg_ctx* ctx, int d, int m, int T, int64_t batch,
         return fail(ctx, RXG_ERR_BAD_ARG, "lgssm_filter_chunk: null pointer argument");
     if (!lgssm_supported(d, m))
         return fail(ctx, RXG_ERR_UNSUPPORTED, "lgssm_filter_chunk: (d=%d, m=%d) is outside the compiled kernel families", d, m);
-    if (lgssm_large_supported(d, m) && (neg_log_evidence || u))
-        return fail(ctx, RXG_ERR_UNSUPPORTED, "lgssm_filter_chunk (d=%d): the large-state family has no evidence / offset", d);
+    if (lgssm_large_supported(d, m) && u)
+        return fail(ctx, RXG_ERR_UNSUPPORTED, "lgssm_filter_chunk (d=%d): the large-state family has no transition offset", d);
     RXG_CUDA(ctx, cudaSetDevice(ctx->device));
     std::vector<float> zero((size_t)d, 0.f);
     LgssmCall c;

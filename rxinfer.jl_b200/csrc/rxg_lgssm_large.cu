@@ -125,6 +125,10 @@ struct LargeWs {
     // tensor-core sweep (rxg_umma_sweep.cu): per-step gain blocks split tf32 hi | lo in the canonical UMMA
     // K-major layout (K = D), or null:  recFE[t] = [F_t ; E_{t-1}] (2D x D),  recG[t] = G_t,  recK[t] = K_t (D x D)
     float *recFE, *recG, *recK;
+    // evidence (optional): evT[t][(D+M)][M] = [-(L_t^-1 B A) | L_t^-1]' (k-major, like fwdT) with S_t = L_t L_t',
+    // evc[t] = M/2 log 2pi + sum_i log L_t(i,i); null when the caller did not ask for neg_log_evidence
+    float* evT;
+    double* evc;
 };
 
 template <int D> struct LD_ { static constexpr int v = D + 1; };   // padded leading dim: no bank conflicts on transposed reads
@@ -259,6 +263,34 @@ __global__ void __launch_bounds__(256) large_gain_tables(LargeWs w, int T, int t
                 const uint32_t off = umma::elem_off(D + idx % D, idx / D, D) / 4;
                 fe[off] = 0.f; fe[2 * D * D + off] = 0.f;
             }
+    }
+    // ---- evidence tables: the whitened innovation is  w_t = L^-1 (y_t - B A x_{t-1}) = [-(L^-1 B A) | L^-1] [x_{t-1} ; y_t]
+    if (w.evT) {
+        float* et = w.evT + (size_t)t * (D + M) * M;
+        for (int idx = threadIdx.x; idx < M * D; idx += blockDim.x) {
+            const int r = idx / D, k = idx % D;
+            X0[r * LD + k] = pred ? w.BA[r * D + k] : w.B[r * D + k];
+        }
+        __syncthreads();
+        btrsm_lower<M, D, LD>(X2, X0);
+        for (int idx = threadIdx.x; idx < M * D; idx += blockDim.x) {
+            const int k = idx / M, r = idx % M;
+            et[k * M + r] = (float)(-X0[r * LD + k]);
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < M * M; idx += blockDim.x) X0[(idx / M) * LD + idx % M] = (idx / M == idx % M) ? 1.0 : 0.0;
+        __syncthreads();
+        btrsm_lower<M, M, LD>(X2, X0);
+        for (int idx = threadIdx.x; idx < M * M; idx += blockDim.x) {
+            const int k = idx / M, r = idx % M;
+            et[(D + k) * M + r] = (float)X0[r * LD + k];
+        }
+        if (threadIdx.x == 0) {
+            double sl = M * 0.91893853320467274178;   // M/2 log 2 pi
+            for (int i = 0; i < M; ++i) sl += log(X2[i * LD + i]);
+            w.evc[t] = sl;
+        }
+        __syncthreads();
     }
     // ---- backward gain
     float* bt = w.bwdT + (size_t)t * 2 * D * D;
@@ -655,6 +687,90 @@ lgssm_block_sweep(const float* __restrict__ fwdT, const float* __restrict__ bwdT
     cpa_wait<0>();
 }
 
+// ------------------------------------------------------------------------------------------------
+// neg_log_evidence of the large-state family: parallel over (chain tile, time slice).  Per step the tile GEMM
+// w_t = [-(L^-1 B A) | L^-1] [mu_f[t-1] ; y_t] (the whitened innovation, tables from large_gain_tables) and
+// q += |w_t|^2; partial[slice][chain] = sum over the slice, reduced deterministically by evidence_finish_kernel:
+// nle = sum_t (M/2 log 2pi + log det L_t) + 1/2 sum_t |w_t|^2   (innovation form; = Bethe free energy on this tree,
+// /root/reference/src/model/plugins/reactivemp_free_energy.jl:84-126).  mean[] must hold the FILTERED means.
+template <int D, int M, int NB>
+__global__ void __launch_bounds__((D / 4) * (NB / 2))
+large_evidence_kernel(const float* __restrict__ evT, const float* __restrict__ m0, const float* __restrict__ m0c,
+                      const float* __restrict__ y, const float* __restrict__ mean, double* __restrict__ partial, int T,
+                      int64_t batch) {
+    constexpr int K2 = D + M;
+    constexpr int NT = (D / 4) * (NB / 2);
+    extern __shared__ __align__(16) float smf[];
+    float* Wb[2] = {smf, smf + K2 * M};
+    float* Zb[2] = {smf + 2 * K2 * M, smf + 2 * K2 * M + K2 * NB};
+    double* red = reinterpret_cast<double*>(smf + 2 * K2 * M + 2 * K2 * NB);     // [D/4][NB]
+    const int tid = threadIdx.x;
+    const int cg = tid % (NB / 2), rg = tid / (NB / 2);
+    const int64_t b0 = (int64_t)blockIdx.x * NB;
+    const int nb = (int)((batch - b0) < NB ? (batch - b0) : NB);
+    const int t_lo = (int)(((int64_t)T * blockIdx.y) / gridDim.y), t_hi = (int)(((int64_t)T * (blockIdx.y + 1)) / gridDim.y);
+    auto load_W = [&](float* dst, const float* src) {
+        for (int p = tid; p < K2 * M / 4; p += NT) cpa16(dst + 4 * p, src + 4 * p);
+    };
+    auto load_rows = [&](float* dst, const float* src_row0, int rows) {
+        for (int p = tid; p < rows * NB; p += NT) {
+            const int r = p / NB, c = p % NB;
+            if (c < nb) cpa4(dst + r * NB + c, src_row0 + (size_t)r * batch + b0 + c);
+        }
+    };
+    auto load_Z = [&](float* dst, int t) {        // [mu_f[t-1] ; y_t]; the prior mean stands in for mu_f[-1]
+        if (t > 0) load_rows(dst, mean + (size_t)(t - 1) * D * batch, D);
+        else
+            for (int p = tid; p < D * NB; p += NT)
+                dst[p] = m0c ? ((p % NB) < nb ? m0c[(size_t)(p / NB) * batch + b0 + (p % NB)] : 0.f) : m0[p / NB];
+        load_rows(dst + D * NB, y + (size_t)t * M * batch, M);
+    };
+    for (int p = tid; p < 2 * K2 * NB; p += NT) Zb[0][p] = 0.f;       // inactive columns stay zero
+    __syncthreads();
+    float q[2] = {0.f, 0.f};
+    double qd[2] = {0.0, 0.0};
+    if (t_lo < t_hi) {
+        load_W(Wb[0], evT + (size_t)t_lo * K2 * M);
+        load_Z(Zb[0], t_lo);
+    }
+    cpa_commit();
+    float acc[4][2];
+    for (int t = t_lo; t < t_hi; ++t) {
+        const int qb = (t - t_lo) & 1;
+        if (t + 1 < t_hi) {
+            load_W(Wb[qb ^ 1], evT + (size_t)(t + 1) * K2 * M);
+            load_Z(Zb[qb ^ 1], t + 1);
+        }
+        cpa_commit();
+        cpa_wait<1>();
+        __syncthreads();
+        tile_step<M, K2, NB>(Wb[qb], Zb[qb], rg, cg, acc);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { q[0] = __fmaf_rn(acc[r][0], acc[r][0], q[0]); q[1] = __fmaf_rn(acc[r][1], acc[r][1], q[1]); }
+        if (((t - t_lo) & 31) == 31) { qd[0] += (double)q[0]; qd[1] += (double)q[1]; q[0] = q[1] = 0.f; }
+        __syncthreads();
+    }
+    cpa_wait<0>();
+    red[rg * NB + 2 * cg] = qd[0] + (double)q[0];
+    red[rg * NB + 2 * cg + 1] = qd[1] + (double)q[1];
+    __syncthreads();
+    if (tid < nb) {
+        double s = 0.0;
+        for (int r = 0; r < D / 4; ++r) s += red[r * NB + tid];
+        partial[(size_t)blockIdx.y * batch + b0 + tid] = s;
+    }
+}
+__global__ void evidence_finish_kernel(const double* __restrict__ partial, const double* __restrict__ evc, int nslices, int T,
+                                       int64_t batch, float* __restrict__ nle) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    double c = 0.0;
+    for (int t = 0; t < T; ++t) c += evc[t];
+    double s = 0.0;
+    for (int i = 0; i < nslices; ++i) s += partial[(size_t)i * batch + b];
+    nle[b] = (float)(c + 0.5 * s);
+}
+
 // cov[t][i][j][b] = tab[t][i*D + j] for every chain b (the contract's per-chain covariance output)
 __global__ void broadcast_cov_kernel(const float* __restrict__ tab, float* __restrict__ cov, int64_t rows, int64_t batch) {
     const int64_t row = blockIdx.x;
@@ -680,9 +796,9 @@ __global__ void ba_kernel(const double* B, const double* A, double* BA) {
 
 template <int D, int M>
 static int run_large(rxg_ctx* ctx, const LgssmCall& c) {
-    if ((c.flags & (RXG_MODEL_PER_CHAIN | RXG_PATH_PER_CHAIN)) || c.ymask || c.nle || c.u)
+    if ((c.flags & (RXG_MODEL_PER_CHAIN | RXG_PATH_PER_CHAIN)) || c.ymask || c.u)
         return fail(ctx, RXG_ERR_UNSUPPORTED,
-                    "lgssm (d=%d): the large-state family covers shared models without mask / evidence / offset", D);
+                    "lgssm (d=%d): the large-state family covers shared models without mask / offset", D);
     const size_t T = (size_t)c.T, DD = (size_t)D * D;
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
@@ -695,6 +811,13 @@ static int run_large(rxg_ctx* ctx, const LgssmCall& c) {
     const bool use_umma = (D >= 16 && M == D) && !(getenv("RXG_NO_UMMA") && atoi(getenv("RXG_NO_UMMA")) != 0);
     const size_t o_fe = carve(use_umma ? T * 4 * DD * 4 : 0), o_gu = carve(use_umma ? T * 2 * DD * 4 : 0);
     const size_t o_ku = carve(use_umma ? T * 2 * DD * 4 : 0);
+    constexpr int EV_NB = 32;
+    const unsigned ev_tiles = (unsigned)((c.batch + EV_NB - 1) / EV_NB);
+    int ev_slices = (int)((4 * (unsigned)ctx->sm_count + ev_tiles - 1) / ev_tiles);      // ~4 CTAs per SM in flight
+    if (ev_slices < 1) ev_slices = 1;
+    if (ev_slices > c.T) ev_slices = c.T;
+    const size_t o_evT = carve(c.nle ? T * (D + M) * M * 4 : 0), o_evc = carve(c.nle ? T * 8 : 0);
+    const size_t o_evp = carve(c.nle ? (size_t)ev_slices * c.batch * 8 : 0);
     const size_t o_scan = carve(6 * DD * 8);                                  // G_r ping-pong (A, C, J) x 2
     const size_t o_E2 = carve(T * DD * 8), o_L2 = carve(T * DD * 8);           // backward scan ping-pong
     const size_t o_flag = carve(4);
@@ -724,6 +847,8 @@ static int run_large(rxg_ctx* ctx, const LgssmCall& c) {
     w.recFE = use_umma ? (float*)(base + o_fe) : nullptr;
     w.recG = use_umma ? (float*)(base + o_gu) : nullptr;
     w.recK = use_umma ? (float*)(base + o_ku) : nullptr;
+    w.evT = c.nle ? (float*)(base + o_evT) : nullptr;
+    w.evc = c.nle ? (double*)(base + o_evc) : nullptr;
     w.b_identity = (M == D) ? 1 : 0;
     for (int i = 0; i < M * D && w.b_identity; ++i) w.b_identity = (c.B[i] == ((i / D == i % D) ? 1.f : 0.f));
     const int tf = (c.flags & RXG_TRANSITION_FIRST) ? 1 : 0;
@@ -802,16 +927,37 @@ static int run_large(rxg_ctx* ctx, const LgssmCall& c) {
         attr_done = true;
     }
     const unsigned blocks = (unsigned)((c.batch + NB - 1) / NB);
-    if (ctx->profile) cudaEventRecord(ctx->ev[1], ctx->stream);
-    if (use_umma) {
-        // tensor-pipe sweep (tcgen05 kind::tf32, 3xTF32): 128 chains per CTA; u_t = K_t y_t pre-pass + recursion
-        rc = launch_umma_sweep(ctx, D, c.smooth, w.recFE, w.recG, w.recK, dm0, c.mean0_chain, c.y, c.mean, c.T, c.batch);
-        if (rc != RXG_OK) return rc;
-    } else {
-        if (c.smooth) lgssm_block_sweep<D, M, NB, true><<<blocks, (D / 4) * (NB / 2), smw, ctx->stream>>>(w.fwdT, w.bwdT, dm0, c.mean0_chain, c.y, c.mean, c.T, c.batch);
-        else          lgssm_block_sweep<D, M, NB, false><<<blocks, (D / 4) * (NB / 2), smw, ctx->stream>>>(w.fwdT, w.bwdT, dm0, c.mean0_chain, c.y, c.mean, c.T, c.batch);
+    auto sweep = [&](bool smooth) -> int {
+        if (use_umma)   // tensor-pipe sweep (tcgen05 kind::tf32, 3xTF32): 128 chains per CTA; u_t = K_t y_t pre-pass + recursion
+            return launch_umma_sweep(ctx, D, smooth, w.recFE, w.recG, w.recK, dm0, c.mean0_chain, c.y, c.mean, c.T, c.batch);
+        if (smooth) lgssm_block_sweep<D, M, NB, true><<<blocks, (D / 4) * (NB / 2), smw, ctx->stream>>>(w.fwdT, w.bwdT, dm0, c.mean0_chain, c.y, c.mean, c.T, c.batch);
+        else        lgssm_block_sweep<D, M, NB, false><<<blocks, (D / 4) * (NB / 2), smw, ctx->stream>>>(w.fwdT, w.bwdT, dm0, c.mean0_chain, c.y, c.mean, c.T, c.batch);
         ctx->launches += 1;
-        rc = check_cuda(ctx, cudaGetLastError(), "lgssm_block_sweep");
+        return check_cuda(ctx, cudaGetLastError(), "lgssm_block_sweep");
+    };
+    if (ctx->profile) cudaEventRecord(ctx->ev[1], ctx->stream);
+    if (c.nle) {
+        // the evidence is a function of the FILTERED means: filter-mode sweep, then the (time-parallel) evidence
+        // kernels; a smoothing call re-runs the sweep in smoothing mode afterwards (the fused smoothing recursion
+        // does not keep the filtered means)
+        rc = sweep(false);
+        if (rc != RXG_OK) return rc;
+        const size_t sme = (size_t)(2 * (D + M) * M + 2 * (D + M) * EV_NB) * 4 + (size_t)(D / 4) * EV_NB * 8;
+        static bool ev_attr = false;
+        if (!ev_attr) {
+            RXG_CUDA(ctx, cudaFuncSetAttribute(large_evidence_kernel<D, M, EV_NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sme));
+            ev_attr = true;
+        }
+        large_evidence_kernel<D, M, EV_NB><<<dim3(ev_tiles, (unsigned)ev_slices), (D / 4) * (EV_NB / 2), sme, ctx->stream>>>(
+            w.evT, dm0, c.mean0_chain, c.y, c.mean, (double*)(base + o_evp), c.T, c.batch);
+        evidence_finish_kernel<<<(unsigned)((c.batch + 255) / 256), 256, 0, ctx->stream>>>(
+            (const double*)(base + o_evp), w.evc, ev_slices, c.T, c.batch, c.nle);
+        ctx->launches += 2;
+        rc = check_cuda(ctx, cudaGetLastError(), "large_evidence_kernel");
+        if (rc != RXG_OK) return rc;
+    }
+    if (c.smooth || !c.nle) {
+        rc = sweep(c.smooth);
         if (rc != RXG_OK) return rc;
     }
     if (ctx->profile) cudaEventRecord(ctx->ev[2], ctx->stream);

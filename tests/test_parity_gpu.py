@@ -330,7 +330,10 @@ def test_large_state_unsupported_options_fail_loudly(rx, ctx):
     mod = f32_model(lgssm.dense_model(16))
     y = torch.zeros(8, 16, 4, device="cuda")
     with pytest.raises(rx.RxGaussError) as e:
-        ctx.lgssm(y, **_kw(mod), smooth=True, want_evidence=True)
+        ctx.lgssm(y, **_kw(mod), smooth=True, u=np.ones(16, np.float32))
+    assert e.value.code == rx._lib.RXG_ERR_UNSUPPORTED
+    with pytest.raises(rx.RxGaussError) as e:
+        ctx.lgssm(y, **_kw(mod), smooth=True, mask=torch.ones(8, 4, dtype=torch.uint8, device="cuda"))
     assert e.value.code == rx._lib.RXG_ERR_UNSUPPORTED
 
 
@@ -372,3 +375,23 @@ def test_large_state_tensor_core_vs_fp32_pipe(ctx, monkeypatch, d, T, batch):
     ref = lgssm.smooth_reference_schedule(y, **mod)
     assert rel_l2(a["mean"].cpu().numpy(), ref["mean"]) < TOL_MEAN
     assert rel_l2(fa["mean"].cpu().numpy(), lgssm.filter_streaming(y, **mod)["mean"]) < TOL_MEAN
+
+
+@pytest.mark.parametrize("d,T,batch,tf", [(8, 60, 45, False), (16, 130, 70, True), (32, 90, 33, False), (64, 120, 130, True)])
+def test_large_state_evidence(ctx, monkeypatch, d, T, batch, tf):
+    """neg_log_evidence (= Bethe free energy on the tree) of the large-state family: filter-mode sweep + time-parallel
+    whitened-innovation kernels; smoothing and filtering calls, both sweep implementations, prior on x[1] or one
+    transition earlier."""
+    mod = f32_model(lgssm.dense_model(d, seed=9))
+    _, y = lgssm.generate_data(mod, T, batch, seed=49)
+    ref = lgssm.smooth_reference_schedule(y, **mod, transition_first=tf)
+    for no_umma in ("0", "1"):
+        monkeypatch.setenv("RXG_NO_UMMA", no_umma)
+        r = ctx.lgssm(dev(y), **_kw(mod), smooth=True, want_evidence=True, transition_first=tf, cov_shared_out=True)
+        n = r["neg_log_evidence"].cpu().numpy().astype(np.float64)
+        assert np.max(np.abs(n - ref["neg_log_evidence"]) / np.abs(ref["neg_log_evidence"])) < TOL_NLE
+        assert rel_l2(r["mean"].cpu().numpy(), ref["mean"]) < TOL_MEAN
+        f = ctx.lgssm(dev(y), **_kw(mod), smooth=False, want_evidence=True, transition_first=tf, cov_shared_out=True)
+        nf = f["neg_log_evidence"].cpu().numpy().astype(np.float64)
+        assert np.max(np.abs(nf - ref["neg_log_evidence"]) / np.abs(ref["neg_log_evidence"])) < TOL_NLE
+        assert rel_l2(f["mean"].cpu().numpy(), ref["filt_mean"]) < TOL_MEAN
