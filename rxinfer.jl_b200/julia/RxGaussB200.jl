@@ -19,6 +19,7 @@ const RXG_ASYNC            = UInt32(1) << 2
 const RXG_COV_SHARED_OUT   = UInt32(1) << 3
 const RXG_PATH_PER_CHAIN   = UInt32(1) << 4
 const RXG_TRANSITION_FIRST = UInt32(1) << 5
+const RXG_COV_REPLICATE    = UInt32(1) << 6
 
 struct RxGaussError <: Exception
     code::Cint
@@ -73,6 +74,45 @@ function smooth(ctx::Context, y::Array{Float32,3}, A, B, P, Q, m0, S0; free_ener
         check(ctx, rc)
     end
     return mean, cov, nle
+end
+
+"""
+    filter_chunk!(ctx, y, A, B, P, Q, prev_mean, carry_cov; u = nothing)
+
+One time-chunk of the streaming engine: replaces `Tc` ticks of the `RxInferenceEngine` executor
+(src/inference/streaming.jl:344-430) with `@autoupdates x_min_t_mean, x_min_t_cov = mean_cov(q(x_t))`
+(src/inference/autoupdates.jl:614-659; run as in benchmarks/...Benchmark.ipynb:199-216).  `y`, `prev_mean`,
+and the outputs are DEVICE arrays here (`CuPtr` reinterpreted as `Ptr`): `y[batch, m, Tc]`, `prev_mean[batch, d]`
+= means of q(x_{t0-1}); `carry_cov` is a host `Matrix{Float32}` (d x d, symmetric, so row/column major agree),
+updated in place.  Returns the device pointers of `(filt_mean[batch, d, Tc], filt_cov[batch, d, d, Tc])`;
+the next chunk's `prev_mean` is the last time slice of `filt_mean`.
+"""
+function filter_chunk!(ctx::Context, y::Ptr{Float32}, dims::NTuple{3,Int}, A, B, P, Q, prev_mean::Ptr{Float32},
+                       carry_cov::Matrix{Float32}, filt_mean::Ptr{Float32}, filt_cov::Ptr{Float32}; u = nothing)
+    batch, m, Tc = dims
+    d = size(A, 1)
+    Ar, Br, Pr, Qr = rowmajor(A), rowmajor(B), rowmajor(P), rowmajor(Q)
+    ur = u === nothing ? Float32[] : Vector{Float32}(u)
+    GC.@preserve Ar Br Pr Qr ur carry_cov begin
+        rc = ccall((:rxg_lgssm_filter_chunk_f32, LIB), Cint,
+            (Ptr{Cvoid}, Cint, Cint, Cint, Int64, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32},
+             Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Cuint),
+            ctx.handle, d, m, Tc, batch, Ar, Br, Pr, Qr, u === nothing ? C_NULL : pointer(ur),
+            prev_mean, carry_cov, y, filt_mean, filt_cov, C_NULL, RXG_PTR_DEVICE)
+        check(ctx, rc)
+    end
+    return filt_mean, filt_cov
+end
+
+# --- multi-GPU (one Julia process per GPU): id from rank 0 broadcast by the host (MPI.jl / Distributed), then
+#     rxg_comm_init; after the sweep one all-gather of the posterior marginals.  With a shared model pass
+#     RXG_COV_REPLICATE: only the means cross NVLink, the chain-independent covariances are filled locally.
+function allgather_posteriors!(ctx::Context, d, T, batch_local, mean::Ptr{Float32}, cov::Ptr{Float32},
+                               gmean::Ptr{Float32}, gcov::Ptr{Float32}; shared_model::Bool = true)
+    flags = RXG_PTR_DEVICE | (shared_model ? RXG_COV_REPLICATE : UInt32(0))
+    check(ctx, ccall((:rxg_allgather_posteriors, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Cint, Int64, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Cuint),
+        ctx.handle, d, T, batch_local, mean, cov, gmean, gcov, flags))
 end
 
 # --- drop-in for the result object: user code only calls mean./cov./var. on posteriors[:x]

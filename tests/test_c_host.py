@@ -1,0 +1,43 @@
+"""The drop-in boundary from plain C: include/rxgauss.h is valid C99 and C++, a C host (tests/c/abi_host.c) links
+librxgauss.so without any Python / torch, fails loudly without a GPU, and on a GPU reproduces the fp64 C twin of the
+reference schedule within the contract tolerances (host-pointer path of rxg_lgssm_smooth_f32)."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CDIR = os.path.join(ROOT, "tests", "c")
+
+
+def _build():
+    import rxinfer_jl_b200 as rx
+    rx._lib.load()                                           # the library must exist (built by __graft_entry__.build())
+    subprocess.check_call(["make", "-s", "-C", CDIR, "abi_host"])
+    return os.path.join(CDIR, "abi_host")
+
+
+def test_header_is_plain_c_and_cxx():
+    hdr = os.path.join(ROOT, "include", "rxgauss.h")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr])
+
+
+def test_c_host_links_and_fails_loudly_without_gpu():
+    import torch
+    exe = _build()
+    ldd = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+    assert "librxgauss.so" in ldd and "python" not in ldd and "torch" not in ldd
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu test")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "no CPU fallback" in (r.stderr + r.stdout) or "no CUDA device" in (r.stderr + r.stdout)
+
+
+@pytest.mark.gpu
+def test_c_host_parity_on_gpu():
+    exe = _build()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "mean relL2" in r.stdout
