@@ -315,9 +315,32 @@ def main():
             te = torch.tensor([e0.elapsed_time(e1) / e_steps], device=dev, dtype=torch.float64)
             if world > 1:
                 dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            bcast = os.environ.get("RXG_HOST_COV_D2H", "0") == "0" and ctx.host_fill_threads() >= 6
             e2e = {"value": msgs / (float(te.item()) * 1e-3), "unit": "messages/s", "ms_per_step": float(te.item()),
-                   "h2d_bytes_per_step": int(yh.numel() * 4), "d2h_bytes_per_step": int((mh.numel() + ch.numel()) * 4),
-                   "api": "rxg_lgssm_smooth_f32 with host (pinned) pointers, sliced 3-stream pipeline"}
+                   "h2d_bytes_per_step": int(yh.numel() * 4),
+                   "d2h_bytes_per_step": int((mh.numel() + (T * D * D if bcast else ch.numel())) * 4),
+                   "host_bytes_written_per_step": int((mh.numel() + ch.numel()) * 4),
+                   "api": "rxg_lgssm_smooth_f32 with host (pinned) pointers, sliced 3-stream pipeline; " +
+                          ("per-chain covariances (chain independent for the shared model) fetched once as a [T][d][d] table "
+                           "and broadcast into the caller's buffer by %d host threads" % ctx.host_fill_threads() if bcast else
+                           "full device->host copy of the per-chain covariances")}
+            # the same call with the covariance broadcast disabled: every byte of the per-chain covariances over PCIe
+            if bcast:
+                os.environ["RXG_HOST_COV_D2H"] = "1"
+                ctx.lgssm(yh, **kw, smooth=True, out_mean=mh, out_cov=ch)
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                e0.record()
+                for _ in range(e_steps):
+                    ctx.lgssm(yh, **kw, smooth=True, out_mean=mh, out_cov=ch, asynchronous=True)
+                e1.record(); torch.cuda.synchronize()
+                os.environ["RXG_HOST_COV_D2H"] = "0"
+                tf_ = torch.tensor([e0.elapsed_time(e1) / e_steps], device=dev, dtype=torch.float64)
+                if world > 1:
+                    dist.all_reduce(tf_, op=dist.ReduceOp.MAX)
+                e2e["full_d2h"] = {"value": msgs / (float(tf_.item()) * 1e-3), "ms_per_step": float(tf_.item()),
+                                   "d2h_bytes_per_step": int((mh.numel() + ch.numel()) * 4)}
             # same call with RXG_COV_SHARED_OUT: the chain-independent covariances come back once ([T][d][d])
             # instead of per chain -- what a host binding that aliases one matrix per time step would request
             del ch

@@ -78,6 +78,11 @@ int rxg_host_alloc(void** out, size_t bytes);
 int rxg_host_free(void* p);
 /* 1 if (d, m) is covered by the thread-per-chain kernel families, 0 otherwise.                 */
 int rxg_supports(int d, int m);
+/* Host threads the library will use to broadcast chain-independent covariances into a HOST output
+ * buffer (host-pointer calls of a shared model fetch the [T][d][d] table once instead of copying the
+ * per-chain duplicates over PCIe): RXG_HOST_THREADS, else min(affinity, cgroup quota, 16) divided by
+ * LOCAL_WORLD_SIZE.  Below 6 the full device->host copy is used (also forced by RXG_HOST_COV_D2H=1). */
+int rxg_host_fill_threads(void);
 /* Number of kernels this ctx has launched so far (for bench.py's gpu_launches).               */
 long long rxg_launch_count(const rxg_ctx* ctx);
 /* Per-kernel timing of the most recent fused LGSSM sweep: when enabled, CUDA events are recorded

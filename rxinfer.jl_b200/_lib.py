@@ -41,6 +41,7 @@ SIGNATURES = {
     "rxg_host_alloc": (c_int, [POINTER(c_void_p), c_size_t]),
     "rxg_host_free": (c_int, [c_void_p]),
     "rxg_supports": (c_int, [c_int, c_int]),
+    "rxg_host_fill_threads": (c_int, []),
     "rxg_launch_count": (c_longlong, [c_void_p]),
     "rxg_set_profiling": (c_int, [c_void_p, c_int]),
     "rxg_profile_last_ms": (c_int, [c_void_p, POINTER(c_float), POINTER(c_float)]),

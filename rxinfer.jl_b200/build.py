@@ -15,7 +15,7 @@ SOURCES = ["rxg_api.cu", "rxg_lgssm.cu", "rxg_lgssm_large.cu", "rxg_umma_sweep.c
 HEADERS = ["rxg_internal.h", "rxg_linalg.cuh", "rxg_gain.cuh", "rxg_lgssm_common.cuh", "rxg_lgssm_shared.cuh", "rxg_umma.cuh", os.path.join("..", "..", "include", "rxgauss.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-mavx2", "-Xcompiler", "-pthread", "--expt-relaxed-constexpr", "-Xptxas", "-v",
 ]
 
 
@@ -58,7 +58,7 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), lib: str =
 
     with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", lib, *objs, "-ldl", "-Xcompiler", "-fPIC"]
+    cmd = [nvcc, "-shared", "-o", lib, *objs, "-ldl", "-lpthread", "-Xcompiler", "-fPIC"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

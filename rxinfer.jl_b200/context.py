@@ -61,6 +61,9 @@ class Context:
     def launches(self) -> int:
         return int(self.lib.rxg_launch_count(self.h))
 
+    def host_fill_threads(self) -> int:
+        return int(self.lib.rxg_host_fill_threads())
+
     def set_profiling(self, on=True):
         self._check(self.lib.rxg_set_profiling(self.h, 1 if on else 0))
 

@@ -7,6 +7,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <immintrin.h>
+
+#include <thread>
 #include <vector>
 
 #include "rxg_internal.h"
@@ -98,6 +101,8 @@ int rxg_destroy(rxg_ctx* ctx) {
         for (int q = 0; q < 2; ++q) { cudaEventDestroy(ctx->ev_in[q]); cudaEventDestroy(ctx->ev_comp[q]); cudaEventDestroy(ctx->ev_out[q]); }
         cudaEventDestroy(ctx->ev_start);
     }
+    if (ctx->h_tab) cudaFreeHost(ctx->h_tab);
+    if (ctx->ev_tab) cudaEventDestroy(ctx->ev_tab);
     if (ctx->s_aux) {
         cudaStreamSynchronize(ctx->s_aux);
         cudaStreamDestroy(ctx->s_aux);
@@ -157,6 +162,47 @@ int rxg_profile_last_ms(rxg_ctx* ctx, float* main_kernel_ms, float* gain_kernels
 // ------------------------------------------------------------------------------------------------
 // whole-chain LGSSM sweeps
 // ------------------------------------------------------------------------------------------------
+// Host threads this process may use for the covariance broadcast of host-pointer calls:
+// RXG_HOST_THREADS, else min(affinity, cgroup quota, 16) shared between the ranks of a local job.
+static int host_fill_threads() {
+    if (const char* e = getenv("RXG_HOST_THREADS")) return atoi(e);
+    long n = (long)std::thread::hardware_concurrency();
+    if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+        char q[64]; long per = 0;
+        if (fscanf(f, "%63s %ld", q, &per) == 2 && strcmp(q, "max") != 0 && per > 0) {
+            const long lim = atol(q) / per;
+            if (lim >= 1 && lim < n) n = lim;
+        }
+        fclose(f);
+    }
+    if (n > 16) n = 16;
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) { const int w = atoi(e); if (w > 1) n /= w; }
+    return (int)(n < 1 ? 1 : n);
+}
+// dst[0..n) = v with non-temporal stores (the caller's buffer is write-only here)
+static void fill_row(float* dst, int64_t n, float v) {
+    int64_t i = 0;
+    while (i < n && (reinterpret_cast<uintptr_t>(dst + i) & 31)) dst[i++] = v;
+    const __m256 vv = _mm256_set1_ps(v);
+    for (; i + 8 <= n; i += 8) _mm256_stream_ps(dst + i, vv);
+    for (; i < n; ++i) dst[i] = v;
+}
+// cov[row][b] = tab[row] for rows [0, rows): the chain-independent covariances of a shared model, broadcast on the
+// HOST side of the PCIe link (4 d^2 bytes per (chain, step) that never have to cross it)
+static void host_broadcast_cov(float* cov, const float* tab, int64_t rows, int64_t batch, int nthreads) {
+    auto work = [=](int tid) {
+        const int64_t lo = rows * tid / nthreads, hi = rows * (tid + 1) / nthreads;
+        for (int64_t r = lo; r < hi; ++r) fill_row(cov + r * batch, batch, tab[r]);
+        _mm_sfence();
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& t : th) t.join();
+}
+
+extern "C" int rxg_host_fill_threads(void) { return host_fill_threads(); }
+
 static int lgssm_entry(rxg_ctx* ctx, bool smooth, int d, int m, int T, int64_t batch, const float* A,
                        const float* B, const float* P, const float* Q, const float* m0, const float* S0,
                        const float* u, const float* y, const uint8_t* ymask, float* mean, float* cov, float* nle,
@@ -194,7 +240,20 @@ static int lgssm_entry(rxg_ctx* ctx, bool smooth, int d, int m, int T, int64_t b
     // Batch is the innermost axis, so a slice is a pitched 2-D region of every host array.
     if (per_chain_model)
         return fail(ctx, RXG_ERR_UNSUPPORTED, "lgssm: per-chain model arrays must be device pointers");
-    const bool cov_shared = (flags & RXG_COV_SHARED_OUT) != 0;
+    // Shared model, per-chain covariances requested into a HOST buffer: they do not depend on the chain, so the device
+    // produces the [T][d][d] table once, that table crosses PCIe (T d^2 floats), and the per-chain copies are
+    // materialised by host threads while the means are still in flight -- same bytes in the caller's buffer, 4 d^2 of
+    // the 4 (d + d^2) bytes per (chain, step) less PCIe traffic.  RXG_HOST_COV_D2H=1 forces the full device->host copy;
+    // with fewer than 6 host threads per rank the PCIe copy wins and is kept.
+    bool host_bcast = cov && !(flags & RXG_COV_SHARED_OUT) && !ymask && !(flags & RXG_PATH_PER_CHAIN);
+    if (const char* e = getenv("RXG_HOST_COV_D2H")) host_bcast = host_bcast && atoi(e) == 0;
+    size_t bcast_min_mb = 64;                    // below this the thread start-up is not worth it
+    if (const char* e = getenv("RXG_HOST_BCAST_MIN_MB")) bcast_min_mb = (size_t)atol(e);
+    if ((size_t)T * d * d * (size_t)batch * 4 < (bcast_min_mb << 20)) host_bcast = false;
+    const int fill_threads = host_bcast ? host_fill_threads() : 0;
+    if (fill_threads < 6) host_bcast = false;
+    if (host_bcast) c.flags |= RXG_COV_SHARED_OUT;
+    const bool cov_shared = (c.flags & RXG_COV_SHARED_OUT) != 0;
     const bool need_cov_dev = cov || ymask || (flags & RXG_PATH_PER_CHAIN);
     int ns = 1;
     if (batch >= 16384) ns = (int)((batch + 8191) / 8192);
@@ -265,7 +324,19 @@ static int lgssm_entry(rxg_ctx* ctx, bool smooth, int d, int m, int T, int64_t b
         // D2H
         RXG_CUDA(ctx, cudaMemcpy2DAsync(mean + b0, hp, c.mean, dp, dp, (size_t)T * d, cudaMemcpyDeviceToHost, s_out));
         if (cov) {
-            if (cov_shared)
+            if (host_bcast) {
+                if (sidx == 0) {      // the table is the same for every slice: fetch it once, into library-owned pinned memory
+                    if (ctx->h_tab_bytes < (size_t)T * d * d * 4) {
+                        if (ctx->h_tab) cudaFreeHost(ctx->h_tab);
+                        ctx->h_tab = nullptr; ctx->h_tab_bytes = 0;
+                        RXG_CUDA(ctx, cudaMallocHost(&ctx->h_tab, (size_t)T * d * d * 4));
+                        ctx->h_tab_bytes = (size_t)T * d * d * 4;
+                    }
+                    if (!ctx->ev_tab) RXG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_tab, cudaEventDisableTiming));
+                    RXG_CUDA(ctx, cudaMemcpyAsync(ctx->h_tab, c.cov, (size_t)T * d * d * 4, cudaMemcpyDeviceToHost, s_out));
+                    RXG_CUDA(ctx, cudaEventRecord(ctx->ev_tab, s_out));
+                }
+            } else if (cov_shared)
                 RXG_CUDA(ctx, cudaMemcpyAsync(cov, c.cov, (size_t)T * d * d * 4, cudaMemcpyDeviceToHost, s_out));
             else
                 RXG_CUDA(ctx, cudaMemcpy2DAsync(cov + b0, hp, c.cov, dp, dp, (size_t)T * d * d, cudaMemcpyDeviceToHost, s_out));
@@ -276,6 +347,11 @@ static int lgssm_entry(rxg_ctx* ctx, bool smooth, int d, int m, int T, int64_t b
     }
     if (ns > 1)      // completion of the call == completion of the ctx stream
         for (int q = 0; q < nbuf; ++q) RXG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out[q], 0));
+    if (host_bcast) {
+        // everything above is enqueued; broadcast the covariances on the host while the slices stream through the GPU
+        RXG_CUDA(ctx, cudaEventSynchronize(ctx->ev_tab));
+        host_broadcast_cov(cov, (const float*)ctx->h_tab, (int64_t)T * d * d, batch, fill_threads);
+    }
     if (!(flags & RXG_ASYNC)) RXG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return RXG_OK;
 }

@@ -26,6 +26,10 @@ struct rxg_ctx {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     cudaEvent_t ev_start = nullptr;
+    // host-pointer calls of a shared model: pinned copy of the [T][d][d] covariance table + its arrival event
+    void* h_tab = nullptr;
+    size_t h_tab_bytes = 0;
+    cudaEvent_t ev_tab = nullptr;
     // side stream for work that overlaps a collective (covariance replication next to the all-gather)
     cudaStream_t s_aux = nullptr;
     cudaEvent_t ev_aux[2] = {nullptr, nullptr};

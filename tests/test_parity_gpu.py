@@ -280,6 +280,29 @@ def test_host_pointer_path_sliced_pipeline(ctx, monkeypatch):
     check(rp, lgssm.smooth_reference_schedule(y, **mod), nle=False)
 
 
+@pytest.mark.parametrize("d,T,batch", [(4, 90, 203), (16, 40, 70)])
+def test_host_pointer_covariance_broadcast_is_bit_identical(ctx, monkeypatch, d, T, batch):
+    """Host-pointer calls of a shared model fetch the chain-independent covariance table once and broadcast it
+    into the caller's per-chain buffer with host threads; the buffer must hold exactly the bits the full
+    device->host copy (RXG_HOST_COV_D2H=1) delivers, for smoothing and filtering, sliced or not."""
+    mod = f32_model(lgssm.notebook_model(d) if d <= 4 else lgssm.dense_model(d))
+    _, y = lgssm.generate_data(mod, T, batch, seed=38)
+    yh = torch.from_numpy(y).pin_memory()
+    monkeypatch.setenv("RXG_HOST_BCAST_MIN_MB", "0")
+    monkeypatch.setenv("RXG_HOST_THREADS", "7")
+    for smooth in (True, False):
+        for ns in ("3", "1"):
+            monkeypatch.setenv("RXG_HOST_SLICES", ns)
+            monkeypatch.setenv("RXG_HOST_COV_D2H", "1")
+            a = ctx.lgssm(yh, **_kw(mod), smooth=smooth, transition_first=not smooth)
+            monkeypatch.setenv("RXG_HOST_COV_D2H", "0")
+            b = ctx.lgssm(yh, **_kw(mod), smooth=smooth, transition_first=not smooth)
+            assert torch.equal(a["cov"], b["cov"]) and torch.equal(a["mean"], b["mean"])
+    ref = lgssm.smooth_reference_schedule(y, **mod)
+    r = ctx.lgssm(yh, **_kw(mod), smooth=True)
+    assert rel_l2(r["cov"].numpy(), ref["cov"]) < TOL_COV and rel_l2(r["mean"].numpy(), ref["mean"]) < TOL_MEAN
+
+
 @pytest.mark.parametrize("tf", [False, True])
 def test_transition_offset_and_prior_on_previous_state(ctx, tf):
     """Fused `+` rule (constant offset u) and RXG_TRANSITION_FIRST, smoothing and filtering, both
