@@ -35,7 +35,7 @@ def timed(fn, warm=3, reps=5):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--which", default="per_chain,filter,hgf,rules,vmp,scaling_T,large")
+    ap.add_argument("--which", default="per_chain,filter,hgf,rules,vmp,scaling_T,large,stream")
     args = ap.parse_args()
     which = set(args.which.split(","))
     ctx = rx.Context(0)
@@ -72,6 +72,18 @@ def main():
             print(json.dumps({"what": "lgssm smooth d=2 (notebook scaling table shape)", "T": TT, "batch": b, "ms": ms,
                               "messages_per_s": 6 * TT * b / ms * 1e3, "ms_per_chain_equiv": ms / b}))
             del y
+
+    if "stream" in which:
+        # what HBM delivers to a dependency-free streaming kernel for a given read : write mix (the sweep kernel moves
+        # 2.14 GB in and 5.25 GB out per launch, i.e. ~2 : 5)
+        n = 1 << 28                                            # 1 GiB per row: far beyond L2
+        for nr, nw in ((1, 1), (2, 5), (0, 4), (4, 1)):
+            src = torch.randn(max(nr, 1), n, device="cuda")[:nr] if nr else torch.empty(0, n, device="cuda")
+            dst = torch.empty(nw, n, device="cuda")
+            ms = timed(lambda: ctx.selftest_stream(src, dst), warm=3, reps=5)
+            print(json.dumps({"what": "stream_mix_kernel (HBM yardstick)", "rows_read": nr, "rows_written": nw, "ms": ms,
+                              "GBs": (nr + nw) * n * 4 / ms / 1e6, "frac_of_copy_peak": (nr + nw) * n * 4 / ms / 1e6 / peak}))
+            del src, dst
 
     if "large" in which:
         # BASELINE configs[2] (d = 64, T = 1000, batch = 4096) and the smaller tensor-core sizes; shared model.

@@ -274,6 +274,12 @@ int rxg_selftest_umma_f32(rxg_ctx*, const float* A, const float* B, float* D, un
 int rxg_selftest_umma_shape_f32(rxg_ctx*, int n, int k, const float* A, const float* B, float* D,
                                 unsigned flags);
 
+/* Diagnostic: stream n floats from each of n_read input rows (src[n_read][n]) and store their sum into each of
+ * n_write output rows (dst[n_write][n]) -- a dependency-free kernel with a chosen HBM read : write mix, the
+ * yardstick for the sweep kernels' achieved bandwidth (bench_extra.py --which stream).  No reference counterpart. */
+int rxg_selftest_stream_f32(rxg_ctx*, int64_t n, int n_read, int n_write, const float* src, float* dst,
+                            unsigned flags);
+
 /* ------------------------------------------------------------------ multi-GPU ----------------
  * Chains are independent: rank g owns chains [g*batch/G, (g+1)*batch/G); the only collective is
  * the all-gather of posterior marginals at the end (the reference has no distributed path).

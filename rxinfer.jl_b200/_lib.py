@@ -71,6 +71,7 @@ SIGNATURES = {
     "rxg_hgf_filter_chunk_f32": (c_int, [c_void_p, c_int, c_int64, c_int, c_float, c_float, c_float, c_float, fp, fp, fp, c_uint]),
     "rxg_selftest_umma_f32": (c_int, [c_void_p, fp, fp, fp, c_uint]),
     "rxg_selftest_umma_shape_f32": (c_int, [c_void_p, c_int, c_int, fp, fp, fp, c_uint]),
+    "rxg_selftest_stream_f32": (c_int, [c_void_p, c_int64, c_int, c_int, fp, fp, c_uint]),
     "rxg_comm_unique_id": (c_int, [c_void_p]),
     "rxg_comm_init": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "rxg_allgather_posteriors": (c_int, [c_void_p, c_int, c_int, c_int64, fp, fp, fp, fp, c_uint]),

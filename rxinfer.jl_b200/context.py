@@ -335,6 +335,15 @@ class Context:
         self._check(self.lib.rxg_selftest_umma_shape_f32(self.h, n, k, _fp(A), _fp(B), _fp(D), L.PTR_DEVICE))
         return D
 
+    def selftest_stream(self, src, dst, asynchronous=True):
+        """dst[w, :] = sum_r src[r, :] -- streaming kernel with a (n_read : n_write) HBM traffic mix."""
+        nr, n = src.shape
+        nw = dst.shape[0]
+        self._dev(src if nr else None, dst if nw else None)
+        self._check(self.lib.rxg_selftest_stream_f32(self.h, n, nr, nw, _fp(src), _fp(dst),
+                                                     L.PTR_DEVICE | (L.ASYNC if asynchronous else 0)))
+        return dst
+
     # ------------------------------------------------------------------ multi-GPU
     def comm_init(self, nranks, rank, uid: bytes):
         buf = ctypes.create_string_buffer(uid, 128)

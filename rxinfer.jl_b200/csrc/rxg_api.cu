@@ -506,7 +506,31 @@ __global__ void __launch_bounds__(256) replicate_cov_kernel(const float* __restr
     }
 }
 
+// Diagnostic: a pure streaming kernel with a chosen read : write mix (nr input rows summed, the sum stored into nw
+// output rows), float4 per thread, grid-stride over a persistent grid.  It has no dependent chain and no tables, i.e. it
+// shows what HBM delivers for the sweep's traffic mix (29 % reads / 71 % writes ~ nr = 2, nw = 5).
+__global__ void __launch_bounds__(256) stream_mix_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int64_t n4,
+                                                         int nr, int nw) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < nr; ++r) { const float4 v = __ldg(src + (int64_t)r * n4 + i); a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+        for (int w = 0; w < nw; ++w) dst[(int64_t)w * n4 + i] = a;
+    }
+}
+
 extern "C" {
+
+int rxg_selftest_stream_f32(rxg_ctx* ctx, int64_t n, int n_read, int n_write, const float* src, float* dst, unsigned flags) {
+    if (!ctx) return RXG_ERR_BAD_ARG;
+    if (!(flags & RXG_PTR_DEVICE) || (!src && n_read > 0) || (!dst && n_write > 0) || n < 4 || (n & 3) || n_read < 0 || n_write < 0)
+        return fail(ctx, RXG_ERR_BAD_ARG, "selftest_stream: device pointers, n a positive multiple of 4");
+    RXG_CUDA(ctx, cudaSetDevice(ctx->device));
+    stream_mix_kernel<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>((const float4*)src, (float4*)dst, n / 4, n_read, n_write);
+    ctx->launches += 1;
+    RXG_CUDA(ctx, cudaGetLastError());
+    if (!(flags & RXG_ASYNC)) RXG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RXG_OK;
+}
 
 int rxg_allgather_posteriors(rxg_ctx* ctx, int d, int T, int64_t batch_local, const float* post_mean,
                              const float* post_cov, float* gathered_mean, float* gathered_cov, unsigned flags) {
