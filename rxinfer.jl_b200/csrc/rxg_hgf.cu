@@ -153,38 +153,24 @@ hgf_filter_kernel(const float* __restrict__ y, float* __restrict__ out, int T, i
         const float wx = 1.0f / vxp;
         const float xiy = yt * wy, xix = mxp * wx;
         GcvJoint j;
-        float lref = 0.f;                       // exponent reference of the quadrature sums (log2 domain)
         for (int it = 0; it < iters; ++it) {
             const float g = gcv_gamma(mz, vz, kappa, omega);
             j = gcv_joint(xiy, wy, xix, wx, g);
             const float dm = j.m1 - j.m2;
             const float psi = __fmaf_rn(dm, dm, j.V11 + j.V22 - 2.0f * j.V12);
             const float b2 = -0.5f * LOG2E * psi * eA;
+            float lmax = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 31; ++i) lmax = fmaxf(lmax, __fmaf_rn(b2, ez[i], c2[i]));
             const float delta = mz - mu0;
-            float S0, S1, S2;
-            // The moments are invariant to the reference exponent, so the exact maximum (a second pass over the 31
-            // nodes) is only needed to keep the sums in range: it is taken in the first iteration of a step and reused
-            // while the zeroth moment stays within 2^+-40 (b2 moves little between iterations); otherwise the
-            // iteration is redone with the exact maximum.
-            bool exact = (it == 0);
-            for (;;) {
-                if (exact) {
-                    float lmax = -INFINITY;
+            float S0 = 0.f, S1 = 0.f, S2 = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 31; ++i) lmax = fmaxf(lmax, __fmaf_rn(b2, ez[i], c2[i]));
-                    lref = lmax;
-                }
-                S0 = 0.f; S1 = 0.f; S2 = 0.f;
-#pragma unroll
-                for (int i = 0; i < 31; ++i) {
-                    const float e = ex2_approx(__fmaf_rn(b2, ez[i], c2[i]) - lref);
-                    const float w = u[i] - delta;
-                    S0 += e;
-                    S1 = __fmaf_rn(e, w, S1);
-                    S2 = __fmaf_rn(e * w, w, S2);
-                }
-                if (exact || (S0 > 9.094947e-13f && S0 < 1.0995116e12f)) break;      // 2^-40 .. 2^40 (false for NaN)
-                exact = true;
+            for (int i = 0; i < 31; ++i) {
+                const float e = ex2_approx(__fmaf_rn(b2, ez[i], c2[i]) - lmax);
+                const float w = u[i] - delta;
+                S0 += e;
+                S1 = __fmaf_rn(e, w, S1);
+                S2 = __fmaf_rn(e * w, w, S2);
             }
             const float r = 1.0f / S0;
             const float dw = S1 * r;
