@@ -111,7 +111,13 @@ class RxInferenceEngine:
         self.ticks += int(chunk.shape[0])
         if self.keephistory:
             for name in self.historyvars:
-                self._hist.setdefault(name, []).append(out[name])
+                parts = self._hist.setdefault(name, [])
+                parts.append(out[name])
+                # circular buffer: drop whole chunks that can no longer contribute to the last `keephistory` ticks
+                field = "mu" if hasattr(out[name], "mu") else "m"
+                total = sum(getattr(p, field).shape[0] for p in parts)
+                while len(parts) > 1 and total - getattr(parts[0], field).shape[0] >= self.keephistory:
+                    total -= getattr(parts.pop(0), field).shape[0]
         return out
 
     # -------------------------------------------------------------- results (streaming.jl:16-140)

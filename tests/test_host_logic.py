@@ -51,3 +51,48 @@ def test_infer_fails_loudly_without_gpu_and_honours_catch_exception(rx):
 def test_call_rule_unknown_rule_raises(rx):
     with pytest.raises(rx.RuleMethodError):
         rx.call_rule(None, "Bernoulli", "out", m_p=None)
+
+
+def test_streaming_engine_host_logic(rx):
+    """RxInferenceEngine bookkeeping without a GPU (the device calls are stubbed): lifecycle flags, bounded history
+    (circular buffer of `keephistory` ticks over uneven chunks), historyvars validation, exhausted engines."""
+    from rxinfer_jl_b200.streaming import RxInferenceEngine
+
+    class StubCtx:
+        device = 0
+
+        def __init__(self):
+            self.t = 0
+
+        def hgf_filter(self, chunk, init=None, **kw):
+            n, b = chunk.shape
+            out = (self.t + torch.arange(n, dtype=torch.float32))[:, None, None].expand(n, 4, b).contiguous()
+            self.t += n
+            return out
+
+        def hgf_filter_chunk(self, chunk, carry, **kw):
+            assert carry.shape == (4, chunk.shape[1]) and float(carry[0, 0]) == self.t - 1     # carry = last output row
+            return self.hgf_filter(chunk)
+
+    eng = RxInferenceEngine(StubCtx(), rx.hgf(), batch=3, iterations=2, keephistory=5, datastream=None)
+    for n in (2, 3, 1, 4, 2):
+        eng.push(torch.zeros(n, 3))
+    h = eng.history
+    assert eng.ticks == 12 and h["xt"].mean().shape == (5, 3)
+    assert torch.equal(h["xt"].mean()[:, 0], torch.arange(7, 12, dtype=torch.float32))       # the LAST five ticks
+    assert sum(p.m.shape[0] for p in eng._hist["xt"]) < 12                                    # older chunks were dropped
+    with pytest.raises(KeyError):
+        RxInferenceEngine(StubCtx(), rx.hgf(), batch=3, keephistory=2, historyvars=("nope",))
+    with pytest.raises(RuntimeError):
+        RxInferenceEngine(StubCtx(), rx.hgf(), batch=3).history                               # keephistory not requested
+    done = RxInferenceEngine(StubCtx(), rx.hgf(), batch=3, keephistory=4, datastream=[torch.zeros(2, 3), torch.zeros(5, 3)])
+    assert done.is_completed and not done.is_running and done.ticks == 7
+    with pytest.raises(RuntimeError):
+        done.start()
+    with pytest.raises(NotImplementedError):
+        RxInferenceEngine(StubCtx(), rx.linear_gaussian_ssm_smoothing(np.eye(2), np.eye(2), np.eye(2), np.eye(2),
+                                                                       (np.zeros(2), np.eye(2))), batch=3)
+    with pytest.raises(ValueError):
+        rx.infer(model=rx.hgf(), data={"y": torch.zeros(2, 3)}, datastream=[torch.zeros(2, 3)])
+    with pytest.raises(ValueError):
+        rx.infer(model=rx.hgf(), autoupdates="zt_min_mean, zt_min_var = mean_var(q(zt))")      # batch missing
