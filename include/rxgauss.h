@@ -265,6 +265,18 @@ int rxg_hgf_filter_chunk_f32(rxg_ctx*, int Tc, int64_t batch, int iters, float k
                              float z_variance, float y_variance, const float* prev, const float* y,
                              float* out, unsigned flags);
 
+/* Streaming mean-field VMP with an unknown observation precision -- the reference's `test_model1`
+ * [ref: test/inference/inference_tests.jl:752-775; @autoupdates :772-776; rules of
+ * test/models/aliases/aliases_gamma_tests.jl]:  x_t_min ~ N(prior), tau ~ Gamma(prior),
+ * x_t ~ N(x_t_min, 1/w), y ~ N(x_t, 1/tau), MeanField(), `iters` iterations per datum, priors autoupdated
+ * from q(x_t), q(tau).  init = (m_x, v_x, shape, rate) of the @initialization, or prev[4][batch] = out[Tc-1]
+ * of the previous time-chunk (then init may be NULL).  y[T][batch]; out[T][4][batch] = (m_x, v_x, shape, rate)
+ * after the last iteration of each datum; free_energy[T][iters][batch] or NULL (Bethe free energy per
+ * datum and iteration; the reference asserts its average over data to be non-increasing, :846).       */
+int rxg_stream_vmp_gamma_f32(rxg_ctx*, int T, int64_t batch, int iters, float w, const float init[4],
+                             const float* prev, const float* y, float* out, float* free_energy,
+                             unsigned flags);
+
 /* Diagnostic: D[128][64] = A[128][128] * B[64][128]' on the tcgen05 tensor pipe (kind::tf32, 3xTF32
  * split, TMEM accumulator), row-major device arrays.  Validates the hand-written UMMA descriptors
  * used by the large-state family; no reference counterpart.                                     */

@@ -106,3 +106,45 @@ def lgssm_gamma_precision(y, A_scalar=1.0, prior=(0.0, 100.0), proc_var=1.0,
         Etau = a / b
         hist.append((mx, vx, a, b))
     return dict(mean=mx, var=vx, shape=np.full(batch, a), rate=b, Etau=Etau)
+
+
+def stream_vmp_gamma(y, iterations=4, w=1.0, init_x=(0.0, 1e3), init_tau=(1.0, 1.0), return_free_energy=False):
+    """Streaming mean-field VMP of the reference's ``test_model1`` (one-step Kalman-like model with unknown
+    observation precision, /root/reference/test/inference/inference_tests.jl:752-775):
+
+        x_t_min ~ Normal(mean = x_t_min_mean, variance = x_t_min_var)     # datavars <- mean_var(q(x_t))
+        tau     ~ Gamma(shape = tau_shape, rate = tau_rate)               # datavars <- shape / rate of q(tau)
+        x_t     ~ Normal(mean = x_t_min, precision = w)                   # w = 1
+        y       ~ Normal(mean = x_t, precision = tau)
+        constraints = MeanField();  init q(x_t) = N(0, 1e3), q(tau) = Gamma(1, 1);  `iterations` per datum.
+
+    Rules: NormalMeanPrecision(:out)(q_mu, q_tau) = N(E mu, 1/E tau), (:mu) symmetric,
+    (:tau)(q_out, q_mu) = Gamma(3/2, 1/2 E(out - mu)^2), prod of Normals / Gammas.  Update order inside an iteration is
+    not pinned by the reference (reactive); dependency order used here: q(x_t_min), q(x_t), q(tau).
+    y[T, batch] -> out[T, 4, batch] = (m_x, v_x, shape, rate) after the last iteration of every datum, and (optional) the
+    Bethe free energy [T, iterations, batch] (fully factorised q: F = sum_nodes U - sum_vars H)."""
+    from scipy.special import digamma, gammaln
+    y = np.asarray(y, dtype=np.float64)
+    T, batch = y.shape
+    mx = np.full(batch, init_x[0]); vx = np.full(batch, init_x[1])
+    a = np.full(batch, init_tau[0]); b = np.full(batch, init_tau[1])
+    out = np.zeros((T, 4, batch))
+    fe = np.zeros((T, iterations, batch)) if return_free_energy else None
+    for t in range(T):
+        mp, vp, ap, bp = mx.copy(), vx.copy(), a.copy(), b.copy()       # autoupdates: priors of this datum
+        for it in range(iterations):
+            mmin, vmin = R.prod_normal_mv((mp, vp), (mx, 1.0 / w))      # q(x_t_min) = prior x NormalMeanPrecision(:mu)(q_out)
+            Etau = a / b
+            mx, vx = R.prod_normal_mv((mmin, 1.0 / w), (y[t], 1.0 / Etau))
+            ga, gb = R.normal_meanprec_tau((y[t], 0.0), (mx, vx))
+            a, b = R.prod_gamma((ap, bp), (ga, gb))
+            if return_free_energy:
+                Etau = a / b; Elog = digamma(a) - np.log(b)
+                U1 = 0.5 * np.log(2 * np.pi * vp) + ((mmin - mp) ** 2 + vmin) / (2 * vp)
+                U2 = -ap * np.log(bp) + gammaln(ap) - (ap - 1.0) * Elog + bp * Etau
+                U3 = 0.5 * np.log(2 * np.pi) - 0.5 * np.log(w) + 0.5 * w * ((mx - mmin) ** 2 + vx + vmin)
+                U4 = 0.5 * np.log(2 * np.pi) - 0.5 * Elog + 0.5 * Etau * ((y[t] - mx) ** 2 + vx)
+                H = R.normal_entropy(vmin) + R.normal_entropy(vx) + R.gamma_entropy((a, b))
+                fe[t, it] = U1 + U2 + U3 + U4 - H
+        out[t, 0], out[t, 1], out[t, 2], out[t, 3] = mx, vx, a, b
+    return (out, fe) if return_free_energy else out

@@ -69,6 +69,7 @@ SIGNATURES = {
     "rxg_hgf_filter_f32": (c_int, [c_void_p, c_int, c_int64, c_int, c_float, c_float, c_float, c_float, fp, fp, fp, c_uint]),
     "rxg_lgssm_filter_chunk_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, c_uint]),
     "rxg_hgf_filter_chunk_f32": (c_int, [c_void_p, c_int, c_int64, c_int, c_float, c_float, c_float, c_float, fp, fp, fp, c_uint]),
+    "rxg_stream_vmp_gamma_f32": (c_int, [c_void_p, c_int, c_int64, c_int, c_float, fp, fp, fp, fp, fp, c_uint]),
     "rxg_selftest_umma_f32": (c_int, [c_void_p, fp, fp, fp, c_uint]),
     "rxg_selftest_umma_shape_f32": (c_int, [c_void_p, c_int, c_int, fp, fp, fp, c_uint]),
     "rxg_selftest_stream_f32": (c_int, [c_void_p, c_int64, c_int, c_int, fp, fp, c_uint]),

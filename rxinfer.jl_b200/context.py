@@ -185,6 +185,18 @@ class Context:
                                                 ini, _fp(y), _fp(out), L.PTR_DEVICE))
         return out
 
+    def stream_vmp_gamma(self, y, iters=4, w=1.0, init=(0.0, 1e3, 1.0, 1.0), prev=None, want_free_energy=False):
+        """Streaming mean-field VMP with a Gamma observation precision (``rxg_stream_vmp_gamma_f32``);
+        y[T, batch] -> out[T, 4, batch] = (m_x, v_x, shape, rate), free energy [T, iters, batch] or None."""
+        self._dev(y, prev)
+        T, batch = y.shape
+        out = self.empty(T, 4, batch)
+        fe = self.empty(T, iters, batch) if want_free_energy else None
+        ini = (ctypes.c_float * 4)(*init)
+        self._check(self.lib.rxg_stream_vmp_gamma_f32(self.h, T, batch, iters, w, ctypes.cast(ini, L.fp), _fp(prev), _fp(y),
+                                                      _fp(out), _fp(fe), L.PTR_DEVICE))
+        return out, fe
+
     def lgssm_vmp_gamma(self, y, iterations=10, a=1.0, v_proc=1.0, prior=(0.0, 100.0), gamma_prior=(1.0, 1.0),
                         init_E_tau=1.0):
         self._dev(y)

@@ -262,6 +262,66 @@ vmp_gamma_kernel(const float* __restrict__ y, float* __restrict__ pm, float* __r
     shape[b] = sh; rate[b] = rt;
 }
 
+// ---- streaming mean-field VMP with a Gamma observation precision (the reference's `test_model1`,
+// /root/reference/test/inference/inference_tests.jl:752-775): per datum, `iters` sweeps of
+//   q(x_t_min) = N(m_p, v_p) x NormalMeanPrecision(:mu)(q_out = q(x_t))            (prior x backward VMP message)
+//   q(x_t)     = NormalMeanPrecision(:out)(q_mu = q(x_t_min)) x NormalMeanPrecision(:mu)(y, q_tau)
+//   q(tau)     = Gamma(a_p, b_p) x NormalMeanPrecision(:tau)(q_out = y, q_mu = q(x_t))
+// with the priors (m_p, v_p, a_p, b_p) autoupdated from the previous datum's q(x_t), q(tau).
+__device__ __forceinline__ float digamma_f(float x) {      // psi(x), x > 0: recurrence up to x >= 6, then the asymptotic series
+    float r = 0.f;
+    while (x < 6.f) { r -= 1.f / x; x += 1.f; }
+    const float i = 1.f / x, i2 = i * i;
+    return r + logf(x) - 0.5f * i - i2 * (1.f / 12.f - i2 * (1.f / 120.f - i2 * (1.f / 252.f)));
+}
+__global__ void __launch_bounds__(128)
+stream_vmp_gamma_kernel(const float* __restrict__ y, const float* __restrict__ prev, float* __restrict__ out,
+                        float* __restrict__ fe, int T, int64_t batch, int iters, float w, float i_mx, float i_vx,
+                        float i_a, float i_b) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    float mx = i_mx, vx = i_vx, a = i_a, rt = i_b;
+    if (prev) { mx = __ldg(prev + b); vx = __ldg(prev + batch + b); a = __ldg(prev + 2 * batch + b); rt = __ldg(prev + 3 * batch + b); }
+    const float iw = 1.0f / w;
+    constexpr float LOG_2PI = 1.8378770664093453f;
+    float ynext = __ldg(y + b);
+    for (int t = 0; t < T; ++t) {
+        const float yt = ynext;
+        if (t + 1 < T) ynext = __ldg(y + (int64_t)(t + 1) * batch + b);
+        const float mp = mx, vp = vx, ap = a, bp = rt;                  // @autoupdates: this datum's priors
+        for (int it = 0; it < iters; ++it) {
+            // q(x_t_min): precision-weighted product of N(mp, vp) and N(E x_t, 1/w)
+            const float wmin = 1.0f / vp + w;
+            const float vmin = 1.0f / wmin;
+            const float mmin = vmin * __fmaf_rn(mx, w, mp / vp);
+            // q(x_t): N(E x_t_min, 1/w) x N(y, 1/E tau)
+            const float Etau = a / rt;
+            const float wx = w + Etau;
+            vx = 1.0f / wx;
+            mx = vx * __fmaf_rn(yt, Etau, mmin * w);
+            // q(tau): Gamma(ap + 3/2 - 1, bp + ((y - m_x)^2 + v_x) / 2)
+            const float d = yt - mx;
+            a = ap + 0.5f;
+            rt = __fmaf_rn(0.5f, __fmaf_rn(d, d, vx), bp);
+            if (fe) {
+                const float Et = a / rt, Elog = digamma_f(a) - logf(rt);
+                const float dm = mmin - mp, dx = mx - mmin;
+                const float U1 = 0.5f * (LOG_2PI + logf(vp)) + __fmaf_rn(dm, dm, vmin) / (2.0f * vp);
+                const float U2 = -ap * logf(bp) + lgammaf(ap) - (ap - 1.0f) * Elog + bp * Et;
+                const float U3 = 0.5f * (LOG_2PI - logf(w)) + 0.5f * w * (__fmaf_rn(dx, dx, vx) + vmin);
+                const float U4 = 0.5f * (LOG_2PI - Elog) + 0.5f * Et * __fmaf_rn(d, d, vx);
+                const float Hn = 0.5f * (LOG_2PI + 1.0f + logf(vmin)) + 0.5f * (LOG_2PI + 1.0f + logf(vx));
+                const float Hg = a - logf(rt) + lgammaf(a) + (1.0f - a) * digamma_f(a);
+                fe[((int64_t)t * iters + it) * batch + b] = U1 + U2 + U3 + U4 - Hn - Hg;
+            }
+        }
+        out[((int64_t)t * 4 + 0) * batch + b] = mx;
+        out[((int64_t)t * 4 + 1) * batch + b] = vx;
+        out[((int64_t)t * 4 + 2) * batch + b] = a;
+        out[((int64_t)t * 4 + 3) * batch + b] = rt;
+    }
+}
+
 }  // namespace rxg
 
 using namespace rxg;
@@ -345,6 +405,23 @@ int rxg_lgssm_vmp_gamma_f32(rxg_ctx* ctx, int T, int64_t batch, int iterations, 
         y, post_mean, post_var, shape, rate, T, batch, iterations, a, v_proc, m0, v0, a0, b0, init_E_tau);
     ctx->launches += 1;
     int rc = rxg::check_cuda(ctx, cudaGetLastError(), "vmp_gamma_kernel");
+    if (rc != RXG_OK) return rc;
+    if (!(flags & RXG_ASYNC)) RXG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RXG_OK;
+}
+
+int rxg_stream_vmp_gamma_f32(rxg_ctx* ctx, int T, int64_t batch, int iters, float w, const float init[4],
+                             const float* prev, const float* y, float* out, float* free_energy, unsigned flags) {
+    if (!ctx) return RXG_ERR_BAD_ARG;
+    if (T < 1 || batch < 1 || iters < 1 || !(w > 0.f) || !y || !out || (!init && !prev))
+        return rxg::fail(ctx, RXG_ERR_BAD_ARG, "stream_vmp_gamma: bad argument");
+    if (!(flags & RXG_PTR_DEVICE)) return rxg::fail(ctx, RXG_ERR_UNSUPPORTED, "stream_vmp_gamma takes device pointers");
+    const float z[4] = {0.f, 1.f, 1.f, 1.f};
+    const float* in = init ? init : z;
+    stream_vmp_gamma_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, ctx->stream>>>(
+        y, prev, out, free_energy, T, batch, iters, w, in[0], in[1], in[2], in[3]);
+    ctx->launches += 1;
+    int rc = rxg::check_cuda(ctx, cudaGetLastError(), "stream_vmp_gamma_kernel");
     if (rc != RXG_OK) return rc;
     if (!(flags & RXG_ASYNC)) RXG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return RXG_OK;

@@ -66,6 +66,15 @@ class univariate_lgssm_gamma_precision:
 
 
 @dataclass
+class kalman_gamma_streaming:
+    """The reference's ``test_model1`` (/root/reference/test/inference/inference_tests.jl:752-775): one-step random
+    walk observed with unknown precision, ``constraints = MeanField()``, ``@autoupdates`` of ``mean_var(q(x_t))`` and
+    ``shape / rate of q(τ)``; ``init = (m_x, v_x, shape, rate)`` of the ``@initialization`` (:766-769)."""
+    transition_precision: float = 1.0
+    init: tuple = (0.0, 1e3, 1.0, 1.0)
+
+
+@dataclass
 class InferenceResult:
     """``InferenceResult`` (/root/reference/src/inference/batch.jl:18-24)."""
     posteriors: dict
@@ -150,6 +159,12 @@ def infer(*, model, iterations=None, free_energy=False, returnvars=None, options
             return InferenceResult(posteriors={}, model=model,
                                    history={"xt": NormalMeanVariance(out[:, 0], out[:, 1]),
                                             "zt": NormalMeanVariance(out[:, 2], out[:, 3])})
+        if isinstance(model, kalman_gamma_streaming):
+            out, fe = ctx.stream_vmp_gamma(y, iters=iterations or 1, w=model.transition_precision, init=model.init,
+                                           want_free_energy=bool(free_energy))
+            return InferenceResult(posteriors={}, model=model, free_energy=None if fe is None else fe.mean(dim=0),
+                                   history={"x_t": NormalMeanVariance(out[:, 0], out[:, 1]),
+                                            "τ": GammaShapeRate(out[:, 2], out[:, 3])})
         if isinstance(model, univariate_lgssm_gamma_precision):
             r = ctx.lgssm_vmp_gamma(y, iterations=iterations or 1, a=model.a, v_proc=model.v_proc, prior=model.x0,
                                     gamma_prior=model.gamma_prior, init_E_tau=model.init_E_tau)

@@ -44,6 +44,10 @@ class RxInferenceEngine:
             if free_energy:
                 raise NotImplementedError("free_energy for the HGF path is not on the hot path")
             self._carry = None               # out[-1] of the previous chunk, [4, batch]
+        elif isinstance(model, I.kalman_gamma_streaming):
+            self._kind = "vmpgamma"
+            names = ("x_t", "τ")
+            self._carry = None
         elif isinstance(model, I.linear_gaussian_ssm_filtering):
             self._kind = "lgssm"
             names = ("x_t",)
@@ -98,6 +102,14 @@ class RxInferenceEngine:
             out = {"x_t": MvNormalMeanCovariance(r["mean"], r["cov"])}
             if self.free_energy_enabled:
                 self._fe.append(r["neg_log_evidence"])
+        elif self._kind == "vmpgamma":
+            mo = self.model
+            o, fe = self.ctx.stream_vmp_gamma(chunk, iters=self.iterations, w=mo.transition_precision, init=mo.init,
+                                              prev=self._carry, want_free_energy=self.free_energy_enabled)
+            self._carry = o[-1]
+            out = {"x_t": NormalMeanVariance(o[:, 0], o[:, 1]), "τ": GammaShapeRate(o[:, 2], o[:, 3])}
+            if self.free_energy_enabled:
+                self._fe.append(fe)
         else:
             mo = self.model
             kw = dict(iters=self.iterations, kappa=mo.real_k, omega=mo.real_w, z_variance=mo.z_variance,
@@ -114,7 +126,7 @@ class RxInferenceEngine:
                 parts = self._hist.setdefault(name, [])
                 parts.append(out[name])
                 # circular buffer: drop whole chunks that can no longer contribute to the last `keephistory` ticks
-                field = "mu" if hasattr(out[name], "mu") else "m"
+                field = "mu" if hasattr(out[name], "mu") else ("m" if hasattr(out[name], "m") else "a")
                 total = sum(getattr(p, field).shape[0] for p in parts)
                 while len(parts) > 1 and total - getattr(parts[0], field).shape[0] >= self.keephistory:
                     total -= getattr(parts.pop(0), field).shape[0]
@@ -126,6 +138,10 @@ class RxInferenceEngine:
         """Most recent marginals (the reference exposes observables; here: the last tick's values)."""
         if self._kind == "lgssm":
             return {"x_t": (self._prev_mean, self._carry_cov.copy())}
+        if self._kind == "vmpgamma":
+            c = self._carry
+            return {"x_t": None if c is None else NormalMeanVariance(c[0], c[1]),
+                    "τ": None if c is None else GammaShapeRate(c[2], c[3])}
         return {"xt": None if self._carry is None else NormalMeanVariance(self._carry[0], self._carry[1]),
                 "zt": None if self._carry is None else NormalMeanVariance(self._carry[2], self._carry[3])}
 
@@ -137,7 +153,7 @@ class RxInferenceEngine:
         out = {}
         for name, parts in self._hist.items():
             first = parts[0]
-            fields = [f for f in ("mu", "Sigma", "m", "v") if hasattr(first, f)]
+            fields = [f for f in ("mu", "Sigma", "m", "v", "a", "b") if hasattr(first, f)]
             cat = {f: torch.cat([getattr(p, f) for p in parts], dim=0)[-self.keephistory:] for f in fields}
             out[name] = type(first)(**cat)
         return out
@@ -148,4 +164,6 @@ class RxInferenceEngine:
         evidence of the whole stream (on this tree BFE = -log evidence)."""
         if not self.free_energy_enabled:
             raise RuntimeError("Bethe Free Energy has not been computed: use `free_energy = true`")
+        if self._kind == "vmpgamma":      # reference semantics (streaming.jl:12): per iteration, averaged over the observations
+            return torch.cat(self._fe, dim=0).mean(dim=0)
         return torch.stack(self._fe)

@@ -121,3 +121,23 @@ def test_gauss_hermite_prod_recovers_gaussian_times_gaussian():
     """ELQ with b = 0 is exp(-a z / 2): the product with N(m, v) is N(m - a v / 2, v) exactly."""
     mz, vz = R.prod_normal_elq((np.array([0.7]), np.array([1.3])), (0.8, np.array([0.0]), -0.8, 0.0))
     assert abs(mz[0] - (0.7 - 0.4 * 1.3)) < 1e-10 and abs(vz[0] - 1.3) < 1e-9
+
+
+def test_stream_vmp_gamma_free_energy_is_monotone():
+    """The reference's streaming `test_model1` (test/inference/inference_tests.jl:752-860) asserts
+    `all(<=(0), diff(engine.free_energy_history))` for 3 and 4 iterations (:846): the Bethe free energy, averaged over
+    the observations, must not increase from one VMP iteration to the next.  Data as in the test (:778-788)."""
+    rng = np.random.default_rng(7)
+    n, batch = 10, 256
+    x = np.cumsum(rng.standard_normal((n, batch)), axis=0)
+    y = x + rng.standard_normal((n, batch)) / np.sqrt(10.0)
+    for iters in (3, 4):
+        out, fe = vmp.stream_vmp_gamma(y, iterations=iters, return_free_energy=True)
+        hist = fe.mean(axis=0)                                   # free_energy_history: [iterations, chain]
+        assert np.all(np.diff(hist, axis=0) <= 1e-12)
+        assert np.all(out[:, 1] > 0) and np.all(out[:, 3] > 0) and np.allclose(out[:, 2], 1.0 + 0.5 * np.arange(1, n + 1)[:, None])
+    # the rules are the pinned ones: one datum, one iteration, by hand
+    o1 = vmp.stream_vmp_gamma(np.array([[2.0]]), iterations=1)
+    mmin = (0.0 / 1e3 + 0.0 * 1.0) / (1 / 1e3 + 1.0); vx = 1.0 / (1.0 + 1.0); mx = vx * (mmin + 2.0 * 1.0)
+    assert abs(o1[0, 0, 0] - mx) < 1e-15 and abs(o1[0, 1, 0] - vx) < 1e-15
+    assert abs(o1[0, 2, 0] - 1.5) < 1e-15 and abs(o1[0, 3, 0] - (1.0 + 0.5 * ((2.0 - mx) ** 2 + vx))) < 1e-15

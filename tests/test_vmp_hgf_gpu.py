@@ -1,6 +1,6 @@
-"""GPU parity of the variational members of the path: fused HGF filter (GCV node, GH-31) and the
-Gamma-precision VMP around a scalar smoother.  HGF posteriors are formula-level parity only
-(PARITY UNPINNED against the reference, see oracle/hgf.py)."""
+"""GPU parity of the variational members of the path: fused HGF filter (GCV node, GH-31), the Gamma-precision VMP
+around a scalar smoother and the streaming mean-field Gamma model.  HGF: pinned by the reference test's posterior
+assertions on its own data stream (tests/test_reference_rng_goldens.py), not by its free-energy value (oracle/hgf.py)."""
 import os
 
 import numpy as np
@@ -61,3 +61,32 @@ def test_vmp_gamma_precision(ctx):
     assert rel_l2(r["var"].cpu().numpy(), ref["var"]) < 1e-4
     assert rel_l2(r["rate"].cpu().numpy(), ref["rate"]) < 1e-4
     assert rel_l2(r["shape"].cpu().numpy(), ref["shape"]) < 1e-6
+
+
+def test_stream_vmp_gamma_vs_oracle_and_chunks(rx, ctx):
+    """Streaming mean-field VMP with a Gamma observation precision (the reference's test_model1): CUDA vs fp64 oracle,
+    free energy included; time-chunks with the carry are bitwise the single call; engine mirror."""
+    rng = np.random.default_rng(3)
+    n, batch = 40, 200
+    x = np.cumsum(rng.standard_normal((n, batch)), axis=0)
+    y = (x + rng.standard_normal((n, batch)) / np.sqrt(10.0)).astype(np.float32)
+    ref, rfe = vmp.stream_vmp_gamma(y.astype(np.float64), iterations=4, return_free_energy=True)
+    out, fe = ctx.stream_vmp_gamma(dev(y), iters=4, want_free_energy=True)
+    o = out.cpu().numpy()
+    assert rel_l2(o[:, 0], ref[:, 0]) < 1e-5 and rel_l2(o[:, 1], ref[:, 1]) < 1e-5
+    assert np.array_equal(o[:, 2], ref[:, 2].astype(np.float32)) and rel_l2(o[:, 3], ref[:, 3]) < 1e-5
+    assert np.max(np.abs(fe.cpu().numpy() - rfe)) < 2e-3 * np.max(np.abs(rfe))
+    hist = fe.double().mean(dim=0)                           # reference: averaged over observations, per iteration
+    assert torch.all(hist[1:] - hist[:-1] <= 1e-4)           # inference_tests.jl:846 (fp32 slack)
+    parts, prev = [], None
+    for a, b in ((0, 1), (1, 17), (17, 40)):
+        p, _ = ctx.stream_vmp_gamma(dev(y[a:b]), iters=4, prev=prev)
+        prev = p[-1].contiguous()
+        parts.append(p)
+    assert torch.equal(torch.cat(parts), out)
+    eng = rx.infer(model=rx.kalman_gamma_streaming(), datastream=[dev(y[:9]), dev(y[9:])], batch=batch, iterations=4,
+                   keephistory=n, free_energy=True, context=ctx)
+    assert torch.equal(eng.history["x_t"].mean(), out[:, 0]) and torch.equal(eng.history["τ"].rate(), out[:, 3])
+    assert eng.free_energy_history.shape == (4, batch)
+    res = rx.infer(model=rx.kalman_gamma_streaming(), data={"y": dev(y)}, iterations=4, free_energy=True, context=ctx)
+    assert torch.equal(res.history["τ"].shape(), out[:, 2])
