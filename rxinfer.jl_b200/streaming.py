@@ -14,7 +14,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .distributions import MvNormalMeanCovariance, NormalMeanVariance
+from .distributions import GammaShapeRate, MvNormalMeanCovariance, NormalMeanVariance
 
 
 class RxInferenceEngine:

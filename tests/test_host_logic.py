@@ -96,3 +96,30 @@ def test_streaming_engine_host_logic(rx):
         rx.infer(model=rx.hgf(), data={"y": torch.zeros(2, 3)}, datastream=[torch.zeros(2, 3)])
     with pytest.raises(ValueError):
         rx.infer(model=rx.hgf(), autoupdates="zt_min_mean, zt_min_var = mean_var(q(zt))")      # batch missing
+
+
+def test_streaming_engine_gamma_model_host_logic(rx):
+    """Engine bookkeeping for the streaming Gamma-precision model (device call stubbed): carry = last output row,
+    history of both variables, free-energy history averaged over the observations (streaming.jl:12)."""
+    from rxinfer_jl_b200.streaming import RxInferenceEngine
+
+    class StubCtx:
+        device = 0
+        t = 0
+
+        def stream_vmp_gamma(self, chunk, iters, w, init, prev, want_free_energy):
+            n, b = chunk.shape
+            assert (prev is None) == (self.t == 0)
+            if prev is not None:
+                assert float(prev[0, 0]) == self.t - 1
+            out = (self.t + torch.arange(n, dtype=torch.float32))[:, None, None].expand(n, 4, b).contiguous()
+            fe = torch.ones(n, iters, b) * torch.arange(iters, dtype=torch.float32)[None, :, None] if want_free_energy else None
+            self.t += n
+            return out, fe
+
+    eng = RxInferenceEngine(StubCtx(), rx.kalman_gamma_streaming(), batch=2, iterations=3, keephistory=4, free_energy=True,
+                            datastream=[torch.zeros(3, 2), torch.zeros(2, 2)])
+    assert eng.is_completed and eng.ticks == 5
+    assert eng.history["x_t"].mean().shape == (4, 2) and eng.history["τ"].rate().shape == (4, 2)
+    assert torch.equal(eng.free_energy_history, torch.arange(3, dtype=torch.float32)[:, None].expand(3, 2))
+    assert float(eng.posteriors["τ"].shape()[0]) == 4.0
