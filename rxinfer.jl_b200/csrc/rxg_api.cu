@@ -290,6 +290,25 @@ static int lgssm_entry(rxg_ctx* ctx, bool smooth, int d, int m, int T, int64_t b
         RXG_CUDA(ctx, cudaStreamWaitEvent(s_in, ctx->ev_start, 0));
         RXG_CUDA(ctx, cudaStreamWaitEvent(s_out, ctx->ev_start, 0));
     }
+    if (host_bcast) {
+        // The covariance table depends on the model only: compute it (gain tables, no sweep) and fetch it BEFORE the first
+        // observation slice is uploaded, so that the host-side broadcast can start right away.
+        if (ctx->h_tab_bytes < (size_t)T * d * d * 4) {
+            if (ctx->h_tab) cudaFreeHost(ctx->h_tab);
+            ctx->h_tab = nullptr; ctx->h_tab_bytes = 0;
+            RXG_CUDA(ctx, cudaMallocHost(&ctx->h_tab, (size_t)T * d * d * 4));
+            ctx->h_tab_bytes = (size_t)T * d * d * 4;
+        }
+        if (!ctx->ev_tab) RXG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_tab, cudaEventDisableTiming));
+        LgssmCall c0 = c;
+        c0.batch = bs; c0.tables_only = true;
+        c0.y = nullptr; c0.mean = nullptr; c0.nle = nullptr; c0.status = nullptr; c0.ymask = nullptr;
+        c0.cov = (float*)(base + o_cov[0]);
+        int rc0 = lgssm_dispatch(ctx, c0);
+        if (rc0 != RXG_OK) return rc0;
+        RXG_CUDA(ctx, cudaMemcpyAsync(ctx->h_tab, c0.cov, (size_t)T * d * d * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        RXG_CUDA(ctx, cudaEventRecord(ctx->ev_tab, ctx->stream));
+    }
     const size_t hp = (size_t)batch * 4;       // host pitch of every fp32 array (bytes)
     for (int sidx = 0; sidx < ns; ++sidx) {
         const int q = sidx & (nbuf - 1);
@@ -325,17 +344,7 @@ static int lgssm_entry(rxg_ctx* ctx, bool smooth, int d, int m, int T, int64_t b
         RXG_CUDA(ctx, cudaMemcpy2DAsync(mean + b0, hp, c.mean, dp, dp, (size_t)T * d, cudaMemcpyDeviceToHost, s_out));
         if (cov) {
             if (host_bcast) {
-                if (sidx == 0) {      // the table is the same for every slice: fetch it once, into library-owned pinned memory
-                    if (ctx->h_tab_bytes < (size_t)T * d * d * 4) {
-                        if (ctx->h_tab) cudaFreeHost(ctx->h_tab);
-                        ctx->h_tab = nullptr; ctx->h_tab_bytes = 0;
-                        RXG_CUDA(ctx, cudaMallocHost(&ctx->h_tab, (size_t)T * d * d * 4));
-                        ctx->h_tab_bytes = (size_t)T * d * d * 4;
-                    }
-                    if (!ctx->ev_tab) RXG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_tab, cudaEventDisableTiming));
-                    RXG_CUDA(ctx, cudaMemcpyAsync(ctx->h_tab, c.cov, (size_t)T * d * d * 4, cudaMemcpyDeviceToHost, s_out));
-                    RXG_CUDA(ctx, cudaEventRecord(ctx->ev_tab, s_out));
-                }
+                // nothing to copy per slice: the table was fetched before the first slice, the host threads fill `cov`
             } else if (cov_shared)
                 RXG_CUDA(ctx, cudaMemcpyAsync(cov, c.cov, (size_t)T * d * d * 4, cudaMemcpyDeviceToHost, s_out));
             else

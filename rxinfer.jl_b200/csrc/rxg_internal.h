@@ -68,6 +68,7 @@ struct LgssmCall {
     int32_t* status;         // device or null
     unsigned flags;
     bool smooth;
+    bool tables_only = false;   // compute the gain tables (and the RXG_COV_SHARED_OUT covariance table) and return: no sweep
 };
 
 // rxg_lgssm.cu

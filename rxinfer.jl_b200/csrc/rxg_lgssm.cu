@@ -469,6 +469,7 @@ static int run_shared_family(rxg_ctx* ctx, const LgssmCall& c) {
     }
     int rc = check_cuda(ctx, cudaGetLastError(), "gain table kernels launch");
     if (rc != RXG_OK) return rc;
+    if (c.tables_only) return RXG_OK;
     const int write_cov = (c.cov != nullptr && !cov_shared) ? 1 : 0;
     const bool al16 = (((uintptr_t)c.y | (uintptr_t)c.mean | (uintptr_t)c.cov | (uintptr_t)c.nle | (uintptr_t)c.mean0_chain) & 15) == 0;
     // chains per thread: keep >= ~2 resident warps per SM sub-partition

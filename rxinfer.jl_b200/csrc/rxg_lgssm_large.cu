@@ -917,6 +917,11 @@ static int run_large(rxg_ctx* ctx, const LgssmCall& c) {
     }
     int rc = check_cuda(ctx, cudaGetLastError(), "large gain kernels");
     if (rc != RXG_OK) return rc;
+    if (c.tables_only) {
+        if (c.cov && (c.flags & RXG_COV_SHARED_OUT))
+            RXG_CUDA(ctx, cudaMemcpyAsync(c.cov, c.smooth ? w.ss : w.sf, T * DD * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        return RXG_OK;
+    }
 
     constexpr int NB = 32;
     constexpr int KMAX = (D + M) > 2 * D ? (D + M) : 2 * D;
