@@ -198,14 +198,14 @@ template <int D, int M>
 __global__ void __launch_bounds__(256) large_gain_tables(LargeWs w, int T, int transition_first) {
     constexpr int LD = LD_<D>::v;
     extern __shared__ double sm[];
+    // three D x D fp64 buffers (100 KB at d = 64: two CTAs per SM).  A is read from global memory in the forward part
+    // (one element-wise use) and staged into X1 -- free by then -- for the products of the backward part.
     double* X0 = sm;
     double* X1 = X0 + D * LD;
     double* X2 = X1 + D * LD;
-    double* As = X2 + D * LD;
     const int t = blockIdx.x;
     const double* Sp = w.Sp + (size_t)t * D * D;
     const double* Sf = w.Sf + (size_t)t * D * D;
-    for (int i = threadIdx.x; i < D * D; i += blockDim.x) As[(i / D) * LD + i % D] = w.A[i];
     // ---- forward gain: X1 = B Sp; X2 = X1 B' + Q = L L'; X1 <- L^-T L^-1 X1 = K'  (M x D)
     if (w.b_identity && M == D) {
         for (int idx = threadIdx.x; idx < D * D; idx += blockDim.x) {
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(256) large_gain_tables(LargeWs w, int T, int t
     // F = A - K (B A)   (or I - K B at t = 0 without a leading transition); stored transposed: ft[k][r] = F(r, k)
     if (pred) {
         bgemm<D, D, M>([&](int r, int k) { return X1[k * LD + r]; }, [&](int k, int j) { return w.BA[k * D + j]; },
-                       [&](int r, int j, double v) { ft[j * D + r] = (float)(As[r * LD + j] - v); });
+                       [&](int r, int j, double v) { ft[j * D + r] = (float)(w.A[r * D + j] - v); });
     } else {
         bgemm<D, D, M>([&](int r, int k) { return X1[k * LD + r]; }, [&](int k, int j) { return w.B[k * D + j]; },
                        [&](int r, int j, double v) { ft[j * D + r] = (float)((r == j ? 1.0 : 0.0) - v); });
@@ -305,7 +305,12 @@ __global__ void __launch_bounds__(256) large_gain_tables(LargeWs w, int T, int t
         return;                  // E_{T-1} = I, G_{T-1} = 0: the tensor-core sweep sets mu_s[T-1] = x_{T-1} directly
     }
     const double* Sp1 = w.Sp + (size_t)(t + 1) * D * D;
-    for (int i = threadIdx.x; i < D * D; i += blockDim.x) X2[(i / D) * LD + i % D] = Sp1[i];
+    double* As = X1;                       // K' (X1) is no longer needed: every reader finished before the barrier above
+    for (int i = threadIdx.x; i < D * D; i += blockDim.x) {
+        As[(i / D) * LD + i % D] = w.A[i];
+        X2[(i / D) * LD + i % D] = Sp1[i];
+    }
+    __syncthreads();
     // X0 = A Sf  (= (Sf A')')
     bgemm<D, D, D>([&](int i, int k) { return As[i * LD + k]; }, [&](int k, int j) { return Sf[k * D + j]; },
                    [&](int i, int j, double v) { X0[i * LD + j] = v; });
@@ -857,7 +862,7 @@ static int run_large(rxg_ctx* ctx, const LgssmCall& c) {
     static bool attr_done = false;
     if (!attr_done) {
         RXG_CUDA(ctx, cudaFuncSetAttribute(large_riccati_seq<D, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
-        RXG_CUDA(ctx, cudaFuncSetAttribute(large_gain_tables<D, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
+        RXG_CUDA(ctx, cudaFuncSetAttribute(large_gain_tables<D, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
         RXG_CUDA(ctx, cudaFuncSetAttribute(large_smooth_seq<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
     }
     const size_t sm4 = (size_t)4 * D * LD * 8, sm6 = (size_t)6 * D * LD * 8;
@@ -891,7 +896,7 @@ static int run_large(rxg_ctx* ctx, const LgssmCall& c) {
         large_predict<D><<<c.T, 256, sm2, ctx->stream>>>(w, c.T, tf);
         ctx->launches += 1;
     }
-    large_gain_tables<D, M><<<c.T, 256, sm3, ctx->stream>>>(w, c.T, tf);
+    large_gain_tables<D, M><<<c.T, 256, sm2, ctx->stream>>>(w, c.T, tf);
     ctx->launches += 1;
     if (c.smooth) {
         if (seq) {
