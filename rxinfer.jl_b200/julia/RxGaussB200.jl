@@ -104,6 +104,27 @@ function filter_chunk!(ctx::Context, y::Ptr{Float32}, dims::NTuple{3,Int}, A, B,
     return filt_mean, filt_cov
 end
 
+"""
+    stream_vmp_gamma!(ctx, y, dims, out; iterations = 4, w = 1f0, init = (0f0, 1f3, 1f0, 1f0), prev = C_NULL, fe = C_NULL)
+
+Time-chunk of the streaming `test_model1` (test/inference/inference_tests.jl:752-775: one-step random walk observed
+with unknown precision τ ~ Gamma, `MeanField()`, priors autoupdated from `q(x_t)`, `q(τ)`).  Device pointers:
+`y[batch, Tc]`, `out[batch, 4, Tc]` = (m_x, v_x, shape, rate) per datum, optional `fe[batch, iterations, Tc]`;
+`prev[batch, 4]` = last slice of the previous chunk's `out` (then `init` is ignored).
+"""
+function stream_vmp_gamma!(ctx::Context, y::Ptr{Float32}, dims::NTuple{2,Int}, out::Ptr{Float32}; iterations::Integer = 4,
+                           w::Float32 = 1f0, init = (0f0, 1f3, 1f0, 1f0), prev::Ptr{Float32} = Ptr{Float32}(C_NULL),
+                           fe::Ptr{Float32} = Ptr{Float32}(C_NULL))
+    batch, Tc = dims
+    ini = Float32[init...]
+    GC.@preserve ini begin
+        check(ctx, ccall((:rxg_stream_vmp_gamma_f32, LIB), Cint,
+            (Ptr{Cvoid}, Cint, Int64, Cint, Cfloat, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Cuint),
+            ctx.handle, Tc, batch, iterations, w, ini, prev, y, out, fe, RXG_PTR_DEVICE))
+    end
+    return out
+end
+
 # --- multi-GPU (one Julia process per GPU): id from rank 0 broadcast by the host (MPI.jl / Distributed), then
 #     rxg_comm_init; after the sweep one all-gather of the posterior marginals.  With a shared model pass
 #     RXG_COV_REPLICATE: only the means cross NVLink, the chain-independent covariances are filled locally.
