@@ -1,6 +1,6 @@
 """GPU parity of the variational members of the path: fused HGF filter (GCV node, GH-31), the Gamma-precision VMP
-around a scalar smoother and the streaming mean-field Gamma model.  HGF: pinned by the reference test's posterior
-assertions on its own data stream (tests/test_reference_rng_goldens.py), not by its free-energy value (oracle/hgf.py)."""
+around a scalar smoother and the streaming mean-field Gamma model.  HGF: the oracle is pinned by the
+reference test on its own data stream, free energy included (tests/test_reference_rng_goldens.py, oracle/hgf.py)."""
 import os
 
 import numpy as np
