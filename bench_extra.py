@@ -17,7 +17,7 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import rxinfer_jl_b200 as rx  # noqa: E402
-from bench import notebook_model_f32, peaks  # noqa: E402
+from bench import dense_model_f32, notebook_model_d2_f32, notebook_model_f32, peaks  # noqa: E402
 
 
 def timed(fn, warm=3, reps=5):
@@ -63,8 +63,7 @@ def main():
 
     if "scaling_T" in which:
         # the notebook's scaling table (ipynb:795-806) at d = 2, batched: T from 50 to 50 000
-        from oracle.lgssm import notebook_model
-        m2 = {k: np.asarray(v, np.float32) for k, v in notebook_model(2).items()}
+        m2 = notebook_model_d2_f32()
         for TT in (50, 1000, 10000, 50000):
             b = max(1024, min(65536, (1 << 26) // TT))
             y = torch.randn(TT, 2, b, device="cuda", generator=g) * 3.3
@@ -88,10 +87,9 @@ def main():
     if "large" in which:
         # BASELINE configs[2] (d = 64, T = 1000, batch = 4096) and the smaller tensor-core sizes; shared model.
         # flops: textbook Kalman + RTS mean recursions only = 2 * (2 d^2 [F x + K y] + 2 d^2 [E x + G x]) per (chain, step)
-        from oracle.lgssm import dense_model
         ctx.set_profiling(True)
         for d, b in ((64, 4096), (64, 18944), (32, 16384), (16, 65536)):
-            md = {k: np.asarray(v, np.float32) for k, v in dense_model(d).items()}
+            md = dense_model_f32(d)
             y = torch.randn(T, d, b, device="cuda", generator=g) * 3.3
             mean = torch.empty(T, d, b, device="cuda")
             for no_umma in ("0", "1"):
