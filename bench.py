@@ -342,7 +342,7 @@ def main():
             te = torch.tensor([e0.elapsed_time(e1) / e_steps], device=dev, dtype=torch.float64)
             if world > 1:
                 dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            bcast = os.environ.get("RXG_HOST_COV_D2H", "0") == "0" and ctx.host_fill_threads() >= 6
+            bcast = ctx.get_option("host_cov_d2h") == 0 and ctx.host_fill_threads() >= 4
             e2e = {"value": msgs / (float(te.item()) * 1e-3), "unit": "messages/s", "ms_per_step": float(te.item()),
                    "h2d_bytes_per_step": int(yh.numel() * 4),
                    "d2h_bytes_per_step": int((mh.numel() + (T * D * D if bcast else ch.numel())) * 4),
@@ -353,7 +353,7 @@ def main():
                            "full device->host copy of the per-chain covariances")}
             # the same call with the covariance broadcast disabled: every byte of the per-chain covariances over PCIe
             if bcast:
-                os.environ["RXG_HOST_COV_D2H"] = "1"
+                ctx.set_option("host_cov_d2h", 1)
                 ctx.lgssm(yh, **kw, smooth=True, out_mean=mh, out_cov=ch)
                 torch.cuda.synchronize()
                 if world > 1:
@@ -362,7 +362,7 @@ def main():
                 for _ in range(e_steps):
                     ctx.lgssm(yh, **kw, smooth=True, out_mean=mh, out_cov=ch, asynchronous=True)
                 e1.record(); torch.cuda.synchronize()
-                os.environ["RXG_HOST_COV_D2H"] = "0"
+                ctx.set_option("host_cov_d2h", 0)
                 tf_ = torch.tensor([e0.elapsed_time(e1) / e_steps], device=dev, dtype=torch.float64)
                 if world > 1:
                     dist.all_reduce(tf_, op=dist.ReduceOp.MAX)

@@ -93,7 +93,7 @@ def main():
             y = torch.randn(T, d, b, device="cuda", generator=g) * 3.3
             mean = torch.empty(T, d, b, device="cuda")
             for no_umma in ("0", "1"):
-                os.environ["RXG_NO_UMMA"] = no_umma
+                ctx.set_option("no_umma", int(no_umma))
                 sw, gn = [], []
                 def run():
                     ctx.lgssm(y, **md, smooth=True, out_mean=mean, cov_shared_out=True)
@@ -104,7 +104,7 @@ def main():
                                   "ms": ms, "sweep_ms": float(np.mean(sw[-3:])), "gain_tables_ms": float(np.mean(gn[-3:])),
                                   "messages_per_s": 6 * T * b / ms * 1e3,
                                   "sweep_TFLOPs": 8 * d * d * T * b / (float(np.mean(sw[-3:])) * 1e-3) / 1e12}))
-            os.environ.pop("RXG_NO_UMMA", None)
+            ctx.set_option("no_umma", 0)
             del y, mean
         ctx.set_profiling(False)
 
@@ -136,7 +136,8 @@ def main():
         rows.append(("MvNormalMeanCovariance(:out)  (mu, S + Sigma)", timed(lambda: ctx.rule_add_cov(mu, S, mod["P"])), 2 * (d + d * d) * 4))
         rows.append(("*(:out)  (A mu, A S A')", timed(lambda: ctx.rule_mul_out(A, mu, S)), 2 * (d + d * d) * 4))
         rows.append(("*(:in)   cholinv + A' W A", timed(lambda: ctx.rule_mul_in(A, mu, S)), 2 * (d + d * d) * 4 + 4))
-        rows.append(("prod (xi1 + xi2, W1 + W2)", timed(lambda: ctx.prod_gaussian(mu, S, mu, S)), 3 * (d + d * d) * 4))
+        mu2, S2 = (mu * 0.5).contiguous(), (S * 2.0).contiguous()          # distinct operands: 2 reads + 1 write per message
+        rows.append(("prod (xi1 + xi2, W1 + W2)", timed(lambda: ctx.prod_gaussian(mu, S, mu2, S2)), 3 * (d + d * d) * 4))
         rows.append(("mean_cov <-> weightedmean_precision (cholinv)", timed(lambda: ctx.meancov_to_wmp(mu, S)), 2 * (d + d * d) * 4 + 4))
         for name, ms, bytes_per in rows:
             # note: torch.empty_like allocations are inside the timed call (caching allocator)

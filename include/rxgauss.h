@@ -63,6 +63,23 @@ enum rxg_flags {
                                       no missing data) -- replicate them locally, gather only means */
 };
 
+/* Per-context options (rxg_set_option).  The RXG_* environment variables of the same name are read
+ * ONCE, inside rxg_create, as the initial values; nothing on a compute path calls getenv.        */
+typedef enum rxg_option {
+    RXG_OPT_GAIN_SEQ = 0,          /* 1: sequential Riccati gain kernels (cross-check of the time-parallel scan)   */
+    RXG_OPT_LARGE_SEQ = 1,         /* 1: sequential gain kernels of the large-state family (cross-check)            */
+    RXG_OPT_NO_UMMA = 2,           /* 1: d >= 16 mean recursions on the FP32 pipe instead of tcgen05 (cross-check)  */
+    RXG_OPT_SWEEP_VARIANT = 3,     /* shared-model sweep: 0 auto, 1 stash, 2 checkpoint+recompute, 3 time-segmented */
+    RXG_OPT_FORCE_CPT = 4,         /* chains per thread of the shared-model sweep (0 = auto)                        */
+    RXG_OPT_HOST_THREADS = 5,      /* host threads of the host-side covariance broadcast (0 = auto)                 */
+    RXG_OPT_HOST_COV_D2H = 6,      /* 1: host-pointer calls copy the per-chain covariances over PCIe (no broadcast) */
+    RXG_OPT_HOST_BCAST_MIN_MB = 7, /* below this covariance size the host broadcast is not used (default 64)        */
+    RXG_OPT_HOST_SLICES = 8,       /* batch slices of the host-pointer pipeline (0 = auto)                          */
+    RXG_OPT_COUNT_ = 9
+} rxg_option;
+
+#define RXG_MAX_PEERS 8            /* ranks of one peer group (one NVSwitch domain)                                 */
+
 /* ------------------------------------------------------------------ context / plumbing ------ */
 int rxg_version(void);
 /* Create a context on CUDA device `device`.  [ref: the reference has no device/ctx notion; this
@@ -70,6 +87,8 @@ int rxg_version(void);
 int rxg_create(rxg_ctx** out, int device, unsigned flags);
 int rxg_destroy(rxg_ctx* ctx);
 const char* rxg_last_error(const rxg_ctx* ctx);
+int rxg_set_option(rxg_ctx* ctx, int option, long long value);
+int rxg_get_option(const rxg_ctx* ctx, int option, long long* value);
 /* Use an externally owned cudaStream_t (e.g. torch's current stream) for all launches/copies.  */
 int rxg_set_stream(rxg_ctx* ctx, void* cuda_stream);
 int rxg_sync(rxg_ctx* ctx);

@@ -146,8 +146,15 @@ def normal_meanvar_out(m_mu, v):
 
 
 def normal_meanprec_out_q_tau(m_mu, E_tau):
-    """@rule NormalMeanPrecision(:out)(m_mu / q_mu, q_tau): (m_mu, v_mu + 1/E[tau])."""
+    """@rule NormalMeanPrecision(:out)(m_mu::UnivariateNormalDistributionsFamily, q_tau): the BP message on the
+    mean edge keeps its variance: (m_mu, v_mu + 1/E[tau])."""
     return m_mu[0], m_mu[1] + 1.0 / E_tau
+
+
+def normal_meanprec_out_q_mu_q_tau(q_mu, E_tau):
+    """@rule NormalMeanPrecision(:out)(q_mu::Any, q_tau::Any) (mean-field):
+    NormalMeanPrecision(mean(q_mu), mean(q_tau)), i.e. variance 1/E[tau] only -- var(q_mu) does not enter."""
+    return q_mu[0], 0.0 * np.asarray(q_mu[1]) + 1.0 / E_tau
 
 
 def prod_normal_mv(l, r):

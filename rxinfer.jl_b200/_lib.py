@@ -36,6 +36,8 @@ SIGNATURES = {
     "rxg_create": (c_int, [POINTER(c_void_p), c_int, c_uint]),
     "rxg_destroy": (c_int, [c_void_p]),
     "rxg_last_error": (c_char_p, [c_void_p]),
+    "rxg_set_option": (c_int, [c_void_p, c_int, c_longlong]),
+    "rxg_get_option": (c_int, [c_void_p, c_int, POINTER(c_longlong)]),
     "rxg_set_stream": (c_int, [c_void_p, c_void_p]),
     "rxg_sync": (c_int, [c_void_p]),
     "rxg_host_alloc": (c_int, [POINTER(c_void_p), c_size_t]),

@@ -64,6 +64,18 @@ class Context:
     def host_fill_threads(self) -> int:
         return int(self.lib.rxg_host_fill_threads())
 
+    OPTIONS = {"gain_seq": 0, "large_seq": 1, "no_umma": 2, "sweep_variant": 3, "force_cpt": 4, "host_threads": 5,
+               "host_cov_d2h": 6, "host_bcast_min_mb": 7, "host_slices": 8}
+
+    def set_option(self, name: str, value: int):
+        """``rxg_set_option``: per-context dispatch switches (cross-check kernels, host-pipeline tuning)."""
+        self._check(self.lib.rxg_set_option(self.h, self.OPTIONS[name], int(value)))
+
+    def get_option(self, name: str) -> int:
+        v = ctypes.c_longlong()
+        self._check(self.lib.rxg_get_option(self.h, self.OPTIONS[name], ctypes.byref(v)))
+        return int(v.value)
+
     def set_profiling(self, on=True):
         self._check(self.lib.rxg_set_profiling(self.h, 1 if on else 0))
 
@@ -89,6 +101,23 @@ class Context:
                 continue
             if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
                 raise ValueError("expected contiguous float32 CUDA tensors")
+            if t.device.index != self.device:
+                raise ValueError(f"tensor lives on cuda:{t.device.index}, this context is bound to cuda:{self.device}")
+
+    def _io(self, t, name, on_dev, dtype=torch.float32, shape=None):
+        """Validate one I/O array of a fused sweep: dtype, contiguity, device (or host), shape."""
+        if t is None:
+            return
+        if t.dtype != dtype or not t.is_contiguous():
+            raise ValueError(f"{name}: expected a contiguous {dtype} tensor, got {t.dtype}, "
+                             f"contiguous={t.is_contiguous()} (call .contiguous() / .to({dtype}) explicitly)")
+        if on_dev:
+            if not t.is_cuda or t.device.index != self.device:
+                raise ValueError(f"{name}: expected a tensor on cuda:{self.device} (y is a device array), got {t.device}")
+        elif t.is_cuda:
+            raise ValueError(f"{name}: y is a host array, so every data array must be on the host; got {t.device}")
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
 
     def empty(self, *shape, dtype=torch.float32):
         return torch.empty(*shape, dtype=dtype, device=f"cuda:{self.device}")
@@ -96,11 +125,15 @@ class Context:
     # ------------------------------------------------------------------ fused sweeps
     def lgssm(self, y, A, B, P, Q, m0, S0, *, u=None, smooth=True, mask=None, want_cov=True, want_evidence=False,
               want_status=False, per_chain_model=False, force_per_chain_path=False, cov_shared_out=False,
-              transition_first=False, out_mean=None, out_cov=None, asynchronous=False):
+              transition_first=False, out_mean=None, out_cov=None, out_status=None, asynchronous=False):
         """y[T, m, batch] (CUDA fp32, or pinned/pageable CPU fp32 for the host-pointer path)
         -> dict(mean[T,d,batch], cov[T,d,d,batch] or [T,d,d], neg_log_evidence[batch], status[batch])."""
         on_dev = y.is_cuda
+        if y.dim() != 3:
+            raise ValueError(f"y: expected [T, m, batch], got shape {tuple(y.shape)}")
         T, m, batch = y.shape
+        self._io(y, "y", on_dev)
+        self._io(mask, "mask", on_dev, dtype=torch.uint8, shape=(T, batch))
         flags = L.PTR_DEVICE if on_dev else 0
         if per_chain_model:
             flags |= L.MODEL_PER_CHAIN
@@ -127,13 +160,16 @@ class Context:
             flags |= L.ASYNC
         mk = lambda *s, dt=torch.float32: (torch.empty(*s, dtype=dt, device=y.device) if on_dev
                                            else torch.empty(*s, dtype=dt).pin_memory())
+        self._io(out_mean, "out_mean", on_dev, shape=(T, d, batch))
+        self._io(out_cov, "out_cov", on_dev, shape=(T, d, d) if cov_shared_out else (T, d, d, batch))
         mean = out_mean if out_mean is not None else mk(T, d, batch)
         need_cov = want_cov or per_chain_model or force_per_chain_path or mask is not None
         cov = out_cov
         if cov is None and need_cov:
             cov = mk(T, d, d) if cov_shared_out else mk(T, d, d, batch)
         nle = mk(batch) if want_evidence else None
-        status = mk(batch, dt=torch.int32) if want_status else None
+        self._io(out_status, "out_status", on_dev, dtype=torch.int32, shape=(batch,))
+        status = out_status if out_status is not None else (mk(batch, dt=torch.int32) if want_status else None)
         fn = self.lib.rxg_lgssm_smooth_f32 if smooth else self.lib.rxg_lgssm_filter_f32
         mask_p = ctypes.cast(c_void_p(mask.data_ptr()), L.u8p) if mask is not None else ctypes.cast(c_void_p(None), L.u8p)
         st_p = ctypes.cast(c_void_p(status.data_ptr()), L.i32p) if status is not None else ctypes.cast(c_void_p(None), L.i32p)
@@ -360,6 +396,7 @@ class Context:
     def comm_init(self, nranks, rank, uid: bytes):
         buf = ctypes.create_string_buffer(uid, 128)
         self._check(self.lib.rxg_comm_init(self.h, nranks, rank, ctypes.cast(buf, c_void_p)))
+        self.comm_nranks, self.comm_rank = int(nranks), int(rank)
 
     def allgather_posteriors(self, mean, cov, nranks, out_mean=None, out_cov=None, replicate_cov=False):
         """Rank-major gathered slabs ([G, T, d, b], [G, T, d, d, b]); pass out_* to reuse buffers.

@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <immintrin.h>
+#include <sched.h>
 
 #include <thread>
 #include <vector>
@@ -52,6 +53,39 @@ static void* grow(rxg_ctx* ctx, void** buf, size_t* have, size_t want) {
     *have = sz;
     return *buf;
 }
+int* bad_flag(rxg_ctx* ctx) {
+    if (!ctx->d_bad) {
+        if (cudaMalloc(&ctx->d_bad, 4) != cudaSuccess || cudaMallocHost(&ctx->h_bad, 4) != cudaSuccess) {
+            check_cuda(ctx, cudaGetLastError(), "bad_flag alloc");
+            return nullptr;
+        }
+        *ctx->h_bad = 0;
+        cudaMemset(ctx->d_bad, 0, 4);
+    }
+    return ctx->d_bad;
+}
+int begin_bad_flag(rxg_ctx* ctx) {
+    if (!bad_flag(ctx)) return RXG_ERR_CUDA;
+    return check_cuda(ctx, cudaMemsetAsync(ctx->d_bad, 0, 4, ctx->stream), "bad flag reset");
+}
+static int examine_bad_flag(rxg_ctx* ctx) {      // the stream has been synchronised
+    if (!ctx->bad_pending) return RXG_OK;
+    ctx->bad_pending = false;
+    if (*ctx->h_bad != 0)
+        return fail(ctx, RXG_ERR_NOT_SPD, "a Cholesky pivot of the model's covariance recursion was not positive "
+                                          "(A, B, P, Q, S0 do not define SPD predicted / innovation covariances)");
+    return RXG_OK;
+}
+int end_bad_flag(rxg_ctx* ctx, bool sync_now) {
+    if (!ctx->d_bad) return RXG_OK;
+    int rc = check_cuda(ctx, cudaMemcpyAsync(ctx->h_bad, ctx->d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream), "bad flag read-back");
+    if (rc != RXG_OK) return rc;
+    ctx->bad_pending = true;
+    if (!sync_now) return RXG_OK;
+    rc = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+    if (rc != RXG_OK) return rc;
+    return examine_bad_flag(ctx);
+}
 void* workspace(rxg_ctx* ctx, size_t bytes) { return grow(ctx, &ctx->ws, &ctx->ws_bytes, bytes); }
 void* staging(rxg_ctx* ctx, size_t bytes) { return grow(ctx, &ctx->stage, &ctx->stage_bytes, bytes); }
 
@@ -64,8 +98,8 @@ extern "C" {
 int rxg_version(void) { return RXG_VERSION; }
 
 int rxg_create(rxg_ctx** out, int device, unsigned flags) {
-    (void)flags;
     if (!out) return RXG_ERR_BAD_ARG;
+    if (flags != 0) return RXG_ERR_BAD_ARG;      // no creation flags are defined (reserved)
     *out = nullptr;
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -81,7 +115,28 @@ int rxg_create(rxg_ctx** out, int device, unsigned flags) {
         return RXG_ERR_CUDA;
     }
     ctx->own_stream = true;
+    // options: defaults, then the RXG_* environment variables (read here and nowhere else)
+    ctx->opt[RXG_OPT_HOST_BCAST_MIN_MB] = 64;
+    static const struct { int id; const char* env; } kEnv[] = {
+        {RXG_OPT_GAIN_SEQ, "RXG_GAIN_SEQ"}, {RXG_OPT_LARGE_SEQ, "RXG_LARGE_SEQ"}, {RXG_OPT_NO_UMMA, "RXG_NO_UMMA"},
+        {RXG_OPT_SWEEP_VARIANT, "RXG_SWEEP_VARIANT"}, {RXG_OPT_FORCE_CPT, "RXG_FORCE_CPT"},
+        {RXG_OPT_HOST_THREADS, "RXG_HOST_THREADS"}, {RXG_OPT_HOST_COV_D2H, "RXG_HOST_COV_D2H"},
+        {RXG_OPT_HOST_BCAST_MIN_MB, "RXG_HOST_BCAST_MIN_MB"}, {RXG_OPT_HOST_SLICES, "RXG_HOST_SLICES"}};
+    for (const auto& e : kEnv)
+        if (const char* v = getenv(e.env)) ctx->opt[e.id] = atoll(v);
     *out = ctx;
+    return RXG_OK;
+}
+
+int rxg_set_option(rxg_ctx* ctx, int option, long long value) {
+    if (!ctx) return RXG_ERR_BAD_ARG;
+    if (option < 0 || option >= RXG_OPT_COUNT_) return fail(ctx, RXG_ERR_BAD_ARG, "rxg_set_option: unknown option %d", option);
+    ctx->opt[option] = value;
+    return RXG_OK;
+}
+int rxg_get_option(const rxg_ctx* ctx, int option, long long* value) {
+    if (!ctx || !value || option < 0 || option >= RXG_OPT_COUNT_) return RXG_ERR_BAD_ARG;
+    *value = ctx->opt[option];
     return RXG_OK;
 }
 
@@ -94,6 +149,8 @@ int rxg_destroy(rxg_ctx* ctx) {
     rxg_comm_destroy_internal(ctx);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->stage) cudaFree(ctx->stage);
+    if (ctx->d_bad) cudaFree(ctx->d_bad);
+    if (ctx->h_bad) cudaFreeHost(ctx->h_bad);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->s_in) {
         cudaStreamSynchronize(ctx->s_in); cudaStreamSynchronize(ctx->s_out);
@@ -129,7 +186,7 @@ int rxg_set_stream(rxg_ctx* ctx, void* cuda_stream) {
 int rxg_sync(rxg_ctx* ctx) {
     if (!ctx) return RXG_ERR_BAD_ARG;
     RXG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return RXG_OK;
+    return examine_bad_flag(ctx);      // a deferred (RXG_ASYNC) call may have flagged a non-SPD model
 }
 
 int rxg_host_alloc(void** out, size_t bytes) {
@@ -163,10 +220,13 @@ int rxg_profile_last_ms(rxg_ctx* ctx, float* main_kernel_ms, float* gain_kernels
 // whole-chain LGSSM sweeps
 // ------------------------------------------------------------------------------------------------
 // Host threads this process may use for the covariance broadcast of host-pointer calls:
-// RXG_HOST_THREADS, else min(affinity, cgroup quota, 16) shared between the ranks of a local job.
+// min(affinity, cgroup CPU quota) shared between the ranks of a local job (LOCAL_WORLD_SIZE, read once).
 static int host_fill_threads() {
-    if (const char* e = getenv("RXG_HOST_THREADS")) return atoi(e);
-    long n = (long)std::thread::hardware_concurrency();
+    static const int cached = [] {
+    long n = 0;
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
+    if (n < 1) n = (long)std::thread::hardware_concurrency();
     if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
         char q[64]; long per = 0;
         if (fscanf(f, "%63s %ld", q, &per) == 2 && strcmp(q, "max") != 0 && per > 0) {
@@ -175,9 +235,11 @@ static int host_fill_threads() {
         }
         fclose(f);
     }
-    if (n > 16) n = 16;
     if (const char* e = getenv("LOCAL_WORLD_SIZE")) { const int w = atoi(e); if (w > 1) n /= w; }
+    if (n > 64) n = 64;        // beyond this the memory controllers, not the cores, are the limit
     return (int)(n < 1 ? 1 : n);
+    }();
+    return cached;
 }
 // dst[0..n) = v with non-temporal stores (the caller's buffer is write-only here)
 static void fill_row(float* dst, int64_t n, float v) {
@@ -228,10 +290,10 @@ static int lgssm_entry(rxg_ctx* ctx, bool smooth, int d, int m, int T, int64_t b
         if (!cov && (ymask || per_chain_model || (flags & RXG_PATH_PER_CHAIN)))
             return fail(ctx, RXG_ERR_BAD_ARG, "lgssm: cov output required on the per-chain path");
         c.y = y; c.ymask = ymask; c.mean = mean; c.cov = cov; c.nle = nle; c.status = status;
-        int rc = lgssm_dispatch(ctx, c);
+        int rc = begin_bad_flag(ctx);
+        if (rc == RXG_OK) rc = lgssm_dispatch(ctx, c);
         if (rc != RXG_OK) return rc;
-        if (!(flags & RXG_ASYNC)) RXG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        return RXG_OK;
+        return end_bad_flag(ctx, !(flags & RXG_ASYNC));
     }
 
     // ---- host-pointer call: stage through device memory.  The batch is cut into slices that are
@@ -246,19 +308,18 @@ static int lgssm_entry(rxg_ctx* ctx, bool smooth, int d, int m, int T, int64_t b
     // the 4 (d + d^2) bytes per (chain, step) less PCIe traffic.  RXG_HOST_COV_D2H=1 forces the full device->host copy;
     // with fewer than 6 host threads per rank the PCIe copy wins and is kept.
     bool host_bcast = cov && !(flags & RXG_COV_SHARED_OUT) && !ymask && !(flags & RXG_PATH_PER_CHAIN);
-    if (const char* e = getenv("RXG_HOST_COV_D2H")) host_bcast = host_bcast && atoi(e) == 0;
-    size_t bcast_min_mb = 64;                    // below this the thread start-up is not worth it
-    if (const char* e = getenv("RXG_HOST_BCAST_MIN_MB")) bcast_min_mb = (size_t)atol(e);
+    if (ctx->opt[RXG_OPT_HOST_COV_D2H] != 0) host_bcast = false;
+    const size_t bcast_min_mb = (size_t)ctx->opt[RXG_OPT_HOST_BCAST_MIN_MB];   // below this the hand-off is not worth it
     if ((size_t)T * d * d * (size_t)batch * 4 < (bcast_min_mb << 20)) host_bcast = false;
-    const int fill_threads = host_bcast ? host_fill_threads() : 0;
-    if (fill_threads < 6) host_bcast = false;
+    const int fill_threads = !host_bcast ? 0 : (ctx->opt[RXG_OPT_HOST_THREADS] > 0 ? (int)ctx->opt[RXG_OPT_HOST_THREADS] : host_fill_threads());
+    if (fill_threads < 4) host_bcast = false;
     if (host_bcast) c.flags |= RXG_COV_SHARED_OUT;
     const bool cov_shared = (c.flags & RXG_COV_SHARED_OUT) != 0;
     const bool need_cov_dev = cov || ymask || (flags & RXG_PATH_PER_CHAIN);
     int ns = 1;
     if (batch >= 16384) ns = (int)((batch + 8191) / 8192);
     if (ns > 64) ns = 64;
-    if (const char* e = getenv("RXG_HOST_SLICES")) { int v = atoi(e); if (v >= 1) ns = v; }
+    if (ctx->opt[RXG_OPT_HOST_SLICES] >= 1) ns = (int)ctx->opt[RXG_OPT_HOST_SLICES];
     const int64_t bs = ((batch + ns - 1) / ns + 3) / 4 * 4;          // slice width, multiple of 4 chains
     ns = (int)((batch + bs - 1) / bs);
     const int nbuf = ns > 1 ? 2 : 1;
@@ -283,6 +344,10 @@ static int lgssm_entry(rxg_ctx* ctx, bool smooth, int d, int m, int T, int64_t b
             RXG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_out[q], cudaEventDisableTiming));
         }
         RXG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
+    }
+    {
+        int rcb = begin_bad_flag(ctx);
+        if (rcb != RXG_OK) return rcb;
     }
     cudaStream_t s_in = ns > 1 ? ctx->s_in : ctx->stream, s_out = ns > 1 ? ctx->s_out : ctx->stream;
     if (ns > 1) {   // the side streams start after whatever the caller queued on the ctx stream
@@ -361,8 +426,7 @@ static int lgssm_entry(rxg_ctx* ctx, bool smooth, int d, int m, int T, int64_t b
         RXG_CUDA(ctx, cudaEventSynchronize(ctx->ev_tab));
         host_broadcast_cov(cov, (const float*)ctx->h_tab, (int64_t)T * d * d, batch, fill_threads);
     }
-    if (!(flags & RXG_ASYNC)) RXG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return RXG_OK;
+    return end_bad_flag(ctx, !(flags & RXG_ASYNC));
 }
 
 int rxg_lgssm_smooth_f32(rxg_ctx* ctx, int d, int m, int T, int64_t batch, const float* A, const float* B,
@@ -409,7 +473,8 @@ int rxg_lgssm_filter_chunk_f32(rxg_ctx* ctx, int d, int m, int T, int64_t batch,
     c.y = y; c.ymask = nullptr; c.mean = filt_mean; c.cov = filt_cov; c.nle = neg_log_evidence; c.status = nullptr;
     c.flags = (flags | RXG_TRANSITION_FIRST) & ~(unsigned)RXG_ASYNC;
     c.smooth = false;
-    int rc = lgssm_dispatch(ctx, c);
+    int rc = begin_bad_flag(ctx);
+    if (rc == RXG_OK) rc = lgssm_dispatch(ctx, c);
     if (rc != RXG_OK) return rc;
     // carry out: the filtered covariance of the last step (chain independent)
     const size_t dd = (size_t)d * d;
@@ -418,8 +483,7 @@ int rxg_lgssm_filter_chunk_f32(rxg_ctx* ctx, int d, int m, int T, int64_t batch,
     else
         RXG_CUDA(ctx, cudaMemcpy2DAsync(carry_cov, 4, filt_cov + (size_t)(T - 1) * dd * batch, (size_t)batch * 4, 4, dd,
                                         cudaMemcpyDeviceToHost, ctx->stream));
-    RXG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // carry_cov is a host output: always synchronous
-    return RXG_OK;
+    return end_bad_flag(ctx, true);      // carry_cov is a host output: always synchronous
 }
 
 // ------------------------------------------------------------------------------------------------

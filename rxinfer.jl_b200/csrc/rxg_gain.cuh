@@ -195,7 +195,7 @@ __device__ __forceinline__ BwdEl<D> bwd_combine(const BwdEl<D>& early, const Bwd
 template <int D, int M>
 __global__ void __cluster_dims__(GS_CTAS, 1, 1) __launch_bounds__(GS_THREADS, 1)
 gain_scan_kernel(const __grid_constant__ ModelF<D, M> mdl, GainWs ws, ScanWs sw, int T, int transition_first,
-                 float* __restrict__ cov_shared_out) {
+                 float* __restrict__ cov_shared_out, int* __restrict__ bad_out) {
     using TB = Tab<D, M>;
     cg::cluster_group cluster = cg::this_cluster();
     const int g = (int)cluster.block_rank() * GS_THREADS + (int)threadIdx.x;
@@ -434,6 +434,7 @@ gain_scan_kernel(const __grid_constant__ ModelF<D, M> mdl, GainWs ws, ScanWs sw,
             if (cov_shared_out) store_f(cov_shared_out + (size_t)t * D * D, Ss);
         }
     }
+    if (bad) atomicOr(bad_out, 1);
 }
 
 }  // namespace rxg

@@ -334,6 +334,7 @@ int rxg_hgf_filter_f32(rxg_ctx* ctx, int T, int64_t batch, int iters, float kapp
     if (T < 1 || batch < 1 || iters < 1 || !y || !out || !init)
         return rxg::fail(ctx, RXG_ERR_BAD_ARG, "hgf_filter: bad argument");
     if (!(flags & RXG_PTR_DEVICE)) return rxg::fail(ctx, RXG_ERR_UNSUPPORTED, "hgf_filter takes device pointers");
+    RXG_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = ensure_gh_tables(ctx);
     if (rc != RXG_OK) return rc;
     hgf_filter_kernel<<<(unsigned)((batch + 63) / 64), 64, 0, ctx->stream>>>(
@@ -351,6 +352,7 @@ int rxg_hgf_filter_chunk_f32(rxg_ctx* ctx, int T, int64_t batch, int iters, floa
     if (T < 1 || batch < 1 || iters < 1 || !y || !out || !prev)
         return rxg::fail(ctx, RXG_ERR_BAD_ARG, "hgf_filter_chunk: bad argument");
     if (!(flags & RXG_PTR_DEVICE)) return rxg::fail(ctx, RXG_ERR_UNSUPPORTED, "hgf_filter_chunk takes device pointers");
+    RXG_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = ensure_gh_tables(ctx);
     if (rc != RXG_OK) return rc;
     hgf_filter_kernel<<<(unsigned)((batch + 63) / 64), 64, 0, ctx->stream>>>(
@@ -366,6 +368,7 @@ int rxg_hgf_filter_chunk_f32(rxg_ctx* ctx, int T, int64_t batch, int iters, floa
     if (!ctx) return RXG_ERR_BAD_ARG;                                                             \
     if (!(flags & RXG_PTR_DEVICE)) return rxg::fail(ctx, RXG_ERR_UNSUPPORTED, "GCV rules take device pointers"); \
     if (n <= 0) return n == 0 ? RXG_OK : rxg::fail(ctx, RXG_ERR_BAD_ARG, "n < 0");                \
+    RXG_CUDA(ctx, cudaSetDevice(ctx->device));                                                    \
     { int rc0 = ensure_gh_tables(ctx); if (rc0 != RXG_OK) return rc0; }
 #define RXG_GCV_EPILOGUE(what)                                                                    \
     ctx->launches += 1;                                                                           \
@@ -401,6 +404,7 @@ int rxg_lgssm_vmp_gamma_f32(rxg_ctx* ctx, int T, int64_t batch, int iterations, 
     if (T < 1 || batch < 1 || iterations < 1 || !y || !post_mean || !post_var || !shape || !rate)
         return rxg::fail(ctx, RXG_ERR_BAD_ARG, "lgssm_vmp_gamma: bad argument");
     if (!(flags & RXG_PTR_DEVICE)) return rxg::fail(ctx, RXG_ERR_UNSUPPORTED, "lgssm_vmp_gamma takes device pointers");
+    RXG_CUDA(ctx, cudaSetDevice(ctx->device));
     vmp_gamma_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, ctx->stream>>>(
         y, post_mean, post_var, shape, rate, T, batch, iterations, a, v_proc, m0, v0, a0, b0, init_E_tau);
     ctx->launches += 1;
@@ -416,6 +420,7 @@ int rxg_stream_vmp_gamma_f32(rxg_ctx* ctx, int T, int64_t batch, int iters, floa
     if (T < 1 || batch < 1 || iters < 1 || !(w > 0.f) || !y || !out || (!init && !prev))
         return rxg::fail(ctx, RXG_ERR_BAD_ARG, "stream_vmp_gamma: bad argument");
     if (!(flags & RXG_PTR_DEVICE)) return rxg::fail(ctx, RXG_ERR_UNSUPPORTED, "stream_vmp_gamma takes device pointers");
+    RXG_CUDA(ctx, cudaSetDevice(ctx->device));
     const float z[4] = {0.f, 1.f, 1.f, 1.f};
     const float* in = init ? init : z;
     stream_vmp_gamma_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, ctx->stream>>>(

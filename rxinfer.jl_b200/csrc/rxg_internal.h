@@ -37,6 +37,18 @@ struct rxg_ctx {
     void* nccl_dl = nullptr;
     void* comm = nullptr;
     int nranks = 1, rank = 0;
+    // options (rxg_set_option); the RXG_* environment variables are read ONCE, in rxg_create, as their initial values
+    long long opt[RXG_OPT_COUNT_] = {};
+    // numerical-failure flag of the chain-independent gain tables (non-SPD model): device word + pinned host mirror
+    int* d_bad = nullptr;
+    int* h_bad = nullptr;
+    bool bad_pending = false;      // a copy d_bad -> h_bad has been enqueued and not yet examined
+    // peer-mapped gather (rxg_peer_*): flags of the device-side barrier, one int per rank, in every rank's buffer
+    int peer_n = 0, peer_rank = 0;
+    int* peer_flags[RXG_MAX_PEERS] = {};     // peer_flags[g] = rank g's flag array as mapped here (own: cudaMalloc'ed)
+    unsigned peer_epoch = 0;
+    // persistent host threads of the host-side covariance broadcast
+    void* fill_pool = nullptr;
 };
 
 namespace rxg {
@@ -46,6 +58,10 @@ int check_cuda(rxg_ctx* ctx, cudaError_t e, const char* what);
 // returns device pointer of >= bytes (grow-only); nullptr on failure (error recorded)
 void* workspace(rxg_ctx* ctx, size_t bytes);
 void* staging(rxg_ctx* ctx, size_t bytes);
+// device word that gain kernels OR a 1 into when a Cholesky pivot is non-positive (cleared by begin_bad_flag)
+int* bad_flag(rxg_ctx* ctx);
+int begin_bad_flag(rxg_ctx* ctx);                   // zero the flag on the ctx stream
+int end_bad_flag(rxg_ctx* ctx, bool sync_now);      // enqueue the read-back; if sync_now: synchronise and return RXG_ERR_NOT_SPD when set
 
 #define RXG_CUDA(ctx, call)                                         \
     do {                                                            \
@@ -73,6 +89,8 @@ struct LgssmCall {
 
 // rxg_lgssm.cu
 int lgssm_dispatch(rxg_ctx* ctx, const LgssmCall& c);
+// status[i] = RXG_ERR_NOT_SPD if the ctx's gain-table failure flag is set on the device, else RXG_OK
+int fill_status_from_flag(rxg_ctx* ctx, int32_t* status, int64_t n);
 bool lgssm_supported(int d, int m);
 // rxg_lgssm_large.cu
 int lgssm_large_dispatch(rxg_ctx* ctx, const LgssmCall& c);

@@ -208,7 +208,7 @@ lgssm_chain_kernel(const __grid_constant__ ModelF<D, M> mdl, PerChainPtrs pc,
 // Phase 1 (sequential in t): Riccati recursion for the predicted / filtered covariances.
 template <int D, int M>
 __global__ void gain_riccati_seq(const __grid_constant__ ModelF<D, M> mdl, GainWs ws, int T,
-                                 int transition_first) {
+                                 int transition_first, int* __restrict__ bad_out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const Mat<double, D, D> A = load_const<double, D, D>(mdl.A), P = load_const<double, D, D>(mdl.P);
     const Mat<double, M, D> B = load_const<double, M, D>(mdl.B);
@@ -228,12 +228,13 @@ __global__ void gain_riccati_seq(const __grid_constant__ ModelF<D, M> mdl, GainW
         S = sym_downdate(S, V);
         store_d(ws.Sf + (size_t)t * D * D, S);
     }
+    if (bad) atomicOr(bad_out, 1);
 }
 
 // Phase 2 (parallel in t): gains, innovation factors, conditional covariances.
 template <int D, int M>
 __global__ void gain_tables(const __grid_constant__ ModelF<D, M> mdl, GainWs ws, int T,
-                            int transition_first) {
+                            int transition_first, int* __restrict__ bad_out) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     using TB = Tab<D, M>;
@@ -322,6 +323,7 @@ __global__ void gain_tables(const __grid_constant__ ModelF<D, M> mdl, GainWs ws,
         store_f(brec + TB::G_OFF, Z);
     }
     store_fv(brec + TB::GB_OFF, gb);
+    if (bad) atomicOr(bad_out, 1);
 }
 
 // Phase 3 (sequential in t): smoothed covariances  Ss[t] = C[t] + G[t] Ss[t+1] G[t]'.
@@ -394,7 +396,7 @@ static int launch_shared(rxg_ctx* ctx, const LgssmCall& c, const ModelF<D, M>& m
     for (int i = 0; i < D; ++i) has_u |= (mdl.u[i] != 0.f);
     // checkpoint + recompute instead of the forward->backward stash (RXG_NO_CKPT=1: A/B switch)
     bool ckpt = c.smooth && (D * D <= 16) && (CPT == 2);   // with one chain per thread the stash path is faster (B200: 1.85 vs 2.06 ms)
-    if (const char* e = getenv("RXG_NO_CKPT")) ckpt = ckpt && atoi(e) == 0;
+    if (ctx->opt[RXG_OPT_SWEEP_VARIANT] == 1) ckpt = false;                     // stash variant (A/B switch)
 #define RXG_LAUNCH_SHARED2(SM, EV, OF, CK)                                                         \
     lgssm_shared_kernel<D, M, CPT, PF, SM, EV, OF, CK><<<blocks, threads, 0, ctx->stream>>>(       \
         mdl, ws.fwd, ws.bwd, ws.sf, c.y, c.mean, c.cov, c.nle, c.T, c.batch, tf, write_cov, c.mean0_chain)
@@ -447,11 +449,10 @@ static int run_shared_family(rxg_ctx* ctx, const LgssmCall& c) {
     const bool cov_shared = (c.flags & RXG_COV_SHARED_OUT) != 0;
     if (ctx->profile) cudaEventRecord(ctx->ev[0], ctx->stream);
     float* cov_once = (cov_shared && c.cov && c.smooth) ? c.cov : nullptr;
-    const char* seq_env = getenv("RXG_GAIN_SEQ");
-    if (seq_env && atoi(seq_env) != 0) {
+    if (ctx->opt[RXG_OPT_GAIN_SEQ] != 0) {
         // sequential Riccati recursion (cross-check of the scan; ~70x slower at T = 1000)
-        gain_riccati_seq<D, M><<<1, 32, 0, ctx->stream>>>(mdl, ws, c.T, tf);
-        gain_tables<D, M><<<(c.T + 63) / 64, 64, 0, ctx->stream>>>(mdl, ws, c.T, tf);
+        gain_riccati_seq<D, M><<<1, 32, 0, ctx->stream>>>(mdl, ws, c.T, tf, bad_flag(ctx));
+        gain_tables<D, M><<<(c.T + 63) / 64, 64, 0, ctx->stream>>>(mdl, ws, c.T, tf, bad_flag(ctx));
         ctx->launches += 2;
         if (c.smooth) {
             gain_smooth_seq<D, M><<<1, 32, 0, ctx->stream>>>(ws, c.T, cov_once);
@@ -459,7 +460,7 @@ static int run_shared_family(rxg_ctx* ctx, const LgssmCall& c) {
         }
     } else {
         // time-parallel associative scans in one 8-CTA cluster
-        gain_scan_kernel<D, M><<<GS_CTAS, GS_THREADS, 0, ctx->stream>>>(mdl, ws, sw, c.T, tf, cov_once);
+        gain_scan_kernel<D, M><<<GS_CTAS, GS_THREADS, 0, ctx->stream>>>(mdl, ws, sw, c.T, tf, cov_once, bad_flag(ctx));
         ctx->launches += 1;
     }
     if (!c.smooth && cov_shared && c.cov) {
@@ -476,15 +477,21 @@ static int run_shared_family(rxg_ctx* ctx, const LgssmCall& c) {
     // Wider per-thread vectors cut the number of (128-byte-per-warp) store instructions per byte;
     // B200, d = m = 4, T = 1000, batch 65 536: CPT 1 / 2 / 4 = 1.85 / 1.50 / 1.58 ms (262 144: 2 beats 4 too).
     int cpt = (c.batch >= (int64_t)ctx->sm_count * 64 * 2) ? 2 : 1;
-    if (const char* e = getenv("RXG_FORCE_CPT")) cpt = atoi(e);      // test / tuning override
+    if (ctx->opt[RXG_OPT_FORCE_CPT] > 0) cpt = (int)ctx->opt[RXG_OPT_FORCE_CPT];      // test / tuning override
     if (D * M > 16 && cpt > 2) cpt = 2;                              // register budget for d = 6
     if (cpt >= 2 && al16 && c.batch % 2 == 0) return launch_shared<D, M, 2>(ctx, c, mdl, ws, write_cov);
     return launch_shared<D, M, 1>(ctx, c, mdl, ws, write_cov);
 }
 
-__global__ void fill_status_kernel(int32_t* s, int64_t n, int32_t v) {
+// shared model: a failed Cholesky of the chain-independent covariance recursion fails every chain alike
+__global__ void fill_status_kernel(int32_t* s, int64_t n, const int* __restrict__ bad) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) s[i] = v;
+    if (i < n) s[i] = (*bad != 0) ? (int32_t)RXG_ERR_NOT_SPD : (int32_t)RXG_OK;
+}
+int fill_status_from_flag(rxg_ctx* ctx, int32_t* status, int64_t n) {
+    fill_status_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(status, n, bad_flag(ctx));
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "fill_status launch");
 }
 
 template <int D, int M>
@@ -492,11 +499,7 @@ static int run_dm(rxg_ctx* ctx, const LgssmCall& c) {
     const bool per_chain = (c.flags & (RXG_MODEL_PER_CHAIN | RXG_PATH_PER_CHAIN)) != 0 || c.ymask != nullptr;
     if (per_chain) return run_chain_family<D, M>(ctx, c);
     int rc = run_shared_family<D, M>(ctx, c);
-    if (rc == RXG_OK && c.status) {
-        fill_status_kernel<<<(unsigned)((c.batch + 255) / 256), 256, 0, ctx->stream>>>(c.status, c.batch, RXG_OK);
-        ctx->launches += 1;
-        rc = check_cuda(ctx, cudaGetLastError(), "fill_status launch");
-    }
+    if (rc == RXG_OK && c.status) rc = fill_status_from_flag(ctx, c.status, c.batch);
     return rc;
 }
 

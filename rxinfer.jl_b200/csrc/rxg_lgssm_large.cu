@@ -10,8 +10,9 @@
 //      GEMMs per step,  X <- [F_t | K_t] [X ; Y_t]  and  X <- [E_t | G_t] [mu_f,t ; X],
 //      executed by lgssm_block_sweep with the per-step gain block streamed through shared memory
 //      (cp.async, double buffered) and a 4 x 2 register tile per thread.
-// Round-1 scope of this family: shared model, no missing data, no evidence, no offset; the
-// matrix products run on the FP32 pipe (a tcgen05 variant of the sweep GEMM is the follow-up).
+// For d >= 16 the mean recursions run on the tensor cores (rxg_umma_sweep.cu: tcgen05 kind::tf32, 3xTF32 split,
+// TMEM accumulators, TMA bulk copies of the gain records); lgssm_block_sweep is the d = 8 path and the
+// RXG_OPT_NO_UMMA cross-check.  The family also produces neg_log_evidence (large_evidence_kernel).
 #include <math.h>
 
 #include <stdlib.h>
@@ -813,7 +814,7 @@ static int run_large(rxg_ctx* ctx, const LgssmCall& c) {
     const size_t o_Sp = carve(T * DD * 8), o_Sf = carve(T * DD * 8), o_Cc = carve(T * DD * 8), o_Gd = carve(T * DD * 8);
     const size_t o_fw = carve(T * (D + M) * D * 4), o_bw = carve(T * 2 * DD * 4), o_ss = carve(T * DD * 4), o_sf = carve(T * DD * 4);
     // d >= 16: the mean recursions run on the tensor cores (RXG_NO_UMMA=1: FP32-pipe block sweep, the cross-check)
-    const bool use_umma = (D >= 16 && M == D) && !(getenv("RXG_NO_UMMA") && atoi(getenv("RXG_NO_UMMA")) != 0);
+    const bool use_umma = (D >= 16 && M == D) && (ctx->opt[RXG_OPT_NO_UMMA] == 0);
     const size_t o_fe = carve(use_umma ? T * 4 * DD * 4 : 0), o_gu = carve(use_umma ? T * 2 * DD * 4 : 0);
     const size_t o_ku = carve(use_umma ? T * 2 * DD * 4 : 0);
     constexpr int EV_NB = 32;
@@ -837,7 +838,6 @@ static int run_large(rxg_ctx* ctx, const LgssmCall& c) {
     RXG_CUDA(ctx, cudaMemcpyAsync(dQ, c.Q, (size_t)M * M * 4, cudaMemcpyHostToDevice, ctx->stream));
     RXG_CUDA(ctx, cudaMemcpyAsync(dS0, c.S0, DD * 4, cudaMemcpyHostToDevice, ctx->stream));
     RXG_CUDA(ctx, cudaMemcpyAsync(dm0, c.m0, (size_t)D * 4, cudaMemcpyHostToDevice, ctx->stream));
-    RXG_CUDA(ctx, cudaMemsetAsync(base + o_flag, 0, 4, ctx->stream));
     LargeWs w;
     double *A64 = (double*)(base + o_A), *B64 = (double*)(base + o_B), *P64 = (double*)(base + o_P);
     double *Q64 = (double*)(base + o_Q), *S064 = (double*)(base + o_S0), *BA64 = (double*)(base + o_BA);
@@ -848,7 +848,8 @@ static int run_large(rxg_ctx* ctx, const LgssmCall& c) {
     w.A = A64; w.B = B64; w.P = P64; w.Q = Q64; w.S0 = S064; w.BA = BA64;
     w.Sp = (double*)(base + o_Sp); w.Sf = (double*)(base + o_Sf); w.Cc = (double*)(base + o_Cc); w.Gd = (double*)(base + o_Gd);
     w.fwdT = (float*)(base + o_fw); w.bwdT = (float*)(base + o_bw); w.ss = (float*)(base + o_ss); w.sf = (float*)(base + o_sf);
-    w.flag = (int*)(base + o_flag);
+    w.flag = bad_flag(ctx);      // shared with the status / return-code plumbing (rxg_api.cu)
+    (void)o_flag;
     w.recFE = use_umma ? (float*)(base + o_fe) : nullptr;
     w.recG = use_umma ? (float*)(base + o_gu) : nullptr;
     w.recK = use_umma ? (float*)(base + o_ku) : nullptr;
@@ -859,22 +860,19 @@ static int run_large(rxg_ctx* ctx, const LgssmCall& c) {
     const int tf = (c.flags & RXG_TRANSITION_FIRST) ? 1 : 0;
     constexpr int LD = LD_<D>::v;
     const size_t sm3 = (size_t)4 * D * LD * 8, sm2 = (size_t)3 * D * LD * 8;
-    static bool attr_done = false;
-    if (!attr_done) {
+    {   // per-DEVICE attributes: set on every call (a few microseconds), never cached per process
         RXG_CUDA(ctx, cudaFuncSetAttribute(large_riccati_seq<D, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
         RXG_CUDA(ctx, cudaFuncSetAttribute(large_gain_tables<D, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
         RXG_CUDA(ctx, cudaFuncSetAttribute(large_smooth_seq<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
     }
     const size_t sm4 = (size_t)4 * D * LD * 8, sm6 = (size_t)6 * D * LD * 8;
-    static bool attr2_done = false;
-    if (!attr2_done) {
+    {
         RXG_CUDA(ctx, cudaFuncSetAttribute(large_fwd_init<D, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4));
         RXG_CUDA(ctx, cudaFuncSetAttribute(large_fwd_doubling<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm6));
         RXG_CUDA(ctx, cudaFuncSetAttribute(large_predict<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
         RXG_CUDA(ctx, cudaFuncSetAttribute(large_bwd_scan_round<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
-        attr2_done = true;
     }
-    const bool seq = getenv("RXG_LARGE_SEQ") && atoi(getenv("RXG_LARGE_SEQ")) != 0;
+    const bool seq = ctx->opt[RXG_OPT_LARGE_SEQ] != 0;
     if (ctx->profile) cudaEventRecord(ctx->ev[0], ctx->stream);
     if (seq) {
         large_riccati_seq<D, M><<<1, 256, sm3, ctx->stream>>>(w, c.T, tf);
@@ -931,10 +929,9 @@ static int run_large(rxg_ctx* ctx, const LgssmCall& c) {
     constexpr int NB = 32;
     constexpr int KMAX = (D + M) > 2 * D ? (D + M) : 2 * D;
     const size_t smw = (size_t)(2 * KMAX * D + 2 * KMAX * NB) * 4;
-    if (!attr_done) {
+    {
         RXG_CUDA(ctx, cudaFuncSetAttribute(lgssm_block_sweep<D, M, NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
         RXG_CUDA(ctx, cudaFuncSetAttribute(lgssm_block_sweep<D, M, NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
-        attr_done = true;
     }
     const unsigned blocks = (unsigned)((c.batch + NB - 1) / NB);
     auto sweep = [&](bool smooth) -> int {
@@ -953,11 +950,7 @@ static int run_large(rxg_ctx* ctx, const LgssmCall& c) {
         rc = sweep(false);
         if (rc != RXG_OK) return rc;
         const size_t sme = (size_t)(2 * (D + M) * M + 2 * (D + M) * EV_NB) * 4 + (size_t)(D / 4) * EV_NB * 8;
-        static bool ev_attr = false;
-        if (!ev_attr) {
-            RXG_CUDA(ctx, cudaFuncSetAttribute(large_evidence_kernel<D, M, EV_NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sme));
-            ev_attr = true;
-        }
+        RXG_CUDA(ctx, cudaFuncSetAttribute(large_evidence_kernel<D, M, EV_NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sme));
         large_evidence_kernel<D, M, EV_NB><<<dim3(ev_tiles, (unsigned)ev_slices), (D / 4) * (EV_NB / 2), sme, ctx->stream>>>(
             w.evT, dm0, c.mean0_chain, c.y, c.mean, (double*)(base + o_evp), c.T, c.batch);
         evidence_finish_kernel<<<(unsigned)((c.batch + 255) / 256), 256, 0, ctx->stream>>>(
@@ -984,7 +977,7 @@ static int run_large(rxg_ctx* ctx, const LgssmCall& c) {
             if (rc != RXG_OK) return rc;
         }
     }
-    if (c.status) RXG_CUDA(ctx, cudaMemsetAsync(c.status, 0, (size_t)c.batch * 4, ctx->stream));
+    if (c.status) return fill_status_from_flag(ctx, c.status, c.batch);
     return RXG_OK;
 }
 

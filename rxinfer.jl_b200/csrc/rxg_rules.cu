@@ -189,7 +189,8 @@ static inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / 
     if (!((flags) & RXG_PTR_DEVICE))                                                  \
         return rxg::fail((ctx), RXG_ERR_UNSUPPORTED,                                  \
                          "per-rule kernels take device pointers (set RXG_PTR_DEVICE)"); \
-    if ((n) == 0) return RXG_OK;
+    if ((n) == 0) return RXG_OK;                                                      \
+    RXG_CUDA((ctx), cudaSetDevice((ctx)->device));
 
 #define RXG_RULE_EPILOGUE(ctx, what)                                                  \
     (ctx)->launches += 1;                                                             \

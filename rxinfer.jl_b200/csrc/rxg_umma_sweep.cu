@@ -420,12 +420,10 @@ static int launch_umma_sweep_d(rxg_ctx* ctx, bool smooth, const float* recFE, co
     using S = US<D>;
     const size_t smem_ky = 2 * S::X_BYTES + 4 * S::G_BYTES + 64;
     const size_t smem_sw = 2 * S::X_BYTES + 4 * S::FE_BYTES + 64;
-    static bool done = false;
-    if (!done) {
+    {   // per-device attributes: set on every call
         RXG_CUDA(ctx, cudaFuncSetAttribute(umma_ky_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ky));
         RXG_CUDA(ctx, cudaFuncSetAttribute(lgssm_umma_sweep<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sw));
         RXG_CUDA(ctx, cudaFuncSetAttribute(lgssm_umma_sweep<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sw));
-        done = true;
     }
     const unsigned tiles = (unsigned)((batch + 127) / 128);
     // time slices of the K y pre-pass: about two CTAs per SM in flight overall

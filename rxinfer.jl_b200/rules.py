@@ -64,9 +64,15 @@ def call_rule(ctx, node: str, edge: str, **kw):
         if edge == "τ" and "q_out" in kw and "q_μ" in kw:
             (mo, vo), (mm, vm) = kw["q_out"].mean_var(), kw["q_μ"].mean_var()
             return GammaShapeRate(*ctx.rule_normal_precision_tau(mo, vo, mm, vm))
-        if edge == "out" and "q_τ" in kw:
-            src = kw.get("m_μ", kw.get("q_μ"))
+        if edge == "out" and "q_τ" in kw and "m_μ" in kw:
+            # (m_μ::Normal, q_τ): belief-propagation message on the mean edge -> N(m_μ, v_μ + 1/E[τ])
+            src = kw["m_μ"]
             return NormalMeanVariance(*ctx.rule_normal_precision_out(src.m, src.v, kw["q_τ"].a, kw["q_τ"].b))
+        if edge == "out" and "q_τ" in kw and "q_μ" in kw:
+            # (q_μ::Any, q_τ::Any): mean-field -> NormalMeanPrecision(mean(q_μ), mean(q_τ)): variance 1/E[τ] ONLY,
+            # var(q_μ) does not enter (same kernel with v_μ = 0)
+            m, _ = kw["q_μ"].mean_var()
+            return NormalMeanVariance(*ctx.rule_normal_precision_out(m, m.new_zeros(m.shape), kw["q_τ"].a, kw["q_τ"].b))
     if node == "GCV":
         k, w = float(kw["q_κ"].value), float(kw["q_ω"].value)
         if edge in ("y", "x"):

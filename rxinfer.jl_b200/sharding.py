@@ -16,9 +16,24 @@ def shard_bounds(batch: int, world: int, rank: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def assemble_gathered(g: torch.Tensor) -> torch.Tensor:
-    """[G, T, ..., b_local] (rank-major slabs, as NCCL delivers them) -> [T, ..., G * b_local]."""
+def padded_shard(batch: int, world: int) -> int:
+    """Common slab width of the gathered layout [G][T][...][b_pad]: the device gathers (NCCL all-gather,
+    peer-mapped stores) need the same count on every rank, so a batch that does not divide evenly is
+    padded to ceil(batch / world) chains per rank; ``assemble_gathered(..., batch=batch)`` drops the pad."""
+    return -(-batch // world)
+
+
+def assemble_gathered(g: torch.Tensor, batch: int | None = None) -> torch.Tensor:
+    """[G, T, ..., b_local] (rank-major slabs, as the gather delivers them) -> [T, ..., G * b_local].
+    With ``batch`` given, slabs are ``padded_shard`` wide and rank r holds ``shard_bounds(batch, G, r)``
+    real chains in its leading columns: the pad columns are dropped."""
     G = g.shape[0]
+    if batch is not None and batch != G * g.shape[-1]:
+        parts = []
+        for r in range(G):
+            lo, hi = shard_bounds(batch, G, r)
+            parts.append(g[r][..., : hi - lo])
+        return torch.cat(parts, dim=-1).contiguous()
     perm = list(range(1, g.dim() - 1)) + [0, g.dim() - 1]
     out = g.permute(*perm).contiguous()
     return out.reshape(*out.shape[:-2], G * g.shape[-1])
@@ -38,6 +53,15 @@ def init_comm(ctx, group=None):
 def allgather_posteriors(ctx, mean, cov, world, backend="rxg"):
     """Returns rank-major gathered slabs ([G, T, d, b], [G, T, d, d, b])."""
     if backend == "rxg":
+        # equal counts on every rank are required (ncclAllGather / peer stores): check instead of hanging
+        n = torch.tensor([mean.shape[-1]], device=mean.device)
+        lo, hi = n.clone(), n.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        if int(lo) != int(hi):
+            raise ValueError(f"allgather_posteriors: shards differ in width ({int(lo)}..{int(hi)}); pad them to "
+                             "sharding.padded_shard(batch, world) chains per rank")
+        if world != getattr(ctx, "comm_nranks", world):
+            raise ValueError("allgather_posteriors: world size differs from the communicator's")
         return ctx.allgather_posteriors(mean, cov, world)
     # host-logic path for gloo tests: same layout through torch.distributed
     gm = [torch.empty_like(mean) for _ in range(world)]

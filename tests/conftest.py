@@ -24,3 +24,20 @@ def ctx(rx):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return rx.Context(0)
+
+
+_OPTION_DEFAULTS = {"gain_seq": 0, "large_seq": 0, "no_umma": 0, "sweep_variant": 0, "force_cpt": 0, "host_threads": 0,
+                    "host_cov_d2h": 0, "host_bcast_min_mb": 64, "host_slices": 0}
+
+
+@pytest.fixture(autouse=True)
+def _reset_ctx_options(request):
+    """The ctx is session scoped; tests flip dispatch options (ctx.set_option) and must not leak them."""
+    yield
+    if "ctx" in request.fixturenames:
+        try:
+            c = request.getfixturevalue("ctx")
+        except Exception:
+            return
+        for k, v in _OPTION_DEFAULTS.items():
+            c.set_option(k, v)

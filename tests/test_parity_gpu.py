@@ -66,12 +66,12 @@ def test_chains_per_thread_2_path(ctx, monkeypatch):
     _, y = lgssm.generate_data(mod, 200, 64, seed=7)
     ref = lgssm.smooth_reference_schedule(y, **mod)
     for cpt in ("2", "1"):
-        monkeypatch.setenv("RXG_FORCE_CPT", cpt)
+        ctx.set_option("force_cpt", int(cpt))
         check(ctx.lgssm(dev(y), **_kw(mod), smooth=True, want_evidence=True), ref)
         check(ctx.lgssm(dev(y), **_kw(mod), smooth=True), ref, nle=False)
         check(ctx.lgssm(dev(y), **_kw(mod), smooth=False, want_evidence=True), ref, smooth=False)
     # ragged: batch not a multiple of 32 * CPT
-    monkeypatch.setenv("RXG_FORCE_CPT", "2")
+    ctx.set_option("force_cpt", 2)
     _, y2 = lgssm.generate_data(mod, 90, 100, seed=8)
     check(ctx.lgssm(dev(y2), **_kw(mod), smooth=True, want_evidence=True), lgssm.smooth_reference_schedule(y2, **mod))
 
@@ -202,9 +202,9 @@ def test_full_size_properties(ctx, monkeypatch):
     r = ctx.lgssm(y, **_kw(mod), smooth=True, want_evidence=True)
     mean, cov = r["mean"], r["cov"]
     assert torch.equal(mean[:, :, 0], mean[:, :, 1])                                   # (3)
-    monkeypatch.setenv("RXG_FORCE_CPT", "2")     # same kernel variant as the full batch (2 chains / thread, checkpoint mode)
+    ctx.set_option("force_cpt", 2)     # same kernel variant as the full batch (2 chains / thread, checkpoint mode)
     sub = ctx.lgssm(y[:, :, 4096:4096 + 512].contiguous(), **_kw(mod), smooth=True, want_evidence=True)
-    monkeypatch.delenv("RXG_FORCE_CPT")
+    ctx.set_option("force_cpt", 0)
     assert torch.equal(sub["mean"], mean[:, :, 4096:4096 + 512])                       # (1)
     r2 = ctx.lgssm((2.0 * y).contiguous(), A=mod["A"], B=mod["B"], P=mod["P"], Q=mod["Q"], m0=2.0 * mod["m0"],
                    S0=mod["S0"], smooth=True)
@@ -231,10 +231,10 @@ def test_time_parallel_gain_scan_vs_sequential_and_oracle(ctx, monkeypatch, T):
     batch = 8
     _, y = lgssm.generate_data(mod, T, batch, seed=29)
     yd = dev(y)
-    monkeypatch.setenv("RXG_GAIN_SEQ", "0")
+    ctx.set_option("gain_seq", 0)
     a = ctx.lgssm(yd, **_kw(mod), smooth=True, want_evidence=True)
     f = ctx.lgssm(yd, **_kw(mod), smooth=False, transition_first=True)
-    monkeypatch.setenv("RXG_GAIN_SEQ", "1")
+    ctx.set_option("gain_seq", 1)
     b = ctx.lgssm(yd, **_kw(mod), smooth=True, want_evidence=True)
     fb = ctx.lgssm(yd, **_kw(mod), smooth=False, transition_first=True)
     assert rel_l2(a["cov"].cpu().numpy(), b["cov"].cpu().numpy()) < 1e-6
@@ -247,7 +247,7 @@ def test_time_parallel_gain_scan_vs_sequential_and_oracle(ctx, monkeypatch, T):
 
 
 def test_gain_scan_other_shapes(ctx, monkeypatch):
-    monkeypatch.setenv("RXG_GAIN_SEQ", "0")
+    ctx.set_option("gain_seq", 0)
     for d, m in [(1, 1), (2, 1), (3, 3), (4, 2), (6, 6)]:
         rng = np.random.default_rng(100 + d * 10 + m)
         Aq, _ = np.linalg.qr(rng.standard_normal((d, d)))
@@ -267,7 +267,7 @@ def test_host_pointer_path_sliced_pipeline(ctx, monkeypatch):
     mask = (rng.random((T, batch)) > 0.2).astype(np.uint8)
     yh = torch.from_numpy(y).pin_memory()
     for ns in ("5", "1"):
-        monkeypatch.setenv("RXG_HOST_SLICES", ns)
+        ctx.set_option("host_slices", int(ns))
         r = ctx.lgssm(yh, **_kw(mod), smooth=True, want_evidence=True, want_status=True)
         check(r, lgssm.smooth_reference_schedule(y, **mod))
         assert int(r["status"].abs().sum()) == 0
@@ -288,14 +288,14 @@ def test_host_pointer_covariance_broadcast_is_bit_identical(ctx, monkeypatch, d,
     mod = f32_model(lgssm.notebook_model(d) if d <= 4 else lgssm.dense_model(d))
     _, y = lgssm.generate_data(mod, T, batch, seed=38)
     yh = torch.from_numpy(y).pin_memory()
-    monkeypatch.setenv("RXG_HOST_BCAST_MIN_MB", "0")
-    monkeypatch.setenv("RXG_HOST_THREADS", "7")
+    ctx.set_option("host_bcast_min_mb", 0)
+    ctx.set_option("host_threads", 7)
     for smooth in (True, False):
         for ns in ("3", "1"):
-            monkeypatch.setenv("RXG_HOST_SLICES", ns)
-            monkeypatch.setenv("RXG_HOST_COV_D2H", "1")
+            ctx.set_option("host_slices", int(ns))
+            ctx.set_option("host_cov_d2h", 1)
             a = ctx.lgssm(yh, **_kw(mod), smooth=smooth, transition_first=not smooth)
-            monkeypatch.setenv("RXG_HOST_COV_D2H", "0")
+            ctx.set_option("host_cov_d2h", 0)
             b = ctx.lgssm(yh, **_kw(mod), smooth=smooth, transition_first=not smooth)
             assert torch.equal(a["cov"], b["cov"]) and torch.equal(a["mean"], b["mean"])
     ref = lgssm.smooth_reference_schedule(y, **mod)
@@ -367,10 +367,10 @@ def test_large_state_doubling_vs_sequential(ctx, monkeypatch, d, T):
     mod = f32_model(lgssm.dense_model(d, seed=11))
     _, y = lgssm.generate_data(mod, T, 8, seed=47)
     yd = dev(y)
-    monkeypatch.setenv("RXG_LARGE_SEQ", "0")
+    ctx.set_option("large_seq", 0)
     a = ctx.lgssm(yd, **_kw(mod), smooth=True)
     fa = ctx.lgssm(yd, **_kw(mod), smooth=False, transition_first=True)
-    monkeypatch.setenv("RXG_LARGE_SEQ", "1")
+    ctx.set_option("large_seq", 1)
     b = ctx.lgssm(yd, **_kw(mod), smooth=True)
     fb = ctx.lgssm(yd, **_kw(mod), smooth=False, transition_first=True)
     for k in ("mean", "cov"):
@@ -387,10 +387,10 @@ def test_large_state_tensor_core_vs_fp32_pipe(ctx, monkeypatch, d, T, batch):
     mod = f32_model(lgssm.dense_model(d, seed=5))
     _, y = lgssm.generate_data(mod, T, batch, seed=48)
     yd = dev(y)
-    monkeypatch.setenv("RXG_NO_UMMA", "0")
+    ctx.set_option("no_umma", 0)
     a = ctx.lgssm(yd, **_kw(mod), smooth=True, cov_shared_out=True)
     fa = ctx.lgssm(yd, **_kw(mod), smooth=False, transition_first=True, cov_shared_out=True)
-    monkeypatch.setenv("RXG_NO_UMMA", "1")
+    ctx.set_option("no_umma", 1)
     b = ctx.lgssm(yd, **_kw(mod), smooth=True, cov_shared_out=True)
     fb = ctx.lgssm(yd, **_kw(mod), smooth=False, transition_first=True, cov_shared_out=True)
     assert rel_l2(a["mean"].cpu().numpy(), b["mean"].cpu().numpy()) < 5e-6
@@ -409,7 +409,7 @@ def test_large_state_evidence(ctx, monkeypatch, d, T, batch, tf):
     _, y = lgssm.generate_data(mod, T, batch, seed=49)
     ref = lgssm.smooth_reference_schedule(y, **mod, transition_first=tf)
     for no_umma in ("0", "1"):
-        monkeypatch.setenv("RXG_NO_UMMA", no_umma)
+        ctx.set_option("no_umma", int(no_umma))
         r = ctx.lgssm(dev(y), **_kw(mod), smooth=True, want_evidence=True, transition_first=tf, cov_shared_out=True)
         n = r["neg_log_evidence"].cpu().numpy().astype(np.float64)
         assert np.max(np.abs(n - ref["neg_log_evidence"]) / np.abs(ref["neg_log_evidence"])) < TOL_NLE
@@ -418,3 +418,47 @@ def test_large_state_evidence(ctx, monkeypatch, d, T, batch, tf):
         nf = f["neg_log_evidence"].cpu().numpy().astype(np.float64)
         assert np.max(np.abs(nf - ref["neg_log_evidence"]) / np.abs(ref["neg_log_evidence"])) < TOL_NLE
         assert rel_l2(f["mean"].cpu().numpy(), ref["filt_mean"]) < TOL_MEAN
+
+
+@pytest.mark.parametrize("d", [4, 16])
+def test_non_spd_shared_model_is_reported(ctx, rx, d):
+    """A shared model whose covariance recursion hits a non-positive Cholesky pivot must not come back as OK
+    (ADVICE r1): synchronous calls return RXG_ERR_NOT_SPD, status[] carries it per chain, and a deferred
+    (asynchronous) call reports it at rxg_sync.  The reference throws from cholinv here."""
+    mod = f32_model(lgssm.notebook_model(4) if d == 4 else lgssm.dense_model(d))
+    _, y = lgssm.generate_data(mod, 30, 40, seed=3)
+    bad = dict(_kw(mod))
+    bad["Q"] = -np.asarray(mod["Q"]) * 1e3          # innovation covariance B S B' + Q indefinite
+    with pytest.raises(rx._lib.RxGaussError) as e:
+        ctx.lgssm(dev(y), **bad, smooth=True)
+    assert e.value.code == rx._lib.RXG_ERR_NOT_SPD
+    with pytest.raises(rx._lib.RxGaussError) as e:
+        ctx.lgssm(dev(y), **bad, smooth=True, asynchronous=True)
+        ctx.sync()
+    assert e.value.code == rx._lib.RXG_ERR_NOT_SPD
+    st = torch.zeros(40, dtype=torch.int32, device="cuda")
+    try:
+        ctx.lgssm(dev(y), **bad, smooth=False, want_status=True, out_status=st)
+    except rx._lib.RxGaussError:
+        pass
+    assert st.cpu().tolist() == [rx._lib.RXG_ERR_NOT_SPD] * 40
+    # and a good model right after is clean again
+    r = ctx.lgssm(dev(y), **_kw(mod), smooth=True, want_status=True)
+    assert int(r["status"].abs().sum()) == 0
+
+
+def test_context_validates_arrays(ctx):
+    """Wrong dtype / layout / device must raise instead of handing a garbage pointer to the library."""
+    mod = f32_model(lgssm.notebook_model(4))
+    _, y = lgssm.generate_data(mod, 20, 16, seed=4)
+    yd = dev(y)
+    with pytest.raises(ValueError):
+        ctx.lgssm(yd.permute(0, 2, 1).contiguous().permute(0, 2, 1), **_kw(mod))          # non-contiguous view
+    with pytest.raises(ValueError):
+        ctx.lgssm(yd.double(), **_kw(mod))
+    with pytest.raises(ValueError):
+        ctx.lgssm(yd, **_kw(mod), mask=torch.ones(20, 16, dtype=torch.uint8))              # host mask, device y
+    with pytest.raises(ValueError):
+        ctx.lgssm(yd, **_kw(mod), out_mean=torch.empty(20, 4, 15, device="cuda"))
+    with pytest.raises(ValueError):
+        ctx.lgssm(yd, **_kw(mod), out_cov=torch.empty(20, 4, 4, device="cuda"))           # table shape without the flag

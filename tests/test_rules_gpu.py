@@ -191,3 +191,24 @@ def test_call_rule_mirror(rx, ctx):
     assert rel_l2(back_m(q.W), refq[1]) < 10 * TOL
     with pytest.raises(rx.RuleMethodError):
         rx.call_rule(ctx, "*", "in", m_out=out, m_A=rx.PointMass(A), meta=object())
+
+
+def test_normal_precision_out_mean_field_variant(ctx, rx):
+    """(q_mu, q_tau) is the mean-field rule NormalMeanPrecision(mean(q_mu), mean(q_tau)): variance 1/E[tau] only;
+    (m_mu, q_tau) is the BP-message rule and adds var(m_mu) (the two were conflated)."""
+    from rxinfer_jl_b200.distributions import GammaShapeRate, NormalMeanVariance
+    from rxinfer_jl_b200.rules import call_rule
+    rng = np.random.default_rng(5)
+    n = 513
+    t = lambda a: torch.as_tensor(a, dtype=torch.float32, device="cuda")
+    mm, vm = r32(rng.standard_normal(n)), r32(rng.random(n) + .1)
+    sh, rt = r32(rng.random(n) + 1), r32(rng.random(n) + 1)
+    q = NormalMeanVariance(t(mm), t(vm))
+    g = GammaShapeRate(t(sh), t(rt))
+    bp = call_rule(ctx, "NormalMeanPrecision", "out", m_μ=q, q_τ=g)
+    mf = call_rule(ctx, "NormalMeanPrecision", "out", q_μ=q, q_τ=g)
+    ref_bp = R.normal_meanprec_out_q_tau((mm, vm), sh / rt)
+    ref_mf = R.normal_meanprec_out_q_mu_q_tau((mm, vm), sh / rt)
+    assert rel_l2(bp.v.cpu().numpy(), ref_bp[1]) < 1e-6 and rel_l2(mf.v.cpu().numpy(), ref_mf[1]) < 1e-6
+    assert rel_l2(mf.v.cpu().numpy(), rt / sh) < 1e-6
+    assert np.array_equal(mf.m.cpu().numpy(), mm) and np.array_equal(bp.m.cpu().numpy(), mm)
