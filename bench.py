@@ -124,10 +124,20 @@ def host_cores():
     return n
 
 
-def cpu_baseline(seconds_target=12.0, chunk=2048):
-    """fp64 C port of the reference schedule on all host cores, bounded sample of the same workload."""
+def cpu_baseline(seconds_target=12.0, chunk=2048, parity_sample=None):
+    """fp64 C port of the reference schedule on all host cores, bounded sample of the same workload.
+    `parity_sample` (chains of the GPU arm's timed buffers): recomputed here by the port and compared -- the parity
+    gate of the timed workload itself (mean relative L2 < 1e-5, covariance relative Frobenius < 1e-4)."""
     from oracle import c_twin
     mod = {k: v.astype(np.float64) for k, v in notebook_model_f32().items()}
+    parity = None
+    if parity_sample is not None:
+        ref = c_twin.smooth(parity_sample["y"], **mod, nthreads=1)
+        parity = {"chains": parity_sample["chains"],
+                  "mean_rel_l2": float(np.linalg.norm(parity_sample["mean"] - ref["mean"]) / np.linalg.norm(ref["mean"])),
+                  "cov_rel_fro": float(np.linalg.norm(parity_sample["cov"] - ref["cov"]) / np.linalg.norm(ref["cov"])),
+                  "tolerance": {"mean": 1e-5, "cov": 1e-4}, "checker": "fp64 C port (oracle/c/rxg_oracle.c), inside the cpu_baseline leg"}
+        assert parity["mean_rel_l2"] < 1e-5 and parity["cov_rel_fro"] < 1e-4, parity
     cores = host_cores()
     rng = np.random.default_rng(0)
     y = (rng.standard_normal((T, M, chunk)) * 3.0).astype(np.float32)
@@ -147,7 +157,7 @@ def cpu_baseline(seconds_target=12.0, chunk=2048):
     for _ in range(50):
         c_twin.smooth(y1, **mod, nthreads=1)
     one_ms = (time.perf_counter() - t1) / 50 * 1e3
-    return {"value": MSG_PER_STEP * T * done / el, "unit": "messages/s", "cores": cores, "kind": "port",
+    return {"parity": parity, "value": MSG_PER_STEP * T * done / el, "unit": "messages/s", "cores": cores, "kind": "port",
             "sample": f"{done} chains x T={T} (d=4) of the same workload, fp64 C port of the reference schedule "
                       f"(oracle/c/rxg_oracle.c), OpenMP over chains, {el:.1f} s",
             "single_chain_ms": one_ms, "single_chain_note": "configs[0]: one chain d=4 T=1000 on one core; the reference "
@@ -232,90 +242,120 @@ def main():
     # synthetic observations of the model's own scale (state O(1), obs noise sd sqrt(10)); generated on device
     g = torch.Generator(device=dev).manual_seed(42 + rank)
     y = torch.randn(T, M, batch, device=dev, generator=g) * 3.3
-    mean = torch.empty(T, D, batch, device=dev)
-    cov = torch.empty(T, D, D, batch, device=dev)
+    if world == 1:
+        mean = torch.empty(T, D, batch, device=dev)
+        cov = torch.empty(T, D, D, batch, device=dev)
+
+    # N > 1: the north_star all-gather of posterior marginals is PART of the step.  Every rank maps its peers'
+    # gathered buffers (CUDA IPC over NVLink) and the sweep kernel stores the posteriors into all of them while it
+    # runs (rxg_lgssm_smooth_gather_f32); `value` is the literal full gather (means AND per-chain covariances cross
+    # NVLink), the RXG_COV_REPLICATE variant (bit-identical buffers, covariances replicated locally) is reported as
+    # `gather.replicated_cov`, the sweep without any gather as `gather.sweep_only`.
+    grp = None
+    if world > 1:
+        from rxinfer_jl_b200.sharding import PeerGroup
+        grp = PeerGroup(ctx, T, D, batch)                     # 8 GPUs: 42 GB of gathered posteriors per GPU
+        mean, cov = grp.mean[rank], grp.cov[rank]             # the plain sweep writes this rank's slab
 
     def step():
         return ctx.lgssm(y, **kw, smooth=True, out_mean=mean, out_cov=cov, asynchronous=True,
                          force_per_chain_path=args.per_chain_path)
 
+    def step_gather(replicate):
+        return grp.smooth_gather(y, mod, replicate_cov=replicate, asynchronous=True,
+                                 force_per_chain_path=args.per_chain_path)
+
+    def timed(fn, steps):
+        """K steps between two events on the launching stream, barrier + synchronize on both sides, max over ranks."""
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0_ = ctx.launches
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t_ = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        return float(t_.item()) / steps, ctx.launches - l0_
+
     ctx.set_profiling(True)
     for _ in range(args.warmup):
         step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+        if world > 1:
+            step_gather(False); step_gather(True)
+    ctx.sync()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = ctx.launches
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    main_ms, gain_ms = [], []
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    launches = ctx.launches - l0
-    el_ms = ev0.elapsed_time(ev1)
+    msgs = MSG_PER_STEP * T * batch * world
+    gather = None
+    if world == 1:
+        ms_per_step, launches = timed(step, args.steps)
+    else:
+        ms_per_step, launches = timed(lambda: step_gather(False), args.steps)          # contract: full gather in the step
+        ms_rep, l_rep = timed(lambda: step_gather(True), args.steps)
+        ms_sweep, _ = timed(step, args.steps)
+        slab = (mean.numel() + cov.numel()) * 4
+        # correctness of what was just timed: every slab of this rank's buffers equals an independent sweep of that shard
+        step_gather(False); ctx.sync(); dist.barrier()
+        own_mean, own_cov = mean.clone(), cov[:8].clone()
+        chk = [grp.mean[r][::97].clone() for r in range(world)]
+        chk_c = [grp.cov[r][:4].clone() for r in range(world)]
+        grp.mean.zero_(); grp.cov.zero_(); torch.cuda.synchronize(); dist.barrier()
+        step_gather(True); ctx.sync(); dist.barrier()
+        assert torch.equal(grp.mean[rank], own_mean) and torch.equal(grp.cov[rank][:8], own_cov)
+        assert all(torch.equal(grp.mean[r][::97], chk[r]) and torch.equal(grp.cov[r][:4], chk_c[r]) for r in range(world)), \
+            "RXG_COV_REPLICATE buffers differ from the full gather"
+        assert bool((grp.mean[(rank + 1) % world].abs().sum() > 0).item())
+        del own_mean, own_cov, chk, chk_c
+        gather = {
+            "in_value": "full gather: (G-1) x (means + per-chain covariances) stored over NVLink by the sweep kernel itself",
+            "ms_per_step_full": ms_per_step, "nvlink_bytes_out_per_gpu_full": (world - 1) * slab,
+            "nvlink_GBs_out_per_gpu_full": (world - 1) * slab / ms_per_step / 1e6,
+            "replicated_cov": {"ms_per_step": ms_rep, "value": msgs / (ms_rep * 1e-3), "gpu_launches": int(l_rep),
+                               "nvlink_bytes_out_per_gpu": (world - 1) * mean.numel() * 4,
+                               "nvlink_GBs_out_per_gpu": (world - 1) * mean.numel() * 4 / ms_rep / 1e6,
+                               "note": "RXG_COV_REPLICATE: shared model => covariances chain independent; means over NVLink, "
+                                       "covariance slabs replicated locally during the sweep; buffers bit-identical (asserted)"},
+            "sweep_only": {"ms_per_step": ms_sweep, "value": msgs / (ms_sweep * 1e-3),
+                           "note": "no gather (round-1 headline); NOT the contract at N > 1"},
+            "nvlink_floor_ms": {"full": (world - 1) * slab / 770e9 * 1e3, "replicated_cov": (world - 1) * mean.numel() * 4 / 770e9 * 1e3,
+                                "note": "bytes that must arrive per GPU / 770 GB/s measured peer bandwidth (B200_PROFILING.md)"},
+        }
+        # the round-1 design for comparison: sweep, then ncclAllGather of the finished posteriors (into the same buffers)
+        try:
+            rx.sharding.init_comm(ctx)
+            ctx.allgather_posteriors(mean, cov, world, out_mean=grp.mean, out_cov=grp.cov)
+            def nccl_step():
+                step()
+                ctx.allgather_posteriors(mean, cov, world, out_mean=grp.mean, out_cov=grp.cov)
+            ms_nccl, _ = timed(nccl_step, max(2, min(args.steps, 3)))
+            gather["nccl_after_sweep"] = {"ms_per_step": ms_nccl, "value": msgs / (ms_nccl * 1e-3),
+                                          "note": "round-1 design: plain ncclAllGather issued after the sweep (in place, same buffers)"}
+        except Exception as ex:       # noqa: BLE001 -- a comparison leg only
+            gather["nccl_after_sweep"] = {"error": str(ex)[:200]}
+    value = msgs / (ms_per_step * 1e-3)
     # per-kernel timing of the dominant kernel: separate pass so the event syncs do not sit in the timed loop
+    main_ms, gain_ms = [], []
     for _ in range(args.steps):
         step()
         a, b = ctx.profile_last_ms()
         main_ms.append(a); gain_ms.append(b)
-    t = torch.tensor([el_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    el_ms = float(t.item())
-    ms_per_step = el_ms / args.steps
-    msgs = MSG_PER_STEP * T * batch * world
-    value = msgs / (ms_per_step * 1e-3)
-
-    # ---- all-gather of posterior marginals (north_star: one NCCL all-gather at the end) -- reported separately
-    allgather = None
-    if world > 1:
-        rx.sharding.init_comm(ctx)
-        gm = torch.empty(world, T, D, batch, device=dev)
-        gc = torch.empty(world, T, D, D, batch, device=dev)          # 8 GPUs: 42 GB of gathered posteriors per GPU
-        ctx.allgather_posteriors(mean, cov, world, out_mean=gm, out_cov=gc)           # warm-up
-        torch.cuda.synchronize(); dist.barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 3
-        g0.record()
-        for _ in range(reps):
-            ctx.allgather_posteriors(mean, cov, world, out_mean=gm, out_cov=gc)
-        g1.record(); torch.cuda.synchronize()
-        tg = torch.tensor([g0.elapsed_time(g1) / reps], device=dev, dtype=torch.float64)
-        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-        gms = float(tg.item())
-        inbound = (world - 1) * (mean.numel() + cov.numel()) * 4
-        allgather = {"ms": gms, "bytes_in_per_gpu": inbound, "in_GBs_per_gpu": inbound / gms / 1e6,
-                     "value_with_allgather": msgs / ((ms_per_step + gms) * 1e-3)}
-        # spot check of the gathered layout: slab r must equal what rank r computed (rank 0's own slab here)
-        assert torch.equal(gm[rank], mean) and torch.equal(gc[rank][:8], cov[:8])
-        # shared model => the covariances do not depend on the chain (nor on the rank): gather the means over
-        # NVLink and replicate the covariance slabs locally (RXG_COV_REPLICATE) -- same gathered buffers,
-        # bit-identical contents, 1/5 of the NVLink traffic
-        ref_rows = [gc[r][:4].clone() for r in range(world)]
-        gc.zero_(); gm.zero_()
-        ctx.allgather_posteriors(mean, cov, world, out_mean=gm, out_cov=gc, replicate_cov=True)
-        torch.cuda.synchronize(); dist.barrier()
-        assert torch.equal(gm[rank], mean) and all(torch.equal(gc[r][:4], ref_rows[r]) for r in range(world))
-        assert torch.equal(gc[world - 1][-1], cov[-1])
-        g0.record()
-        for _ in range(reps):
-            ctx.allgather_posteriors(mean, cov, world, out_mean=gm, out_cov=gc, replicate_cov=True)
-        g1.record(); torch.cuda.synchronize()
-        tg = torch.tensor([g0.elapsed_time(g1) / reps], device=dev, dtype=torch.float64)
-        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-        allgather["replicated_cov_ms"] = float(tg.item())
-        allgather["replicated_cov_bytes_in_per_gpu"] = (world - 1) * mean.numel() * 4
-        allgather["value_with_replicated_cov_allgather"] = msgs / ((ms_per_step + float(tg.item())) * 1e-3)
-        del gc, gm, ref_rows
-        torch.cuda.empty_cache()
+    # parity of the timed workload itself: sampled chains of the buffers the timed loop wrote go to the CPU leg below,
+    # where the fp64 port recomputes them (the oracle is only ever executed inside cpu_baseline())
+    parity_sample = None
+    if rank == 0 and not args.no_cpu:
+        idx = [0, 1, batch // 2 + 1, batch - 1]
+        step(); ctx.sync()
+        parity_sample = {"chains": idx, "y": y[:, :, idx].cpu().numpy(), "mean": mean[:, :, idx].cpu().numpy(),
+                         "cov": cov[:, :, :, idx].cpu().numpy()}
 
     # ---- e2e through the C ABI with host buffers (rank-local; all ranks run it concurrently)
     e2e = None
@@ -389,6 +429,8 @@ def main():
             del yh, mh, cs
         elif world > 1:
             dist.barrier()
+    if grp is not None:
+        grp.close()
 
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
@@ -406,7 +448,13 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "batched LGSSM smoothing (BASELINE configs[1]): d=4 m=4 T=1000 batch=%d per GPU, "
                                    "notebook model lifted to d=4, shared (A,B,P,Q,prior)" % batch,
-                       "global_batch": batch * world, "parallelism": f"batch-sharded x{world}, no data-path collective",
+                       "global_batch": batch * world,
+                       "parallelism": (f"batch-sharded x{world}; all-gather of posterior marginals INSIDE the timed step "
+                                       "(peer-mapped NVLink stores fused into the sweep kernel, device-side barrier)") if world > 1
+                                      else "single GPU (no gather needed: the posteriors are already where they end up)",
+                       "data_note": "y = randn * 3.3 per chain (the model's observation scale), not sampled from the model: the "
+                                    "sweep is linear in y, timing is value independent; parity of the timed buffers is checked "
+                                    "against the fp64 oracle on sampled chains (`parity`)",
                        "path": "per-chain covariance recursion" if args.per_chain_path else "gain tables + mean sweeps",
                        "messages_per_chain_step": MSG_PER_STEP, "l2_policy": "inputs+outputs (6.3 GB) larger than L2"},
             "roofline": {"bound": "hbm", "kernel": "lgssm_chain_kernel" if args.per_chain_path else "lgssm_shared_kernel",
@@ -416,10 +464,11 @@ def main():
                          "algorithmic_bytes_per_launch": algo},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
-        if allgather:
-            out["allgather"] = allgather
+        if gather:
+            out["gather"] = gather
         if not args.no_cpu:
-            out["cpu_baseline"] = cpu_baseline()
+            out["cpu_baseline"] = cpu_baseline(parity_sample=parity_sample)
+            out["parity"] = out["cpu_baseline"].pop("parity", None)
         emit(out)
     if world > 1:
         dist.barrier()

@@ -328,6 +328,47 @@ int rxg_allgather_posteriors(rxg_ctx*, int d, int T, int64_t batch_local, const 
                              const float* post_cov, float* gathered_mean, float* gathered_cov,
                              unsigned flags);
 
+
+/* ------------------------------------------------------------------ peer-mapped gather ---------
+ * The all-gather WITHOUT a collective launch: every rank maps its peers' gathered buffers (CUDA IPC over
+ * NVLink / NVSwitch) and the fused smoothing sweep stores each smoothed posterior straight into all G
+ * buffers while the backward recursion is still running ("issue ... finished time-slabs
+ * ... while earlier slabs are still being computed" -- here at the granularity of one time step).
+ * Host protocol (one process per GPU; the host exchanges the 64-byte handles out of band, e.g.
+ * torch.distributed / MPI / a Julia Distributed channel):
+ *   1. rxg_device_alloc the gathered buffers [G][T][d][b_local] (+ [G][T][d][d][b_local]) and one flag
+ *      buffer of RXG_MAX_PEERS ints (zero it with rxg_device_memset);
+ *   2. rxg_peer_export each, all-gather the handles, rxg_peer_open the G-1 remote ones;
+ *   3. rxg_peer_group(nranks, rank, flag pointers as mapped here);
+ *   4. rxg_lgssm_smooth_gather_f32 (or any compute + rxg_peer_allgather_f32) per step.
+ * Ranks inside ONE process (several contexts) skip step 2's export/open and pass plain device pointers.   */
+int rxg_device_alloc(rxg_ctx*, size_t bytes, void** dev_ptr);
+int rxg_device_free(rxg_ctx*, void* dev_ptr);
+int rxg_device_memset(rxg_ctx*, void* dev_ptr, int value, size_t bytes);
+int rxg_peer_export(rxg_ctx*, const void* dev_ptr, void* handle64);
+int rxg_peer_open(rxg_ctx*, const void* handle64, void** dev_ptr);
+int rxg_peer_close(rxg_ctx*, void* dev_ptr);
+/* flag_ptrs[g] = rank g's flag buffer as mapped in this process (own buffer for g == rank); nranks <= RXG_MAX_PEERS */
+int rxg_peer_group(rxg_ctx*, int nranks, int rank, void* const* flag_ptrs);
+/* device-side barrier over the group on the ctx stream (st.release.sys / ld.acquire.sys on the flags)     */
+int rxg_peer_barrier(rxg_ctx*, unsigned flags);
+/* generic all-gather of any posterior array (HGF outputs, filtered means, ...): `local` (n_local floats, may
+ * already be the own slab gathered[rank] + rank * n_local) is stored into slab `rank` of every gathered[g],
+ * then the barrier.  On completion gathered[rank] holds all G slabs.                                       */
+int rxg_peer_allgather_f32(rxg_ctx*, int64_t n_local, const float* local, float* const* gathered, unsigned flags);
+/* rxg_lgssm_smooth_f32 + the all-gather of its posteriors in one call: gathered_mean[g] / gathered_cov[g] are the
+ * bases of rank g's [G][T][d][b_local] / [G][T][d][d][b_local] buffers as mapped here.  Shared-model gain-table
+ * path: the sweep kernel itself stores to the peers (no second pass); other paths push their finished slab.
+ * RXG_COV_REPLICATE (shared model, no mask): only the means cross NVLink, the other ranks' covariance slabs are
+ * replicated locally from the [T][d][d] table concurrently with the sweep (gathered_cov[g != rank] may be NULL);
+ * the buffers end up bit-identical to the full gather.  neg_log_evidence / status are local ([b_local]).
+ * A caller must not start the next gather into the same buffers before every rank has consumed the result.   */
+int rxg_lgssm_smooth_gather_f32(rxg_ctx*, int d, int m, int T, int64_t batch_local, const float* A,
+                                const float* B, const float* P, const float* Q, const float* m0,
+                                const float* S0, const float* u, const float* y, const uint8_t* ymask,
+                                float* const* gathered_mean, float* const* gathered_cov,
+                                float* neg_log_evidence, int32_t* status, unsigned flags);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,17 @@ SIGNATURES = {
     "rxg_comm_unique_id": (c_int, [c_void_p]),
     "rxg_comm_init": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "rxg_allgather_posteriors": (c_int, [c_void_p, c_int, c_int, c_int64, fp, fp, fp, fp, c_uint]),
+    "rxg_device_alloc": (c_int, [c_void_p, c_size_t, POINTER(c_void_p)]),
+    "rxg_device_free": (c_int, [c_void_p, c_void_p]),
+    "rxg_device_memset": (c_int, [c_void_p, c_void_p, c_int, c_size_t]),
+    "rxg_peer_export": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "rxg_peer_open": (c_int, [c_void_p, c_void_p, POINTER(c_void_p)]),
+    "rxg_peer_close": (c_int, [c_void_p, c_void_p]),
+    "rxg_peer_group": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p)]),
+    "rxg_peer_barrier": (c_int, [c_void_p, c_uint]),
+    "rxg_peer_allgather_f32": (c_int, [c_void_p, c_int64, fp, POINTER(fp), c_uint]),
+    "rxg_lgssm_smooth_gather_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, fp, fp, fp, fp, fp, fp, fp, fp, u8p,
+                                            POINTER(fp), POINTER(fp), fp, i32p, c_uint]),
 }
 
 

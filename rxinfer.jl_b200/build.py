@@ -11,7 +11,12 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librxgauss.so")
-SOURCES = ["rxg_api.cu", "rxg_lgssm.cu", "rxg_lgssm_large.cu", "rxg_umma_sweep.cu", "rxg_rules.cu", "rxg_hgf.cu"]
+LGSSM_SHAPES = [(1, 1), (2, 1), (2, 2), (3, 3), (4, 1), (4, 2), (4, 4), (6, 6)]
+# (source, object stem, extra flags): rxg_lgssm.cu is compiled once per (d, m) shape (explicit instantiation) + once for the dispatch
+UNITS = ([("rxg_lgssm.cu", f"rxg_lgssm_d{d}m{m}", (f"-DRXG_INST_D={d}", f"-DRXG_INST_M={m}")) for d, m in reversed(LGSSM_SHAPES)] +
+         [(s, s.replace(".cu", ""), ()) for s in
+          ("rxg_lgssm_large.cu", "rxg_lgssm.cu", "rxg_umma_sweep.cu", "rxg_api.cu", "rxg_peer.cu", "rxg_rules.cu", "rxg_hgf.cu")])
+SOURCES = sorted({u[0] for u in UNITS})
 HEADERS = ["rxg_internal.h", "rxg_linalg.cuh", "rxg_gain.cuh", "rxg_lgssm_common.cuh", "rxg_lgssm_shared.cuh", "rxg_umma.cuh", os.path.join("..", "..", "include", "rxgauss.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -43,11 +48,12 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), lib: str =
     objdir = os.path.join(HERE, objdir_name)
     os.makedirs(objdir, exist_ok=True)
 
-    def compile_one(src):
-        obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-c", os.path.join(CSRC, src), "-o", obj]
+    def compile_one(unit):
+        src, stem, defs = unit
+        obj = os.path.join(objdir, stem + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, *defs, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
-        log = os.path.join(objdir, src.replace(".cu", ".ptxas.log"))
+        log = os.path.join(objdir, stem + ".ptxas.log")
         with open(log, "w") as f:
             f.write(r.stdout + r.stderr)
         if r.returncode != 0:
@@ -56,8 +62,8 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), lib: str =
             print(r.stderr)
         return obj
 
-    with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
-        objs = list(ex.map(compile_one, SOURCES))
+    with cf.ThreadPoolExecutor(max_workers=min(len(UNITS), os.cpu_count() or 4)) as ex:
+        objs = list(ex.map(compile_one, UNITS))
     cmd = [nvcc, "-shared", "-o", lib, *objs, "-ldl", "-lpthread", "-Xcompiler", "-fPIC"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

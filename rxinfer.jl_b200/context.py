@@ -398,6 +398,65 @@ class Context:
         self._check(self.lib.rxg_comm_init(self.h, nranks, rank, ctypes.cast(buf, c_void_p)))
         self.comm_nranks, self.comm_rank = int(nranks), int(rank)
 
+    # ---- peer-mapped gather (NVLink P2P stores from the sweep itself; rxg_peer.cu)
+    def peer_open(self, handle: bytes) -> int:
+        buf = ctypes.create_string_buffer(handle, 64)
+        p = c_void_p()
+        self._check(self.lib.rxg_peer_open(self.h, ctypes.cast(buf, c_void_p), ctypes.byref(p)))
+        return int(p.value)
+
+    def peer_close(self, ptr: int):
+        self._check(self.lib.rxg_peer_close(self.h, c_void_p(ptr)))
+
+    def peer_group(self, nranks: int, rank: int, flag_ptrs):
+        arr = (c_void_p * max(nranks, 1))(*[c_void_p(int(p)) for p in flag_ptrs]) if nranks > 1 else None
+        self._check(self.lib.rxg_peer_group(self.h, nranks, rank, arr))
+        self.peer_nranks, self.peer_rank = int(nranks), int(rank)
+
+    def peer_barrier(self, asynchronous=False):
+        self._check(self.lib.rxg_peer_barrier(self.h, L.ASYNC if asynchronous else 0))
+
+    def peer_allgather(self, local, gathered_ptrs, asynchronous=False):
+        """``local`` (contiguous CUDA fp32) -> slab ``rank`` of every rank's gathered buffer, then the barrier."""
+        self._dev(local)
+        arr = (L.fp * len(gathered_ptrs))(*[L.as_fp(p) for p in gathered_ptrs])
+        self._check(self.lib.rxg_peer_allgather_f32(self.h, local.numel(), _fp(local), arr,
+                                                    L.PTR_DEVICE | (L.ASYNC if asynchronous else 0)))
+
+    def lgssm_smooth_gather(self, y, A, B, P, Q, m0, S0, gathered_mean_ptrs, gathered_cov_ptrs=None, *, u=None, mask=None,
+                            replicate_cov=False, want_evidence=False, want_status=False, force_per_chain_path=False,
+                            transition_first=False, asynchronous=False):
+        """Fused smoothing sweep + all-gather (``rxg_lgssm_smooth_gather_f32``).  ``gathered_*_ptrs[g]`` = base address
+        of rank g's gathered buffer as mapped in this process (see ``sharding.PeerGroup``)."""
+        self._io(y, "y", True)
+        T, m, batch = y.shape
+        self._io(mask, "mask", True, dtype=torch.uint8, shape=(T, batch))
+        d = np.asarray(A).shape[-1]
+        keep = [_model32(x) for x in (A, B, P, Q, m0, S0)]
+        ptrs = [k[1] for k in keep]
+        if u is not None:
+            keep.append(_model32(u)); ptrs.append(keep[-1][1])
+        else:
+            ptrs.append(L.as_fp(0))
+        flags = L.PTR_DEVICE
+        if replicate_cov:
+            flags |= L.COV_REPLICATE
+        if force_per_chain_path:
+            flags |= L.PATH_PER_CHAIN
+        if transition_first:
+            flags |= L.TRANSITION_FIRST
+        if asynchronous:
+            flags |= L.ASYNC
+        G = len(gathered_mean_ptrs)
+        gm = (L.fp * G)(*[L.as_fp(p) for p in gathered_mean_ptrs])
+        gc = (L.fp * G)(*[L.as_fp(p) for p in gathered_cov_ptrs]) if gathered_cov_ptrs is not None else None
+        nle = self.empty(batch) if want_evidence else None
+        status = self.empty(batch, dtype=torch.int32) if want_status else None
+        mask_p = ctypes.cast(c_void_p(mask.data_ptr() if mask is not None else None), L.u8p)
+        st_p = ctypes.cast(c_void_p(status.data_ptr() if status is not None else None), L.i32p)
+        self._check(self.lib.rxg_lgssm_smooth_gather_f32(self.h, d, m, T, batch, *ptrs, _fp(y), mask_p, gm, gc, _fp(nle), st_p, flags))
+        return dict(neg_log_evidence=nle, status=status)
+
     def allgather_posteriors(self, mean, cov, nranks, out_mean=None, out_cov=None, replicate_cov=False):
         """Rank-major gathered slabs ([G, T, d, b], [G, T, d, d, b]); pass out_* to reuse buffers.
         ``replicate_cov=True`` (shared model on every rank, no missing data: chain-independent
@@ -418,6 +477,46 @@ class Context:
                 raise ValueError("a [T, d, d] covariance table can only be replicated (replicate_cov=True)")
         self._check(self.lib.rxg_allgather_posteriors(self.h, d, T, bl, _fp(mean), _fp(cov), _fp(gm), _fp(gc), flags))
         return gm, gc
+
+
+class DeviceBuffer:
+    """Device memory from ``rxg_device_alloc`` (plain cudaMalloc: exportable as a CUDA IPC handle at offset 0),
+    viewable as a torch tensor through ``__cuda_array_interface__``.  Freed with the object."""
+
+    def __init__(self, ctx: "Context", nbytes: int, zero: bool = False):
+        self.ctx, self.nbytes = ctx, int(nbytes)
+        p = c_void_p()
+        ctx._check(ctx.lib.rxg_device_alloc(ctx.h, self.nbytes, ctypes.byref(p)))
+        self.ptr = int(p.value)
+        if zero:
+            ctx._check(ctx.lib.rxg_device_memset(ctx.h, c_void_p(self.ptr), 0, self.nbytes))
+
+    def export(self) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        self.ctx._check(self.ctx.lib.rxg_peer_export(self.ctx.h, c_void_p(self.ptr), ctypes.cast(buf, c_void_p)))
+        return buf.raw
+
+    def tensor(self, *shape, dtype=torch.float32):
+        n = int(np.prod(shape))
+        itemsize = torch.empty((), dtype=dtype).element_size()
+        assert n * itemsize <= self.nbytes
+        typestr = {torch.float32: "<f4", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
+        holder = type("_CAI", (), {})()
+        holder.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": typestr,
+                                           "data": (self.ptr, False), "version": 2, "strides": None}
+        holder._keep = self
+        return torch.as_tensor(holder, device=f"cuda:{self.ctx.device}")
+
+    def free(self):
+        if getattr(self, "ptr", None) and getattr(self.ctx, "h", None):
+            self.ctx.lib.rxg_device_free(self.ctx.h, c_void_p(self.ptr))
+        self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def comm_unique_id() -> bytes:

@@ -71,6 +71,8 @@ int begin_bad_flag(rxg_ctx* ctx) {
 static int examine_bad_flag(rxg_ctx* ctx) {      // the stream has been synchronised
     if (!ctx->bad_pending) return RXG_OK;
     ctx->bad_pending = false;
+    if (*ctx->h_bad & 2)
+        return fail(ctx, RXG_ERR_NCCL, "peer barrier timed out: a rank of the peer group never reached the gather");
     if (*ctx->h_bad != 0)
         return fail(ctx, RXG_ERR_NOT_SPD, "a Cholesky pivot of the model's covariance recursion was not positive "
                                           "(A, B, P, Q, S0 do not define SPD predicted / innovation covariances)");
@@ -150,6 +152,7 @@ int rxg_destroy(rxg_ctx* ctx) {
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->stage) cudaFree(ctx->stage);
     if (ctx->d_bad) cudaFree(ctx->d_bad);
+    if (ctx->d_tab) cudaFree(ctx->d_tab);
     if (ctx->h_bad) cudaFreeHost(ctx->h_bad);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->s_in) {
@@ -556,29 +559,6 @@ int rxg_comm_destroy_internal(rxg_ctx* ctx) {
 
 }  // extern "C"
 
-// Replicates the chain-independent covariances of a shared model into the rank-major gathered layout
-// [G][rows][b] without moving them over NVLink: every rank holds the same rows = T*d*d values (the
-// gain tables depend on the model only), so the gather of 4 d^2 of the 4 (d + d^2) bytes per
-// (chain, step) degenerates into a broadcast fill at HBM write speed.  src_stride = b (value taken
-// from the first chain of the local slab) or 1 (RXG_COV_SHARED_OUT table).
-__global__ void __launch_bounds__(256) replicate_cov_kernel(const float* __restrict__ src, int64_t src_stride,
-                                                            float* __restrict__ dst, int64_t rows, int64_t b, int G) {
-    const int64_t row = blockIdx.x;
-    const float v = __ldg(src + row * src_stride);
-    for (int g = blockIdx.y; g < G; g += gridDim.y) {
-        float* out = dst + ((int64_t)g * rows + row) * b;
-        const int64_t head = (4 - ((reinterpret_cast<uintptr_t>(out) >> 2) & 3)) & 3;   // floats to 16-byte alignment
-        const int64_t h = head < b ? head : b;
-        if (threadIdx.x < h) out[threadIdx.x] = v;
-        const int64_t n4 = (b - h) / 4;
-        float4* o4 = reinterpret_cast<float4*>(out + h);
-        const float4 v4 = make_float4(v, v, v, v);
-        for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) __stcs(o4 + i, v4);     // streaming: never re-read here
-        const int64_t tail = h + 4 * n4;
-        if (tail + threadIdx.x < b) out[tail + threadIdx.x] = v;
-    }
-}
-
 // Diagnostic: a pure streaming kernel with a chosen read : write mix (nr input rows summed, the sum stored into nw
 // output rows), float4 per thread, grid-stride over a persistent grid.  It has no dependent chain and no tables, i.e. it
 // shows what HBM delivers for the sweep's traffic mix (29 % reads / 71 % writes ~ nr = 2, nw = 5).
@@ -620,20 +600,14 @@ int rxg_allgather_posteriors(rxg_ctx* ctx, int d, int T, int64_t batch_local, co
     RXG_CUDA(ctx, cudaSetDevice(ctx->device));
     if (replicate) {
         // local broadcast fill on a side stream, concurrent with the NVLink gather of the means
-        if (!ctx->s_aux) {
-            RXG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking));
-            RXG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_aux[0], cudaEventDisableTiming));
-            RXG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_aux[1], cudaEventDisableTiming));
-        }
+        int rca = ensure_aux_stream(ctx);
+        if (rca != RXG_OK) return rca;
         RXG_CUDA(ctx, cudaEventRecord(ctx->ev_aux[0], ctx->stream));
         RXG_CUDA(ctx, cudaStreamWaitEvent(ctx->s_aux, ctx->ev_aux[0], 0));
-        const int64_t rows = (int64_t)T * d * d;
-        const int gy = ctx->nranks < 8 ? ctx->nranks : 8;
-        replicate_cov_kernel<<<dim3((unsigned)rows, (unsigned)gy), 256, 0, ctx->s_aux>>>(
-            post_cov, (flags & RXG_COV_SHARED_OUT) ? 1 : batch_local, gathered_cov, rows, batch_local, ctx->nranks);
-        RXG_CUDA(ctx, cudaGetLastError());
+        rca = launch_replicate_cov(ctx, ctx->s_aux, post_cov, (flags & RXG_COV_SHARED_OUT) ? 1 : batch_local, gathered_cov,
+                                   (int64_t)T * d * d, batch_local, ctx->nranks, -1);
+        if (rca != RXG_OK) return rca;
         RXG_CUDA(ctx, cudaEventRecord(ctx->ev_aux[1], ctx->s_aux));
-        ctx->launches += 1;
     }
     int r = p_group_start();
     if (r == 0) r = p_allgather(post_mean, gathered_mean, n_mean, nccl_float, ctx->comm, ctx->stream);

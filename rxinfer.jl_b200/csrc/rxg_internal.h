@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 #include <string>
 
 #include "../../include/rxgauss.h"
@@ -47,6 +48,9 @@ struct rxg_ctx {
     int peer_n = 0, peer_rank = 0;
     int* peer_flags[RXG_MAX_PEERS] = {};     // peer_flags[g] = rank g's flag array as mapped here (own: cudaMalloc'ed)
     unsigned peer_epoch = 0;
+    // [T][d][d] posterior-covariance table of the fused sweep + gather (source of the local replication)
+    void* d_tab = nullptr;
+    size_t tab_bytes = 0;
     // persistent host threads of the host-side covariance broadcast
     void* fill_pool = nullptr;
 };
@@ -69,6 +73,15 @@ int end_bad_flag(rxg_ctx* ctx, bool sync_now);      // enqueue the read-back; if
         if (_rc != RXG_OK) return _rc;                              \
     } while (0)
 
+// Extra destinations of the smoothed posteriors of a fused sweep + all-gather: pointers into the PEER ranks'
+// gathered buffers (mapped into this process), already offset to this rank's slab.  n = 0: plain sweep.
+struct PeerOut {
+    float* mean[RXG_MAX_PEERS - 1];
+    float* cov[RXG_MAX_PEERS - 1];
+    int n_mean;
+    int n_cov;
+};
+
 struct LgssmCall {
     int d, m, T;
     int64_t batch;
@@ -85,15 +98,24 @@ struct LgssmCall {
     unsigned flags;
     bool smooth;
     bool tables_only = false;   // compute the gain tables (and the RXG_COV_SHARED_OUT covariance table) and return: no sweep
+    PeerOut po = {};            // fused all-gather: peer destinations of the final mean (and covariance) stores
+    float* cov_table = nullptr; // device [T][d][d] or null: the gain kernels also leave the chain-independent posterior
+                                // covariance table here (source of the local covariance replication)
+    cudaEvent_t ev_tables = nullptr;   // recorded on the ctx stream once the gain tables are complete (before the sweep)
+    bool fused_peer_stores = false;    // out: the sweep kernel itself stored to c.po (else the caller pushes the slabs)
 };
 
+// rxg_peer.cu
+int launch_replicate_cov(rxg_ctx* ctx, cudaStream_t st, const float* src, int64_t src_stride, float* dst, int64_t rows,
+                         int64_t b, int G, int skip);
+int ensure_aux_stream(rxg_ctx* ctx);
 // rxg_lgssm.cu
-int lgssm_dispatch(rxg_ctx* ctx, const LgssmCall& c);
+int lgssm_dispatch(rxg_ctx* ctx, LgssmCall& c);
 // status[i] = RXG_ERR_NOT_SPD if the ctx's gain-table failure flag is set on the device, else RXG_OK
 int fill_status_from_flag(rxg_ctx* ctx, int32_t* status, int64_t n);
 bool lgssm_supported(int d, int m);
 // rxg_lgssm_large.cu
-int lgssm_large_dispatch(rxg_ctx* ctx, const LgssmCall& c);
+int lgssm_large_dispatch(rxg_ctx* ctx, LgssmCall& c);
 bool lgssm_large_supported(int d, int m);
 // rxg_umma_sweep.cu (d = 16 / 32 / 64 mean recursions on tcgen05)
 int launch_umma_sweep(rxg_ctx* ctx, int d, bool smooth, const float* recFE, const float* recG, const float* recK,

@@ -345,7 +345,7 @@ __global__ void gain_smooth_seq(GainWs ws, int T, float* cov_shared_out) {
 }
 
 // Filter with shared cov output requested: copy the sf table (padded records) to [T][D][D].
-__global__ void copy_table_kernel(const float* __restrict__ tab, int rec, int n, int T, float* __restrict__ out) {
+static __global__ void copy_table_kernel(const float* __restrict__ tab, int rec, int n, int T, float* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < T * n) out[i] = tab[(size_t)(i / n) * rec + (i % n)];
 }
@@ -362,7 +362,7 @@ static void fill_model(ModelF<D, M>& mdl, const LgssmCall& c) {
 }
 
 template <int D, int M>
-static int run_chain_family(rxg_ctx* ctx, const LgssmCall& c) {
+static int run_chain_family(rxg_ctx* ctx, LgssmCall& c) {
     ModelF<D, M> mdl = {};
     PerChainPtrs pc = {};
     const bool per_chain = (c.flags & RXG_MODEL_PER_CHAIN) != 0;
@@ -384,7 +384,7 @@ static int run_chain_family(rxg_ctx* ctx, const LgssmCall& c) {
 }
 
 template <int D, int M, int CPT>
-static int launch_shared(rxg_ctx* ctx, const LgssmCall& c, const ModelF<D, M>& mdl, const GainWs& ws,
+static int launch_shared(rxg_ctx* ctx, LgssmCall& c, const ModelF<D, M>& mdl, const GainWs& ws,
                          int write_cov) {
     constexpr int PF = 4;
     const int threads = 32;                     // one warp per CTA (see rxg_lgssm_shared.cuh)
@@ -399,7 +399,7 @@ static int launch_shared(rxg_ctx* ctx, const LgssmCall& c, const ModelF<D, M>& m
     if (ctx->opt[RXG_OPT_SWEEP_VARIANT] == 1) ckpt = false;                     // stash variant (A/B switch)
 #define RXG_LAUNCH_SHARED2(SM, EV, OF, CK)                                                         \
     lgssm_shared_kernel<D, M, CPT, PF, SM, EV, OF, CK><<<blocks, threads, 0, ctx->stream>>>(       \
-        mdl, ws.fwd, ws.bwd, ws.sf, c.y, c.mean, c.cov, c.nle, c.T, c.batch, tf, write_cov, c.mean0_chain)
+        mdl, ws.fwd, ws.bwd, ws.sf, c.y, c.mean, c.cov, c.nle, c.T, c.batch, tf, write_cov, c.mean0_chain, c.po)
 #define RXG_LAUNCH_SHARED(SM, EV)                                                                  \
     do {                                                                                           \
         if (SM && ckpt) { if (has_u) RXG_LAUNCH_SHARED2(SM, EV, true, true); else RXG_LAUNCH_SHARED2(SM, EV, false, true); } \
@@ -412,11 +412,12 @@ static int launch_shared(rxg_ctx* ctx, const LgssmCall& c, const ModelF<D, M>& m
 #undef RXG_LAUNCH_SHARED2
     if (ctx->profile) cudaEventRecord(ctx->ev[2], ctx->stream);
     ctx->launches += 1;
+    c.fused_peer_stores = c.smooth;      // the smoothing kernels store the final posteriors to c.po themselves
     return check_cuda(ctx, cudaGetLastError(), "lgssm_shared_kernel launch");
 }
 
 template <int D, int M>
-static int run_shared_family(rxg_ctx* ctx, const LgssmCall& c) {
+static int run_shared_family(rxg_ctx* ctx, LgssmCall& c) {
     using TB = Tab<D, M>;
     ModelF<D, M> mdl = {};
     fill_model<D, M>(mdl, c);
@@ -448,7 +449,7 @@ static int run_shared_family(rxg_ctx* ctx, const LgssmCall& c) {
     const int tf = (c.flags & RXG_TRANSITION_FIRST) ? 1 : 0;
     const bool cov_shared = (c.flags & RXG_COV_SHARED_OUT) != 0;
     if (ctx->profile) cudaEventRecord(ctx->ev[0], ctx->stream);
-    float* cov_once = (cov_shared && c.cov && c.smooth) ? c.cov : nullptr;
+    float* cov_once = (cov_shared && c.cov && c.smooth) ? c.cov : (c.smooth ? c.cov_table : nullptr);
     if (ctx->opt[RXG_OPT_GAIN_SEQ] != 0) {
         // sequential Riccati recursion (cross-check of the scan; ~70x slower at T = 1000)
         gain_riccati_seq<D, M><<<1, 32, 0, ctx->stream>>>(mdl, ws, c.T, tf, bad_flag(ctx));
@@ -470,6 +471,7 @@ static int run_shared_family(rxg_ctx* ctx, const LgssmCall& c) {
     }
     int rc = check_cuda(ctx, cudaGetLastError(), "gain table kernels launch");
     if (rc != RXG_OK) return rc;
+    if (c.ev_tables) RXG_CUDA(ctx, cudaEventRecord(c.ev_tables, ctx->stream));
     if (c.tables_only) return RXG_OK;
     const int write_cov = (c.cov != nullptr && !cov_shared) ? 1 : 0;
     const bool al16 = (((uintptr_t)c.y | (uintptr_t)c.mean | (uintptr_t)c.cov | (uintptr_t)c.nle | (uintptr_t)c.mean0_chain) & 15) == 0;
@@ -483,6 +485,29 @@ static int run_shared_family(rxg_ctx* ctx, const LgssmCall& c) {
     return launch_shared<D, M, 1>(ctx, c, mdl, ws, write_cov);
 }
 
+template <int D, int M>
+int run_dm(rxg_ctx* ctx, LgssmCall& c) {
+    const bool per_chain = (c.flags & (RXG_MODEL_PER_CHAIN | RXG_PATH_PER_CHAIN)) != 0 || c.ymask != nullptr;
+    if (per_chain) return run_chain_family<D, M>(ctx, c);
+    int rc = run_shared_family<D, M>(ctx, c);
+    if (rc == RXG_OK && c.status) rc = fill_status_from_flag(ctx, c.status, c.batch);
+    return rc;
+}
+
+// This translation unit is compiled once per (d, m) shape with -DRXG_INST_D / -DRXG_INST_M (explicit instantiation
+// of run_dm: the ~30 kernel variants of one shape), in parallel, and once without them for the dispatch below.
+#ifdef RXG_INST_D
+template int run_dm<RXG_INST_D, RXG_INST_M>(rxg_ctx*, LgssmCall&);
+#else
+extern template int run_dm<1, 1>(rxg_ctx*, LgssmCall&);
+extern template int run_dm<2, 1>(rxg_ctx*, LgssmCall&);
+extern template int run_dm<2, 2>(rxg_ctx*, LgssmCall&);
+extern template int run_dm<3, 3>(rxg_ctx*, LgssmCall&);
+extern template int run_dm<4, 1>(rxg_ctx*, LgssmCall&);
+extern template int run_dm<4, 2>(rxg_ctx*, LgssmCall&);
+extern template int run_dm<4, 4>(rxg_ctx*, LgssmCall&);
+extern template int run_dm<6, 6>(rxg_ctx*, LgssmCall&);
+
 // shared model: a failed Cholesky of the chain-independent covariance recursion fails every chain alike
 __global__ void fill_status_kernel(int32_t* s, int64_t n, const int* __restrict__ bad) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -494,15 +519,6 @@ int fill_status_from_flag(rxg_ctx* ctx, int32_t* status, int64_t n) {
     return check_cuda(ctx, cudaGetLastError(), "fill_status launch");
 }
 
-template <int D, int M>
-static int run_dm(rxg_ctx* ctx, const LgssmCall& c) {
-    const bool per_chain = (c.flags & (RXG_MODEL_PER_CHAIN | RXG_PATH_PER_CHAIN)) != 0 || c.ymask != nullptr;
-    if (per_chain) return run_chain_family<D, M>(ctx, c);
-    int rc = run_shared_family<D, M>(ctx, c);
-    if (rc == RXG_OK && c.status) rc = fill_status_from_flag(ctx, c.status, c.batch);
-    return rc;
-}
-
 bool lgssm_supported(int d, int m) {
     switch (d * 16 + m) {
         case 1 * 16 + 1: case 2 * 16 + 1: case 2 * 16 + 2: case 3 * 16 + 3:
@@ -512,7 +528,7 @@ bool lgssm_supported(int d, int m) {
     }
 }
 
-int lgssm_dispatch(rxg_ctx* ctx, const LgssmCall& c) {
+int lgssm_dispatch(rxg_ctx* ctx, LgssmCall& c) {
     switch (c.d * 16 + c.m) {
         case 1 * 16 + 1: return run_dm<1, 1>(ctx, c);
         case 2 * 16 + 1: return run_dm<2, 1>(ctx, c);
@@ -528,5 +544,7 @@ int lgssm_dispatch(rxg_ctx* ctx, const LgssmCall& c) {
                         "lgssm: (d=%d, m=%d) is outside the compiled kernel families", c.d, c.m);
     }
 }
+
+#endif  // RXG_INST_D
 
 }  // namespace rxg

@@ -801,7 +801,7 @@ __global__ void ba_kernel(const double* B, const double* A, double* BA) {
 }
 
 template <int D, int M>
-static int run_large(rxg_ctx* ctx, const LgssmCall& c) {
+static int run_large(rxg_ctx* ctx, LgssmCall& c) {
     if ((c.flags & (RXG_MODEL_PER_CHAIN | RXG_PATH_PER_CHAIN)) || c.ymask || c.u)
         return fail(ctx, RXG_ERR_UNSUPPORTED,
                     "lgssm (d=%d): the large-state family covers shared models without mask / offset", D);
@@ -983,7 +983,7 @@ static int run_large(rxg_ctx* ctx, const LgssmCall& c) {
 
 bool lgssm_large_supported(int d, int m) { return d == m && (d == 8 || d == 16 || d == 32 || d == 64); }
 
-int lgssm_large_dispatch(rxg_ctx* ctx, const LgssmCall& c) {
+int lgssm_large_dispatch(rxg_ctx* ctx, LgssmCall& c) {
     switch (c.d) {
         case 8: return run_large<8, 8>(ctx, c);
         case 16: return run_large<16, 16>(ctx, c);

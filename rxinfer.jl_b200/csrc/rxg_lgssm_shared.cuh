@@ -101,7 +101,7 @@ lgssm_shared_kernel(const __grid_constant__ ModelF<D, M> mdl, const float* __res
                     const float* __restrict__ bwd_tab, const float* __restrict__ sf_tab,
                     const float* __restrict__ y, float* __restrict__ mean, float* __restrict__ cov,
                     float* __restrict__ nle, int T, int64_t batch, int transition_first,
-                    int write_cov, const float* __restrict__ mu0c) {
+                    int write_cov, const float* __restrict__ mu0c, const __grid_constant__ PeerOut po) {
     using TB = Tab<D, M>;
     constexpr int TC = 4 * PF;                                   // table chunk, in time steps
     constexpr int REC_MAX = TB::FWD_REC > TB::BWD_REC ? TB::FWD_REC : TB::BWD_REC;
@@ -423,7 +423,11 @@ lgssm_shared_kernel(const __grid_constant__ ModelF<D, M> mdl, const float* __res
                     for (int i = 0; i < D; ++i) {
 #pragma unroll
                         for (int c = 0; c < CPT; ++c) ms[i][c] = nm[i][c];
-                        if (active) Pack<CPT>::st(mean + ((int64_t)t * D + i) * batch + b, ms[i]);
+                        if (active) {
+                            const int64_t off = ((int64_t)t * D + i) * batch + b;
+                            Pack<CPT>::st(mean + off, ms[i]);
+                            for (int g = 0; g < po.n_mean; ++g) Pack<CPT>::st(po.mean[g] + off, ms[i]);   // fused all-gather: NVLink P2P stores
+                        }
                     }
                     if (write_cov && active) {
                         float Sst[pad4(D * D)];
@@ -433,7 +437,9 @@ lgssm_shared_kernel(const __grid_constant__ ModelF<D, M> mdl, const float* __res
                             float v[CPT];
 #pragma unroll
                             for (int c = 0; c < CPT; ++c) v[c] = Sst[i];
-                            Pack<CPT>::st(cov + ((int64_t)t * D * D + i) * batch + b, v);
+                            const int64_t off = ((int64_t)t * D * D + i) * batch + b;
+                            Pack<CPT>::st(cov + off, v);
+                            for (int g = 0; g < po.n_cov; ++g) Pack<CPT>::st(po.cov[g] + off, v);
                         }
                     }
                 }
@@ -501,7 +507,11 @@ lgssm_shared_kernel(const __grid_constant__ ModelF<D, M> mdl, const float* __res
                 for (int i = 0; i < D; ++i) {
 #pragma unroll
                     for (int c = 0; c < CPT; ++c) ms[i][c] = nm[i][c];
-                    if (active) Pack<CPT>::st(mean + ((int64_t)t * D + i) * batch + b, ms[i]);
+                    if (active) {
+                        const int64_t off = ((int64_t)t * D + i) * batch + b;
+                        Pack<CPT>::st(mean + off, ms[i]);
+                        for (int g = 0; g < po.n_mean; ++g) Pack<CPT>::st(po.mean[g] + off, ms[i]);
+                    }
                 }
                 if (write_cov && active) {
                     float Sst[pad4(D * D)];
@@ -511,7 +521,9 @@ lgssm_shared_kernel(const __grid_constant__ ModelF<D, M> mdl, const float* __res
                         float v[CPT];
 #pragma unroll
                         for (int c = 0; c < CPT; ++c) v[c] = Sst[i];
-                        Pack<CPT>::st(cov + ((int64_t)t * D * D + i) * batch + b, v);
+                        const int64_t off = ((int64_t)t * D * D + i) * batch + b;
+                        Pack<CPT>::st(cov + off, v);
+                        for (int g = 0; g < po.n_cov; ++g) Pack<CPT>::st(po.cov[g] + off, v);
                     }
                 }
             }

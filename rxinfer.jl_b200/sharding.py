@@ -50,6 +50,75 @@ def init_comm(ctx, group=None):
     return world, rank
 
 
+class PeerGroup:
+    """Peer-mapped gathered buffers of one rank (``rxg_peer_*``): allocates this rank's ``[G, T, d, b]`` /
+    ``[G, T, d, d, b]`` buffers and flag words, exchanges the CUDA IPC handles over ``torch.distributed`` (plumbing
+    only) and maps the peers' buffers, so that the fused sweep can store its posteriors into every rank's buffer.
+
+    ``PeerGroup.local(ctxs, ...)`` builds the same thing for several contexts inside ONE process (tests on a single
+    GPU: every "rank" is a context with its own stream; no IPC involved)."""
+
+    def __init__(self, ctx, T, d, b_local, with_cov=True, group=None, _local=None):
+        from .context import DeviceBuffer
+        self.ctx, self.T, self.d, self.b = ctx, T, d, b_local
+        if _local is None:
+            self.world, self.rank = (dist.get_world_size(group), dist.get_rank(group)) if dist.is_initialized() else (1, 0)
+        else:
+            self.world, self.rank = _local
+        G = self.world
+        self.buf_mean = DeviceBuffer(ctx, 4 * G * T * d * b_local)
+        self.buf_cov = DeviceBuffer(ctx, 4 * G * T * d * d * b_local) if with_cov else None
+        self.buf_flags = DeviceBuffer(ctx, 4 * 8, zero=True)
+        self.mean = self.buf_mean.tensor(G, T, d, b_local)
+        self.cov = self.buf_cov.tensor(G, T, d, d, b_local) if with_cov else None
+        self._opened = []
+        if _local is not None:
+            return                      # PeerGroup.local wires the pointers
+        mine = (self.buf_mean.export(), self.buf_cov.export() if with_cov else None, self.buf_flags.export())
+        if G > 1:
+            allh = [None] * G
+            dist.all_gather_object(allh, mine, group=group)
+        else:
+            allh = [mine]
+        self.mean_ptrs, self.cov_ptrs, flag_ptrs = [], [], []
+        for g in range(G):
+            if g == self.rank:
+                self.mean_ptrs.append(self.buf_mean.ptr)
+                self.cov_ptrs.append(self.buf_cov.ptr if with_cov else 0)
+                flag_ptrs.append(self.buf_flags.ptr)
+            else:
+                hm, hc, hf = allh[g]
+                pm, pf = ctx.peer_open(hm), ctx.peer_open(hf)
+                pc = ctx.peer_open(hc) if with_cov else 0
+                self._opened += [p for p in (pm, pc, pf) if p]
+                self.mean_ptrs.append(pm); self.cov_ptrs.append(pc); flag_ptrs.append(pf)
+        ctx.peer_group(G, self.rank, flag_ptrs)
+        if G > 1:
+            dist.barrier(group=group)
+
+    @classmethod
+    def local(cls, ctxs, T, d, b_local, with_cov=True):
+        groups = [cls(c, T, d, b_local, with_cov, _local=(len(ctxs), r)) for r, c in enumerate(ctxs)]
+        for gr in groups:
+            gr.mean_ptrs = [o.buf_mean.ptr for o in groups]
+            gr.cov_ptrs = [o.buf_cov.ptr if with_cov else 0 for o in groups]
+            gr.ctx.peer_group(len(ctxs), gr.rank, [o.buf_flags.ptr for o in groups])
+        return groups
+
+    def smooth_gather(self, y, model, *, replicate_cov=False, **kw):
+        cov_ptrs = self.cov_ptrs if self.cov is not None else None
+        return self.ctx.lgssm_smooth_gather(y, model["A"], model["B"], model["P"], model["Q"], model["m0"], model["S0"],
+                                            self.mean_ptrs, cov_ptrs, replicate_cov=replicate_cov, **kw)
+
+    def close(self):
+        for p in self._opened:
+            try:
+                self.ctx.peer_close(p)
+            except Exception:
+                pass
+        self._opened = []
+
+
 def allgather_posteriors(ctx, mean, cov, world, backend="rxg"):
     """Returns rank-major gathered slabs ([G, T, d, b], [G, T, d, d, b])."""
     if backend == "rxg":

@@ -123,3 +123,21 @@ def test_streaming_engine_gamma_model_host_logic(rx):
     assert eng.history["x_t"].mean().shape == (4, 2) and eng.history["τ"].rate().shape == (4, 2)
     assert torch.equal(eng.free_energy_history, torch.arange(3, dtype=torch.float32)[:, None].expand(3, 2))
     assert float(eng.posteriors["τ"].shape()[0]) == 4.0
+
+
+def test_padded_shards_and_assembly():
+    """Unequal shards (batch % world != 0) are padded to a common slab width for the device gathers and the pad
+    columns are dropped again on assembly (unequal counts would hang ncclAllGather)."""
+    import torch
+    from rxinfer_jl_b200.sharding import assemble_gathered, padded_shard, shard_bounds
+    batch, world, T, d = 10, 4, 3, 2
+    bp = padded_shard(batch, world)
+    assert bp == 3 and sum(hi - lo for lo, hi in (shard_bounds(batch, world, r) for r in range(world))) == batch
+    full = torch.arange(T * d * batch, dtype=torch.float32).reshape(T, d, batch)
+    g = torch.full((world, T, d, bp), -1.0)
+    for r in range(world):
+        lo, hi = shard_bounds(batch, world, r)
+        g[r, :, :, : hi - lo] = full[:, :, lo:hi]
+    assert torch.equal(assemble_gathered(g, batch=batch), full)
+    g2 = torch.stack([full[:, :, r * 5:(r + 1) * 5] for r in range(2)])
+    assert torch.equal(assemble_gathered(g2), full)
