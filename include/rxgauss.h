@@ -259,6 +259,15 @@ int rxg_hgf_filter_f32(rxg_ctx*, int T, int64_t batch, int iters, float kappa, f
                        float z_variance, float y_variance, const float init[4], const float* y,
                        float* out, unsigned flags);
 
+/* Same filter with the streaming carry and the Bethe free energy as optional arguments: `init` (first chunk) or
+ * `prev[4][batch]` (out[Tc-1] of the previous chunk), exactly one of them non-NULL; free_energy[T][iters][batch] or
+ * NULL = the Bethe free energy of each datum's graph after every VMP iteration [ref: definition
+ * src/model/plugins/reactivemp_free_energy.jl:84-126; the reference's regression pin for this model is the average
+ * over the data after the last iteration, test/models/statespace/hgf_tests.jl:112-119 (1.009879989585)].        */
+int rxg_hgf_filter_fe_f32(rxg_ctx*, int T, int64_t batch, int iters, float kappa, float omega,
+                          float z_variance, float y_variance, const float init[4], const float* prev,
+                          const float* y, float* out, float* free_energy, unsigned flags);
+
 /* ------------------------------------------------------------------ streaming engine ----------
  * The reference's second entry point: infer(..., autoupdates = ..., keephistory = ...) builds an
  * RxInferenceEngine that re-triggers a ONE-step graph per datum and feeds q(x_t) back as the next

@@ -202,24 +202,24 @@ class Context:
                                                         _fp(mean), _fp(cov), _fp(nle), flags))
         return dict(mean=mean, cov=cov, neg_log_evidence=nle)
 
-    def hgf_filter_chunk(self, y, prev, iters=20, kappa=1.0, omega=0.0, z_variance=0.04, y_variance=0.01, out=None):
+    def hgf_filter_chunk(self, y, prev, iters=20, kappa=1.0, omega=0.0, z_variance=0.04, y_variance=0.01, out=None,
+                         want_free_energy=False):
         """HGF datastream chunk; ``prev[4, batch]`` = ``out[-1]`` of the previous chunk."""
-        self._dev(y, prev)
-        T, batch = y.shape
-        out = out if out is not None else self.empty(T, 4, batch)
-        self._check(self.lib.rxg_hgf_filter_chunk_f32(self.h, T, batch, iters, kappa, omega, z_variance, y_variance,
-                                                      _fp(prev), _fp(y), _fp(out), L.PTR_DEVICE))
-        return out
+        return self.hgf_filter(y, iters, kappa, omega, z_variance, y_variance, init=None, out=out, prev=prev,
+                               want_free_energy=want_free_energy)
 
     def hgf_filter(self, y, iters=20, kappa=1.0, omega=0.0, z_variance=0.04, y_variance=0.01,
-                   init=(0.0, 5.0, 0.0, 5.0), out=None):
-        self._dev(y)
+                   init=(0.0, 5.0, 0.0, 5.0), out=None, prev=None, want_free_energy=False):
+        """``rxg_hgf_filter_fe_f32``: y[T, batch] -> out[T, 4, batch] = (m_x, v_x, m_z, v_z); with
+        ``want_free_energy`` also the Bethe free energy [T, iters, batch] (returned as a pair)."""
+        self._dev(y, prev, out)
         T, batch = y.shape
         out = out if out is not None else self.empty(T, 4, batch)
-        ini = (ctypes.c_float * 4)(*init)
-        self._check(self.lib.rxg_hgf_filter_f32(self.h, T, batch, iters, kappa, omega, z_variance, y_variance,
-                                                ini, _fp(y), _fp(out), L.PTR_DEVICE))
-        return out
+        fe = self.empty(T, iters, batch) if want_free_energy else None
+        ini = ctypes.cast((ctypes.c_float * 4)(*init), L.fp) if prev is None else L.as_fp(0)
+        self._check(self.lib.rxg_hgf_filter_fe_f32(self.h, T, batch, iters, kappa, omega, z_variance, y_variance,
+                                                   ini, _fp(prev), _fp(y), _fp(out), _fp(fe), L.PTR_DEVICE))
+        return (out, fe) if want_free_energy else out
 
     def stream_vmp_gamma(self, y, iters=4, w=1.0, init=(0.0, 1e3, 1.0, 1.0), prev=None, want_free_energy=False):
         """Streaming mean-field VMP with a Gamma observation precision (``rxg_stream_vmp_gamma_f32``);

@@ -61,16 +61,25 @@ int ensure_gh_tables(rxg_ctx* ctx) {
 
 struct GcvJoint { float m1, m2, V11, V12, V22; };
 
-// @marginalrule GCV(:y_x): W = [[w_y + g, -g], [-g, w_x + g]], xi = [xi_y, xi_x]
+// @marginalrule GCV(:y_x): W = [[w_y + g, -g], [-g, w_x + g]], xi = [xi_y, xi_x].
+// det = w_y w_x + g (w_y + w_x) is formed without the cancellation of (w_y + g)(w_x + g) - g^2 (g can exceed
+// w_y, w_x by orders of magnitude when the volatility level is low).
 __device__ __forceinline__ GcvJoint gcv_joint(float xiy, float wy, float xix, float wx, float g) {
     const float a = wy + g, c = wx + g;
-    const float det = __fmaf_rn(a, c, -g * g);
+    const float det = __fmaf_rn(g, wy + wx, wy * wx);
     const float r = 1.0f / det;
     GcvJoint j;
     j.V11 = c * r; j.V12 = g * r; j.V22 = a * r;
     j.m1 = __fmaf_rn(j.V11, xiy, j.V12 * xix);
     j.m2 = __fmaf_rn(j.V12, xiy, j.V22 * xix);
     return j;
+}
+// psi = E[(y - x)^2] under the joint = (m1 - m2)^2 + V11 + V22 - 2 V12, in closed form: the variance part is
+// (w_y + w_x) / det and the mean difference w_y w_x (m_y - m_x) / det -- no subtraction of nearly equal numbers.
+__device__ __forceinline__ float gcv_psi(float my, float wy, float mx, float wx, float g) {
+    const float r = 1.0f / __fmaf_rn(g, wy + wx, wy * wx);
+    const float dm = wy * wx * (my - mx) * r;
+    return __fmaf_rn(dm, dm, (wy + wx) * r);
 }
 // A * B of the node with PointMass kappa, omega
 __device__ __forceinline__ float gcv_gamma(float mz, float vz, float kappa, float omega) {
@@ -119,13 +128,34 @@ __device__ __forceinline__ float ex2_approx(float x) {
 //   pass 2:  e = ex2(l_i - lmax); w = u_i - delta; S0 += e; S1 += e w; S2 += e w w  (8 instr, 1 MUFU)
 // with b2 = -(log2e / 2) psi A and delta = previous iterate minus prior mean (moments are
 // accumulated around the previous iterate, which removes the fp32 cancellation in the variance).
+//
+// FE: Bethe free energy of each datum's graph after every VMP iteration, fe[T][iters][batch]
+// [ref: definition /root/reference/src/model/plugins/reactivemp_free_energy.jl:84-126; the reference pins its average
+//  over the data for this model, test/models/statespace/hgf_tests.jl:112-119].  Single-variable clusters cancel, leaving
+//   F = U[zt_min prior] + U[xt_min prior] + U[zt | zt_min] + U[GCV] + U[y | xt] - H[q(zt, zt_min)] - H[q(xt, xt_min)],
+// where q(zt, zt_min) is the (out, mu) marginal of the Normal node whose inbound message on `out` is the GCV node's
+// ExponentialLinearQuadratic read through mean_var: GaussHermiteCubature(31) against N(0, 1) with the density
+// re-weighted by exp(z^2 / 2) -- nodes sqrt(2) t_i are fixed, so exp(-kappa z_i) and the log-weights are per-launch
+// constants kept in shared memory (s_e0, s_c0).  All differences of nearly equal terms are taken in closed form.
+template <bool FE>
 __global__ void __launch_bounds__(64)
 hgf_filter_kernel(const float* __restrict__ y, float* __restrict__ out, int T, int64_t batch, int iters,
                   float kappa, float omega, float zvar, float yvar, float i_mz, float i_vz, float i_mx,
-                  float i_vx, const float* __restrict__ prev) {
+                  float i_vx, const float* __restrict__ prev, float* __restrict__ fe) {
+    __shared__ float s_e0[32], s_c0[32], s_z0[32];
+    if (FE) {
+        if (threadIdx.x < 31) {
+            const float z = 1.41421356237309505f * c_gh_t[threadIdx.x];
+            s_z0[threadIdx.x] = z;
+            s_e0[threadIdx.x] = expf(-kappa * z);
+            s_c0[threadIdx.x] = c_gh_lw[threadIdx.x] + 0.5f * z * z - 0.5f * kappa * z;     // log w_i + z^2/2 - kappa z / 2
+        }
+        __syncthreads();
+    }
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
     constexpr float LOG2E = 1.4426950408889634f;
+    constexpr float LOG_2PI = 1.8378770664093453f;
     if (prev) {   // streaming carry: out[T-1] of the previous chunk, rows (m_x, v_x, m_z, v_z)
         i_mx = __ldg(prev + b); i_vx = __ldg(prev + batch + b);
         i_mz = __ldg(prev + 2 * batch + b); i_vz = __ldg(prev + 3 * batch + b);
@@ -156,8 +186,7 @@ hgf_filter_kernel(const float* __restrict__ y, float* __restrict__ out, int T, i
         for (int it = 0; it < iters; ++it) {
             const float g = gcv_gamma(mz, vz, kappa, omega);
             j = gcv_joint(xiy, wy, xix, wx, g);
-            const float dm = j.m1 - j.m2;
-            const float psi = __fmaf_rn(dm, dm, j.V11 + j.V22 - 2.0f * j.V12);
+            const float psi = gcv_psi(yt, wy, mxp, wx, g);
             const float b2 = -0.5f * LOG2E * psi * eA;
             float lmax = -INFINITY;
 #pragma unroll
@@ -176,6 +205,44 @@ hgf_filter_kernel(const float* __restrict__ y, float* __restrict__ out, int T, i
             const float dw = S1 * r;
             mz = mz + dw;
             vz = __fmaf_rn(-dw, dw, S2 * r);
+            if (FE) {
+                // mean_var(ELQ(kappa, psi A, -kappa, 0)) by GH-31 against N(0, 1), pdf re-weighted by exp(z^2 / 2)
+                const float hb = -0.5f * psi * eA;
+                float lm = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 31; ++i) lm = fmaxf(lm, __fmaf_rn(hb, s_e0[i], s_c0[i]));
+                float T0 = 0.f, T1 = 0.f, T2 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 31; ++i) {
+                    const float e = __expf(__fmaf_rn(hb, s_e0[i], s_c0[i]) - lm);
+                    const float z = s_z0[i];
+                    T0 += e; T1 = __fmaf_rn(e, z, T1); T2 = __fmaf_rn(e * z, z, T2);
+                }
+                const float me = T1 / T0;
+                const float ve = fmaxf(__fmaf_rn(-me, me, T2 / T0), 1e-30f);
+                // q(zt, zt_min) = N(zt_min; mzp, vzp) N(zt; zt_min, zvar) N(zt; me, ve)
+                const float iz = 1.0f / zvar, ie = 1.0f / ve, ip = 1.0f / vzp;
+                const float w11 = iz + ie, w22 = ip + iz;
+                const float detz = __fmaf_rn(iz, ip + ie, ie * ip);             // w11 w22 - iz^2, cancellation free
+                const float rz = 1.0f / detz;
+                const float v22 = w11 * rz;
+                const float xi1 = me * ie, xi2 = mzp * ip;
+                const float j2 = (iz * xi1 + w11 * xi2) * rz;
+                const float dj = (ip * xi1 - ie * xi2) * rz;                     // E zt - E zt_min
+                const float U_nz = 0.5f * (LOG_2PI + logf(zvar)) + 0.5f * __fmaf_rn(dj, dj, (ip + ie) * rz) * iz;
+                const float dz2 = j2 - mzp;
+                const float U_pz = 0.5f * (LOG_2PI + logf(vzp)) + 0.5f * __fmaf_rn(dz2, dz2, v22) * ip;
+                const float dx2 = j.m2 - mxp;
+                const float U_px = 0.5f * (LOG_2PI + logf(vxp)) + 0.5f * __fmaf_rn(dx2, dx2, j.V22) * wx;
+                const float Bn = expf(-kappa * mz + 0.5f * kappa * kappa * vz);
+                const float U_g = 0.5f * (LOG_2PI + (kappa * mz + omega) + psi * eA * Bn);
+                const float dy = yt - j.m1;
+                const float U_o = 0.5f * (LOG_2PI + logf(yvar)) + 0.5f * __fmaf_rn(dy, dy, j.V11) * wy;
+                const float detx = __fmaf_rn(g, wy + wx, wy * wx);
+                const float H_z = LOG_2PI + 1.0f - 0.5f * logf(detz);           // 1/2 log((2 pi e)^2 / det W)
+                const float H_x = LOG_2PI + 1.0f - 0.5f * logf(detx);
+                fe[((int64_t)t * iters + it) * batch + b] = U_nz + U_pz + U_px + U_g + U_o - H_z - H_x;
+            }
         }
         out[((int64_t)t * 4 + 0) * batch + b] = j.m1;
         out[((int64_t)t * 4 + 1) * batch + b] = j.V11;
@@ -328,17 +395,25 @@ using namespace rxg;
 
 extern "C" {
 
-int rxg_hgf_filter_f32(rxg_ctx* ctx, int T, int64_t batch, int iters, float kappa, float omega, float z_variance,
-                       float y_variance, const float init[4], const float* y, float* out, unsigned flags) {
+int rxg_hgf_filter_fe_f32(rxg_ctx* ctx, int T, int64_t batch, int iters, float kappa, float omega, float z_variance,
+                          float y_variance, const float init[4], const float* prev, const float* y, float* out,
+                          float* free_energy, unsigned flags) {
     if (!ctx) return RXG_ERR_BAD_ARG;
-    if (T < 1 || batch < 1 || iters < 1 || !y || !out || !init)
+    if (T < 1 || batch < 1 || iters < 1 || !y || !out || (!init && !prev) || !(z_variance > 0.f) || !(y_variance > 0.f))
         return rxg::fail(ctx, RXG_ERR_BAD_ARG, "hgf_filter: bad argument");
     if (!(flags & RXG_PTR_DEVICE)) return rxg::fail(ctx, RXG_ERR_UNSUPPORTED, "hgf_filter takes device pointers");
     RXG_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = ensure_gh_tables(ctx);
     if (rc != RXG_OK) return rc;
-    hgf_filter_kernel<<<(unsigned)((batch + 63) / 64), 64, 0, ctx->stream>>>(
-        y, out, T, batch, iters, kappa, omega, z_variance, y_variance, init[0], init[1], init[2], init[3], nullptr);
+    const float z4[4] = {0.f, 1.f, 0.f, 1.f};
+    const float* in = init ? init : z4;
+    const unsigned grid = (unsigned)((batch + 63) / 64);
+    if (free_energy)
+        hgf_filter_kernel<true><<<grid, 64, 0, ctx->stream>>>(y, out, T, batch, iters, kappa, omega, z_variance, y_variance,
+                                                             in[0], in[1], in[2], in[3], prev, free_energy);
+    else
+        hgf_filter_kernel<false><<<grid, 64, 0, ctx->stream>>>(y, out, T, batch, iters, kappa, omega, z_variance, y_variance,
+                                                              in[0], in[1], in[2], in[3], prev, nullptr);
     ctx->launches += 1;
     rc = rxg::check_cuda(ctx, cudaGetLastError(), "hgf_filter_kernel");
     if (rc != RXG_OK) return rc;
@@ -346,22 +421,16 @@ int rxg_hgf_filter_f32(rxg_ctx* ctx, int T, int64_t batch, int iters, float kapp
     return RXG_OK;
 }
 
+int rxg_hgf_filter_f32(rxg_ctx* ctx, int T, int64_t batch, int iters, float kappa, float omega, float z_variance,
+                       float y_variance, const float init[4], const float* y, float* out, unsigned flags) {
+    if (ctx && !init) return rxg::fail(ctx, RXG_ERR_BAD_ARG, "hgf_filter: init is required");
+    return rxg_hgf_filter_fe_f32(ctx, T, batch, iters, kappa, omega, z_variance, y_variance, init, nullptr, y, out, nullptr, flags);
+}
+
 int rxg_hgf_filter_chunk_f32(rxg_ctx* ctx, int T, int64_t batch, int iters, float kappa, float omega, float z_variance,
                              float y_variance, const float* prev, const float* y, float* out, unsigned flags) {
-    if (!ctx) return RXG_ERR_BAD_ARG;
-    if (T < 1 || batch < 1 || iters < 1 || !y || !out || !prev)
-        return rxg::fail(ctx, RXG_ERR_BAD_ARG, "hgf_filter_chunk: bad argument");
-    if (!(flags & RXG_PTR_DEVICE)) return rxg::fail(ctx, RXG_ERR_UNSUPPORTED, "hgf_filter_chunk takes device pointers");
-    RXG_CUDA(ctx, cudaSetDevice(ctx->device));
-    int rc = ensure_gh_tables(ctx);
-    if (rc != RXG_OK) return rc;
-    hgf_filter_kernel<<<(unsigned)((batch + 63) / 64), 64, 0, ctx->stream>>>(
-        y, out, T, batch, iters, kappa, omega, z_variance, y_variance, 0.f, 1.f, 0.f, 1.f, prev);
-    ctx->launches += 1;
-    rc = rxg::check_cuda(ctx, cudaGetLastError(), "hgf_filter_kernel (chunk)");
-    if (rc != RXG_OK) return rc;
-    if (!(flags & RXG_ASYNC)) RXG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return RXG_OK;
+    if (ctx && !prev) return rxg::fail(ctx, RXG_ERR_BAD_ARG, "hgf_filter_chunk: prev is required");
+    return rxg_hgf_filter_fe_f32(ctx, T, batch, iters, kappa, omega, z_variance, y_variance, nullptr, prev, y, out, nullptr, flags);
 }
 
 #define RXG_GCV_PROLOGUE                                                                          \

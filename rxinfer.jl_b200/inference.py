@@ -152,11 +152,14 @@ def infer(*, model, iterations=None, free_energy=False, returnvars=None, options
             return InferenceResult(posteriors={"x": MvNormalMeanCovariance(r["mean"], r["cov"])},
                                    free_energy=r["neg_log_evidence"], model=model)
         if isinstance(model, hgf):
-            if free_energy:
-                raise NotImplementedError("free_energy for the HGF path is not on the hot path yet")
             out = ctx.hgf_filter(y, iters=iterations or 1, kappa=model.real_k, omega=model.real_w,
-                                 z_variance=model.z_variance, y_variance=model.y_variance, init=model.init)
-            return InferenceResult(posteriors={}, model=model,
+                                 z_variance=model.z_variance, y_variance=model.y_variance, init=model.init,
+                                 want_free_energy=bool(free_energy))
+            fe = None
+            if free_energy:      # free_energy_history of the streaming engine: average over the data, per iteration
+                out, fe_all = out
+                fe = fe_all.mean(dim=0)
+            return InferenceResult(posteriors={}, model=model, free_energy=fe,
                                    history={"xt": NormalMeanVariance(out[:, 0], out[:, 1]),
                                             "zt": NormalMeanVariance(out[:, 2], out[:, 3])})
         if isinstance(model, kalman_gamma_streaming):

@@ -41,8 +41,6 @@ class RxInferenceEngine:
         if isinstance(model, I.hgf):
             self._kind = "hgf"
             names = ("xt", "zt")
-            if free_energy:
-                raise NotImplementedError("free_energy for the HGF path is not on the hot path")
             self._carry = None               # out[-1] of the previous chunk, [4, batch]
         elif isinstance(model, I.kalman_gamma_streaming):
             self._kind = "vmpgamma"
@@ -114,10 +112,14 @@ class RxInferenceEngine:
             mo = self.model
             kw = dict(iters=self.iterations, kappa=mo.real_k, omega=mo.real_w, z_variance=mo.z_variance,
                       y_variance=mo.y_variance)
+            kw["want_free_energy"] = self.free_energy_enabled
             if self._carry is None:
                 o = self.ctx.hgf_filter(chunk, init=mo.init, **kw)
             else:
                 o = self.ctx.hgf_filter_chunk(chunk, self._carry, **kw)
+            if self.free_energy_enabled:
+                o, fe = o
+                self._fe.append(fe)
             self._carry = o[-1]
             out = {"xt": NormalMeanVariance(o[:, 0], o[:, 1]), "zt": NormalMeanVariance(o[:, 2], o[:, 3])}
         self.ticks += int(chunk.shape[0])
@@ -164,6 +166,6 @@ class RxInferenceEngine:
         evidence of the whole stream (on this tree BFE = -log evidence)."""
         if not self.free_energy_enabled:
             raise RuntimeError("Bethe Free Energy has not been computed: use `free_energy = true`")
-        if self._kind == "vmpgamma":      # reference semantics (streaming.jl:12): per iteration, averaged over the observations
+        if self._kind in ("vmpgamma", "hgf"):   # reference semantics (streaming.jl:12): per iteration, averaged over the observations
             return torch.cat(self._fe, dim=0).mean(dim=0)
         return torch.stack(self._fe)

@@ -125,6 +125,24 @@ def test_gpu_hgf_reference_data_assertions(ctx):
 
 
 @pytest.mark.gpu
+def test_gpu_hgf_free_energy_reproduces_reference_pin(ctx):
+    """hgf_tests.jl:112-119 on the CUDA output: `fe = result.free_energy_history`, `length(fe) == 10`,
+    `abs(last(fe) - 1.009879989585) < 0.01`, decreasing -- with the free energy computed ON THE DEVICE
+    (rxg_hgf_filter_fe_f32), not by the oracle."""
+    import torch
+    z, x, y = hgf_reference_data()
+    yb = np.repeat(y[:, None], 32, axis=1).astype(np.float32)
+    out, fe = ctx.hgf_filter(torch.as_tensor(yb, device="cuda"), iters=10, want_free_energy=True)
+    hist = fe.double().mean(dim=0).cpu().numpy()            # [iters, batch]: averaged over the observations
+    assert hist.shape == (10, 32)                                                   # :117
+    print("device HGF free energy history (chain 0):", hist[:, 0])
+    assert np.all(np.abs(hist[-1] - 1.009879989585) < 0.01)                         # :118, the reference's tolerance
+    d = np.diff(hist[:, 0])
+    assert np.all(d[np.abs(d) > 0.1] < 0)                                           # :119
+    hgf_reference_assertions(out[:, :, 0].cpu().numpy(), z, x)
+
+
+@pytest.mark.gpu
 def test_gpu_reproduces_reference_goldens(ctx):
     import torch
     dev = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32, device="cuda")
