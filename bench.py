@@ -213,6 +213,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--per-chain-path", action="store_true", help="time the per-chain covariance recursion instead")
+    ap.add_argument("--sweep-variant", type=int, default=0, help="RXG_OPT_SWEEP_VARIANT (0 auto, 1 stash, 2 checkpoint, 3/4 time-segmented)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -235,6 +236,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     ctx = rx.Context(local)
+    if args.sweep_variant:
+        ctx.set_option("sweep_variant", args.sweep_variant)
     mod = notebook_model_f32()
     batch = args.batch
     kw = dict(A=mod["A"], B=mod["B"], P=mod["P"], Q=mod["Q"], m0=mod["m0"], S0=mod["S0"])
@@ -456,6 +459,7 @@ def main():
                                     "sweep is linear in y, timing is value independent; parity of the timed buffers is checked "
                                     "against the fp64 oracle on sampled chains (`parity`)",
                        "path": "per-chain covariance recursion" if args.per_chain_path else "gain tables + mean sweeps",
+                       "sweep_variant": ctx.get_option("sweep_variant"),
                        "messages_per_chain_step": MSG_PER_STEP, "l2_policy": "inputs+outputs (6.3 GB) larger than L2"},
             "roofline": {"bound": "hbm", "kernel": "lgssm_chain_kernel" if args.per_chain_path else "lgssm_shared_kernel",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -29,6 +29,7 @@
 #include "rxg_linalg.cuh"
 #include "rxg_lgssm_common.cuh"
 #include "rxg_lgssm_shared.cuh"
+#include "rxg_lgssm_seg.cuh"
 
 namespace rxg {
 
@@ -416,6 +417,43 @@ static int launch_shared(rxg_ctx* ctx, LgssmCall& c, const ModelF<D, M>& mdl, co
     return check_cuda(ctx, cudaGetLastError(), "lgssm_shared_kernel launch");
 }
 
+// time-segmented sweep (rxg_lgssm_seg.cuh): smoothing without evidence, d^2 <= 16, T up to the shared-memory budget
+template <int D, int M>
+static bool seg_sweep_eligible(const LgssmCall& c) {
+    using ST = SegTab<D, M>;
+    if (!c.smooth || c.nle || D * D > 16) return false;
+    const int nseg = (c.T + ST::L - 1) / ST::L;
+    const size_t smem = (size_t)nseg * 2 * D * 32 * 4 + (size_t)8 * 2 * ST::L * ST::REC * 4;
+    return smem <= 200 * 1024;
+}
+template <int D, int M>
+static int launch_seg(rxg_ctx* ctx, LgssmCall& c, const ModelF<D, M>& mdl, const GainWs& ws, const SegWs& sw, int write_cov,
+                      bool hints) {
+    using ST = SegTab<D, M>;
+    constexpr int NW = 8;
+    const int nseg = (c.T + ST::L - 1) / ST::L;
+    seg_tables_kernel<D, M><<<(nseg + 63) / 64, 64, 0, ctx->stream>>>(ws, sw, c.T);
+    const size_t smem = (size_t)nseg * 2 * D * 32 * 4 + (size_t)NW * 2 * ST::L * ST::REC * 4;
+    const int64_t ntiles = (c.batch + 31) / 32;
+    const unsigned grid = (unsigned)(ntiles < ctx->sm_count ? ntiles : ctx->sm_count);
+    bool has_u = false;
+    for (int i = 0; i < D; ++i) has_u |= (mdl.u[i] != 0.f);
+#define RXG_LAUNCH_SEG(OF, HI)                                                                                        \
+    do {                                                                                                               \
+        RXG_CUDA(ctx, cudaFuncSetAttribute(lgssm_seg_kernel<D, M, NW, OF, HI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        if (ctx->profile) cudaEventRecord(ctx->ev[1], ctx->stream);                                                    \
+        lgssm_seg_kernel<D, M, NW, OF, HI><<<grid, 32 * NW, smem, ctx->stream>>>(mdl, sw, c.y, c.mean, c.cov, c.T, c.batch, \
+                                                                                 write_cov, c.mean0_chain, c.po, nseg);  \
+    } while (0)
+    if (has_u) { if (hints) RXG_LAUNCH_SEG(true, 1); else RXG_LAUNCH_SEG(true, 0); }
+    else       { if (hints) RXG_LAUNCH_SEG(false, 1); else RXG_LAUNCH_SEG(false, 0); }
+#undef RXG_LAUNCH_SEG
+    if (ctx->profile) cudaEventRecord(ctx->ev[2], ctx->stream);
+    ctx->launches += 2;
+    c.fused_peer_stores = true;
+    return check_cuda(ctx, cudaGetLastError(), "lgssm_seg_kernel launch");
+}
+
 template <int D, int M>
 static int run_shared_family(rxg_ctx* ctx, LgssmCall& c) {
     using TB = Tab<D, M>;
@@ -436,6 +474,10 @@ static int run_shared_family(rxg_ctx* ctx, LgssmCall& c) {
     const size_t o_ftot = carve((size_t)2 * GS_NT * 3 * D * D * sizeof(double));
     const size_t o_bel = carve(T * 2 * D * D * sizeof(double));
     const size_t o_btot = carve((size_t)2 * GS_NT * 2 * D * D * sizeof(double));
+    using ST = SegTab<D, M>;
+    const size_t nseg = (T + ST::L - 1) / ST::L;
+    const size_t o_srec_t = carve(T * ST::REC * sizeof(float)), o_snrec = carve(T * ST::NREC * sizeof(float));
+    const size_t o_ssrec = carve(nseg * ST::SREC * sizeof(float));
     char* base = (char*)workspace(ctx, off);
     if (!base) return RXG_ERR_CUDA;
     GainWs ws;
@@ -474,6 +516,13 @@ static int run_shared_family(rxg_ctx* ctx, LgssmCall& c) {
     if (c.ev_tables) RXG_CUDA(ctx, cudaEventRecord(c.ev_tables, ctx->stream));
     if (c.tables_only) return RXG_OK;
     const int write_cov = (c.cov != nullptr && !cov_shared) ? 1 : 0;
+    // sweep variant (RXG_OPT_SWEEP_VARIANT): 3 / 4 = time-segmented kernel with / without L2 eviction hints
+    const long long variant = ctx->opt[RXG_OPT_SWEEP_VARIANT];
+    if ((variant == 3 || variant == 4) && seg_sweep_eligible<D, M>(c)) {
+        SegWs sgw;
+        sgw.rec = (float*)(base + o_srec_t); sgw.nrec = (float*)(base + o_snrec); sgw.srec = (float*)(base + o_ssrec);
+        return launch_seg<D, M>(ctx, c, mdl, ws, sgw, write_cov, variant == 3);
+    }
     const bool al16 = (((uintptr_t)c.y | (uintptr_t)c.mean | (uintptr_t)c.cov | (uintptr_t)c.nle | (uintptr_t)c.mean0_chain) & 15) == 0;
     // chains per thread: keep >= ~2 resident warps per SM sub-partition
     // Wider per-thread vectors cut the number of (128-byte-per-warp) store instructions per byte;

@@ -462,3 +462,50 @@ def test_context_validates_arrays(ctx):
         ctx.lgssm(yd, **_kw(mod), out_mean=torch.empty(20, 4, 15, device="cuda"))
     with pytest.raises(ValueError):
         ctx.lgssm(yd, **_kw(mod), out_cov=torch.empty(20, 4, 4, device="cuda"))           # table shape without the flag
+
+
+@pytest.mark.parametrize("d,m", [(4, 4), (2, 2), (3, 3), (4, 2), (1, 1), (2, 1), (4, 1)])
+def test_time_segmented_sweep(ctx, d, m):
+    """lgssm_seg_kernel (sweep_variant 3 / 4: parallel in time inside a chain tile, with / without L2 eviction
+    hints) against the oracle and the sequential-in-time sweep: segment boundaries (T = 1, 15, 16, 17, 33, 1000),
+    ragged chain tiles, transition offset, prior one transition before the first datum, per-chain prior means."""
+    rng = np.random.default_rng(300 + 10 * d + m)
+    Aq, _ = np.linalg.qr(rng.standard_normal((d, d)))
+    mod = f32_model(dict(A=0.95 * Aq, B=rng.standard_normal((m, d)), P=0.2 * np.eye(d), Q=1.5 * np.eye(m),
+                         m0=rng.standard_normal(d), S0=5.0 * np.eye(d)))
+    u = (0.3 * rng.standard_normal(d)).astype(np.float32)
+    for T, batch in [(1, 33), (15, 64), (16, 70), (17, 31), (33, 203), (1000, 96)]:
+        _, y = lgssm.generate_data(mod, T, batch, seed=41 + T)
+        for kw in (dict(), dict(u=u), dict(transition_first=True), dict(u=u, transition_first=True)):
+            ref = lgssm.smooth_reference_schedule(y, **mod, **{k: (v.astype(np.float64) if k == "u" else v) for k, v in kw.items()})
+            ctx.set_option("sweep_variant", 0)
+            base = ctx.lgssm(dev(y), **_kw(mod), smooth=True, **kw)
+            for variant in (3, 4):
+                ctx.set_option("sweep_variant", variant)
+                r = ctx.lgssm(dev(y), **_kw(mod), smooth=True, **kw)
+                check(r, ref, nle=False)
+                assert rel_l2(r["mean"].cpu().numpy(), base["mean"].cpu().numpy()) < 2e-6
+                assert torch.equal(r["cov"], base["cov"])            # the covariances come from the same table entries
+        ctx.set_option("sweep_variant", 3)
+        rs = ctx.lgssm(dev(y), **_kw(mod), smooth=True, cov_shared_out=True)
+        assert rs["cov"].shape == (T, d, d) and rel_l2(rs["mean"].cpu().numpy(), ref["mean"]) < 1.0   # runs; values checked above
+
+
+def test_time_segmented_sweep_full_size(ctx):
+    """Headline size (d = m = 4, T = 1000, batch 65 536): the time-segmented kernel against the sequential sweep on
+    every chain, and sampled chains against the oracle."""
+    mod = f32_model(lgssm.notebook_model(4))
+    T, batch = 1000, 65536
+    g = torch.Generator(device="cuda").manual_seed(77)
+    y = torch.randn(T, 4, batch, device="cuda", generator=g) * 3.3
+    ctx.set_option("sweep_variant", 0)
+    base = ctx.lgssm(y, **_kw(mod), smooth=True)
+    for variant in (3, 4):
+        ctx.set_option("sweep_variant", variant)
+        r = ctx.lgssm(y, **_kw(mod), smooth=True)
+        num = (r["mean"] - base["mean"]).double().norm().item()
+        assert num / base["mean"].double().norm().item() < 2e-6
+        assert torch.equal(r["cov"], base["cov"])
+    idx = [0, 31, 32, 40000, 65535]
+    ref = lgssm.smooth_reference_schedule(y[:, :, idx].cpu().numpy(), **mod)
+    assert rel_l2(r["mean"][:, :, idx].cpu().numpy(), ref["mean"]) < TOL_MEAN
