@@ -69,7 +69,7 @@ typedef enum rxg_option {
     RXG_OPT_GAIN_SEQ = 0,          /* 1: sequential Riccati gain kernels (cross-check of the time-parallel scan)   */
     RXG_OPT_LARGE_SEQ = 1,         /* 1: sequential gain kernels of the large-state family (cross-check)            */
     RXG_OPT_NO_UMMA = 2,           /* 1: d >= 16 mean recursions on the FP32 pipe instead of tcgen05 (cross-check)  */
-    RXG_OPT_SWEEP_VARIANT = 3,     /* shared-model sweep: 0 auto, 1 stash, 2 checkpoint+recompute, 3 time-segmented */
+    RXG_OPT_SWEEP_VARIANT = 3,     /* shared-model sweep: 0 auto, 1 stash, 3 time-segmented (experimental, slower)  */
     RXG_OPT_FORCE_CPT = 4,         /* chains per thread of the shared-model sweep (0 = auto)                        */
     RXG_OPT_HOST_THREADS = 5,      /* host threads of the host-side covariance broadcast (0 = auto)                 */
     RXG_OPT_HOST_COV_D2H = 6,      /* 1: host-pointer calls copy the per-chain covariances over PCIe (no broadcast) */
@@ -95,7 +95,9 @@ int rxg_sync(rxg_ctx* ctx);
 /* Pinned host memory for asynchronous staging of host-pointer calls.                           */
 int rxg_host_alloc(void** out, size_t bytes);
 int rxg_host_free(void* p);
-/* 1 if (d, m) is covered by the thread-per-chain kernel families, 0 otherwise.                 */
+/* 1 if the fused sweeps accept (d, m): any 1 <= d, m <= 64.  Shapes without a dedicated kernel family are
+ * embedded in the next larger one (shared model) or run on the generic one-CTA-per-chain kernel (per-chain
+ * models, missing data); see csrc/rxg_lgssm_general.cu.                                          */
 int rxg_supports(int d, int m);
 /* Host threads the library will use to broadcast chain-independent covariances into a HOST output
  * buffer (host-pointer calls of a shared model fetch the [T][d][d] table once instead of copying the
@@ -354,6 +356,9 @@ int rxg_allgather_posteriors(rxg_ctx*, int d, int T, int64_t batch_local, const 
 int rxg_device_alloc(rxg_ctx*, size_t bytes, void** dev_ptr);
 int rxg_device_free(rxg_ctx*, void* dev_ptr);
 int rxg_device_memset(rxg_ctx*, void* dev_ptr, int value, size_t bytes);
+/* synchronous copies on the ctx stream -- for hosts without a CUDA binding of their own (the Julia shim, C hosts)  */
+int rxg_memcpy_h2d(rxg_ctx*, void* dst_dev, const void* src_host, size_t bytes);
+int rxg_memcpy_d2h(rxg_ctx*, void* dst_host, const void* src_dev, size_t bytes);
 int rxg_peer_export(rxg_ctx*, const void* dev_ptr, void* handle64);
 int rxg_peer_open(rxg_ctx*, const void* handle64, void** dev_ptr);
 int rxg_peer_close(rxg_ctx*, void* dev_ptr);

@@ -82,6 +82,8 @@ SIGNATURES = {
     "rxg_device_alloc": (c_int, [c_void_p, c_size_t, POINTER(c_void_p)]),
     "rxg_device_free": (c_int, [c_void_p, c_void_p]),
     "rxg_device_memset": (c_int, [c_void_p, c_void_p, c_int, c_size_t]),
+    "rxg_memcpy_h2d": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
+    "rxg_memcpy_d2h": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
     "rxg_peer_export": (c_int, [c_void_p, c_void_p, c_void_p]),
     "rxg_peer_open": (c_int, [c_void_p, c_void_p, POINTER(c_void_p)]),
     "rxg_peer_close": (c_int, [c_void_p, c_void_p]),

@@ -153,6 +153,7 @@ int rxg_destroy(rxg_ctx* ctx) {
     if (ctx->stage) cudaFree(ctx->stage);
     if (ctx->d_bad) cudaFree(ctx->d_bad);
     if (ctx->d_tab) cudaFree(ctx->d_tab);
+    for (int i = 0; i < 4; ++i) if (ctx->aux_buf[i]) cudaFree(ctx->aux_buf[i]);
     if (ctx->h_bad) cudaFreeHost(ctx->h_bad);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->s_in) {
@@ -278,7 +279,7 @@ static int lgssm_entry(rxg_ctx* ctx, bool smooth, int d, int m, int T, int64_t b
     if (!cov && smooth && (flags & (RXG_MODEL_PER_CHAIN | RXG_PATH_PER_CHAIN)))
         return fail(ctx, RXG_ERR_BAD_ARG, "lgssm: post_cov is required on the per-chain path (it is the stash)");
     if (!lgssm_supported(d, m))
-        return fail(ctx, RXG_ERR_UNSUPPORTED, "lgssm: (d=%d, m=%d) is outside the thread-per-chain kernel families", d, m);
+        return fail(ctx, RXG_ERR_UNSUPPORTED, "lgssm: d and m must be in 1..64 (got d=%d, m=%d)", d, m);
     const bool per_chain_model = (flags & RXG_MODEL_PER_CHAIN) != 0;
     if ((flags & RXG_COV_SHARED_OUT) && (per_chain_model || (flags & RXG_PATH_PER_CHAIN) || ymask))
         return fail(ctx, RXG_ERR_BAD_ARG, "lgssm: RXG_COV_SHARED_OUT needs the shared-model gain-table path");
@@ -465,8 +466,6 @@ int rxg_lgssm_filter_chunk_f32(rxg_ctx* ctx, int d, int m, int T, int64_t batch,
         return fail(ctx, RXG_ERR_BAD_ARG, "lgssm_filter_chunk: null pointer argument");
     if (!lgssm_supported(d, m))
         return fail(ctx, RXG_ERR_UNSUPPORTED, "lgssm_filter_chunk: (d=%d, m=%d) is outside the compiled kernel families", d, m);
-    if (lgssm_large_supported(d, m) && u)
-        return fail(ctx, RXG_ERR_UNSUPPORTED, "lgssm_filter_chunk (d=%d): the large-state family has no transition offset", d);
     RXG_CUDA(ctx, cudaSetDevice(ctx->device));
     std::vector<float> zero((size_t)d, 0.f);
     LgssmCall c;

@@ -51,6 +51,9 @@ struct rxg_ctx {
     // [T][d][d] posterior-covariance table of the fused sweep + gather (source of the local replication)
     void* d_tab = nullptr;
     size_t tab_bytes = 0;
+    // grow-only scratch of the general-shape front end (padded operands, shifted observations)
+    void* aux_buf[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t aux_bytes[4] = {0, 0, 0, 0};
     // persistent host threads of the host-side covariance broadcast
     void* fill_pool = nullptr;
 };
@@ -109,8 +112,10 @@ struct LgssmCall {
 int launch_replicate_cov(rxg_ctx* ctx, cudaStream_t st, const float* src, int64_t src_stride, float* dst, int64_t rows,
                          int64_t b, int G, int skip);
 int ensure_aux_stream(rxg_ctx* ctx);
-// rxg_lgssm.cu
+// rxg_lgssm_general.cu: any (d, m) in 1..64 (native families, embedding, generic per-chain kernel)
 int lgssm_dispatch(rxg_ctx* ctx, LgssmCall& c);
+// rxg_lgssm.cu: the register-resident families (d <= 6 shapes)
+int lgssm_dispatch_native(rxg_ctx* ctx, LgssmCall& c);
 // status[i] = RXG_ERR_NOT_SPD if the ctx's gain-table failure flag is set on the device, else RXG_OK
 int fill_status_from_flag(rxg_ctx* ctx, int32_t* status, int64_t n);
 bool lgssm_supported(int d, int m);

@@ -398,9 +398,18 @@ static int launch_shared(rxg_ctx* ctx, LgssmCall& c, const ModelF<D, M>& mdl, co
     // checkpoint + recompute instead of the forward->backward stash (RXG_NO_CKPT=1: A/B switch)
     bool ckpt = c.smooth && (D * D <= 16) && (CPT == 2);   // with one chain per thread the stash path is faster (B200: 1.85 vs 2.06 ms)
     if (ctx->opt[RXG_OPT_SWEEP_VARIANT] == 1) ckpt = false;                     // stash variant (A/B switch)
+    // fused all-gather: only the headline variant (smoothing, no evidence, no offset) has a PEER instantiation;
+    // everything else leaves fused_peer_stores false and the caller pushes the finished slab
+    const bool peer = c.smooth && !evid && !has_u && (c.po.n_mean > 0 || c.po.n_cov > 0);
 #define RXG_LAUNCH_SHARED2(SM, EV, OF, CK)                                                         \
-    lgssm_shared_kernel<D, M, CPT, PF, SM, EV, OF, CK><<<blocks, threads, 0, ctx->stream>>>(       \
-        mdl, ws.fwd, ws.bwd, ws.sf, c.y, c.mean, c.cov, c.nle, c.T, c.batch, tf, write_cov, c.mean0_chain, c.po)
+    do {                                                                                           \
+        if (SM && !EV && !OF && peer)                                                              \
+            lgssm_shared_kernel<D, M, CPT, PF, SM, false, false, CK, true><<<blocks, threads, 0, ctx->stream>>>( \
+                mdl, ws.fwd, ws.bwd, ws.sf, c.y, c.mean, c.cov, c.nle, c.T, c.batch, tf, write_cov, c.mean0_chain, c.po); \
+        else                                                                                       \
+            lgssm_shared_kernel<D, M, CPT, PF, SM, EV, OF, CK><<<blocks, threads, 0, ctx->stream>>>( \
+                mdl, ws.fwd, ws.bwd, ws.sf, c.y, c.mean, c.cov, c.nle, c.T, c.batch, tf, write_cov, c.mean0_chain, c.po); \
+    } while (0)
 #define RXG_LAUNCH_SHARED(SM, EV)                                                                  \
     do {                                                                                           \
         if (SM && ckpt) { if (has_u) RXG_LAUNCH_SHARED2(SM, EV, true, true); else RXG_LAUNCH_SHARED2(SM, EV, false, true); } \
@@ -413,7 +422,7 @@ static int launch_shared(rxg_ctx* ctx, LgssmCall& c, const ModelF<D, M>& mdl, co
 #undef RXG_LAUNCH_SHARED2
     if (ctx->profile) cudaEventRecord(ctx->ev[2], ctx->stream);
     ctx->launches += 1;
-    c.fused_peer_stores = c.smooth;      // the smoothing kernels store the final posteriors to c.po themselves
+    c.fused_peer_stores = peer;          // the PEER instantiation stored the final posteriors to c.po itself
     return check_cuda(ctx, cudaGetLastError(), "lgssm_shared_kernel launch");
 }
 
@@ -445,12 +454,12 @@ static int launch_seg(rxg_ctx* ctx, LgssmCall& c, const ModelF<D, M>& mdl, const
         lgssm_seg_kernel<D, M, NW, OF, HI><<<grid, 32 * NW, smem, ctx->stream>>>(mdl, sw, c.y, c.mean, c.cov, c.T, c.batch, \
                                                                                  write_cov, c.mean0_chain, c.po, nseg);  \
     } while (0)
-    if (has_u) { if (hints) RXG_LAUNCH_SEG(true, 1); else RXG_LAUNCH_SEG(true, 0); }
-    else       { if (hints) RXG_LAUNCH_SEG(false, 1); else RXG_LAUNCH_SEG(false, 0); }
+    (void)hints;
+    if (has_u) RXG_LAUNCH_SEG(true, 1); else RXG_LAUNCH_SEG(false, 1);
 #undef RXG_LAUNCH_SEG
     if (ctx->profile) cudaEventRecord(ctx->ev[2], ctx->stream);
     ctx->launches += 2;
-    c.fused_peer_stores = true;
+    c.fused_peer_stores = false;
     return check_cuda(ctx, cudaGetLastError(), "lgssm_seg_kernel launch");
 }
 
@@ -518,7 +527,7 @@ static int run_shared_family(rxg_ctx* ctx, LgssmCall& c) {
     const int write_cov = (c.cov != nullptr && !cov_shared) ? 1 : 0;
     // sweep variant (RXG_OPT_SWEEP_VARIANT): 3 / 4 = time-segmented kernel with / without L2 eviction hints
     const long long variant = ctx->opt[RXG_OPT_SWEEP_VARIANT];
-    if ((variant == 3 || variant == 4) && seg_sweep_eligible<D, M>(c)) {
+    if (variant == 3 && seg_sweep_eligible<D, M>(c)) {
         SegWs sgw;
         sgw.rec = (float*)(base + o_srec_t); sgw.nrec = (float*)(base + o_snrec); sgw.srec = (float*)(base + o_ssrec);
         return launch_seg<D, M>(ctx, c, mdl, ws, sgw, write_cov, variant == 3);
@@ -568,16 +577,7 @@ int fill_status_from_flag(rxg_ctx* ctx, int32_t* status, int64_t n) {
     return check_cuda(ctx, cudaGetLastError(), "fill_status launch");
 }
 
-bool lgssm_supported(int d, int m) {
-    switch (d * 16 + m) {
-        case 1 * 16 + 1: case 2 * 16 + 1: case 2 * 16 + 2: case 3 * 16 + 3:
-        case 4 * 16 + 1: case 4 * 16 + 2: case 4 * 16 + 4: case 6 * 16 + 6:
-            return true;
-        default: return lgssm_large_supported(d, m);
-    }
-}
-
-int lgssm_dispatch(rxg_ctx* ctx, LgssmCall& c) {
+int lgssm_dispatch_native(rxg_ctx* ctx, LgssmCall& c) {
     switch (c.d * 16 + c.m) {
         case 1 * 16 + 1: return run_dm<1, 1>(ctx, c);
         case 2 * 16 + 1: return run_dm<2, 1>(ctx, c);
@@ -588,9 +588,8 @@ int lgssm_dispatch(rxg_ctx* ctx, LgssmCall& c) {
         case 4 * 16 + 4: return run_dm<4, 4>(ctx, c);
         case 6 * 16 + 6: return run_dm<6, 6>(ctx, c);
         default:
-            if (lgssm_large_supported(c.d, c.m)) return lgssm_large_dispatch(ctx, c);
             return fail(ctx, RXG_ERR_UNSUPPORTED,
-                        "lgssm: (d=%d, m=%d) is outside the compiled kernel families", c.d, c.m);
+                        "lgssm: (d=%d, m=%d) is outside the register-resident kernel families", c.d, c.m);
     }
 }
 

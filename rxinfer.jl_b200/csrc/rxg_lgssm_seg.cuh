@@ -21,7 +21,12 @@
 // the headline config -- inside the 126 MB L2 when the y lines are loaded evict_last in pass A, evict_first in pass B
 // and the 80 B/step of posterior stores are evict_first (createpolicy + .L2::cache_hint).  DRAM traffic per
 // (chain, step) then is 4 (m + d + d^2) = the algorithmic 96 B at d = m = 4 (checkpoint kernel: 114 B).
-// The fused all-gather (PeerOut) stores go out from pass B exactly as in lgssm_shared_kernel.
+// STATUS (B200, round 2): EXPERIMENTAL, not the default.  Measured 8.2 ms against 1.35 ms for lgssm_shared_kernel at
+// the headline config: with the 16-step segment held in registers the three fully unrolled loops make 31 K
+// instructions (500 KB of code) and the eight warps of a CTA sit at eight different places of it -- the kernel is
+// instruction-fetch bound (the same sensitivity showed on lgssm_shared_kernel when peer-store loops grew it from 3.4 K
+// to 11 K instructions: 1.35 -> 2.25 ms).  Kept selectable (RXG_OPT_SWEEP_VARIANT = 3) with its parity tests as the
+// record of the experiment; see DESIGN.md.
 #pragma once
 #include "rxg_lgssm_common.cuh"
 #include "rxg_lgssm_shared.cuh"
@@ -362,7 +367,6 @@ lgssm_seg_kernel(const __grid_constant__ ModelF<D, M> mdl, SegWs sw, const float
                             for (int i = 0; i < D; ++i) {
                                 const int64_t off = ((int64_t)t * D + i) * batch + b;
                                 if (HINTS) stg_hint(mean + off, sv[i], pol_stream); else mean[off] = sv[i];
-                                for (int g = 0; g < po.n_mean; ++g) po.mean[g][off] = sv[i];      // fused all-gather: NVLink P2P stores
                             }
                             if (write_cov) {
                                 float Ss[pad4(D * D)];
@@ -371,7 +375,6 @@ lgssm_seg_kernel(const __grid_constant__ ModelF<D, M> mdl, SegWs sw, const float
                                 for (int i = 0; i < D * D; ++i) {
                                     const int64_t off = ((int64_t)t * D * D + i) * batch + b;
                                     if (HINTS) stg_hint(cov + off, Ss[i], pol_stream); else cov[off] = Ss[i];
-                                    for (int g = 0; g < po.n_cov; ++g) po.cov[g][off] = Ss[i];
                                 }
                             }
                         }

@@ -95,7 +95,35 @@ __device__ __forceinline__ void stage_tables(float* sdst, const float* __restric
     cp_async_commit();
 }
 
-template <int D, int M, int CPT, int PF, bool SMOOTH, bool EVID, bool OFFSET, bool CKPT>
+// One step's posteriors to every peer: ONE rolled loop over the peers per step (not one per store site).
+template <int D, int CPT>
+__device__ __forceinline__ void peer_store(const PeerOut& po, int write_cov, int t, int64_t batch, int64_t b,
+                                           const float (&ms)[D][CPT], const float* Sst) {
+#pragma unroll 1
+    for (int g = 0; g < po.n_mean; ++g) {
+        float* pm = po.mean[g] + (int64_t)t * D * batch + b;
+#pragma unroll
+        for (int i = 0; i < D; ++i) Pack<CPT>::st(pm + (int64_t)i * batch, ms[i]);      // NVLink P2P stores
+    }
+    if (write_cov) {
+#pragma unroll 1
+        for (int g = 0; g < po.n_cov; ++g) {
+            float* pc = po.cov[g] + (int64_t)t * D * D * batch + b;
+#pragma unroll
+            for (int i = 0; i < D * D; ++i) {
+                float v[CPT];
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) v[c] = Sst[i];
+                Pack<CPT>::st(pc + (int64_t)i * batch, v);
+            }
+        }
+    }
+}
+
+// PEER: the final posteriors are also stored to the peer ranks' gathered buffers (fused all-gather, rxg_peer.cu).
+// A separate instantiation, because the kernel is instruction-cache sensitive: the loops over peers inside the
+// unrolled step bodies took the single-GPU kernel from 3.4 K to 11 K instructions and from 1.35 to 2.25 ms on B200.
+template <int D, int M, int CPT, int PF, bool SMOOTH, bool EVID, bool OFFSET, bool CKPT, bool PEER = false>
 __global__ void __launch_bounds__(32, 16 / CPT)   // CPT=1: <= 128 regs so ~14 warps/SM stay resident; wider CPT trades warps for ILP
 lgssm_shared_kernel(const __grid_constant__ ModelF<D, M> mdl, const float* __restrict__ fwd_tab,
                     const float* __restrict__ bwd_tab, const float* __restrict__ sf_tab,
@@ -423,25 +451,20 @@ lgssm_shared_kernel(const __grid_constant__ ModelF<D, M> mdl, const float* __res
                     for (int i = 0; i < D; ++i) {
 #pragma unroll
                         for (int c = 0; c < CPT; ++c) ms[i][c] = nm[i][c];
-                        if (active) {
-                            const int64_t off = ((int64_t)t * D + i) * batch + b;
-                            Pack<CPT>::st(mean + off, ms[i]);
-                            for (int g = 0; g < po.n_mean; ++g) Pack<CPT>::st(po.mean[g] + off, ms[i]);   // fused all-gather: NVLink P2P stores
-                        }
+                        if (active) Pack<CPT>::st(mean + ((int64_t)t * D + i) * batch + b, ms[i]);
                     }
+                    float Sst[pad4(D * D)];
                     if (write_cov && active) {
-                        float Sst[pad4(D * D)];
                         load_smem<pad4(D * D)>(rec + TB::SS_OFF, Sst);
 #pragma unroll
                         for (int i = 0; i < D * D; ++i) {
                             float v[CPT];
 #pragma unroll
                             for (int c = 0; c < CPT; ++c) v[c] = Sst[i];
-                            const int64_t off = ((int64_t)t * D * D + i) * batch + b;
-                            Pack<CPT>::st(cov + off, v);
-                            for (int g = 0; g < po.n_cov; ++g) Pack<CPT>::st(po.cov[g] + off, v);
+                            Pack<CPT>::st(cov + ((int64_t)t * D * D + i) * batch + b, v);
                         }
                     }
+                    if (PEER && active) peer_store<D, CPT>(po, write_cov, t, batch, b, ms, Sst);
                 }
             }
         }
@@ -507,25 +530,20 @@ lgssm_shared_kernel(const __grid_constant__ ModelF<D, M> mdl, const float* __res
                 for (int i = 0; i < D; ++i) {
 #pragma unroll
                     for (int c = 0; c < CPT; ++c) ms[i][c] = nm[i][c];
-                    if (active) {
-                        const int64_t off = ((int64_t)t * D + i) * batch + b;
-                        Pack<CPT>::st(mean + off, ms[i]);
-                        for (int g = 0; g < po.n_mean; ++g) Pack<CPT>::st(po.mean[g] + off, ms[i]);
-                    }
+                    if (active) Pack<CPT>::st(mean + ((int64_t)t * D + i) * batch + b, ms[i]);
                 }
+                float Sst[pad4(D * D)];
                 if (write_cov && active) {
-                    float Sst[pad4(D * D)];
                     load_smem<pad4(D * D)>(rec + TB::SS_OFF, Sst);
 #pragma unroll
                     for (int i = 0; i < D * D; ++i) {
                         float v[CPT];
 #pragma unroll
                         for (int c = 0; c < CPT; ++c) v[c] = Sst[i];
-                        const int64_t off = ((int64_t)t * D * D + i) * batch + b;
-                        Pack<CPT>::st(cov + off, v);
-                        for (int g = 0; g < po.n_cov; ++g) Pack<CPT>::st(po.cov[g] + off, v);
+                        Pack<CPT>::st(cov + ((int64_t)t * D * D + i) * batch + b, v);
                     }
                 }
+                if (PEER && active) peer_store<D, CPT>(po, write_cov, t, batch, b, ms, Sst);
             }
         }
 #pragma unroll

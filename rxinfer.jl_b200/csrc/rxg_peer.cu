@@ -155,6 +155,21 @@ int rxg_device_memset(rxg_ctx* ctx, void* dev_ptr, int value, size_t bytes) {
     return RXG_OK;
 }
 
+int rxg_memcpy_h2d(rxg_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+    if (!ctx || (bytes && (!dst_dev || !src_host))) return RXG_ERR_BAD_ARG;
+    RXG_CUDA(ctx, cudaSetDevice(ctx->device));
+    RXG_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    RXG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RXG_OK;
+}
+int rxg_memcpy_d2h(rxg_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+    if (!ctx || (bytes && (!dst_host || !src_dev))) return RXG_ERR_BAD_ARG;
+    RXG_CUDA(ctx, cudaSetDevice(ctx->device));
+    RXG_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    RXG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RXG_OK;
+}
+
 int rxg_peer_export(rxg_ctx* ctx, const void* dev_ptr, void* handle64) {
     if (!ctx || !dev_ptr || !handle64) return RXG_ERR_BAD_ARG;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");

@@ -5,5 +5,5 @@ mkdir -p gpurun_out
 timeout 2400 python -m pytest tests -m gpu -x -q -s 2>&1 | tail -60 > gpurun_out/r2a_pytest.txt
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/r2a_bench.json 2> gpurun_out/r2a_bench.err
 timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu --sweep-variant 3 > gpurun_out/r2a_bench_v3.json 2> gpurun_out/r2a_bench_v3.err
-timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu --sweep-variant 4 > gpurun_out/r2a_bench_v4.json 2> gpurun_out/r2a_bench_v4.err
-tail -12 gpurun_out/r2a_pytest.txt; head -c 1500 gpurun_out/r2a_bench.json; echo; head -c 900 gpurun_out/r2a_bench_v3.json; echo; head -c 900 gpurun_out/r2a_bench_v4.json; tail -3 gpurun_out/r2a_bench.err gpurun_out/r2a_bench_v3.err
+
+tail -12 gpurun_out/r2a_pytest.txt; head -c 1500 gpurun_out/r2a_bench.json; echo; head -c 900 gpurun_out/r2a_bench_v3.json; tail -n 3 gpurun_out/r2a_bench.err; tail -n 3 gpurun_out/r2a_bench_v3.err

@@ -466,8 +466,7 @@ def test_context_validates_arrays(ctx):
 
 @pytest.mark.parametrize("d,m", [(4, 4), (2, 2), (3, 3), (4, 2), (1, 1), (2, 1), (4, 1)])
 def test_time_segmented_sweep(ctx, d, m):
-    """lgssm_seg_kernel (sweep_variant 3 / 4: parallel in time inside a chain tile, with / without L2 eviction
-    hints) against the oracle and the sequential-in-time sweep: segment boundaries (T = 1, 15, 16, 17, 33, 1000),
+    """lgssm_seg_kernel (sweep_variant 3: parallel in time inside a chain tile; experimental, see the kernel header) against the oracle and the sequential-in-time sweep: segment boundaries (T = 1, 15, 16, 17, 33, 1000),
     ragged chain tiles, transition offset, prior one transition before the first datum, per-chain prior means."""
     rng = np.random.default_rng(300 + 10 * d + m)
     Aq, _ = np.linalg.qr(rng.standard_normal((d, d)))
@@ -480,7 +479,7 @@ def test_time_segmented_sweep(ctx, d, m):
             ref = lgssm.smooth_reference_schedule(y, **mod, **{k: (v.astype(np.float64) if k == "u" else v) for k, v in kw.items()})
             ctx.set_option("sweep_variant", 0)
             base = ctx.lgssm(dev(y), **_kw(mod), smooth=True, **kw)
-            for variant in (3, 4):
+            for variant in (3,):
                 ctx.set_option("sweep_variant", variant)
                 r = ctx.lgssm(dev(y), **_kw(mod), smooth=True, **kw)
                 check(r, ref, nle=False)
@@ -488,7 +487,8 @@ def test_time_segmented_sweep(ctx, d, m):
                 assert torch.equal(r["cov"], base["cov"])            # the covariances come from the same table entries
         ctx.set_option("sweep_variant", 3)
         rs = ctx.lgssm(dev(y), **_kw(mod), smooth=True, cov_shared_out=True)
-        assert rs["cov"].shape == (T, d, d) and rel_l2(rs["mean"].cpu().numpy(), ref["mean"]) < 1.0   # runs; values checked above
+        assert rs["cov"].shape == (T, d, d)
+        assert rel_l2(rs["mean"].cpu().numpy(), lgssm.smooth_reference_schedule(y, **mod)["mean"]) < TOL_MEAN
 
 
 def test_time_segmented_sweep_full_size(ctx):
@@ -500,7 +500,7 @@ def test_time_segmented_sweep_full_size(ctx):
     y = torch.randn(T, 4, batch, device="cuda", generator=g) * 3.3
     ctx.set_option("sweep_variant", 0)
     base = ctx.lgssm(y, **_kw(mod), smooth=True)
-    for variant in (3, 4):
+    for variant in (3,):
         ctx.set_option("sweep_variant", variant)
         r = ctx.lgssm(y, **_kw(mod), smooth=True)
         num = (r["mean"] - base["mean"]).double().norm().item()
