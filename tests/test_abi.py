@@ -48,7 +48,8 @@ def test_exports_are_plain_c(rx):
 def test_version_and_supports(rx):
     lib = rx._lib.load()
     assert lib.rxg_version() == 100
-    assert lib.rxg_supports(4, 4) == 1 and lib.rxg_supports(2, 2) == 1 and lib.rxg_supports(64, 64) == 1 and lib.rxg_supports(5, 5) == 0 and lib.rxg_supports(64, 32) == 0
+    assert lib.rxg_supports(4, 4) == 1 and lib.rxg_supports(2, 2) == 1 and lib.rxg_supports(64, 64) == 1 and lib.rxg_supports(5, 5) == 1 and lib.rxg_supports(64, 32) == 1 \
+        and lib.rxg_supports(65, 4) == 0 and lib.rxg_supports(4, 0) == 0
 
 
 def test_fails_loudly_without_gpu(rx):

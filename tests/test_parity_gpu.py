@@ -181,8 +181,8 @@ def test_infer_entry_point(rx, ctx):
 
 
 def test_unsupported_shape_errors_loudly(rx, ctx):
-    mod = lgssm.dense_model(5)
-    y = torch.zeros(4, 5, 2, device="cuda")
+    mod = lgssm.dense_model(65)
+    y = torch.zeros(4, 65, 2, device="cuda")
     with pytest.raises(rx.RxGaussError) as e:
         ctx.lgssm(y, **_kw(mod), smooth=True)
     assert e.value.code == rx._lib.RXG_ERR_UNSUPPORTED
@@ -349,15 +349,76 @@ def test_large_state_family(ctx, d, T, batch):
     assert rel_l2(f["cov"].cpu().numpy(), reff["cov"]) < TOL_COV
 
 
-def test_large_state_unsupported_options_fail_loudly(rx, ctx):
+def _random_model(rng, d, m, scale_a=0.9):
+    Aq, _ = np.linalg.qr(rng.standard_normal((d, d)))
+    L = rng.standard_normal((d, d)) * 0.1
+    return f32_model(dict(A=scale_a * Aq, B=rng.standard_normal((m, d)) / np.sqrt(d), P=0.2 * np.eye(d) + L @ L.T,
+                          Q=1.5 * np.eye(m), m0=rng.standard_normal(d), S0=5.0 * np.eye(d)))
+
+
+@pytest.mark.parametrize("d,m", [(5, 5), (5, 3), (7, 7), (3, 2), (2, 3), (6, 4), (10, 10), (12, 7), (24, 24), (33, 20), (64, 32)])
+def test_general_shapes_shared_model(ctx, d, m):
+    """Any (d, m) <= 64: shapes without a dedicated kernel family are embedded in the next native one (decoupled
+    dummy coordinates; the evidence is corrected for the dummy observations).  Smoothing, filtering, evidence,
+    transition offset, prior one transition earlier, de-duplicated covariance output."""
+    rng = np.random.default_rng(1000 + 64 * d + m)
+    mod = _random_model(rng, d, m)
+    T, batch = 40, 37
+    _, y = lgssm.generate_data(mod, T, batch, seed=d * 100 + m)
+    u = (0.2 * rng.standard_normal(d)).astype(np.float32)
+    for kw in (dict(), dict(u=u, transition_first=True)):
+        kw64 = {k: (v.astype(np.float64) if k == "u" else v) for k, v in kw.items()}
+        ref = lgssm.smooth_reference_schedule(y, **mod, **kw64)
+        check(ctx.lgssm(dev(y), **_kw(mod), smooth=True, want_evidence=True, **kw), ref)
+        check(ctx.lgssm(dev(y), **_kw(mod), smooth=False, want_evidence=True, **kw), ref, smooth=False)
+    r = ctx.lgssm(dev(y), **_kw(mod), smooth=True, cov_shared_out=True)
+    assert r["cov"].shape == (T, d, d)
+    assert rel_l2(r["cov"].cpu().numpy(), ref0 := lgssm.smooth_reference_schedule(y, **mod)["cov"][..., 0]) < TOL_COV
+
+
+@pytest.mark.parametrize("d,m", [(5, 3), (8, 8), (9, 4), (16, 16), (20, 12), (64, 64)])
+def test_general_shapes_per_chain_and_masks(ctx, d, m):
+    """Per-chain models, missing data and the forced per-chain path for shapes beyond the register kernels:
+    lgssm_generic_chain_kernel (one CTA per chain, runtime d and m) -- round 1 returned RXG_ERR_UNSUPPORTED for d >= 8."""
+    rng = np.random.default_rng(2000 + 64 * d + m)
+    mod = _random_model(rng, d, m)
+    T, batch = (24, 9) if d < 64 else (12, 5)
+    _, y = lgssm.generate_data(mod, T, batch, seed=d + m)
+    mask = (rng.random((T, batch)) > 0.3).astype(np.uint8)
+    mask[-3:, 0] = 0                                         # trailing gap
+    mask[:, 1] = 0                                           # prior only
+    u = (0.2 * rng.standard_normal(d)).astype(np.float32)
+    ref = lgssm.smooth_reference_schedule(y, **mod, mask=mask)
+    r = ctx.lgssm(dev(y), **_kw(mod), smooth=True, mask=dev(mask, torch.uint8), want_evidence=True, want_status=True)
+    check(r, ref)
+    assert int(r["status"].abs().sum()) == 0
+    f = ctx.lgssm(dev(y), **_kw(mod), smooth=False, mask=dev(mask, torch.uint8), want_evidence=True)
+    check(f, ref, smooth=False)
+    refu = lgssm.smooth_reference_schedule(y, **mod, u=u.astype(np.float64), transition_first=True)
+    check(ctx.lgssm(dev(y), **_kw(mod), u=u, smooth=True, transition_first=True, force_per_chain_path=True, want_evidence=True), refu)
+    # per-chain models: every chain its own (A, B, P, Q, m0, S0)
+    mods = [_random_model(rng, d, m) for _ in range(batch)]
+    stack = lambda k: dev(np.stack([mm[k] for mm in mods], axis=-1))
+    rp = ctx.lgssm(dev(y), stack("A"), stack("B"), stack("P"), stack("Q"), stack("m0"), stack("S0"), smooth=True,
+                   per_chain_model=True, want_evidence=True)
+    for b in range(batch):
+        rb = lgssm.smooth_reference_schedule(y[:, :, b:b + 1], **mods[b])
+        assert rel_l2(rp["mean"][:, :, b].cpu().numpy(), rb["mean"][:, :, 0]) < 3 * TOL_MEAN
+        assert rel_l2(rp["cov"][..., b].cpu().numpy(), rb["cov"][..., 0]) < TOL_COV
+        assert abs(float(rp["neg_log_evidence"][b]) - rb["neg_log_evidence"][0]) / abs(rb["neg_log_evidence"][0]) < 5 * TOL_NLE
+
+
+def test_large_state_offset_by_linearity(ctx):
+    """Transition offset on the tensor-core family (round 1: RXG_ERR_UNSUPPORTED): removed by linearity, the sweep
+    itself runs offset free; also through the streaming chunk entry."""
+    rng = np.random.default_rng(9)
     mod = f32_model(lgssm.dense_model(16))
-    y = torch.zeros(8, 16, 4, device="cuda")
-    with pytest.raises(rx.RxGaussError) as e:
-        ctx.lgssm(y, **_kw(mod), smooth=True, u=np.ones(16, np.float32))
-    assert e.value.code == rx._lib.RXG_ERR_UNSUPPORTED
-    with pytest.raises(rx.RxGaussError) as e:
-        ctx.lgssm(y, **_kw(mod), smooth=True, mask=torch.ones(8, 4, dtype=torch.uint8, device="cuda"))
-    assert e.value.code == rx._lib.RXG_ERR_UNSUPPORTED
+    u = (0.3 * rng.standard_normal(16)).astype(np.float32)
+    _, y = lgssm.generate_data(mod, 50, 70, seed=12)
+    for tf in (False, True):
+        ref = lgssm.smooth_reference_schedule(y, **mod, u=u.astype(np.float64), transition_first=tf)
+        check(ctx.lgssm(dev(y), **_kw(mod), u=u, smooth=True, transition_first=tf, want_evidence=True), ref)
+        check(ctx.lgssm(dev(y), **_kw(mod), u=u, smooth=False, transition_first=tf, want_evidence=True), ref, smooth=False)
 
 
 @pytest.mark.parametrize("d,T", [(16, 1), (16, 2), (16, 37), (32, 130), (64, 257)])
