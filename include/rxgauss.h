@@ -322,6 +322,9 @@ int rxg_selftest_umma_shape_f32(rxg_ctx*, int n, int k, const float* A, const fl
 int rxg_selftest_stream_f32(rxg_ctx*, int64_t n, int n_read, int n_write, const float* src, float* dst,
                             unsigned flags);
 
+/* Diagnostic: write bandwidth (GB/s) of the host-side covariance broadcast into dst[rows][batch] (host memory).      */
+double rxg_selftest_host_fill_gbs(float* dst, int64_t rows, int64_t batch, int nthreads, int reps);
+
 /* ------------------------------------------------------------------ multi-GPU ----------------
  * Chains are independent: rank g owns chains [g*batch/G, (g+1)*batch/G); the only collective is
  * the all-gather of posterior marginals at the end (the reference has no distributed path).

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_longlong, c_size_t, c_uint, c_uint8, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_longlong, c_size_t, c_uint, c_uint8, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 # RXG_LIB selects an A/B build of the same library (tuning experiments); the product is librxgauss.so
@@ -76,6 +76,7 @@ SIGNATURES = {
     "rxg_selftest_umma_f32": (c_int, [c_void_p, fp, fp, fp, c_uint]),
     "rxg_selftest_umma_shape_f32": (c_int, [c_void_p, c_int, c_int, fp, fp, fp, c_uint]),
     "rxg_selftest_stream_f32": (c_int, [c_void_p, c_int64, c_int, c_int, fp, fp, c_uint]),
+    "rxg_selftest_host_fill_gbs": (c_double, [fp, c_int64, c_int64, c_int, c_int]),
     "rxg_comm_unique_id": (c_int, [c_void_p]),
     "rxg_comm_init": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "rxg_allgather_posteriors": (c_int, [c_void_p, c_int, c_int, c_int64, fp, fp, fp, fp, c_uint]),

@@ -16,7 +16,8 @@ LGSSM_SHAPES = [(1, 1), (2, 1), (2, 2), (3, 3), (4, 1), (4, 2), (4, 4), (6, 6)]
 UNITS = ([("rxg_lgssm.cu", f"rxg_lgssm_d{d}m{m}", (f"-DRXG_INST_D={d}", f"-DRXG_INST_M={m}")) for d, m in reversed(LGSSM_SHAPES)] +
          [(s, s.replace(".cu", ""), ()) for s in
           ("rxg_lgssm_large.cu", "rxg_lgssm.cu", "rxg_umma_sweep.cu", "rxg_api.cu", "rxg_peer.cu", "rxg_rules.cu", "rxg_hgf.cu",
-           "rxg_lgssm_general.cu", "rxg_lgssm_generic.cu")])
+           "rxg_lgssm_general.cu", "rxg_lgssm_generic.cu")] +
+         [("rxg_hostfill.cpp", "rxg_hostfill", ())])        # plain C++ (g++): host-side covariance broadcast
 SOURCES = sorted({u[0] for u in UNITS})
 HEADERS = ["rxg_internal.h", "rxg_linalg.cuh", "rxg_gain.cuh", "rxg_lgssm_common.cuh", "rxg_lgssm_shared.cuh", "rxg_lgssm_seg.cuh", "rxg_umma.cuh", os.path.join("..", "..", "include", "rxgauss.h")]
 NVCC_FLAGS = [
@@ -52,7 +53,10 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), lib: str =
     def compile_one(unit):
         src, stem, defs = unit
         obj = os.path.join(objdir, stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, *defs, "-c", os.path.join(CSRC, src), "-o", obj]
+        if src.endswith(".cpp"):
+            cmd = ["g++", "-O3", "-std=c++17", "-fPIC", "-pthread", "-Wall", "-c", os.path.join(CSRC, src), "-o", obj]
+        else:
+            cmd = [nvcc, *NVCC_FLAGS, *extra_flags, *defs, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = os.path.join(objdir, stem + ".ptxas.log")
         with open(log, "w") as f:

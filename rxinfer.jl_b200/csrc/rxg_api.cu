@@ -245,28 +245,6 @@ static int host_fill_threads() {
     }();
     return cached;
 }
-// dst[0..n) = v with non-temporal stores (the caller's buffer is write-only here)
-static void fill_row(float* dst, int64_t n, float v) {
-    int64_t i = 0;
-    while (i < n && (reinterpret_cast<uintptr_t>(dst + i) & 31)) dst[i++] = v;
-    const __m256 vv = _mm256_set1_ps(v);
-    for (; i + 8 <= n; i += 8) _mm256_stream_ps(dst + i, vv);
-    for (; i < n; ++i) dst[i] = v;
-}
-// cov[row][b] = tab[row] for rows [0, rows): the chain-independent covariances of a shared model, broadcast on the
-// HOST side of the PCIe link (4 d^2 bytes per (chain, step) that never have to cross it)
-static void host_broadcast_cov(float* cov, const float* tab, int64_t rows, int64_t batch, int nthreads) {
-    auto work = [=](int tid) {
-        const int64_t lo = rows * tid / nthreads, hi = rows * (tid + 1) / nthreads;
-        for (int64_t r = lo; r < hi; ++r) fill_row(cov + r * batch, batch, tab[r]);
-        _mm_sfence();
-    };
-    std::vector<std::thread> th;
-    for (int t = 1; t < nthreads; ++t) th.emplace_back(work, t);
-    work(0);
-    for (auto& t : th) t.join();
-}
-
 extern "C" int rxg_host_fill_threads(void) { return host_fill_threads(); }
 
 static int lgssm_entry(rxg_ctx* ctx, bool smooth, int d, int m, int T, int64_t batch, const float* A,

@@ -108,6 +108,8 @@ struct LgssmCall {
     bool fused_peer_stores = false;    // out: the sweep kernel itself stored to c.po (else the caller pushes the slabs)
 };
 
+// rxg_hostfill.cpp (plain C++): cov[row][b] = tab[row], non-temporal stores by NUMA-pinned host threads
+void host_broadcast_cov(float* cov, const float* tab, int64_t rows, int64_t batch, int nthreads);
 // rxg_peer.cu
 int launch_replicate_cov(rxg_ctx* ctx, cudaStream_t st, const float* src, int64_t src_stride, float* dst, int64_t rows,
                          int64_t b, int G, int skip);
