@@ -182,6 +182,31 @@ int rxg_rule_normal_precision_tau_f32(rxg_ctx*, int64_t n, const float* m_out, c
 int rxg_rule_normal_precision_out_f32(rxg_ctx*, int64_t n, const float* m_mu, const float* v_mu,
                                       const float* shape, const float* rate, float* m_out,
                                       float* v_out, unsigned flags);
+/* structured variant (q_out_mu jointly Gaussian, m_joint[2][n], V_joint[2][2][n]): GammaShapeRate(3/2,
+ * 1/2 [V11 + V22 - V12 - V21 + (m1 - m2)^2])  (upstream rules/normal_mean_precision/precision.jl)              */
+int rxg_rule_normal_precision_tau_joint_f32(rxg_ctx*, int64_t n, const float* m_joint, const float* V_joint,
+                                            float* shape, float* rate, unsigned flags);
+/* Wishart precision -- the multivariate twin of the Gamma rules, in the WishartFast parametrisation (df, INVERSE
+ * scale) so that products are additions [ref: test/models/iid/mv_iid_precision_tests.jl:10-41]:
+ * @rule MvNormalMeanPrecision(:Lambda)(q_out, q_mu) -> Wishart(d + 2, inv(V_out + V_mu + (m_out - m_mu)(m_out - m_mu)'))  */
+int rxg_rule_mvnormal_precision_lambda_f32(rxg_ctx*, int64_t n, int d, const float* m_out, const float* V_out,
+                                           const float* m_mu, const float* V_mu, float* df, float* inv_scale,
+                                           unsigned flags);
+/* prod(Wishart, Wishart) = Wishart(df1 + df2 - d - 1, inv(inv(S1) + inv(S2)))                                   */
+int rxg_prod_wishart_f32(rxg_ctx*, int64_t n, int d, const float* df1, const float* inv_scale1, const float* df2,
+                         const float* inv_scale2, float* df, float* inv_scale, unsigned flags);
+/* mean(Wishart(df, S)) = df * S = df * inv(inv_scale); status[n] optional                                      */
+int rxg_wishart_mean_f32(rxg_ctx*, int64_t n, int d, const float* df, const float* inv_scale, float* mean,
+                         int32_t* status, unsigned flags);
+/* Fused mean-field VMP of the multivariate IID model with unknown mean and precision, `batch` independent data sets:
+ *   m ~ MvNormal(mu0, inv(Lambda0)),  P ~ Wishart(nu0, inv(inv_scale0)),  y[i] ~ MvNormal(m, inv(P)),  q(m) q(P)
+ * [ref: model, constraints and initialisation test/models/iid/mv_iid_precision_tests.jl:10-41].  y[N][d][batch];
+ * init_E_P[d][d] = mean of the initial q(P) (host); outputs q(m) = (m_mean[d][batch], m_cov[d][d][batch]),
+ * q(P) = Wishart(df[batch], inv(inv_scale[d][d][batch])).  d <= 6.                                                */
+int rxg_mv_iid_wishart_vmp_f32(rxg_ctx*, int d, int N, int64_t batch, int iterations, const float* mu0,
+                               const float* Lambda0, float nu0, const float* inv_scale0, const float* init_E_P,
+                               const float* y, float* m_mean, float* m_cov, float* df, float* inv_scale,
+                               int32_t* status, unsigned flags);
 /* prod(GammaShapeRate, GammaShapeRate) = (a1 + a2 - 1, b1 + b2)                                 */
 int rxg_prod_gamma_f32(rxg_ctx*, int64_t n, const float* a1, const float* b1, const float* a2,
                        const float* b2, float* a, float* b, unsigned flags);

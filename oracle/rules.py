@@ -182,6 +182,27 @@ def normal_meanprec_tau_structured(m, V):
     )
 
 
+def mvnormal_meanprec_lambda(q_out, q_mu):
+    """@rule MvNormalMeanPrecision(:Lambda)(q_out, q_mu) (mean-field): Wishart(d + 2, inv(V_out + V_mu + (m_out - m_mu)
+    (m_out - m_mu)')) -- returned in the WishartFast parametrisation (df, INVERSE scale).  Exercised by
+    /root/reference/test/models/iid/mv_iid_precision_tests.jl:10-16 (upstream rules/mv_normal_mean_precision/precision.jl)."""
+    (mo, Vo), (mm, Vm) = q_out, q_mu
+    dlt = mo - mm
+    d = mo.shape[-1]
+    return d + 2.0 + 0.0 * mo[..., 0], Vo + Vm + dlt[..., :, None] * dlt[..., None, :]
+
+
+def prod_wishart(l, r):
+    """prod(Wishart(nu1, S1), Wishart(nu2, S2)) = Wishart(nu1 + nu2 - d - 1, inv(inv(S1) + inv(S2))); (df, inverse scale) I/O."""
+    d = l[1].shape[-1]
+    return l[0] + r[0] - d - 1.0, l[1] + r[1]
+
+
+def wishart_mean(w):
+    """mean(Wishart(df, S)) = df S, with S = inv(inverse scale)."""
+    return w[0][..., None, None] * np.linalg.inv(w[1])
+
+
 def prod_gamma(l, r):
     """``prod(GammaShapeRate, GammaShapeRate)`` = GammaShapeRate(a1 + a2 - 1, b1 + b2)."""
     return l[0] + r[0] - 1.0, l[1] + r[1]

@@ -148,3 +148,36 @@ def stream_vmp_gamma(y, iterations=4, w=1.0, init_x=(0.0, 1e3), init_tau=(1.0, 1
                 fe[t, it] = U1 + U2 + U3 + U4 - H
         out[t, 0], out[t, 1], out[t, 2], out[t, 3] = mx, vx, a, b
     return (out, fe) if return_free_energy else out
+
+
+def mv_iid_wishart(y, iterations=10, mu0=None, Lambda0=None, nu0=None, inv_scale0=None, init_E_P=None):
+    """Mean-field VMP of /root/reference/test/models/iid/mv_iid_precision_tests.jl:10-41, message by message:
+
+        m ~ MvNormal(mu = 0, Lambda = 100 I);  P ~ Wishart(d + 1, I);  y[i] ~ MvNormal(mu = m, Lambda = P);  q(m) q(P)
+
+    y[N, d, batch] -> dict(m_mean[d, batch], m_cov[d, d, batch], df[batch], inv_scale[d, d, batch]).
+    Per iteration: q(m) = prior x prod_i MvNormalMeanPrecision(:mu)(q_out = y_i, q_Lambda) (precision E[P] each);
+    q(P) = prior x prod_i MvNormalMeanPrecision(:Lambda)(q_out = y_i, q_mu) (rules.mvnormal_meanprec_lambda / prod_wishart).
+    The initial q(P) enters through its mean only (``vague(Wishart, d)`` in the reference: df = d, scale 1e12 I)."""
+    y = np.asarray(y, dtype=np.float64)
+    N, d, batch = y.shape
+    mu0 = np.zeros(d) if mu0 is None else np.asarray(mu0, np.float64)
+    Lambda0 = 100.0 * np.eye(d) if Lambda0 is None else np.asarray(Lambda0, np.float64)
+    nu0 = d + 1.0 if nu0 is None else float(nu0)
+    inv_scale0 = np.eye(d) if inv_scale0 is None else np.asarray(inv_scale0, np.float64)
+    EP = np.broadcast_to(d * 1e12 * np.eye(d) if init_E_P is None else np.asarray(init_E_P, np.float64), (batch, d, d)).copy()
+    yb = np.moveaxis(y, 2, 0)                                  # [batch, N, d]
+    for _ in range(iterations):
+        Lm = Lambda0 + N * EP
+        Vm = np.linalg.inv(Lm)
+        xi = Lambda0 @ mu0 + np.einsum("bij,bj->bi", EP, yb.sum(axis=1))
+        m = np.einsum("bij,bj->bi", Vm, xi)
+        w = (np.full(batch, nu0), np.broadcast_to(inv_scale0, (batch, d, d)).copy())
+        # fold the N Wishart messages (left to right, as the reference's product fold does)
+        df_acc, is_acc = w
+        msg = R.mvnormal_meanprec_lambda((yb, np.zeros((batch, N, d, d))), (m[:, None, :], Vm[:, None, :, :]))
+        for i in range(N):
+            df_acc, is_acc = R.prod_wishart((df_acc, is_acc), (msg[0][:, i], msg[1][:, i]))
+        EP = R.wishart_mean((df_acc, is_acc))
+    return dict(m_mean=m.T.copy(), m_cov=np.moveaxis(Vm, 0, 2).copy(), df=df_acc, inv_scale=np.moveaxis(is_acc, 0, 2).copy(),
+                E_P=np.moveaxis(EP, 0, 2).copy())

@@ -346,6 +346,57 @@ class Context:
     def rule_normal_precision_out(self, m_mu, v_mu, shape, rate):
         return self._six(self.lib.rxg_rule_normal_precision_out_f32, m_mu, v_mu, shape, rate)
 
+    def rule_normal_precision_tau_joint(self, m_joint, V_joint):
+        """Structured tau rule: q(out, mu) jointly Gaussian, m_joint[2, n], V_joint[2, 2, n]."""
+        self._dev(m_joint, V_joint)
+        n = m_joint.shape[-1]
+        sh, rt = self.empty(n), self.empty(n)
+        self._check(self.lib.rxg_rule_normal_precision_tau_joint_f32(self.h, n, _fp(m_joint), _fp(V_joint), _fp(sh), _fp(rt), L.PTR_DEVICE))
+        return sh, rt
+
+    def rule_mvnormal_precision_lambda(self, m_out, V_out, m_mu, V_mu):
+        self._dev(m_out, V_out, m_mu, V_mu)
+        d, n = m_out.shape
+        df, iS = self.empty(n), self.empty(d, d, n)
+        self._check(self.lib.rxg_rule_mvnormal_precision_lambda_f32(self.h, n, d, _fp(m_out), _fp(V_out), _fp(m_mu), _fp(V_mu),
+                                                                    _fp(df), _fp(iS), L.PTR_DEVICE))
+        return df, iS
+
+    def prod_wishart(self, df1, iS1, df2, iS2):
+        self._dev(df1, iS1, df2, iS2)
+        d, n = iS1.shape[0], iS1.shape[-1]
+        df, iS = self.empty(n), self.empty(d, d, n)
+        self._check(self.lib.rxg_prod_wishart_f32(self.h, n, d, _fp(df1), _fp(iS1), _fp(df2), _fp(iS2), _fp(df), _fp(iS), L.PTR_DEVICE))
+        return df, iS
+
+    def wishart_mean(self, df, iS):
+        self._dev(df, iS)
+        d, n = iS.shape[0], iS.shape[-1]
+        out = self.empty(d, d, n)
+        st = self.empty(n, dtype=torch.int32)
+        self._check(self.lib.rxg_wishart_mean_f32(self.h, n, d, _fp(df), _fp(iS), _fp(out),
+                                                  ctypes.cast(c_void_p(st.data_ptr()), L.i32p), L.PTR_DEVICE))
+        return out, st
+
+    def mv_iid_wishart_vmp(self, y, iterations=10, mu0=None, Lambda0=None, nu0=None, inv_scale0=None, init_E_P=None):
+        """Fused mean-field VMP of the multivariate IID model with Wishart precision (``rxg_mv_iid_wishart_vmp_f32``);
+        y[N, d, batch]; defaults = the reference test's priors (mv_iid_precision_tests.jl:10-30)."""
+        self._dev(y)
+        N, d, batch = y.shape
+        mu0 = np.zeros(d) if mu0 is None else mu0
+        Lambda0 = 100.0 * np.eye(d) if Lambda0 is None else Lambda0
+        nu0 = d + 1.0 if nu0 is None else nu0
+        inv_scale0 = np.eye(d) if inv_scale0 is None else inv_scale0
+        init_E_P = d * 1e12 * np.eye(d) if init_E_P is None else init_E_P       # mean of vague(Wishart, d)
+        keep = [_model32(x) for x in (mu0, Lambda0, inv_scale0, init_E_P)]
+        mm, mc = self.empty(d, batch), self.empty(d, d, batch)
+        df, iS = self.empty(batch), self.empty(d, d, batch)
+        st = self.empty(batch, dtype=torch.int32)
+        self._check(self.lib.rxg_mv_iid_wishart_vmp_f32(self.h, d, N, batch, iterations, keep[0][1], keep[1][1], float(nu0),
+                                                        keep[2][1], keep[3][1], _fp(y), _fp(mm), _fp(mc), _fp(df), _fp(iS),
+                                                        ctypes.cast(c_void_p(st.data_ptr()), L.i32p), L.PTR_DEVICE))
+        return dict(m_mean=mm, m_cov=mc, df=df, inv_scale=iS, status=st)
+
     def prod_gamma(self, a1, b1, a2, b2):
         return self._six(self.lib.rxg_prod_gamma_f32, a1, b1, a2, b2)
 

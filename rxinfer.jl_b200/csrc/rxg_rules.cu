@@ -177,6 +177,126 @@ __global__ void k_prod_normal(int64_t n, const float* m1, const float* v1, const
     v[i] = vv;
 }
 
+// structured variant of the tau rule: q(out, mu) jointly Gaussian (m[2][n], V[2][2][n]):
+// GammaShapeRate(3/2, 1/2 [V11 + V22 - V12 - V21 + (m1 - m2)^2])
+__global__ void k_normal_precision_tau_joint(int64_t n, const float* m, const float* V, float* shape, float* rate) {
+    RXG_TID
+    const float d = m[i] - m[n + i];
+    shape[i] = 1.5f;
+    rate[i] = 0.5f * (__fmaf_rn(d, d, V[i] + V[3 * n + i]) - V[n + i] - V[2 * n + i]);
+}
+
+// ---- Wishart precision (multivariate twin of the Gamma rules), WishartFast parametrisation (df, inverse scale)
+// @rule MvNormalMeanPrecision(:Lambda)(q_out, q_mu) -> Wishart(d + 2, inv(V_out + V_mu + (m_out - m_mu)(m_out - m_mu)'))
+template <int D>
+__global__ void k_mvn_precision_lambda(int64_t n, const float* mo, const float* Vo, const float* mm, const float* Vm,
+                                       float* df, float* invS) {
+    RXG_TID
+    Vec<float, D> a = ld_vec<D>(mo, n, i), b = ld_vec<D>(mm, n, i);
+    Mat<float, D, D> S = add(ld_soa<D, D>(Vo, n, i), ld_soa<D, D>(Vm, n, i));
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+        for (int c = 0; c < D; ++c) S(r, c) = __fmaf_rn(a(r) - b(r), a(c) - b(c), S(r, c));
+    df[i] = (float)(D + 2);
+    st_soa<D, D>(invS, n, i, S);
+}
+// prod(Wishart(nu1, S1), Wishart(nu2, S2)) = Wishart(nu1 + nu2 - d - 1, inv(inv(S1) + inv(S2))): adds in this parametrisation
+template <int D>
+__global__ void k_prod_wishart(int64_t n, const float* df1, const float* iS1, const float* df2, const float* iS2,
+                               float* df, float* iS) {
+    RXG_TID
+    df[i] = df1[i] + df2[i] - (float)(D + 1);
+    st_soa<D, D>(iS, n, i, add(ld_soa<D, D>(iS1, n, i), ld_soa<D, D>(iS2, n, i)));
+}
+// mean(Wishart(nu, S)) = nu S = nu inv(invS)
+template <int D>
+__global__ void k_wishart_mean(int64_t n, const float* df, const float* iS, float* EL, int32_t* status) {
+    RXG_TID
+    bool bad = false;
+    Mat<float, D, D> S = cholinv(ld_soa<D, D>(iS, n, i), bad);
+    const float nu = df[i];
+#pragma unroll
+    for (int k = 0; k < D * D; ++k) S.a[k] *= nu;
+    st_soa<D, D>(EL, n, i, S);
+    if (status) status[i] = bad ? RXG_ERR_NOT_SPD : RXG_OK;
+}
+
+// Fused mean-field VMP of the multivariate IID model with unknown mean and precision
+//   m ~ MvNormal(mu0, Lambda0^-1),  P ~ Wishart(nu0, S0),  y_i ~ MvNormal(m, P^-1),  q(m, P) = q(m) q(P)
+// [ref: /root/reference/test/models/iid/mv_iid_precision_tests.jl:10-41].  One thread = one dataset: the sufficient
+// statistics (sum y, sum y y') are accumulated in ONE coalesced pass over y[N][d][batch]; every VMP iteration is then
+// O(d^3) in registers:   q(m): Lambda = Lambda0 + N E[P],  xi = Lambda0 mu0 + E[P] sum y
+//                        q(P): Wishart(nu0 + N, inv(inv(S0) + sum_i [(y_i - m)(y_i - m)' + V_m]))
+template <int D>
+__global__ void __launch_bounds__(128)
+mv_iid_wishart_vmp_kernel(const float* __restrict__ y, int N, int64_t batch, int iters, const float* __restrict__ prior,
+                          float* __restrict__ m_out, float* __restrict__ V_out, float* __restrict__ df_out,
+                          float* __restrict__ iS_out, int32_t* __restrict__ status) {
+    // prior (device, row-major): mu0[D], Lambda0[D*D], nu0, invS0[D*D], E[P] of the initial q(P) [D*D]
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    Vec<double, D> sy;
+    Mat<double, D, D> syy;
+#pragma unroll
+    for (int i = 0; i < D; ++i) sy(i) = 0.0;
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) syy.a[i] = 0.0;
+    for (int t = 0; t < N; ++t) {
+        float v[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) v[i] = __ldg(y + ((int64_t)t * D + i) * batch + b);
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            sy(i) += (double)v[i];
+#pragma unroll
+            for (int j = 0; j <= i; ++j) syy(i, j) += (double)v[i] * (double)v[j];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = i + 1; j < D; ++j) syy(i, j) = syy(j, i);
+    Vec<double, D> mu0;
+    Mat<double, D, D> L0, iS0, EP;
+#pragma unroll
+    for (int i = 0; i < D; ++i) mu0(i) = (double)prior[i];
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) { L0.a[i] = (double)prior[D + i]; iS0.a[i] = (double)prior[D + D * D + 1 + i]; EP.a[i] = (double)prior[D + 2 * D * D + 1 + i]; }
+    const double nu0 = (double)prior[D + D * D];
+    const Vec<double, D> xi0 = mulv(L0, mu0);
+    bool bad = false;
+    Vec<double, D> m;
+    Mat<double, D, D> Vm, iS;
+    const double nu = nu0 + (double)N;
+    for (int it = 0; it < iters; ++it) {
+        // q(m)
+        Mat<double, D, D> Lm;
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) Lm.a[i] = L0.a[i] + (double)N * EP.a[i];
+        Vm = cholinv(Lm, bad);
+        Vec<double, D> xi = mulv(EP, sy);
+#pragma unroll
+        for (int i = 0; i < D; ++i) xi(i) += xi0(i);
+        m = mulv(Vm, xi);
+        // q(P): inverse scale = invS0 + sum (y - m)(y - m)' + N V_m = invS0 + syy - sy m' - m sy' + N (m m' + V_m)
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j < D; ++j)
+                iS(i, j) = iS0(i, j) + syy(i, j) - sy(i) * m(j) - m(i) * sy(j) + (double)N * (m(i) * m(j) + Vm(i, j));
+        Mat<double, D, D> S = cholinv(iS, bad);
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) EP.a[i] = nu * S.a[i];
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) m_out[(int64_t)i * batch + b] = (float)m(i);
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) { V_out[(int64_t)i * batch + b] = (float)Vm.a[i]; iS_out[(int64_t)i * batch + b] = (float)iS.a[i]; }
+    df_out[b] = (float)nu;
+    if (status) status[b] = bad ? RXG_ERR_NOT_SPD : RXG_OK;
+}
+
 }  // namespace rxg
 
 using namespace rxg;
@@ -316,6 +436,59 @@ int rxg_prod_gamma_f32(rxg_ctx* ctx, int64_t n, const float* a1, const float* b1
     RXG_RULE_PROLOGUE(ctx, n)
     k_prod_gamma<<<nblk(n, 256), 256, 0, ctx->stream>>>(n, a1, b1, a2, b2, a, b);
     RXG_RULE_EPILOGUE(ctx, "k_prod_gamma")
+}
+int rxg_rule_normal_precision_tau_joint_f32(rxg_ctx* ctx, int64_t n, const float* m_joint, const float* V_joint,
+                                            float* shape, float* rate, unsigned flags) {
+    RXG_RULE_PROLOGUE(ctx, n)
+    k_normal_precision_tau_joint<<<nblk(n, 256), 256, 0, ctx->stream>>>(n, m_joint, V_joint, shape, rate);
+    RXG_RULE_EPILOGUE(ctx, "k_normal_precision_tau_joint")
+}
+int rxg_rule_mvnormal_precision_lambda_f32(rxg_ctx* ctx, int64_t n, int d, const float* m_out, const float* V_out,
+                                           const float* m_mu, const float* V_mu, float* df, float* inv_scale,
+                                           unsigned flags) {
+    RXG_RULE_PROLOGUE(ctx, n)
+    RXG_DISPATCH_D(d, (k_mvn_precision_lambda<D><<<nblk(n, 128), 128, 0, ctx->stream>>>(n, m_out, V_out, m_mu, V_mu, df, inv_scale)))
+    RXG_RULE_EPILOGUE(ctx, "k_mvn_precision_lambda")
+}
+int rxg_prod_wishart_f32(rxg_ctx* ctx, int64_t n, int d, const float* df1, const float* inv_scale1, const float* df2,
+                         const float* inv_scale2, float* df, float* inv_scale, unsigned flags) {
+    RXG_RULE_PROLOGUE(ctx, n)
+    RXG_DISPATCH_D(d, (k_prod_wishart<D><<<nblk(n, 128), 128, 0, ctx->stream>>>(n, df1, inv_scale1, df2, inv_scale2, df, inv_scale)))
+    RXG_RULE_EPILOGUE(ctx, "k_prod_wishart")
+}
+int rxg_wishart_mean_f32(rxg_ctx* ctx, int64_t n, int d, const float* df, const float* inv_scale, float* mean,
+                         int32_t* status, unsigned flags) {
+    RXG_RULE_PROLOGUE(ctx, n)
+    RXG_DISPATCH_D(d, (k_wishart_mean<D><<<nblk(n, 128), 128, 0, ctx->stream>>>(n, df, inv_scale, mean, status)))
+    RXG_RULE_EPILOGUE(ctx, "k_wishart_mean")
+}
+int rxg_mv_iid_wishart_vmp_f32(rxg_ctx* ctx, int d, int N, int64_t batch, int iterations, const float* mu0,
+                               const float* Lambda0, float nu0, const float* inv_scale0, const float* init_E_P,
+                               const float* y, float* m_mean, float* m_cov, float* df, float* inv_scale,
+                               int32_t* status, unsigned flags) {
+    if (!ctx) return RXG_ERR_BAD_ARG;
+    if (!(flags & RXG_PTR_DEVICE)) return rxg::fail(ctx, RXG_ERR_UNSUPPORTED, "mv_iid_wishart_vmp takes device pointers");
+    if (d < 1 || N < 1 || batch < 1 || iterations < 1 || !mu0 || !Lambda0 || !inv_scale0 || !init_E_P || !y || !m_mean ||
+        !m_cov || !df || !inv_scale)
+        return rxg::fail(ctx, RXG_ERR_BAD_ARG, "mv_iid_wishart_vmp: bad argument");
+    if (d > 6) return rxg::fail(ctx, RXG_ERR_UNSUPPORTED, "mv_iid_wishart_vmp: d=%d unsupported (1-6)", d);
+    RXG_CUDA(ctx, cudaSetDevice(ctx->device));
+    // prior block (host) -> device workspace: mu0[d], Lambda0[d*d], nu0, invS0[d*d], E[P]_init[d*d]
+    const int dd = d * d;
+    float hp[6 + 3 * 36 + 1];
+    for (int i = 0; i < d; ++i) hp[i] = mu0[i];
+    for (int i = 0; i < dd; ++i) { hp[d + i] = Lambda0[i]; hp[d + dd + 1 + i] = inv_scale0[i]; hp[d + 2 * dd + 1 + i] = init_E_P[i]; }
+    hp[d + dd] = nu0;
+    float* dp = (float*)rxg::workspace(ctx, sizeof(hp));
+    if (!dp) return RXG_ERR_CUDA;
+    RXG_CUDA(ctx, cudaMemcpyAsync(dp, hp, (size_t)(d + 3 * dd + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const unsigned grid = (unsigned)((batch + 127) / 128);
+    switch (d) {
+#define RXG_WISH(DD) case DD: mv_iid_wishart_vmp_kernel<DD><<<grid, 128, 0, ctx->stream>>>(y, N, batch, iterations, dp, m_mean, m_cov, df, inv_scale, status); break;
+        RXG_WISH(1) RXG_WISH(2) RXG_WISH(3) RXG_WISH(4) RXG_WISH(5) RXG_WISH(6)
+#undef RXG_WISH
+    }
+    RXG_RULE_EPILOGUE(ctx, "mv_iid_wishart_vmp_kernel")
 }
 int rxg_prod_normal_f32(rxg_ctx* ctx, int64_t n, const float* m1, const float* v1, const float* m2, const float* v2,
                         float* m, float* v, unsigned flags) {

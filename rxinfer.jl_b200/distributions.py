@@ -77,6 +77,14 @@ class GammaShapeRate:
         return self.b
 
 
+@dataclass
+class WishartFast:
+    """Wishart in the (df, INVERSE scale) parametrisation ReactiveMP uses for messages (``WishartFast``):
+    ``df[n]``, ``invS[d, d, n]``; products are additions."""
+    df: torch.Tensor
+    invS: torch.Tensor
+
+
 def vague(kind, like: torch.Tensor):
     """``vague(NormalMeanVariance)`` = N(0, 1e12); ``vague(GammaShapeRate)`` = Gamma(1, 1e-12)
     (TinyHugeNumbers, upstream)."""

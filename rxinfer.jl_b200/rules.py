@@ -7,7 +7,7 @@ like a missing ``@rule`` method would in ReactiveMP.
 from __future__ import annotations
 
 from .distributions import (GammaShapeRate, MvNormalMeanCovariance, MvNormalWeightedMeanPrecision,
-                            NormalMeanVariance, PointMass)
+                            NormalMeanVariance, PointMass, WishartFast)
 
 
 class RuleMethodError(NotImplementedError):
@@ -64,6 +64,10 @@ def call_rule(ctx, node: str, edge: str, **kw):
         if edge == "τ" and "q_out" in kw and "q_μ" in kw:
             (mo, vo), (mm, vm) = kw["q_out"].mean_var(), kw["q_μ"].mean_var()
             return GammaShapeRate(*ctx.rule_normal_precision_tau(mo, vo, mm, vm))
+        if edge == "τ" and "q_out_μ" in kw:
+            # structured: q(out, mu) jointly Gaussian (MvNormalMeanCovariance with d = 2)
+            j = kw["q_out_μ"]
+            return GammaShapeRate(*ctx.rule_normal_precision_tau_joint(j.mu, j.Sigma))
         if edge == "out" and "q_τ" in kw and "m_μ" in kw:
             # (m_μ::Normal, q_τ): belief-propagation message on the mean edge -> N(m_μ, v_μ + 1/E[τ])
             src = kw["m_μ"]
@@ -73,6 +77,10 @@ def call_rule(ctx, node: str, edge: str, **kw):
             # var(q_μ) does not enter (same kernel with v_μ = 0)
             m, _ = kw["q_μ"].mean_var()
             return NormalMeanVariance(*ctx.rule_normal_precision_out(m, m.new_zeros(m.shape), kw["q_τ"].a, kw["q_τ"].b))
+    if node == "MvNormalMeanPrecision":
+        if edge == "Λ" and "q_out" in kw and "q_μ" in kw:
+            (mo, Vo), (mm, Vm) = _mc(ctx, kw["q_out"]), _mc(ctx, kw["q_μ"])
+            return WishartFast(*ctx.rule_mvnormal_precision_lambda(mo, Vo, mm, Vm))
     if node == "GCV":
         k, w = float(kw["q_κ"].value), float(kw["q_ω"].value)
         if edge in ("y", "x"):
@@ -85,6 +93,8 @@ def prod(ctx, left, right):
     """``BayesBase.prod(GenericProd(), left, right)`` for the Gaussian / Gamma family."""
     if isinstance(left, GammaShapeRate) and isinstance(right, GammaShapeRate):
         return GammaShapeRate(*ctx.prod_gamma(left.a, left.b, right.a, right.b))
+    if isinstance(left, WishartFast) and isinstance(right, WishartFast):
+        return WishartFast(*ctx.prod_wishart(left.df, left.invS, right.df, right.invS))
     if isinstance(left, NormalMeanVariance) and isinstance(right, NormalMeanVariance):
         return NormalMeanVariance(*ctx.prod_normal(left.m, left.v, right.m, right.v))
     l, r = _wmp(ctx, left), _wmp(ctx, right)

@@ -141,3 +141,21 @@ def test_stream_vmp_gamma_free_energy_is_monotone():
     mmin = (0.0 / 1e3 + 0.0 * 1.0) / (1 / 1e3 + 1.0); vx = 1.0 / (1.0 + 1.0); mx = vx * (mmin + 2.0 * 1.0)
     assert abs(o1[0, 0, 0] - mx) < 1e-15 and abs(o1[0, 1, 0] - vx) < 1e-15
     assert abs(o1[0, 2, 0] - 1.5) < 1e-15 and abs(o1[0, 3, 0] - (1.0 + 0.5 * ((2.0 - mx) ** 2 + vx))) < 1e-15
+
+
+def test_mv_iid_wishart_oracle_meets_the_reference_assertions():
+    """mv_iid_precision_tests.jl:44-66: n = 1500, d = 2, 10 iterations; `mean(q(m)) ~ m (atol 0.05)`,
+    `mean(q(P)) ~ P (atol 0.07)`.  The reference's data come from a StableRNG stream through Distributions.jl's
+    MvNormal sampler (not restated), so this is the reference's STATISTICAL assertion on data of the same model --
+    parity for this model is unpinned beyond that (stated in DESIGN.md)."""
+    from oracle import vmp
+    rng = np.random.default_rng(11)      # like the reference's StableRNG(123) draw, a draw with a well-conditioned C: the
+    n, d = 1500, 2                       # thresholds are tied to it (the Lambda = 100 I prior shrinks m along weak directions of P)
+    m = rng.random(d)
+    Lc = rng.standard_normal((d, d))
+    C = Lc @ Lc.T
+    P = np.linalg.inv(C)
+    y = (m[None, :] + rng.standard_normal((n, d)) @ np.linalg.cholesky(C).T)[:, :, None]
+    r = vmp.mv_iid_wishart(y, iterations=10)
+    assert np.allclose(r["m_mean"][:, 0], m, atol=0.05)
+    assert np.allclose(r["E_P"][:, :, 0], P, atol=0.07)

@@ -212,3 +212,43 @@ def test_normal_precision_out_mean_field_variant(ctx, rx):
     assert rel_l2(bp.v.cpu().numpy(), ref_bp[1]) < 1e-6 and rel_l2(mf.v.cpu().numpy(), ref_mf[1]) < 1e-6
     assert rel_l2(mf.v.cpu().numpy(), rt / sh) < 1e-6
     assert np.array_equal(mf.m.cpu().numpy(), mm) and np.array_equal(bp.m.cpu().numpy(), mm)
+
+
+def test_structured_tau_and_wishart_rules(ctx, rx):
+    """Structured NormalMeanPrecision(:tau)(q_out_mu) and the Wishart-precision rules against the oracle; then the
+    fused IID Wishart VMP (rxg_mv_iid_wishart_vmp_f32) against the message-by-message oracle on several data sets."""
+    from oracle import vmp
+    rng = np.random.default_rng(8)
+    n = 777
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32, device="cuda")
+    mj = r32(rng.standard_normal((n, 2)))
+    Vj = r32(spd(rng, n, 2))
+    sh, rt = ctx.rule_normal_precision_tau_joint(soa_v(mj), soa_m(Vj))
+    ra, rb = R.normal_meanprec_tau_structured(mj.astype(np.float64), Vj.astype(np.float64))
+    assert rel_l2(sh.cpu().numpy(), ra) < 1e-6 and rel_l2(rt.cpu().numpy(), rb) < 1e-5
+    for d in (2, 3, 4):
+        mo, mm = r32(rng.standard_normal((n, d))), r32(rng.standard_normal((n, d)))
+        Vo, Vm = r32(spd(rng, n, d)), r32(spd(rng, n, d))
+        df, iS = ctx.rule_mvnormal_precision_lambda(soa_v(mo), soa_m(Vo), soa_v(mm), soa_m(Vm))
+        rdf, riS = R.mvnormal_meanprec_lambda((mo.astype(np.float64), Vo.astype(np.float64)), (mm.astype(np.float64), Vm.astype(np.float64)))
+        assert rel_l2(df.cpu().numpy(), rdf) < 1e-6 and rel_l2(back_m(iS), riS) < 1e-5
+        df2, iS2 = ctx.prod_wishart(df, iS, df, iS)
+        pdf, piS = R.prod_wishart((rdf, riS), (rdf, riS))
+        assert rel_l2(df2.cpu().numpy(), pdf) < 1e-6 and rel_l2(back_m(iS2), piS) < 1e-5
+        EL, st = ctx.wishart_mean(df2, iS2)
+        assert int(st.abs().sum()) == 0 and rel_l2(back_m(EL), R.wishart_mean((pdf, piS))) < 1e-4
+    # fused VMP, d = 2 and 3, a few data sets of different size
+    for d, N, batch in ((2, 300, 33), (3, 200, 10)):
+        ys = []
+        for b in range(batch):
+            Lc = rng.standard_normal((d, d))
+            C = Lc @ Lc.T + 0.1 * np.eye(d)
+            ys.append(rng.random(d)[None, :] + rng.standard_normal((N, d)) @ np.linalg.cholesky(C).T)
+        y = r32(np.stack(ys, axis=-1))
+        ref = vmp.mv_iid_wishart(y, iterations=6)
+        got = ctx.mv_iid_wishart_vmp(t(y), iterations=6)
+        assert int(got["status"].abs().sum()) == 0
+        assert rel_l2(got["m_mean"].cpu().numpy(), ref["m_mean"]) < 1e-5
+        assert rel_l2(got["m_cov"].cpu().numpy(), ref["m_cov"]) < 1e-4
+        assert rel_l2(got["df"].cpu().numpy(), ref["df"]) < 1e-6
+        assert rel_l2(got["inv_scale"].cpu().numpy(), ref["inv_scale"]) < 1e-4
