@@ -195,6 +195,102 @@ def run_reference_arm(args, rank, world, emit=lambda o: print(json.dumps(o))):
     }))
 
 
+def bench_other_config(args, ctx, dev, emit):
+    """BASELINE configs[2] (d = 64, T = 1000, batch = 4096, contract output: per-chain covariances) and configs[3]
+    (HGF, T = 1000, batch = 32 768, 20 VMP iterations): same timing protocol and JSON keys as the headline line."""
+    import torch
+    sampler = ClockSampler(dev.index or 0)
+    g = torch.Generator(device=dev).manual_seed(7)
+    peak, peak_src = peaks()
+
+    def timed(fn):
+        for _ in range(args.warmup):
+            fn()
+        torch.cuda.synchronize()
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launches
+        e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / args.steps, ctx.launches - l0, sampler.stop()
+
+    if args.config == 2:
+        d, batch = 64, 4096
+        md = dense_model_f32(d)
+        y = torch.randn(T, d, batch, device=dev, generator=g) * 3.3
+        mean = torch.empty(T, d, batch, device=dev)
+        cov = torch.empty(T, d, d, batch, device=dev)            # 67 GB: the contract output
+        ctx.set_profiling(True)
+        parts = []
+        def step():
+            ctx.lgssm(y, **md, smooth=True, out_mean=mean, out_cov=cov, asynchronous=True)
+        ms, launches, clocks = timed(step)
+        for _ in range(3):
+            step(); parts.append(ctx.profile_last_ms())
+        sweep_ms, gain_ms = float(np.mean([p[0] for p in parts])), float(np.mean([p[1] for p in parts]))
+        bcast_ms = ms - sweep_ms - gain_ms
+        algo = 4 * (d + d + d * d) * T * batch
+        cov_bytes = 4 * d * d * T * batch
+        out = {"metric": "gaussian_messages_per_sec_batched_lgssm_d64_T1000", "value": MSG_PER_STEP * T * batch / (ms * 1e-3),
+               "unit": "messages/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (tensor pipe: 3xTF32 split, fp32 accumulate; gain tables fp64)",
+               "data": "synthetic",
+               "config": {"workload": "BASELINE configs[2]: LGSSM d=64 m=64 T=1000 batch=4096, dense A = 0.99 Orth, shared model; "
+                                      "contract output = per-chain covariances [T][64][64][4096] (67 GB)",
+                          "l2_policy": "outputs (68 GB) larger than L2", "data_note": "y = randn * 3.3"},
+               "roofline": {"bound": "hbm", "kernel": "broadcast_cov_kernel (per-chain covariance materialisation)",
+                            "achieved": cov_bytes / (bcast_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                            "frac": cov_bytes / (bcast_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                            "kernel_ms": bcast_ms, "algorithmic_bytes_per_launch": cov_bytes,
+                            "whole_step_frac": algo / (ms * 1e-3) / 1e9 / peak,
+                            "breakdown_ms": {"gain_tables_fp64": gain_ms, "mean_sweep_tcgen05": sweep_ms, "covariance_broadcast": bcast_ms},
+                            "mean_sweep_TFLOPs": 8 * d * d * T * batch / (sweep_ms * 1e-3) / 1e12},
+               "e2e": None, "e2e_note": "not measured for this config: the contract output alone is 67 GB of pinned host memory",
+               "gpu_launches": int(launches), "clocks": clocks}
+        emit(out)
+        return
+    # config 3: HGF
+    batch, iters = 32768, 20
+    yh = (torch.randn(T, batch, device=dev, generator=g).cumsum(0) * 0.5).contiguous()
+    outb = torch.empty(T, 4, batch, device=dev)
+    ms, launches, clocks = timed(lambda: ctx.hgf_filter(yh, iters=iters, out=outb))
+    msgs = 6 * iters * T * batch
+    # end to end: host observations in, host posteriors out through the same entry point
+    yhh = torch.empty(T, batch).pin_memory(); yhh.copy_(yh)
+    outh = torch.empty(T, 4, batch).pin_memory()
+    ydev = torch.empty_like(yh)
+    def e2e_step():
+        ydev.copy_(yhh, non_blocking=True)
+        ctx.hgf_filter(ydev, iters=iters, out=outb)
+        outh.copy_(outb, non_blocking=True)
+    e2e_step(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        e2e_step()
+    e1.record(); torch.cuda.synchronize()
+    e_ms = e0.elapsed_time(e1) / 3
+    io = 20 * T * batch
+    out = {"metric": "gaussian_messages_per_sec_hgf_T1000_20its", "value": msgs / (ms * 1e-3), "unit": "messages/s", "n_gpus": 1,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "BASELINE configs[3]: Hierarchical Gaussian Filter (GCV node, GH-31), T=1000 batch=32768, 20 VMP iterations per datum",
+                      "vmp_iterations_per_s": iters * T * batch / (ms * 1e-3), "exp_per_s": (31 + 1 + iters * 32) * T * batch / (ms * 1e-3),
+                      "messages_per_chain_step_iteration": 6},
+           "roofline": {"bound": "hbm", "kernel": "hgf_filter_kernel", "achieved": io / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": io / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": ms,
+                        "algorithmic_bytes_per_launch": io,
+                        "note": "SFU / FP32-issue bound (652 ex2 + ~5 k FMA per 20 B of I/O): the HBM fraction is not the meaningful "
+                                "ceiling here (SURVEY.md 8d); see profiles/ for the pipe utilisation"},
+           "e2e": {"value": msgs / (e_ms * 1e-3), "unit": "messages/s", "ms_per_step": e_ms, "h2d_bytes_per_step": int(yhh.numel() * 4),
+                   "d2h_bytes_per_step": int(outh.numel() * 4)},
+           "gpu_launches": int(launches), "clocks": clocks}
+    emit(out)
+
+
 def main():
     # keep stdout clean for the ONE JSON line: libraries (NCCL's version banner, torchrun notes) print to
     # fd 1 as well, so everything else is routed to stderr and the result goes to the saved descriptor
@@ -213,6 +309,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--per-chain-path", action="store_true", help="time the per-chain covariance recursion instead")
+    ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3],
+                    help="BASELINE.json configs[] index: 1 = headline (d=4, batch 65536), 2 = d=64 batch 4096 (tensor-core family), "
+                         "3 = HGF T=1000 batch 32768, 20 VMP iterations")
     ap.add_argument("--sweep-variant", type=int, default=0, help="RXG_OPT_SWEEP_VARIANT (0 auto, 1 stash, 2 checkpoint, 3/4 time-segmented)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -238,6 +337,10 @@ def main():
     ctx = rx.Context(local)
     if args.sweep_variant:
         ctx.set_option("sweep_variant", args.sweep_variant)
+    if args.config != 1:
+        if world > 1:
+            raise SystemExit("bench.py --config 2/3 are single-GPU configurations")
+        return bench_other_config(args, ctx, dev, emit)
     mod = notebook_model_f32()
     batch = args.batch
     kw = dict(A=mod["A"], B=mod["B"], P=mod["P"], Q=mod["Q"], m0=mod["m0"], S0=mod["S0"])

@@ -152,7 +152,6 @@ int rxg_destroy(rxg_ctx* ctx) {
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->stage) cudaFree(ctx->stage);
     if (ctx->d_bad) cudaFree(ctx->d_bad);
-    if (ctx->d_tab) cudaFree(ctx->d_tab);
     for (int i = 0; i < 4; ++i) if (ctx->aux_buf[i]) cudaFree(ctx->aux_buf[i]);
     if (ctx->h_bad) cudaFreeHost(ctx->h_bad);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);

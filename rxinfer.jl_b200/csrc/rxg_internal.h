@@ -48,9 +48,6 @@ struct rxg_ctx {
     int peer_n = 0, peer_rank = 0;
     int* peer_flags[RXG_MAX_PEERS] = {};     // peer_flags[g] = rank g's flag array as mapped here (own: cudaMalloc'ed)
     unsigned peer_epoch = 0;
-    // [T][d][d] posterior-covariance table of the fused sweep + gather (source of the local replication)
-    void* d_tab = nullptr;
-    size_t tab_bytes = 0;
     // grow-only scratch of the general-shape front end (padded operands, shifted observations)
     void* aux_buf[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t aux_bytes[4] = {0, 0, 0, 0};
@@ -102,8 +99,8 @@ struct LgssmCall {
     bool smooth;
     bool tables_only = false;   // compute the gain tables (and the RXG_COV_SHARED_OUT covariance table) and return: no sweep
     PeerOut po = {};            // fused all-gather: peer destinations of the final mean (and covariance) stores
-    float* cov_table = nullptr; // device [T][d][d] or null: the gain kernels also leave the chain-independent posterior
-                                // covariance table here (source of the local covariance replication)
+    bool want_cov_table = false; // in: also leave the chain-independent posterior covariance table [T][d][d] in the workspace
+    float* cov_table = nullptr;  // out: that table (source of the local covariance replication), or null if the family has none
     cudaEvent_t ev_tables = nullptr;   // recorded on the ctx stream once the gain tables are complete (before the sweep)
     bool fused_peer_stores = false;    // out: the sweep kernel itself stored to c.po (else the caller pushes the slabs)
 };

@@ -487,6 +487,7 @@ static int run_shared_family(rxg_ctx* ctx, LgssmCall& c) {
     const size_t nseg = (T + ST::L - 1) / ST::L;
     const size_t o_srec_t = carve(T * ST::REC * sizeof(float)), o_snrec = carve(T * ST::NREC * sizeof(float));
     const size_t o_ssrec = carve(nseg * ST::SREC * sizeof(float));
+    const size_t o_ctab = carve(c.want_cov_table ? T * D * D * sizeof(float) : 0);
     char* base = (char*)workspace(ctx, off);
     if (!base) return RXG_ERR_CUDA;
     GainWs ws;
@@ -499,6 +500,7 @@ static int run_shared_family(rxg_ctx* ctx, LgssmCall& c) {
 
     const int tf = (c.flags & RXG_TRANSITION_FIRST) ? 1 : 0;
     const bool cov_shared = (c.flags & RXG_COV_SHARED_OUT) != 0;
+    c.cov_table = (c.want_cov_table && c.smooth) ? (float*)(base + o_ctab) : nullptr;
     if (ctx->profile) cudaEventRecord(ctx->ev[0], ctx->stream);
     float* cov_once = (cov_shared && c.cov && c.smooth) ? c.cov : (c.smooth ? c.cov_table : nullptr);
     if (ctx->opt[RXG_OPT_GAIN_SEQ] != 0) {

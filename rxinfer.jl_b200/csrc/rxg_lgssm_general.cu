@@ -129,10 +129,12 @@ int large_with_offset(rxg_ctx* ctx, LgssmCall& c) {
     RXG_CUDA(ctx, cudaMemcpyAsync(tr, traj.data(), traj.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     RXG_CUDA(ctx, cudaMemcpyAsync(btr, btraj.data(), btraj.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     RXG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    shift_rows_kernel<<<grid_for(ctx, (int64_t)ny), 256, 0, ctx->stream>>>(c.y, ys, btr, (int64_t)T * m, c.batch, -1.f);
     LgssmCall c2 = c;
     c2.u = nullptr;
-    c2.y = ys;
+    if (!c.tables_only) {
+        shift_rows_kernel<<<grid_for(ctx, (int64_t)ny), 256, 0, ctx->stream>>>(c.y, ys, btr, (int64_t)T * m, c.batch, -1.f);
+        c2.y = ys;
+    }
     int rc = lgssm_large_dispatch(ctx, c2);
     if (rc != RXG_OK) return rc;
     if (!c.tables_only && c.mean) {
@@ -175,7 +177,7 @@ int embedded(rxg_ctx* ctx, LgssmCall& c, int D, int M) {
     c2.A = A.data(); c2.B = B.data(); c2.P = P.data(); c2.Q = Q.data(); c2.m0 = m0.data(); c2.S0 = S0.data();
     c2.u = c.u ? u.data() : nullptr;
     c2.po = PeerOut{};                       // the embedded sweep writes padded rows: no in-kernel peer stores
-    c2.cov_table = nullptr; c2.ev_tables = nullptr;
+    c2.want_cov_table = false; c2.cov_table = nullptr; c2.ev_tables = nullptr;
     if (!c.tables_only) {
         pad_rows_kernel<<<grid_for(ctx, (int64_t)n_y), 256, 0, ctx->stream>>>(c.y, yp, T, m, M, batch);
         c2.y = yp; c2.mean = meanp;

@@ -198,6 +198,12 @@ int rxg_peer_close(rxg_ctx* ctx, void* dev_ptr) {
 int rxg_peer_group(rxg_ctx* ctx, int nranks, int rank, void* const* flag_ptrs) {
     if (!ctx || nranks < 1 || nranks > RXG_MAX_PEERS || rank < 0 || rank >= nranks || (nranks > 1 && !flag_ptrs))
         return ctx ? fail(ctx, RXG_ERR_BAD_ARG, "peer_group: 1 <= nranks <= %d, 0 <= rank < nranks", RXG_MAX_PEERS) : RXG_ERR_BAD_ARG;
+    if (nranks > 1) {      // everything the gather calls need later is created now (no allocation inside a gather)
+        RXG_CUDA(ctx, cudaSetDevice(ctx->device));
+        int rc0 = ensure_aux_stream(ctx);
+        if (rc0 != RXG_OK) return rc0;
+        if (!bad_flag(ctx)) return RXG_ERR_CUDA;
+    }
     ctx->peer_n = nranks;
     ctx->peer_rank = rank;
     ctx->peer_epoch = 0;
@@ -283,16 +289,10 @@ int rxg_lgssm_smooth_gather_f32(rxg_ctx* ctx, int d, int m, int T, int64_t batch
     for (int k = 0; k < np; ++k) { c.po.mean[k] = pm[k]; c.po.cov[k] = pc[k]; }
     c.po.n_mean = np;
     c.po.n_cov = (gathered_cov && !replicate) ? np : 0;
-    const size_t tab_bytes = (size_t)T * d * d * 4;
     if (replicate && G > 1) {
-        int rc = ensure_aux_stream(ctx);
-        if (rc != RXG_OK) return rc;
-        if (ctx->tab_bytes < tab_bytes) {
-            if (ctx->d_tab) { cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->s_aux); cudaFree(ctx->d_tab); ctx->d_tab = nullptr; ctx->tab_bytes = 0; }
-            RXG_CUDA(ctx, cudaMalloc(&ctx->d_tab, tab_bytes));
-            ctx->tab_bytes = tab_bytes;
-        }
-        c.cov_table = (float*)ctx->d_tab;
+        // the kernel family leaves the chain-independent covariance table in its workspace (no allocation here: a
+        // device allocation may synchronise with a peer's spinning barrier when several ranks share one process)
+        c.want_cov_table = true;
         c.ev_tables = ctx->ev_aux[0];
     }
     int rc = begin_bad_flag(ctx);
@@ -302,7 +302,7 @@ int rxg_lgssm_smooth_gather_f32(rxg_ctx* ctx, int d, int m, int T, int64_t batch
         if (replicate) {
             // local broadcast fill of the other ranks' covariance slabs on the low-priority side stream
             const int64_t rows = (int64_t)T * d * d;
-            if (c.fused_peer_stores) {      // the table exists as soon as the gain kernels are done: overlaps the whole sweep
+            if (c.fused_peer_stores && c.cov_table) {      // the table exists as soon as the gain kernels are done: overlaps the whole sweep
                 RXG_CUDA(ctx, cudaStreamWaitEvent(ctx->s_aux, ctx->ev_aux[0], 0));
                 rc = launch_replicate_cov(ctx, ctx->s_aux, c.cov_table, 1, gathered_cov[r], rows, batch_local, G, r);
             } else {                        // other kernel families: replicate from the finished local slab

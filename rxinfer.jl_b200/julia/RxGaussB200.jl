@@ -1,17 +1,40 @@
-# RxGaussB200.jl -- the Julia-side shim a maintainer would add next to RxInfer to route the batched
-# Gaussian hot path to librxgauss.so (include/rxgauss.h) through plain `ccall`.  No CUDA.jl codegen:
-# the kernels are the hand-written sm_100a ones in csrc/.
+# RxGaussB200.jl -- the Julia side of the drop-in: routes the batched Gaussian hot path of RxInfer's `infer`
+# to librxgauss.so (include/rxgauss.h) through plain `ccall`.  No CUDA.jl, no code generation: device memory,
+# copies and peer mapping all go through the C ABI (rxg_device_alloc / rxg_memcpy_* / rxg_peer_*), the kernels
+# are the hand-written sm_100a ones in csrc/.
 #
-# NOT RUNNABLE IN THE BUILD IMAGE (no Julia there); it is the reference-side binding that
-# INTEGRATION.md describes, kept next to the C ABI it binds.  The Python package in this directory
-# (`_lib.py`, `context.py`, `inference.py`, `rules.py`) is the same binding in the host language
-# that *is* available, and is what the parity tests drive.
+# Layers (each usable on its own):
+#   1. `Lib`      one thin wrapper per export of include/rxgauss.h (every export is bound: tests/test_julia_shim.py
+#                 checks the list against the header)
+#   2. device arrays + batched message types (`BatchedMvNormalMeanCovariance`, ...) with `@rule` / `prod` methods
+#      whose bodies are one ccall -- the per-rule hook (reference: src/model/plugins/reactivemp_inference.jl:509-540,
+#      `@call_rule` test/inference/inference_tests.jl:547-585)
+#   3. `smooth`, `filter`, `hgf_filter`, ... whole-chain calls on host arrays
+#   4. `recognise` + `infer_batched`: the GraphPPL pattern recogniser and the transparent entry point with the
+#      SURVEY.md appendix-C fallback list (anything outside the hot path goes to stock `RxInfer.infer`)
+#   5. `BatchedInferenceEngine`: the streaming twin (autoupdates carry held between time-chunks)
+#   6. multi-GPU: NCCL communicator or the peer-mapped gather (one Julia process per GPU)
+#
+# STATUS: written against RxInfer 4.x / ReactiveMP ~6.0 / GraphPPL 4.x as vendored under /root/reference; the build
+# image has no Julia, so this file is parsed by `julia/check_syntax.jl` when a toolchain is present and is
+# structurally checked (block balance, every export bound) by tests/test_julia_shim.py here.  The ctypes mirror
+# (`_lib.py`, `context.py`, `inference.py`, `rules.py`, `streaming.py`) is the same binding in Python and is what the
+# parity tests drive.
 module RxGaussB200
 
 using LinearAlgebra
-# using RxInfer, ReactiveMP, ExponentialFamily, BayesBase    # in a real checkout
+
+import RxInfer
+import RxInfer: ReactiveMP, GraphPPL, BayesBase, ExponentialFamily
+import RxInfer.ReactiveMP: @rule, Marginalisation, PointMass
+import RxInfer.ExponentialFamily: MvNormalMeanCovariance, MvNormalWeightedMeanPrecision, MvNormalMeanPrecision, NormalMeanVariance,
+    NormalMeanPrecision, GammaShapeRate
 
 const LIB = get(ENV, "RXGAUSS_LIB", joinpath(@__DIR__, "..", "librxgauss.so"))
+
+# ---------------------------------------------------------------------------------------------- constants
+const RXG_OK, RXG_ERR_BAD_ARG, RXG_ERR_CUDA, RXG_ERR_NCCL = Cint(0), Cint(1), Cint(2), Cint(3)
+const RXG_ERR_NOT_SPD, RXG_ERR_NAN, RXG_ERR_UNSUPPORTED, RXG_ERR_NO_DEVICE = Cint(4), Cint(5), Cint(6), Cint(7)
 
 const RXG_PTR_DEVICE       = UInt32(1) << 0
 const RXG_MODEL_PER_CHAIN  = UInt32(1) << 1
@@ -21,147 +44,789 @@ const RXG_PATH_PER_CHAIN   = UInt32(1) << 4
 const RXG_TRANSITION_FIRST = UInt32(1) << 5
 const RXG_COV_REPLICATE    = UInt32(1) << 6
 
+const RXG_OPT_GAIN_SEQ, RXG_OPT_LARGE_SEQ, RXG_OPT_NO_UMMA, RXG_OPT_SWEEP_VARIANT, RXG_OPT_FORCE_CPT = 0, 1, 2, 3, 4
+const RXG_OPT_HOST_THREADS, RXG_OPT_HOST_COV_D2H, RXG_OPT_HOST_BCAST_MIN_MB, RXG_OPT_HOST_SLICES = 5, 6, 7, 8
+const RXG_MAX_PEERS = 8
+
+const F32P = Ptr{Float32}
+const NULLF = F32P(C_NULL)
+
 struct RxGaussError <: Exception
     code::Cint
     msg::String
 end
+Base.showerror(io::IO, e::RxGaussError) = print(io, "librxgauss error ", e.code, ": ", e.msg)
 
+# ---------------------------------------------------------------------------------------------- context
 mutable struct Context
     handle::Ptr{Cvoid}
+    device::Int
     function Context(device::Integer = 0)
         h = Ref{Ptr{Cvoid}}(C_NULL)
         rc = ccall((:rxg_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint, Cuint), h, device, 0)
-        rc == 0 || throw(RxGaussError(rc, "rxg_create failed (no CUDA device? there is no CPU fallback)"))
-        ctx = new(h[])
+        rc == RXG_OK || throw(RxGaussError(rc, "rxg_create failed (no CUDA device? there is no CPU fallback)"))
+        ctx = new(h[], Int(device))
         finalizer(c -> ccall((:rxg_destroy, LIB), Cint, (Ptr{Cvoid},), c.handle), ctx)
         return ctx
     end
 end
 
-function check(ctx::Context, rc::Cint)
-    rc == 0 && return nothing
+const CTX = Ref{Union{Nothing, Context}}(nothing)
+default_context() = (CTX[] === nothing && (CTX[] = Context(0)); CTX[]::Context)
+
+function check(ctx::Context, rc::Integer)
+    rc == RXG_OK && return nothing
     msg = unsafe_string(ccall((:rxg_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx.handle))
-    throw(RxGaussError(rc, msg))
+    throw(RxGaussError(Cint(rc), msg))
 end
 
-f32(M) = Matrix{Float32}(M)      # shared model matrices are host constants, row-major on the C side
-rowmajor(M::AbstractMatrix) = collect(transpose(f32(M)))   # Julia is column-major
+# ---------------------------------------------------------------------------------------------- 1. Lib: one wrapper per export
+module Lib
+import ..LIB, ..Context, ..check, ..F32P
 
-"""
-    smooth(ctx, y, A, B, P, Q, m0, S0; free_energy = false)
+version() = ccall((:rxg_version, LIB), Cint, ())
+supports(d, m) = ccall((:rxg_supports, LIB), Cint, (Cint, Cint), d, m) == 1
+host_fill_threads() = ccall((:rxg_host_fill_threads, LIB), Cint, ())
+launch_count(ctx::Context) = ccall((:rxg_launch_count, LIB), Clonglong, (Ptr{Cvoid},), ctx.handle)
+last_error(ctx::Context) = unsafe_string(ccall((:rxg_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx.handle))
+set_option!(ctx::Context, opt, v) = check(ctx, ccall((:rxg_set_option, LIB), Cint, (Ptr{Cvoid}, Cint, Clonglong), ctx.handle, opt, v))
+function get_option(ctx::Context, opt)
+    v = Ref{Clonglong}(0)
+    check(ctx, ccall((:rxg_get_option, LIB), Cint, (Ptr{Cvoid}, Cint, Ref{Clonglong}), ctx.handle, opt, v))
+    return v[]
+end
+set_stream!(ctx::Context, stream::Ptr{Cvoid}) = check(ctx, ccall((:rxg_set_stream, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), ctx.handle, stream))
+sync(ctx::Context) = check(ctx, ccall((:rxg_sync, LIB), Cint, (Ptr{Cvoid},), ctx.handle))
+set_profiling!(ctx::Context, on::Bool) = check(ctx, ccall((:rxg_set_profiling, LIB), Cint, (Ptr{Cvoid}, Cint), ctx.handle, on))
+function profile_last_ms(ctx::Context)
+    a, b = Ref{Cfloat}(0), Ref{Cfloat}(0)
+    check(ctx, ccall((:rxg_profile_last_ms, LIB), Cint, (Ptr{Cvoid}, Ref{Cfloat}, Ref{Cfloat}), ctx.handle, a, b))
+    return a[], b[]
+end
+function host_alloc(bytes)
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    ccall((:rxg_host_alloc, LIB), Cint, (Ref{Ptr{Cvoid}}, Csize_t), p, bytes) == 0 || error("rxg_host_alloc failed")
+    return p[]
+end
+host_free(p) = ccall((:rxg_host_free, LIB), Cint, (Ptr{Cvoid},), p)
+function device_alloc(ctx::Context, bytes)
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ctx, ccall((:rxg_device_alloc, LIB), Cint, (Ptr{Cvoid}, Csize_t, Ref{Ptr{Cvoid}}), ctx.handle, bytes, p))
+    return p[]
+end
+device_free(ctx::Context, p) = check(ctx, ccall((:rxg_device_free, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), ctx.handle, p))
+device_memset(ctx::Context, p, v, bytes) = check(ctx, ccall((:rxg_device_memset, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Csize_t), ctx.handle, p, v, bytes))
+memcpy_h2d(ctx::Context, dst, src, bytes) = check(ctx, ccall((:rxg_memcpy_h2d, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t), ctx.handle, dst, src, bytes))
+memcpy_d2h(ctx::Context, dst, src, bytes) = check(ctx, ccall((:rxg_memcpy_d2h, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t), ctx.handle, dst, src, bytes))
 
-Batched replacement for `infer(model = linear_gaussian_ssm_smoothing(A = A, B = B, P = P, Q = Q),
-data = (y = observations,))` (benchmarks/...Benchmark.ipynb:186-196) over `batch` independent series.
-`y` is `Array{Float32,3}` of size `(batch, m, T)` -- i.e. the C layout `y[T][m][batch]` seen from
-column-major Julia -- so no transposition is needed for the data.
-Returns `(mean[batch, d, T], cov[batch, d, d, T], neg_log_evidence[batch])`.
-"""
-function smooth(ctx::Context, y::Array{Float32,3}, A, B, P, Q, m0, S0; free_energy::Bool = false)
-    batch, m, T = size(y)
-    d = size(A, 1)
-    mean = Array{Float32}(undef, batch, d, T)
-    cov  = Array{Float32}(undef, batch, d, d, T)
-    nle  = free_energy ? Vector{Float32}(undef, batch) : Float32[]
-    Ar, Br, Pr, Qr, S0r = rowmajor(A), rowmajor(B), rowmajor(P), rowmajor(Q), rowmajor(S0)
-    m0r = Vector{Float32}(m0)
-    GC.@preserve y mean cov nle Ar Br Pr Qr S0r m0r begin
-        rc = ccall((:rxg_lgssm_smooth_f32, LIB), Cint,
-            (Ptr{Cvoid}, Cint, Cint, Cint, Int64,
-             Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32},
-             Ptr{Float32}, Ptr{UInt8}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Int32}, Cuint),
-            ctx.handle, d, m, T, batch, Ar, Br, Pr, Qr, m0r, S0r, C_NULL,     # u = NULL: no transition offset
-            y, C_NULL, mean, cov, free_energy ? pointer(nle) : C_NULL, C_NULL, 0)   # host pointers: flags = 0
-        check(ctx, rc)
+# ---- per-rule kernels (device pointers; n messages, batch index innermost)
+const R9 = (Ptr{Cvoid}, Int64, Cint, F32P, F32P, F32P, Cint, F32P, F32P, Cuint)
+rule_mvnormal_meancov_out(ctx, n, d, mu, S, Sigma, shared, mu_o, S_o, fl) =
+    check(ctx, ccall((:rxg_rule_mvnormal_meancov_out_f32, LIB), Cint, R9, ctx.handle, n, d, mu, S, Sigma, shared, mu_o, S_o, fl))
+rule_mvnormal_meancov_mean(ctx, n, d, mu, S, Sigma, shared, mu_o, S_o, fl) =
+    check(ctx, ccall((:rxg_rule_mvnormal_meancov_mean_f32, LIB), Cint, R9, ctx.handle, n, d, mu, S, Sigma, shared, mu_o, S_o, fl))
+rule_mvnormal_meancov_mean_data(ctx, n, d, y, Sigma, shared, mu_o, S_o, fl) =
+    check(ctx, ccall((:rxg_rule_mvnormal_meancov_mean_data_f32, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Cint, F32P, F32P, Cint, F32P, F32P, Cuint), ctx.handle, n, d, y, Sigma, shared, mu_o, S_o, fl))
+rule_mul_out(ctx, n, dout, din, A, shared, mu, S, mu_o, S_o, fl) =
+    check(ctx, ccall((:rxg_rule_mul_out_f32, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Cint, Cint, F32P, Cint, F32P, F32P, F32P, F32P, Cuint), ctx.handle, n, dout, din, A, shared, mu, S, mu_o, S_o, fl))
+rule_mul_in(ctx, n, dout, din, A, shared, mu, S, xi, W, status, fl) =
+    check(ctx, ccall((:rxg_rule_mul_in_f32, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Cint, Cint, F32P, Cint, F32P, F32P, F32P, F32P, Ptr{Int32}, Cuint),
+        ctx.handle, n, dout, din, A, shared, mu, S, xi, W, status, fl))
+const P8 = (Ptr{Cvoid}, Int64, Cint, F32P, F32P, F32P, F32P, F32P, F32P, Cuint)
+rule_add_out(ctx, n, d, m1, S1, m2, S2, mo, So, fl) = check(ctx, ccall((:rxg_rule_add_out_f32, LIB), Cint, P8, ctx.handle, n, d, m1, S1, m2, S2, mo, So, fl))
+rule_add_in(ctx, n, d, m1, S1, m2, S2, mo, So, fl) = check(ctx, ccall((:rxg_rule_add_in_f32, LIB), Cint, P8, ctx.handle, n, d, m1, S1, m2, S2, mo, So, fl))
+prod_gaussian(ctx, n, d, x1, W1, x2, W2, xo, Wo, fl) = check(ctx, ccall((:rxg_prod_gaussian_f32, LIB), Cint, P8, ctx.handle, n, d, x1, W1, x2, W2, xo, Wo, fl))
+const C7 = (Ptr{Cvoid}, Int64, Cint, F32P, F32P, F32P, F32P, Ptr{Int32}, Cuint)
+meancov_to_wmp(ctx, n, d, mu, S, xi, W, st, fl) = check(ctx, ccall((:rxg_meancov_to_wmp_f32, LIB), Cint, C7, ctx.handle, n, d, mu, S, xi, W, st, fl))
+wmp_to_meancov(ctx, n, d, xi, W, mu, S, st, fl) = check(ctx, ccall((:rxg_wmp_to_meancov_f32, LIB), Cint, C7, ctx.handle, n, d, xi, W, mu, S, st, fl))
+marginal_gaussian(ctx, n, d, k, xis::Vector{F32P}, Ws::Vector{F32P}, mu, S, st, fl) =
+    check(ctx, ccall((:rxg_marginal_gaussian_f32, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Cint, Cint, Ptr{F32P}, Ptr{F32P}, F32P, F32P, Ptr{Int32}, Cuint), ctx.handle, n, d, k, xis, Ws, mu, S, st, fl))
+const S6 = (Ptr{Cvoid}, Int64, F32P, F32P, F32P, F32P, F32P, F32P, Cuint)
+rule_normal_precision_tau(ctx, n, mo, vo, mm, vm, sh, rt, fl) = check(ctx, ccall((:rxg_rule_normal_precision_tau_f32, LIB), Cint, S6, ctx.handle, n, mo, vo, mm, vm, sh, rt, fl))
+rule_normal_precision_out(ctx, n, mm, vm, sh, rt, mo, vo, fl) = check(ctx, ccall((:rxg_rule_normal_precision_out_f32, LIB), Cint, S6, ctx.handle, n, mm, vm, sh, rt, mo, vo, fl))
+prod_gamma(ctx, n, a1, b1, a2, b2, a, b, fl) = check(ctx, ccall((:rxg_prod_gamma_f32, LIB), Cint, S6, ctx.handle, n, a1, b1, a2, b2, a, b, fl))
+prod_normal(ctx, n, m1, v1, m2, v2, m, v, fl) = check(ctx, ccall((:rxg_prod_normal_f32, LIB), Cint, S6, ctx.handle, n, m1, v1, m2, v2, m, v, fl))
+rule_normal_precision_tau_joint(ctx, n, mj, Vj, sh, rt, fl) =
+    check(ctx, ccall((:rxg_rule_normal_precision_tau_joint_f32, LIB), Cint, (Ptr{Cvoid}, Int64, F32P, F32P, F32P, F32P, Cuint), ctx.handle, n, mj, Vj, sh, rt, fl))
+rule_mvnormal_precision_lambda(ctx, n, d, mo, Vo, mm, Vm, df, iS, fl) =
+    check(ctx, ccall((:rxg_rule_mvnormal_precision_lambda_f32, LIB), Cint, P8, ctx.handle, n, d, mo, Vo, mm, Vm, df, iS, fl))
+prod_wishart(ctx, n, d, df1, iS1, df2, iS2, df, iS, fl) = check(ctx, ccall((:rxg_prod_wishart_f32, LIB), Cint, P8, ctx.handle, n, d, df1, iS1, df2, iS2, df, iS, fl))
+wishart_mean(ctx, n, d, df, iS, out, st, fl) =
+    check(ctx, ccall((:rxg_wishart_mean_f32, LIB), Cint, (Ptr{Cvoid}, Int64, Cint, F32P, F32P, F32P, Ptr{Int32}, Cuint), ctx.handle, n, d, df, iS, out, st, fl))
+rule_gcv_out(ctx, n, mx, vx, mz, vz, kappa, omega, mo, vo, fl) =
+    check(ctx, ccall((:rxg_rule_gcv_out_f32, LIB), Cint,
+        (Ptr{Cvoid}, Int64, F32P, F32P, F32P, F32P, Cfloat, Cfloat, F32P, F32P, Cuint), ctx.handle, n, mx, vx, mz, vz, kappa, omega, mo, vo, fl))
+marginalrule_gcv_yx(ctx, n, my, vy, mx, vx, mz, vz, kappa, omega, m, V, fl) =
+    check(ctx, ccall((:rxg_marginalrule_gcv_yx_f32, LIB), Cint,
+        (Ptr{Cvoid}, Int64, F32P, F32P, F32P, F32P, F32P, F32P, Cfloat, Cfloat, F32P, F32P, Cuint),
+        ctx.handle, n, my, vy, mx, vx, mz, vz, kappa, omega, m, V, fl))
+rule_gcv_z_prod(ctx, n, myx, Vyx, mzp, vzp, kappa, omega, mz, vz, fl) =
+    check(ctx, ccall((:rxg_rule_gcv_z_prod_f32, LIB), Cint,
+        (Ptr{Cvoid}, Int64, F32P, F32P, F32P, F32P, Cfloat, Cfloat, F32P, F32P, Cuint), ctx.handle, n, myx, Vyx, mzp, vzp, kappa, omega, mz, vz, fl))
+
+# ---- fused whole-chain sweeps
+const SWEEP = (Ptr{Cvoid}, Cint, Cint, Cint, Int64, F32P, F32P, F32P, F32P, F32P, F32P, F32P, F32P, Ptr{UInt8}, F32P, F32P, F32P, Ptr{Int32}, Cuint)
+lgssm_smooth(ctx, d, m, T, batch, A, B, P, Q, m0, S0, u, y, mask, mean, cov, nle, st, fl) =
+    check(ctx, ccall((:rxg_lgssm_smooth_f32, LIB), Cint, SWEEP, ctx.handle, d, m, T, batch, A, B, P, Q, m0, S0, u, y, mask, mean, cov, nle, st, fl))
+lgssm_filter(ctx, d, m, T, batch, A, B, P, Q, m0, S0, u, y, mask, mean, cov, nle, st, fl) =
+    check(ctx, ccall((:rxg_lgssm_filter_f32, LIB), Cint, SWEEP, ctx.handle, d, m, T, batch, A, B, P, Q, m0, S0, u, y, mask, mean, cov, nle, st, fl))
+lgssm_filter_chunk(ctx, d, m, T, batch, A, B, P, Q, u, prev_mean, carry_cov, y, mean, cov, nle, fl) =
+    check(ctx, ccall((:rxg_lgssm_filter_chunk_f32, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Cint, Cint, Int64, F32P, F32P, F32P, F32P, F32P, F32P, F32P, F32P, F32P, F32P, F32P, Cuint),
+        ctx.handle, d, m, T, batch, A, B, P, Q, u, prev_mean, carry_cov, y, mean, cov, nle, fl))
+lgssm_vmp_gamma(ctx, T, batch, its, a, vproc, m0, v0, a0, b0, Etau, y, pm, pv, sh, rt, fl) =
+    check(ctx, ccall((:rxg_lgssm_vmp_gamma_f32, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Int64, Cint, Cfloat, Cfloat, Cfloat, Cfloat, Cfloat, Cfloat, Cfloat, F32P, F32P, F32P, F32P, F32P, Cuint),
+        ctx.handle, T, batch, its, a, vproc, m0, v0, a0, b0, Etau, y, pm, pv, sh, rt, fl))
+hgf_filter(ctx, T, batch, its, kappa, omega, zvar, yvar, init, y, out, fl) =
+    check(ctx, ccall((:rxg_hgf_filter_f32, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Int64, Cint, Cfloat, Cfloat, Cfloat, Cfloat, F32P, F32P, F32P, Cuint), ctx.handle, T, batch, its, kappa, omega, zvar, yvar, init, y, out, fl))
+hgf_filter_chunk(ctx, T, batch, its, kappa, omega, zvar, yvar, prev, y, out, fl) =
+    check(ctx, ccall((:rxg_hgf_filter_chunk_f32, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Int64, Cint, Cfloat, Cfloat, Cfloat, Cfloat, F32P, F32P, F32P, Cuint), ctx.handle, T, batch, its, kappa, omega, zvar, yvar, prev, y, out, fl))
+hgf_filter_fe(ctx, T, batch, its, kappa, omega, zvar, yvar, init, prev, y, out, fe, fl) =
+    check(ctx, ccall((:rxg_hgf_filter_fe_f32, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Int64, Cint, Cfloat, Cfloat, Cfloat, Cfloat, F32P, F32P, F32P, F32P, F32P, Cuint),
+        ctx.handle, T, batch, its, kappa, omega, zvar, yvar, init, prev, y, out, fe, fl))
+stream_vmp_gamma(ctx, T, batch, its, w, init, prev, y, out, fe, fl) =
+    check(ctx, ccall((:rxg_stream_vmp_gamma_f32, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Int64, Cint, Cfloat, F32P, F32P, F32P, F32P, F32P, Cuint), ctx.handle, T, batch, its, w, init, prev, y, out, fe, fl))
+mv_iid_wishart_vmp(ctx, d, N, batch, its, mu0, L0, nu0, iS0, EP0, y, mm, mc, df, iS, st, fl) =
+    check(ctx, ccall((:rxg_mv_iid_wishart_vmp_f32, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Cint, Int64, Cint, F32P, F32P, Cfloat, F32P, F32P, F32P, F32P, F32P, F32P, F32P, Ptr{Int32}, Cuint),
+        ctx.handle, d, N, batch, its, mu0, L0, nu0, iS0, EP0, y, mm, mc, df, iS, st, fl))
+
+# ---- diagnostics
+selftest_umma(ctx, A, B, D, fl) = check(ctx, ccall((:rxg_selftest_umma_f32, LIB), Cint, (Ptr{Cvoid}, F32P, F32P, F32P, Cuint), ctx.handle, A, B, D, fl))
+selftest_umma_shape(ctx, n, k, A, B, D, fl) = check(ctx, ccall((:rxg_selftest_umma_shape_f32, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, F32P, F32P, F32P, Cuint), ctx.handle, n, k, A, B, D, fl))
+selftest_stream(ctx, n, nr, nw, src, dst, fl) = check(ctx, ccall((:rxg_selftest_stream_f32, LIB), Cint, (Ptr{Cvoid}, Int64, Cint, Cint, F32P, F32P, Cuint), ctx.handle, n, nr, nw, src, dst, fl))
+selftest_host_fill_gbs(dst, rows, batch, nthreads, reps) = ccall((:rxg_selftest_host_fill_gbs, LIB), Cdouble, (F32P, Int64, Int64, Cint, Cint), dst, rows, batch, nthreads, reps)
+
+# ---- multi-GPU
+function comm_unique_id()
+    id = zeros(UInt8, 128)
+    ccall((:rxg_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id) == 0 || error("rxg_comm_unique_id failed (libnccl not loadable?)")
+    return id
+end
+comm_init(ctx, nranks, rank, id::Vector{UInt8}) = check(ctx, ccall((:rxg_comm_init, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), ctx.handle, nranks, rank, id))
+allgather_posteriors(ctx, d, T, bl, mean, cov, gmean, gcov, fl) =
+    check(ctx, ccall((:rxg_allgather_posteriors, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, F32P, F32P, F32P, F32P, Cuint), ctx.handle, d, T, bl, mean, cov, gmean, gcov, fl))
+function peer_export(ctx, p)
+    h = zeros(UInt8, 64)
+    check(ctx, ccall((:rxg_peer_export, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{UInt8}), ctx.handle, p, h))
+    return h
+end
+function peer_open(ctx, h::Vector{UInt8})
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ctx, ccall((:rxg_peer_open, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Ref{Ptr{Cvoid}}), ctx.handle, h, p))
+    return p[]
+end
+peer_close(ctx, p) = check(ctx, ccall((:rxg_peer_close, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), ctx.handle, p))
+peer_group(ctx, nranks, rank, flags::Vector{Ptr{Cvoid}}) = check(ctx, ccall((:rxg_peer_group, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Ptr{Cvoid}}), ctx.handle, nranks, rank, flags))
+peer_barrier(ctx, fl) = check(ctx, ccall((:rxg_peer_barrier, LIB), Cint, (Ptr{Cvoid}, Cuint), ctx.handle, fl))
+peer_allgather(ctx, n, loc, gathered::Vector{F32P}, fl) = check(ctx, ccall((:rxg_peer_allgather_f32, LIB), Cint, (Ptr{Cvoid}, Int64, F32P, Ptr{F32P}, Cuint), ctx.handle, n, loc, gathered, fl))
+lgssm_smooth_gather(ctx, d, m, T, bl, A, B, P, Q, m0, S0, u, y, mask, gm::Vector{F32P}, gc, nle, st, fl) =
+    check(ctx, ccall((:rxg_lgssm_smooth_gather_f32, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Cint, Cint, Int64, F32P, F32P, F32P, F32P, F32P, F32P, F32P, F32P, Ptr{UInt8}, Ptr{F32P}, Ptr{F32P}, F32P, Ptr{Int32}, Cuint),
+        ctx.handle, d, m, T, bl, A, B, P, Q, m0, S0, u, y, mask, gm, gc, nle, st, fl))
+end # module Lib
+
+# ---------------------------------------------------------------------------------------------- 2. device arrays and batched messages
+"""Device memory owned through the C ABI (`rxg_device_alloc`); column-major Julia dims `(n, ...)` = C layout `[...][n]`."""
+mutable struct DeviceArray{N}
+    ptr::F32P
+    dims::NTuple{N, Int}
+    ctx::Context
+    function DeviceArray(ctx::Context, dims::Vararg{Int, N}) where {N}
+        p = Lib.device_alloc(ctx, 4 * prod(dims))
+        a = new{N}(F32P(p), dims, ctx)
+        finalizer(x -> Lib.device_free(x.ctx, Ptr{Cvoid}(x.ptr)), a)
+        return a
     end
-    return mean, cov, nle
+end
+Base.size(a::DeviceArray) = a.dims
+Base.length(a::DeviceArray) = prod(a.dims)
+Base.unsafe_convert(::Type{F32P}, a::DeviceArray) = a.ptr
+function upload(ctx::Context, h::Array{Float32})
+    a = DeviceArray(ctx, size(h)...)
+    GC.@preserve h Lib.memcpy_h2d(ctx, Ptr{Cvoid}(a.ptr), Ptr{Cvoid}(pointer(h)), sizeof(h))
+    return a
+end
+function download(a::DeviceArray)
+    h = Array{Float32}(undef, a.dims...)
+    GC.@preserve h Lib.memcpy_d2h(a.ctx, Ptr{Cvoid}(pointer(h)), Ptr{Cvoid}(a.ptr), sizeof(h))
+    return h
 end
 
-"""
-    filter_chunk!(ctx, y, A, B, P, Q, prev_mean, carry_cov; u = nothing)
-
-One time-chunk of the streaming engine: replaces `Tc` ticks of the `RxInferenceEngine` executor
-(src/inference/streaming.jl:344-430) with `@autoupdates x_min_t_mean, x_min_t_cov = mean_cov(q(x_t))`
-(src/inference/autoupdates.jl:614-659; run as in benchmarks/...Benchmark.ipynb:199-216).  `y`, `prev_mean`,
-and the outputs are DEVICE arrays here (`CuPtr` reinterpreted as `Ptr`): `y[batch, m, Tc]`, `prev_mean[batch, d]`
-= means of q(x_{t0-1}); `carry_cov` is a host `Matrix{Float32}` (d x d, symmetric, so row/column major agree),
-updated in place.  Returns the device pointers of `(filt_mean[batch, d, Tc], filt_cov[batch, d, d, Tc])`;
-the next chunk's `prev_mean` is the last time slice of `filt_mean`.
-"""
-function filter_chunk!(ctx::Context, y::Ptr{Float32}, dims::NTuple{3,Int}, A, B, P, Q, prev_mean::Ptr{Float32},
-                       carry_cov::Matrix{Float32}, filt_mean::Ptr{Float32}, filt_cov::Ptr{Float32}; u = nothing)
-    batch, m, Tc = dims
-    d = size(A, 1)
-    Ar, Br, Pr, Qr = rowmajor(A), rowmajor(B), rowmajor(P), rowmajor(Q)
-    ur = u === nothing ? Float32[] : Vector{Float32}(u)
-    GC.@preserve Ar Br Pr Qr ur carry_cov begin
-        rc = ccall((:rxg_lgssm_filter_chunk_f32, LIB), Cint,
-            (Ptr{Cvoid}, Cint, Cint, Cint, Int64, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32},
-             Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Cuint),
-            ctx.handle, d, m, Tc, batch, Ar, Br, Pr, Qr, u === nothing ? C_NULL : pointer(ur),
-            prev_mean, carry_cov, y, filt_mean, filt_cov, C_NULL, RXG_PTR_DEVICE)
-        check(ctx, rc)
-    end
-    return filt_mean, filt_cov
+# Batched messages: n independent messages, structure of arrays, message index innermost (fastest) -- in
+# column-major Julia `mu` is (n, d) and `Sigma` is (n, d, d) [entry (i, r, c) = C element [r][c][i]].
+struct BatchedMvNormalMeanCovariance
+    mu::DeviceArray{2}
+    Sigma::DeviceArray{3}
 end
+struct BatchedMvNormalWeightedMeanPrecision
+    xi::DeviceArray{2}
+    W::DeviceArray{3}
+end
+struct BatchedNormalMeanVariance
+    m::DeviceArray{1}
+    v::DeviceArray{1}
+end
+struct BatchedGammaShapeRate
+    a::DeviceArray{1}
+    b::DeviceArray{1}
+end
+struct BatchedWishartFast          # (df, INVERSE scale): products are additions
+    df::DeviceArray{1}
+    invS::DeviceArray{3}
+end
+nmsg(q::BatchedMvNormalMeanCovariance) = q.mu.dims[1]
+ndim(q::BatchedMvNormalMeanCovariance) = q.mu.dims[2]
+nmsg(q::BatchedMvNormalWeightedMeanPrecision) = q.xi.dims[1]
+ndim(q::BatchedMvNormalWeightedMeanPrecision) = q.xi.dims[2]
+Base.similar(q::BatchedMvNormalMeanCovariance, d::Int = ndim(q)) =
+    BatchedMvNormalMeanCovariance(DeviceArray(q.mu.ctx, nmsg(q), d), DeviceArray(q.mu.ctx, nmsg(q), d, d))
+similar_wmp(ctx::Context, n::Int, d::Int) = BatchedMvNormalWeightedMeanPrecision(DeviceArray(ctx, n, d), DeviceArray(ctx, n, d, d))
 
-"""
-    stream_vmp_gamma!(ctx, y, dims, out; iterations = 4, w = 1f0, init = (0f0, 1f3, 1f0, 1f0), prev = C_NULL, fe = C_NULL)
+# `mean(q)`, `cov(q)`: what user code calls on posteriors (test/models/statespace/mlgssm_test.jl:121-126); host copies
+BayesBase.mean(q::BatchedMvNormalMeanCovariance) = download(q.mu)
+BayesBase.cov(q::BatchedMvNormalMeanCovariance) = download(q.Sigma)
+BayesBase.mean(q::BatchedNormalMeanVariance) = download(q.m)
+BayesBase.var(q::BatchedNormalMeanVariance) = download(q.v)
+BayesBase.mean(q::BatchedGammaShapeRate) = download(q.a) ./ download(q.b)
 
-Time-chunk of the streaming `test_model1` (test/inference/inference_tests.jl:752-775: one-step random walk observed
-with unknown precision τ ~ Gamma, `MeanField()`, priors autoupdated from `q(x_t)`, `q(τ)`).  Device pointers:
-`y[batch, Tc]`, `out[batch, 4, Tc]` = (m_x, v_x, shape, rate) per datum, optional `fe[batch, iterations, Tc]`;
-`prev[batch, 4]` = last slice of the previous chunk's `out` (then `init` is ignored).
-"""
-function stream_vmp_gamma!(ctx::Context, y::Ptr{Float32}, dims::NTuple{2,Int}, out::Ptr{Float32}; iterations::Integer = 4,
-                           w::Float32 = 1f0, init = (0f0, 1f3, 1f0, 1f0), prev::Ptr{Float32} = Ptr{Float32}(C_NULL),
-                           fe::Ptr{Float32} = Ptr{Float32}(C_NULL))
-    batch, Tc = dims
-    ini = Float32[init...]
-    GC.@preserve ini begin
-        check(ctx, ccall((:rxg_stream_vmp_gamma_f32, LIB), Cint,
-            (Ptr{Cvoid}, Cint, Int64, Cint, Cfloat, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Cuint),
-            ctx.handle, Tc, batch, iterations, w, ini, prev, y, out, fe, RXG_PTR_DEVICE))
-    end
+rowmajor32(M::AbstractMatrix) = Matrix{Float32}(transpose(M))     # Julia is column-major, the C side wants row-major constants
+rowmajor32(v::AbstractVector) = Vector{Float32}(v)
+
+# mean_cov / weightedmean_precision of a batched message: one cholinv kernel, like the reference's conversions
+function mean_cov(q::BatchedMvNormalWeightedMeanPrecision)
+    ctx = q.xi.ctx
+    out = BatchedMvNormalMeanCovariance(DeviceArray(ctx, nmsg(q), ndim(q)), DeviceArray(ctx, nmsg(q), ndim(q), ndim(q)))
+    Lib.wmp_to_meancov(ctx, nmsg(q), ndim(q), q.xi.ptr, q.W.ptr, out.mu.ptr, out.Sigma.ptr, Ptr{Int32}(C_NULL), RXG_PTR_DEVICE)
+    return out
+end
+mean_cov(q::BatchedMvNormalMeanCovariance) = q
+function weightedmean_precision(q::BatchedMvNormalMeanCovariance)
+    out = similar_wmp(q.mu.ctx, nmsg(q), ndim(q))
+    Lib.meancov_to_wmp(q.mu.ctx, nmsg(q), ndim(q), q.mu.ptr, q.Sigma.ptr, out.xi.ptr, out.W.ptr, Ptr{Int32}(C_NULL), RXG_PTR_DEVICE)
+    return out
+end
+weightedmean_precision(q::BatchedMvNormalWeightedMeanPrecision) = q
+
+const BatchedMvNormal = Union{BatchedMvNormalMeanCovariance, BatchedMvNormalWeightedMeanPrecision}
+
+# ---- @rule methods on the batched types (SURVEY.md 8a rows 1-9).  ReactiveMP dispatches rules on the message types,
+# so these coexist with the stock rules; every body is one kernel launch over all n messages.
+@rule typeof(*)(:out, Marginalisation) (m_A::PointMass{<:AbstractMatrix}, m_in::BatchedMvNormal, meta::Any) = begin
+    q = mean_cov(m_in)
+    A = rowmajor32(BayesBase.mean(m_A))
+    out = similar(q, size(A, 2))                     # rowmajor32 transposed: size(A, 2) = rows of the original matrix
+    ctx = q.mu.ctx
+    dA = upload(ctx, A)
+    Lib.rule_mul_out(ctx, nmsg(q), size(A, 2), size(A, 1), dA.ptr, 1, q.mu.ptr, q.Sigma.ptr, out.mu.ptr, out.Sigma.ptr, RXG_PTR_DEVICE)
+    return out
+end
+@rule typeof(*)(:in, Marginalisation) (m_out::BatchedMvNormal, m_A::PointMass{<:AbstractMatrix}, meta::Any) = begin
+    meta === nothing || error("`*`(:in) with a correction meta is outside the batched hot path (SURVEY.md appendix C)")
+    q = mean_cov(m_out)
+    A = rowmajor32(BayesBase.mean(m_A))
+    ctx = q.mu.ctx
+    out = similar_wmp(ctx, nmsg(q), size(A, 1))
+    dA = upload(ctx, A)
+    Lib.rule_mul_in(ctx, nmsg(q), size(A, 2), size(A, 1), dA.ptr, 1, q.mu.ptr, q.Sigma.ptr, out.xi.ptr, out.W.ptr, Ptr{Int32}(C_NULL), RXG_PTR_DEVICE)
+    return out
+end
+@rule MvNormalMeanCovariance(:out, Marginalisation) (m_μ::BatchedMvNormal, q_Σ::PointMass) = begin
+    q = mean_cov(m_μ)
+    out = similar(q)
+    dS = upload(q.mu.ctx, rowmajor32(BayesBase.mean(q_Σ)))
+    Lib.rule_mvnormal_meancov_out(q.mu.ctx, nmsg(q), ndim(q), q.mu.ptr, q.Sigma.ptr, dS.ptr, 1, out.mu.ptr, out.Sigma.ptr, RXG_PTR_DEVICE)
+    return out
+end
+@rule MvNormalMeanCovariance(:μ, Marginalisation) (m_out::BatchedMvNormal, q_Σ::PointMass) = begin
+    q = mean_cov(m_out)
+    out = similar(q)
+    dS = upload(q.mu.ctx, rowmajor32(BayesBase.mean(q_Σ)))
+    Lib.rule_mvnormal_meancov_mean(q.mu.ctx, nmsg(q), ndim(q), q.mu.ptr, q.Sigma.ptr, dS.ptr, 1, out.mu.ptr, out.Sigma.ptr, RXG_PTR_DEVICE)
+    return out
+end
+# data: a batched datum is a DeviceArray (n, d) wrapped in a PointMass
+@rule MvNormalMeanCovariance(:μ, Marginalisation) (q_out::PointMass{<:DeviceArray}, q_Σ::PointMass) = begin
+    y = BayesBase.mean(q_out)
+    n, d = y.dims
+    out = BatchedMvNormalMeanCovariance(DeviceArray(y.ctx, n, d), DeviceArray(y.ctx, n, d, d))
+    dS = upload(y.ctx, rowmajor32(BayesBase.mean(q_Σ)))
+    Lib.rule_mvnormal_meancov_mean_data(y.ctx, n, d, y.ptr, dS.ptr, 1, out.mu.ptr, out.Sigma.ptr, RXG_PTR_DEVICE)
+    return out
+end
+@rule typeof(+)(:out, Marginalisation) (m_in1::BatchedMvNormal, m_in2::BatchedMvNormal) = begin
+    a, b = mean_cov(m_in1), mean_cov(m_in2)
+    out = similar(a)
+    Lib.rule_add_out(a.mu.ctx, nmsg(a), ndim(a), a.mu.ptr, a.Sigma.ptr, b.mu.ptr, b.Sigma.ptr, out.mu.ptr, out.Sigma.ptr, RXG_PTR_DEVICE)
+    return out
+end
+@rule typeof(+)(:in1, Marginalisation) (m_out::BatchedMvNormal, m_in2::BatchedMvNormal) = begin
+    a, b = mean_cov(m_out), mean_cov(m_in2)
+    out = similar(a)
+    Lib.rule_add_in(a.mu.ctx, nmsg(a), ndim(a), a.mu.ptr, a.Sigma.ptr, b.mu.ptr, b.Sigma.ptr, out.mu.ptr, out.Sigma.ptr, RXG_PTR_DEVICE)
+    return out
+end
+@rule typeof(+)(:in2, Marginalisation) (m_out::BatchedMvNormal, m_in1::BatchedMvNormal) = begin
+    a, b = mean_cov(m_out), mean_cov(m_in1)
+    out = similar(a)
+    Lib.rule_add_in(a.mu.ctx, nmsg(a), ndim(a), a.mu.ptr, a.Sigma.ptr, b.mu.ptr, b.Sigma.ptr, out.mu.ptr, out.Sigma.ptr, RXG_PTR_DEVICE)
+    return out
+end
+@rule NormalMeanPrecision(:τ, Marginalisation) (q_out::BatchedNormalMeanVariance, q_μ::BatchedNormalMeanVariance) = begin
+    n = q_out.m.dims[1]
+    ctx = q_out.m.ctx
+    out = BatchedGammaShapeRate(DeviceArray(ctx, n), DeviceArray(ctx, n))
+    Lib.rule_normal_precision_tau(ctx, n, q_out.m.ptr, q_out.v.ptr, q_μ.m.ptr, q_μ.v.ptr, out.a.ptr, out.b.ptr, RXG_PTR_DEVICE)
+    return out
+end
+@rule NormalMeanPrecision(:τ, Marginalisation) (q_out_μ::BatchedMvNormalMeanCovariance,) = begin      # structured: joint (out, μ)
+    n = nmsg(q_out_μ)
+    ctx = q_out_μ.mu.ctx
+    out = BatchedGammaShapeRate(DeviceArray(ctx, n), DeviceArray(ctx, n))
+    Lib.rule_normal_precision_tau_joint(ctx, n, q_out_μ.mu.ptr, q_out_μ.Sigma.ptr, out.a.ptr, out.b.ptr, RXG_PTR_DEVICE)
+    return out
+end
+@rule NormalMeanPrecision(:out, Marginalisation) (m_μ::BatchedNormalMeanVariance, q_τ::BatchedGammaShapeRate) = begin
+    n = m_μ.m.dims[1]
+    ctx = m_μ.m.ctx
+    out = BatchedNormalMeanVariance(DeviceArray(ctx, n), DeviceArray(ctx, n))
+    Lib.rule_normal_precision_out(ctx, n, m_μ.m.ptr, m_μ.v.ptr, q_τ.a.ptr, q_τ.b.ptr, out.m.ptr, out.v.ptr, RXG_PTR_DEVICE)
+    return out
+end
+@rule NormalMeanPrecision(:out, Marginalisation) (q_μ::BatchedNormalMeanVariance, q_τ::BatchedGammaShapeRate) = begin
+    # mean-field: NormalMeanPrecision(mean(q_μ), mean(q_τ)) -- var(q_μ) does not enter: same kernel with v_μ = 0
+    n = q_μ.m.dims[1]
+    ctx = q_μ.m.ctx
+    zero_v = DeviceArray(ctx, n)
+    Lib.device_memset(ctx, Ptr{Cvoid}(zero_v.ptr), 0, 4n)
+    out = BatchedNormalMeanVariance(DeviceArray(ctx, n), DeviceArray(ctx, n))
+    Lib.rule_normal_precision_out(ctx, n, q_μ.m.ptr, zero_v.ptr, q_τ.a.ptr, q_τ.b.ptr, out.m.ptr, out.v.ptr, RXG_PTR_DEVICE)
+    return out
+end
+@rule MvNormalMeanPrecision(:Λ, Marginalisation) (q_out::BatchedMvNormal, q_μ::BatchedMvNormal) = begin
+    a, b = mean_cov(q_out), mean_cov(q_μ)
+    n, d = nmsg(a), ndim(a)
+    out = BatchedWishartFast(DeviceArray(a.mu.ctx, n), DeviceArray(a.mu.ctx, n, d, d))
+    Lib.rule_mvnormal_precision_lambda(a.mu.ctx, n, d, a.mu.ptr, a.Sigma.ptr, b.mu.ptr, b.Sigma.ptr, out.df.ptr, out.invS.ptr, RXG_PTR_DEVICE)
     return out
 end
 
-# --- multi-GPU (one Julia process per GPU): id from rank 0 broadcast by the host (MPI.jl / Distributed), then
-#     rxg_comm_init; after the sweep one all-gather of the posterior marginals.  With a shared model pass
-#     RXG_COV_REPLICATE: only the means cross NVLink, the chain-independent covariances are filled locally.
-function allgather_posteriors!(ctx::Context, d, T, batch_local, mean::Ptr{Float32}, cov::Ptr{Float32},
-                               gmean::Ptr{Float32}, gcov::Ptr{Float32}; shared_model::Bool = true)
-    flags = RXG_PTR_DEVICE | (shared_model ? RXG_COV_REPLICATE : UInt32(0))
-    check(ctx, ccall((:rxg_allgather_posteriors, LIB), Cint,
-        (Ptr{Cvoid}, Cint, Cint, Int64, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Cuint),
-        ctx.handle, d, T, batch_local, mean, cov, gmean, gcov, flags))
+# ---- products (override mechanism as in test/models/statespace/collision_tests.jl:35-36)
+function BayesBase.prod(::BayesBase.GenericProd, l::BatchedMvNormal, r::BatchedMvNormal)
+    a, b = weightedmean_precision(l), weightedmean_precision(r)
+    out = similar_wmp(a.xi.ctx, nmsg(a), ndim(a))
+    Lib.prod_gaussian(a.xi.ctx, nmsg(a), ndim(a), a.xi.ptr, a.W.ptr, b.xi.ptr, b.W.ptr, out.xi.ptr, out.W.ptr, RXG_PTR_DEVICE)
+    return out
+end
+function BayesBase.prod(::BayesBase.GenericProd, l::BatchedNormalMeanVariance, r::BatchedNormalMeanVariance)
+    n = l.m.dims[1]
+    out = BatchedNormalMeanVariance(DeviceArray(l.m.ctx, n), DeviceArray(l.m.ctx, n))
+    Lib.prod_normal(l.m.ctx, n, l.m.ptr, l.v.ptr, r.m.ptr, r.v.ptr, out.m.ptr, out.v.ptr, RXG_PTR_DEVICE)
+    return out
+end
+function BayesBase.prod(::BayesBase.GenericProd, l::BatchedGammaShapeRate, r::BatchedGammaShapeRate)
+    n = l.a.dims[1]
+    out = BatchedGammaShapeRate(DeviceArray(l.a.ctx, n), DeviceArray(l.a.ctx, n))
+    Lib.prod_gamma(l.a.ctx, n, l.a.ptr, l.b.ptr, r.a.ptr, r.b.ptr, out.a.ptr, out.b.ptr, RXG_PTR_DEVICE)
+    return out
+end
+function BayesBase.prod(::BayesBase.GenericProd, l::BatchedWishartFast, r::BatchedWishartFast)
+    n, d = l.invS.dims[1], l.invS.dims[2]
+    out = BatchedWishartFast(DeviceArray(l.df.ctx, n), DeviceArray(l.df.ctx, n, d, d))
+    Lib.prod_wishart(l.df.ctx, n, d, l.df.ptr, l.invS.ptr, r.df.ptr, r.invS.ptr, out.df.ptr, out.invS.ptr, RXG_PTR_DEVICE)
+    return out
+end
+"""Marginal at a random variable: product of all inbound messages, then `mean_cov` (one kernel)."""
+function marginal(msgs::Vector{<:BatchedMvNormal})
+    w = map(weightedmean_precision, msgs)
+    ctx = w[1].xi.ctx
+    n, d = nmsg(w[1]), ndim(w[1])
+    out = BatchedMvNormalMeanCovariance(DeviceArray(ctx, n, d), DeviceArray(ctx, n, d, d))
+    xis, Ws = F32P[q.xi.ptr for q in w], F32P[q.W.ptr for q in w]
+    GC.@preserve w xis Ws Lib.marginal_gaussian(ctx, n, d, length(w), xis, Ws, out.mu.ptr, out.Sigma.ptr, Ptr{Int32}(C_NULL), RXG_PTR_DEVICE)
+    return out
 end
 
-# --- drop-in for the result object: user code only calls mean./cov./var. on posteriors[:x]
-#     (test/models/statespace/mlgssm_test.jl:121-126), so unpack into MvNormalMeanCovariance:
-#
-# function infer_batched(; model, data, free_energy = false, kwargs...)
-#     pattern = recognise(model)                       # GraphPPL graph -> (A, B, P, Q, prior) or nothing
-#     pattern === nothing && return RxInfer.infer(; model, data, free_energy, kwargs...)   # stock path
-#     isempty(intersect(keys(kwargs), (:callbacks, :constraints, :meta, :predictvars, :annotations))) ||
-#         return RxInfer.infer(; model, data, free_energy, kwargs...)                       # never silently ignore
-#     μ, Σ, F = smooth(CTX[], pack(data.y), pattern...; free_energy)
-#     posteriors = Dict(:x => [MvNormalMeanCovariance(Float64.(μ[b, :, t]), Float64.(Σ[b, :, :, t]))
-#                              for t in axes(μ, 3), b in axes(μ, 1)])
-#     return InferenceResult(posteriors, nothing, free_energy ? F : nothing, model, nothing)
-# end
-#
-# --- per-rule drop-in: ReactiveMP dispatches rules by message type, so a batched message type
-#     makes `@rule` bodies one-liners over the C ABI:
-#
-# struct BatchedMvNormalMeanCovariance{P}; μ::P; Σ::P; n::Int; d::Int; end     # device pointers, SoA
-# @rule typeof(*)(:out, Marginalisation) (m_A::PointMass{<:AbstractMatrix}, m_in::BatchedMvNormalMeanCovariance) = begin
-#     out = similar(m_in)
-#     check(CTX[], ccall((:rxg_rule_mul_out_f32, LIB), Cint,
-#         (Ptr{Cvoid}, Int64, Cint, Cint, Ptr{Float32}, Cint, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Cuint),
-#         CTX[].handle, m_in.n, m_in.d, m_in.d, rowmajor(mean(m_A)), 1, m_in.μ, m_in.Σ, out.μ, out.Σ, RXG_PTR_DEVICE))
-#     return out
-# end
-# BayesBase.prod(::GenericProd, l::BatchedMvNormalWeightedMeanPrecision, r::BatchedMvNormalWeightedMeanPrecision) =
-#     ...ccall((:rxg_prod_gaussian_f32, LIB), ...)
+# ---------------------------------------------------------------------------------------------- 3. whole-chain calls on host arrays
+struct LGSSMPattern
+    A::Matrix{Float64}
+    B::Matrix{Float64}
+    P::Matrix{Float64}
+    Q::Matrix{Float64}
+    m0::Vector{Float64}
+    S0::Matrix{Float64}
+    u::Union{Nothing, Vector{Float64}}
+    transition_first::Bool            # the prior sits on the state BEFORE the first datum (mlgssm_test.jl:8-17)
+    smoothing::Bool
+end
+struct HGFPattern
+    kappa::Float64
+    omega::Float64
+    z_variance::Float64
+    y_variance::Float64
+    init::NTuple{4, Float64}          # (m_z, v_z, m_x, v_x) of the @initialization (hgf_tests.jl:51-54)
+end
+
+"""
+    pack(ys) -> Array{Float32, 3} of size (batch, m, T)
+
+`ys` is a vector (batch) of series, each a `Vector{Vector{Float64}}` of length T as `infer` takes it
+(benchmarks/...Benchmark.ipynb:140-148), or already a `(batch, m, T)` array.  The column-major `(batch, m, T)` array IS
+the C layout `y[T][m][batch]`: no transposition of the data is needed.
+"""
+pack(y::Array{Float32, 3}) = y
+pack(y::AbstractArray{<:Real, 3}) = Array{Float32, 3}(y)
+function pack(ys::AbstractVector{<:AbstractVector{<:AbstractVector{<:Real}}})
+    batch, T, m = length(ys), length(first(ys)), length(first(first(ys)))
+    out = Array{Float32}(undef, batch, m, T)
+    for b in 1:batch, t in 1:T, k in 1:m
+        out[b, k, t] = ys[b][t][k]
+    end
+    return out
+end
+"""`missing` entries -> (data with zeros, mask[batch, T] of UInt8): docs/src/manuals/inference/static.md:98-125"""
+function pack_missing(ys::AbstractVector)
+    batch, T = length(ys), length(first(ys))
+    m = length(first(skipmissing(first(ys))))
+    out = zeros(Float32, batch, m, T)
+    mask = ones(UInt8, batch, T)
+    for b in 1:batch, t in 1:T
+        if ismissing(ys[b][t])
+            mask[b, t] = 0x00
+        else
+            out[b, :, t] .= ys[b][t]
+        end
+    end
+    return out, mask
+end
+
+"""
+    sweep(ctx, p::LGSSMPattern, y; mask = nothing, free_energy = false, status = false)
+
+One fused forward(+backward) sum-product sweep over `batch` series through `rxg_lgssm_smooth_f32` /
+`rxg_lgssm_filter_f32` with HOST pointers (the library pipelines H2D | sweep | D2H itself).
+Returns `(mean[batch, d, T], cov[batch, d, d, T], neg_log_evidence[batch] or nothing, status or nothing)`.
+"""
+function sweep(ctx::Context, p::LGSSMPattern, y::Array{Float32, 3}; mask::Union{Nothing, Matrix{UInt8}} = nothing,
+               free_energy::Bool = false, status::Bool = false)
+    batch, m, T = size(y)
+    d = size(p.A, 1)
+    mean = Array{Float32}(undef, batch, d, T)
+    cov = Array{Float32}(undef, batch, d, d, T)
+    nle = free_energy ? Vector{Float32}(undef, batch) : Float32[]
+    st = status ? Vector{Int32}(undef, batch) : Int32[]
+    Ar, Br, Pr, Qr, S0r = rowmajor32(p.A), rowmajor32(p.B), rowmajor32(p.P), rowmajor32(p.Q), rowmajor32(p.S0)
+    m0r = rowmajor32(p.m0)
+    ur = p.u === nothing ? Float32[] : rowmajor32(p.u)
+    flags = p.transition_first ? RXG_TRANSITION_FIRST : UInt32(0)
+    f = p.smoothing ? Lib.lgssm_smooth : Lib.lgssm_filter
+    GC.@preserve y mask mean cov nle st Ar Br Pr Qr S0r m0r ur begin
+        f(ctx, d, m, T, batch, pointer(Ar), pointer(Br), pointer(Pr), pointer(Qr), pointer(m0r), pointer(S0r),
+          p.u === nothing ? NULLF : pointer(ur), pointer(y), mask === nothing ? Ptr{UInt8}(C_NULL) : pointer(mask),
+          pointer(mean), pointer(cov), free_energy ? pointer(nle) : NULLF, status ? pointer(st) : Ptr{Int32}(C_NULL), flags)
+    end
+    return mean, cov, free_energy ? nle : nothing, status ? st : nothing
+end
+
+"""HGF filter on host data `y[batch, T]`; returns `out[batch, 4, T]` = (m_x, v_x, m_z, v_z) and, on request, the
+Bethe free energy `[batch, iterations, T]` (its mean over T is `free_energy_history`, hgf_tests.jl:112-119)."""
+function hgf_filter(ctx::Context, p::HGFPattern, y::Matrix{Float32}; iterations::Integer = 1, free_energy::Bool = false)
+    batch, T = size(y)
+    dy = upload(ctx, y)
+    out = DeviceArray(ctx, batch, 4, T)
+    fe = free_energy ? DeviceArray(ctx, batch, Int(iterations), T) : nothing
+    init = Float32[p.init...]
+    GC.@preserve init Lib.hgf_filter_fe(ctx, T, batch, iterations, p.kappa, p.omega, p.z_variance, p.y_variance, pointer(init), NULLF,
+                                        dy.ptr, out.ptr, fe === nothing ? NULLF : fe.ptr, RXG_PTR_DEVICE)
+    return download(out), fe === nothing ? nothing : download(fe)
+end
+
+"""Gamma-precision VMP around the scalar smoother (`rxg_lgssm_vmp_gamma_f32`), host data `y[batch, T]`."""
+function vmp_gamma(ctx::Context, y::Matrix{Float32}; iterations = 10, a = 1f0, v_proc = 1f0, prior = (0f0, 100f0),
+                   gamma_prior = (1f0, 1f0), init_E_tau = 1f0)
+    batch, T = size(y)
+    dy, pm, pv = upload(ctx, y), DeviceArray(ctx, batch, T), DeviceArray(ctx, batch, T)
+    sh, rt = DeviceArray(ctx, batch), DeviceArray(ctx, batch)
+    Lib.lgssm_vmp_gamma(ctx, T, batch, iterations, a, v_proc, prior[1], prior[2], gamma_prior[1], gamma_prior[2], init_E_tau,
+                        dy.ptr, pm.ptr, pv.ptr, sh.ptr, rt.ptr, RXG_PTR_DEVICE)
+    return download(pm), download(pv), download(sh), download(rt)
+end
+
+"""Fused mean-field VMP of the multivariate IID model with Wishart precision (mv_iid_precision_tests.jl:10-41); `y[batch, d, N]`."""
+function mv_iid_wishart(ctx::Context, y::Array{Float32, 3}; iterations = 10)
+    batch, d, N = size(y)
+    dy = upload(ctx, y)
+    mm, mc, df, iS = DeviceArray(ctx, batch, d), DeviceArray(ctx, batch, d, d), DeviceArray(ctx, batch), DeviceArray(ctx, batch, d, d)
+    mu0, L0, iS0 = zeros(Float32, d), Matrix{Float32}(100I, d, d), Matrix{Float32}(I, d, d)
+    EP0 = Matrix{Float32}(d * 1f12 * I, d, d)                    # mean of vague(Wishart, d)
+    GC.@preserve mu0 L0 iS0 EP0 Lib.mv_iid_wishart_vmp(ctx, d, N, batch, iterations, pointer(mu0), pointer(L0), Float32(d + 1), pointer(iS0),
+                                                       pointer(EP0), dy.ptr, mm.ptr, mc.ptr, df.ptr, iS.ptr, Ptr{Int32}(C_NULL), RXG_PTR_DEVICE)
+    return download(mm), download(mc), download(df), download(iS)
+end
+
+# ---------------------------------------------------------------------------------------------- 4. pattern recogniser + infer_batched
+# Keyword arguments of `infer` that the fused path cannot honour: their presence routes the call to stock RxInfer
+# (SURVEY.md appendix C) -- never silently ignored.
+const FALLBACK_KEYWORDS = (:callbacks, :trace, :benchmark, :annotations, :predictvars, :meta, :options, :addons, :postprocess,
+                           :events, :uselock, :warn, :session, :showprogress)
+
+# constant (PointMass) neighbour of a factor node on interface `name`, or `nothing`
+function constant_on(model, nodeprops, name::Symbol)
+    for (label, edge, data) in GraphPPL.neighbors(nodeprops)
+        GraphPPL.getname(edge) === name || continue
+        vp = GraphPPL.getproperties(data)
+        return GraphPPL.is_constant(vp) ? GraphPPL.value(vp) : nothing
+    end
+    return nothing
+end
+variable_on(nodeprops, name::Symbol) = begin
+    for (label, edge, data) in GraphPPL.neighbors(nodeprops)
+        GraphPPL.getname(edge) === name && return label
+    end
+    nothing
+end
+
+"""
+    recognise(generator, one_series) -> LGSSMPattern | nothing
+
+Instantiates the GraphPPL graph of `generator` conditioned on ONE series (as `infer` does: `RxInfer.create_model(generator |
+data)`, src/model/model.jl:146-178) and pattern-matches it against the linear-Gaussian state-space chain
+
+    x[1] ~ MvNormal(m0, S0) [or x_prior ~ ...; x[1] ~ MvNormal(A * x_prior (+ u), P)]
+    x[t] ~ MvNormal(mean = A * x[t-1] (+ u), cov = P),   y[t] ~ MvNormal(mean = B * x[t], cov = Q)
+
+with constant A, B, P, Q shared by all steps (benchmarks/...Benchmark.ipynb:95-105; test/models/statespace/mlgssm_test.jl:8-17;
+ulgssm_tests.jl:7-16).  Anything else -- other node types, random-variable parameters, non-constant matrices, form
+constraints -- returns `nothing` and the caller falls back to stock ReactiveMP.
+"""
+function recognise(generator, one_series)
+    model = RxInfer.getmodel(RxInfer.create_model(generator | (y = one_series,)))
+    mvn = Any[]      # (label, props) of MvNormalMeanCovariance nodes
+    muls = Any[]
+    adds = Any[]
+    ok = Ref(true)
+    GraphPPL.factor_nodes(model) do label, node
+        props = GraphPPL.getproperties(node)
+        f = GraphPPL.fform(props)
+        if f === MvNormalMeanCovariance
+            push!(mvn, props)
+        elseif f === typeof(*) || f === (*)
+            push!(muls, props)
+        elseif f === typeof(+) || f === (+)
+            push!(adds, props)
+        else
+            ok[] = false
+        end
+    end
+    ok[] || return nothing
+    T = length(one_series)
+    # observation nodes: `out` is a data variable; transition nodes: `out` random, mean = result of `*` (or `+`)
+    Qs, Ps, priors = Any[], Any[], Any[]
+    for props in mvn
+        Σ = constant_on(model, props, :Σ)
+        Σ === nothing && return nothing
+        out = variable_on(props, :out)
+        vp = GraphPPL.getproperties(model[out])
+        μc = constant_on(model, props, :μ)
+        if GraphPPL.is_data(vp)
+            push!(Qs, Σ)
+        elseif μc !== nothing
+            push!(priors, (μc, Σ))
+        else
+            push!(Ps, Σ)
+        end
+    end
+    length(priors) == 1 && length(Qs) == T || return nothing
+    allsame(v) = all(x -> x == first(v), v)
+    (allsame(Qs) && (isempty(Ps) || allsame(Ps))) || return nothing
+    As = Any[]
+    for props in muls
+        Ac = constant_on(model, props, :in)          # GraphPPL names the first operand of `A * x` by position
+        Ac === nothing && (Ac = constant_on(model, props, :A))
+        Ac isa AbstractMatrix || return nothing
+        push!(As, Ac)
+    end
+    mats = unique(As)
+    length(mats) <= 2 || return nothing
+    d = length(priors[1][1])
+    # B multiplies into observation means (T uses), A into transition means (T-1 or T uses)
+    counts = [count(==(M), As) for M in mats]
+    B = mats[findfirst(==(T), counts)]
+    Aidx = findfirst(c -> c == T - 1 || (c == T && length(mats) == 1), counts)
+    transition_first = false
+    if length(mats) == 1                      # A == B numerically: ambiguous only if T - 1 transitions + T observations = 2T - 1 uses
+        A = mats[1]
+        transition_first = length(As) == 2T
+    else
+        iA = findfirst(!=(B), mats)
+        A = mats[iA]
+        transition_first = count(==(A), As) == T
+    end
+    us = Any[]
+    for props in adds
+        c = constant_on(model, props, :in)
+        c === nothing && return nothing
+        push!(us, c)
+    end
+    (isempty(us) || allsame(us)) || return nothing
+    P = isempty(Ps) ? zeros(d, d) : first(Ps)
+    return LGSSMPattern(Matrix{Float64}(A), Matrix{Float64}(B), Matrix{Float64}(P), Matrix{Float64}(first(Qs)),
+                        Vector{Float64}(priors[1][1]), Matrix{Float64}(priors[1][2]),
+                        isempty(us) ? nothing : Vector{Float64}(first(us)), transition_first, true)
+end
+
+"""
+    infer_batched(; model, data, iterations = nothing, free_energy = false, context = default_context(), kwargs...)
+
+Drop-in for `RxInfer.infer` over a BATCH of independent series: `data = (y = ys,)` with `ys[b]` the series `infer` would
+take.  When the model is recognised as a linear-Gaussian state-space chain with constant parameters and no keyword of
+`FALLBACK_KEYWORDS` is present, the whole batch runs as ONE fused sweep on the GPU and the result is an
+`InferenceResult` whose `posteriors[:x]` is a `T x batch` matrix of `MvNormalMeanCovariance` (user code calling
+`mean.`, `cov.`, `var.` is unchanged; src/inference/batch.jl:475-481).  Otherwise every series goes through stock
+`RxInfer.infer` -- same results as today, nothing silently ignored.
+"""
+function infer_batched(; model, data, iterations = nothing, free_energy = false, context::Context = default_context(),
+                       constraints = nothing, initialization = nothing, returnvars = nothing, materialize::Bool = true, kwargs...)
+    ys = data.y
+    stock() = map(b -> RxInfer.infer(; model, data = (y = ys[b],), iterations, free_energy, constraints, initialization, returnvars, kwargs...),
+                  collect(eachindex(ys)))
+    any(k -> haskey(kwargs, k), FALLBACK_KEYWORDS) && return stock()
+    (constraints === nothing && initialization === nothing) || return stock()      # BP on a tree needs neither
+    (iterations === nothing || iterations == 1) || return stock()                  # KeepEach on BP is per-iteration output
+    has_missing = any(s -> any(ismissing, s), ys)
+    pattern = recognise(model, has_missing ? collect(skipmissing(first(ys))) : first(ys))
+    pattern === nothing && return stock()
+    RxInfer.ReactiveMP.is_predefined_node(MvNormalMeanCovariance)                 # touches the node registry: fails early if RxInfer is broken
+    y, mask = has_missing ? pack_missing(ys) : (pack(ys), nothing)
+    μ, Σ, F, _ = sweep(context, pattern, y; mask, free_energy = free_energy !== false)
+    batch, d, T = size(μ)
+    posteriors = if materialize
+        Dict(:x => [MvNormalMeanCovariance(Float64.(μ[b, :, t]), Float64.(Σ[b, :, :, t])) for t in 1:T, b in 1:batch])
+    else
+        Dict(:x => (mean = μ, cov = Σ))                # structure of arrays: (batch, d, T) / (batch, d, d, T)
+    end
+    fe = free_energy === false ? nothing : Float64.(F)
+    return RxInfer.InferenceResult(posteriors, Dict{Symbol, Any}(), fe, model, nothing)
+end
+
+# ---------------------------------------------------------------------------------------------- 5. streaming engine in time-chunks
+"""
+Twin of `RxInferenceEngine` (src/inference/streaming.jl:16-140) for `batch` lock-step datastreams of the filtering
+model with `@autoupdates x_min_t_mean, x_min_t_cov = mean_cov(q(x_t))` (src/inference/autoupdates.jl:614-659): the
+stream is consumed in time-chunks, one `rxg_lgssm_filter_chunk_f32` call per chunk; the carry (per-chain means on the
+device, the chain-independent covariance on the host) lives here between chunks.
+"""
+mutable struct BatchedInferenceEngine
+    ctx::Context
+    pattern::LGSSMPattern
+    batch::Int
+    prev_mean::DeviceArray{2}          # (batch, d)
+    carry_cov::Matrix{Float32}         # d x d (symmetric: row/column major agree)
+    keephistory::Int
+    history::Vector{Any}
+    free_energy::Vector{Vector{Float32}}
+    ticks::Int
+    running::Bool
+    completed::Bool
+end
+function BatchedInferenceEngine(ctx::Context, p::LGSSMPattern, batch::Integer; keephistory::Integer = 0)
+    d = length(p.m0)
+    pm = upload(ctx, repeat(Float32.(p.m0)', batch, 1))
+    return BatchedInferenceEngine(ctx, p, batch, pm, Matrix{Float32}(p.S0), keephistory, Any[], Vector{Float32}[], 0, false, false)
+end
+function start!(e::BatchedInferenceEngine)
+    e.completed && error("The engine has been completed or errored. Cannot start an exhausted engine.")   # streaming.jl:188-191
+    e.running = true
+    return e
+end
+stop!(e::BatchedInferenceEngine) = (e.running = false; e)
+"""Consume one chunk `y[batch, m, Tc]` (host); returns `(filt_mean, filt_cov)` on the host."""
+function push_chunk!(e::BatchedInferenceEngine, y::Array{Float32, 3}; free_energy::Bool = false)
+    e.running || error("the engine is not running: call start!")
+    batch, m, Tc = size(y)
+    d = length(e.pattern.m0)
+    p = e.pattern
+    dy = upload(e.ctx, y)
+    fm, fc = DeviceArray(e.ctx, batch, d, Tc), DeviceArray(e.ctx, batch, d, d, Tc)
+    nle = free_energy ? DeviceArray(e.ctx, batch) : nothing
+    Ar, Br, Pr, Qr = rowmajor32(p.A), rowmajor32(p.B), rowmajor32(p.P), rowmajor32(p.Q)
+    ur = p.u === nothing ? Float32[] : rowmajor32(p.u)
+    cc = e.carry_cov
+    GC.@preserve Ar Br Pr Qr ur cc Lib.lgssm_filter_chunk(e.ctx, d, m, Tc, batch, pointer(Ar), pointer(Br), pointer(Pr), pointer(Qr),
+        p.u === nothing ? NULLF : pointer(ur), e.prev_mean.ptr, pointer(cc), dy.ptr, fm.ptr, fc.ptr, nle === nothing ? NULLF : nle.ptr, RXG_PTR_DEVICE)
+    hm = download(fm)
+    e.prev_mean = upload(e.ctx, hm[:, :, end])                     # q(x_t) of the last tick = next chunk's prior means
+    e.ticks += Tc
+    free_energy && push!(e.free_energy, download(nle))
+    if e.keephistory > 0
+        push!(e.history, hm)
+        while length(e.history) > 1 && sum(h -> size(h, 3), e.history) - size(first(e.history), 3) >= e.keephistory
+            popfirst!(e.history)
+        end
+    end
+    return hm, download(fc)
+end
+
+# ---------------------------------------------------------------------------------------------- 6. multi-GPU (one Julia process per GPU)
+"""
+Peer-mapped gathered buffers of one rank (`rxg_peer_*`): allocate, export the CUDA IPC handles, let the HOST exchange
+them (`exchange(handles) -> Vector of every rank's handles`, e.g. `MPI.Allgather` or a `Distributed` channel), map the
+peers, register the group.  Afterwards `smooth_gather!` is the fused sweep + all-gather: the sweep kernel stores the
+posteriors into every rank's buffer over NVLink while it runs.
+"""
+mutable struct PeerGroup
+    ctx::Context
+    nranks::Int
+    rank::Int
+    T::Int
+    d::Int
+    b::Int
+    mean_ptrs::Vector{F32P}
+    cov_ptrs::Vector{F32P}
+    own_mean::Ptr{Cvoid}
+    own_cov::Ptr{Cvoid}
+    own_flags::Ptr{Cvoid}
+end
+function PeerGroup(ctx::Context, nranks::Integer, rank::Integer, T::Integer, d::Integer, b::Integer, exchange::Function)
+    nm, nc = 4 * nranks * T * d * b, 4 * nranks * T * d * d * b
+    pm, pc, pf = Lib.device_alloc(ctx, nm), Lib.device_alloc(ctx, nc), Lib.device_alloc(ctx, 4 * RXG_MAX_PEERS)
+    Lib.device_memset(ctx, pf, 0, 4 * RXG_MAX_PEERS)
+    mine = (Lib.peer_export(ctx, pm), Lib.peer_export(ctx, pc), Lib.peer_export(ctx, pf))
+    all = exchange(mine)                                            # Vector (length nranks, rank order) of the same triples
+    mp, cp, fp = F32P[], F32P[], Ptr{Cvoid}[]
+    for g in 0:(nranks - 1)
+        if g == rank
+            push!(mp, F32P(pm)); push!(cp, F32P(pc)); push!(fp, pf)
+        else
+            hm, hc, hf = all[g + 1]
+            push!(mp, F32P(Lib.peer_open(ctx, hm))); push!(cp, F32P(Lib.peer_open(ctx, hc))); push!(fp, Lib.peer_open(ctx, hf))
+        end
+    end
+    Lib.peer_group(ctx, nranks, rank, fp)
+    return PeerGroup(ctx, nranks, rank, T, d, b, mp, cp, pm, pc, pf)
+end
+"""Fused smoothing sweep + all-gather of this rank's shard `y` (device array (b, m, T)); `replicate_cov` for shared models."""
+function smooth_gather!(g::PeerGroup, p::LGSSMPattern, y::DeviceArray{3}; replicate_cov::Bool = true)
+    b, m, T = y.dims
+    Ar, Br, Pr, Qr, S0r, m0r = rowmajor32(p.A), rowmajor32(p.B), rowmajor32(p.P), rowmajor32(p.Q), rowmajor32(p.S0), rowmajor32(p.m0)
+    flags = RXG_PTR_DEVICE | (replicate_cov ? RXG_COV_REPLICATE : UInt32(0)) | (p.transition_first ? RXG_TRANSITION_FIRST : UInt32(0))
+    GC.@preserve Ar Br Pr Qr S0r m0r Lib.lgssm_smooth_gather(g.ctx, g.d, m, T, b, pointer(Ar), pointer(Br), pointer(Pr), pointer(Qr),
+        pointer(m0r), pointer(S0r), NULLF, y.ptr, Ptr{UInt8}(C_NULL), g.mean_ptrs, g.cov_ptrs, NULLF, Ptr{Int32}(C_NULL), flags)
+    return g
+end
+"""NCCL variant (round-1 design): communicator from a unique id broadcast by the host, one all-gather after the sweep."""
+function allgather_posteriors!(ctx::Context, d, T, batch_local, mean::F32P, cov::F32P, gmean::F32P, gcov::F32P; shared_model::Bool = true)
+    flags = RXG_PTR_DEVICE | (shared_model ? RXG_COV_REPLICATE : UInt32(0))
+    Lib.allgather_posteriors(ctx, d, T, batch_local, mean, cov, gmean, gcov, flags)
+end
 
 end # module
