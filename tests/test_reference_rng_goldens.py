@@ -120,8 +120,8 @@ def test_gpu_hgf_reference_data_assertions(ctx):
     ref = hgf.hgf_filter(yb.astype(np.float64)[:, :1], iters=10)[:, :, 0]
     for c in (0, 63):
         hgf_reference_assertions(out[:, :, c], z, x)
-    assert np.linalg.norm(out[:, 0, 0] - ref[:, 0]) / np.linalg.norm(ref[:, 0]) < 1e-4
-    assert np.linalg.norm(out[:, 2, 0] - ref[:, 2]) / np.linalg.norm(ref[:, 2]) < 5e-3
+    assert np.linalg.norm(out[:, 0, 0] - ref[:, 0]) / np.linalg.norm(ref[:, 0]) < 1e-6
+    assert np.linalg.norm(out[:, 2, 0] - ref[:, 2]) / np.linalg.norm(ref[:, 2]) < 1e-5
 
 
 @pytest.mark.gpu
@@ -137,6 +137,7 @@ def test_gpu_hgf_free_energy_reproduces_reference_pin(ctx):
     assert hist.shape == (10, 32)                                                   # :117
     print("device HGF free energy history (chain 0):", hist[:, 0])
     assert np.all(np.abs(hist[-1] - 1.009879989585) < 0.01)                         # :118, the reference's tolerance
+    assert np.all(np.abs(hist[-1] - 1.009879989585) < 2e-4)                         # what the device actually achieves (~1e-5)
     d = np.diff(hist[:, 0])
     assert np.all(d[np.abs(d) > 0.1] < 0)                                           # :119
     hgf_reference_assertions(out[:, :, 0].cpu().numpy(), z, x)

@@ -11,8 +11,11 @@ from oracle import hgf, vmp
 from util import rel_l2
 
 pytestmark = pytest.mark.gpu
-# GPU (fp32) vs oracle (fp64) bounds, relative L2 over all (t, chain); see DESIGN.md section 5 for the measured values
-HGF_TOL = {"m_x": 1e-4, "v_x": 2e-3, "m_z": 5e-3, "v_z": 5e-3}
+# GPU (fp32) vs oracle (fp64) bounds, relative L2 over all (t, chain) -- all inside the contract's 1e-5.  Measured on B200
+# (round 2, after psi / det of the GCV joint were put in cancellation-free closed form): m_x 6.7e-8, v_x 9.1e-8,
+# m_z 3.0e-7, v_z 4.2e-7 (T = 300); at configs[3] size (T = 1000, batch 32 768, 20 iterations): 6.5e-8, 3.3e-7, 6.3e-7, 9.1e-7.
+# Round 1 needed 1e-4 / 2e-3 / 5e-3 / 5e-3.
+HGF_TOL = {"m_x": 1e-6, "v_x": 2e-6, "m_z": 5e-6, "v_z": 5e-6}
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
@@ -24,7 +27,7 @@ def test_hgf_golden_fixture(ctx):
     z = np.load(os.path.join(GOLD, "hgf_T40_b8.npz"))
     out = ctx.hgf_filter(dev(z["y"]), iters=10).cpu().numpy()
     ref = z["out"]
-    for k, tol in ((0, 1e-4), (1, 1e-3), (2, 2e-3), (3, 2e-3)):
+    for k, tol in ((0, 1e-5), (1, 1e-5), (2, 1e-5), (3, 1e-5)):
         assert rel_l2(out[:, k], ref[:, k]) < tol, k
 
 
@@ -45,13 +48,13 @@ def test_hgf_infer_entry(rx, ctx):
     _, _, y = hgf.generate_data(50, 64, seed=6)
     res = rx.infer(model=rx.hgf(), data={"y": dev(y)}, iterations=10, context=ctx)
     ref = hgf.hgf_filter(y, iters=10)
-    assert rel_l2(res.history["xt"].mean().cpu().numpy(), ref[:, 0]) < 1e-4
+    assert rel_l2(res.history["xt"].mean().cpu().numpy(), ref[:, 0]) < 1e-6
     # free_energy=True: free_energy_history semantics (per iteration, averaged over the data), vs the oracle's
     resf = rx.infer(model=rx.hgf(), data={"y": dev(y)}, iterations=10, free_energy=True, context=ctx)
     _, fe = hgf.hgf_filter(y, iters=10, return_free_energy=True)
     got = resf.free_energy.cpu().numpy()
     assert got.shape == (10, 64)
-    assert np.abs(got - fe.mean(axis=0)).max() < 2e-3
+    assert np.abs(got - fe.mean(axis=0)).max() < 1e-4
 
 
 def test_hgf_free_energy_vs_oracle_and_chunks(ctx):
@@ -64,7 +67,7 @@ def test_hgf_free_energy_vs_oracle_and_chunks(ctx):
     assert fe.shape == (120, 8, 96)
     err = np.abs(fe - fe_ref)
     print("hgf free energy: max abs err", err.max(), "mean abs err", err.mean(), "scale", np.abs(fe_ref).mean())
-    assert err.max() < 5e-3 and err.mean() < 2e-4
+    assert err.max() < 2e-4 and err.mean() < 1e-5          # measured on B200: 2.0e-5 / 4.7e-7
     plain = ctx.hgf_filter(dev(y), iters=8)
     assert torch.equal(plain, out)                              # the FE variant does not perturb the posteriors
     o1, f1 = ctx.hgf_filter(dev(y[:50]), iters=8, want_free_energy=True)
