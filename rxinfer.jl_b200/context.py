@@ -530,6 +530,24 @@ class Context:
         return gm, gc
 
 
+def host_empty(*shape, dtype=torch.float32):
+    """Pinned host tensor from ``rxg_host_alloc`` -- what a C / Julia host of the ABI would use: page-locked and, on a
+    multi-socket machine, interleaved over the NUMA nodes (see rxg_api.cu).  Freed when the tensor is collected."""
+    lib = L.load()
+    n = int(np.prod(shape))
+    item = torch.empty((), dtype=dtype).element_size()
+    p = c_void_p()
+    rc = lib.rxg_host_alloc(ctypes.byref(p), max(n * item, 1))
+    if rc != 0:
+        raise L.RxGaussError(rc, "rxg_host_alloc failed")
+    buf = (ctypes.c_char * (n * item)).from_address(p.value)
+    t = torch.frombuffer(buf, dtype=dtype, count=n).reshape(*shape)
+    import weakref
+    weakref.finalize(buf, lib.rxg_host_free, c_void_p(p.value))
+    t._rxg_keep = buf
+    return t
+
+
 class DeviceBuffer:
     """Device memory from ``rxg_device_alloc`` (plain cudaMalloc: exportable as a CUDA IPC handle at offset 0),
     viewable as a torch tensor through ``__cuda_array_interface__``.  Freed with the object."""

@@ -6,10 +6,15 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <immintrin.h>
 #include <sched.h>
 
+#include <map>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -94,6 +99,20 @@ void* staging(rxg_ctx* ctx, size_t bytes) { return grow(ctx, &ctx->stage, &ctx->
 }  // namespace rxg
 
 using namespace rxg;
+
+static std::mutex g_host_mu;
+static std::map<void*, size_t> g_host_mapped;      // interleaved allocations: base -> length
+
+static int numa_node_count() {
+    int n = 0;
+    for (; n < 64; ++n) {
+        char path[96];
+        snprintf(path, sizeof(path), "/sys/devices/system/node/node%d", n);
+        if (access(path, F_OK) != 0) break;
+    }
+    return n;
+}
+
 
 extern "C" {
 
@@ -192,11 +211,48 @@ int rxg_sync(rxg_ctx* ctx) {
     return examine_bad_flag(ctx);      // a deferred (RXG_ASYNC) call may have flagged a non-SPD model
 }
 
+// Pinned host memory.  On a multi-socket host the pages are INTERLEAVED over the NUMA nodes (mmap + mbind +
+// cudaHostRegister): a host-pointer call writes 4 (d + d^2) bytes per (chain, step) into the caller's output, and one
+// socket's DRAM write bandwidth (~170 GB/s measured on the 2 x 8562Y+ box) is then the end-to-end limit; interleaving
+// lets the host-side covariance broadcast and the PCIe DMA use the memory controllers of every socket.
 int rxg_host_alloc(void** out, size_t bytes) {
-    if (!out) return RXG_ERR_BAD_ARG;
+    if (!out || bytes == 0) return RXG_ERR_BAD_ARG;
+    *out = nullptr;
+    const int nodes = numa_node_count();
+    const char* off = getenv("RXG_HOST_NO_INTERLEAVE");
+    if (nodes > 1 && bytes >= ((size_t)64 << 20) && !(off && atoi(off) != 0)) {
+        const size_t len = (bytes + 4095) / 4096 * 4096;
+        void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (p != MAP_FAILED) {
+            unsigned long mask = (nodes >= 64) ? ~0UL : ((1UL << nodes) - 1);
+            const long rc = syscall(SYS_mbind, p, len, 3 /* MPOL_INTERLEAVE */, &mask, (unsigned long)(nodes + 1), 0U);
+            if (rc == 0 && cudaHostRegister(p, len, cudaHostRegisterDefault) == cudaSuccess) {
+                std::lock_guard<std::mutex> lk(g_host_mu);
+                g_host_mapped[p] = len;
+                *out = p;
+                return RXG_OK;
+            }
+            cudaGetLastError();
+            munmap(p, len);
+        }
+    }
     return cudaMallocHost(out, bytes) == cudaSuccess ? RXG_OK : RXG_ERR_CUDA;
 }
-int rxg_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? RXG_OK : RXG_ERR_CUDA; }
+int rxg_host_free(void* p) {
+    if (!p) return RXG_OK;
+    size_t len = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_host_mu);
+        auto it = g_host_mapped.find(p);
+        if (it != g_host_mapped.end()) { len = it->second; g_host_mapped.erase(it); }
+    }
+    if (len) {
+        cudaHostUnregister(p);
+        munmap(p, len);
+        return RXG_OK;
+    }
+    return cudaFreeHost(p) == cudaSuccess ? RXG_OK : RXG_ERR_CUDA;
+}
 
 int rxg_supports(int d, int m) { return lgssm_supported(d, m) ? 1 : 0; }
 

@@ -60,6 +60,14 @@ __global__ void __launch_bounds__(256) peer_push_kernel(const float4* __restrict
     }
 }
 
+// unaligned slabs (odd element counts): same copy, one float per thread
+__global__ void __launch_bounds__(256) peer_push_scalar_kernel(const float* __restrict__ src, PushDst d, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = __ldg(src + i);
+        for (int g = 0; g < d.n; ++g) d.p[g][i] = v;
+    }
+}
+
 // Replicates the chain-independent covariances of a shared model into the rank-major gathered layout
 // [G][rows][b] without moving them over NVLink: every rank holds the same rows = T*d*d values (the
 // gain tables depend on the model only), so the gather of 4 d^2 of the 4 (d + d^2) bytes per
@@ -108,7 +116,14 @@ static int peer_push(rxg_ctx* ctx, const float* local, float* const* dst, int nd
     d.n = ndst;
     bool al = (reinterpret_cast<uintptr_t>(local) & 15) == 0;
     for (int g = 0; g < ndst; ++g) { d.p[g] = dst[g]; al = al && (reinterpret_cast<uintptr_t>(dst[g]) & 15) == 0; }
-    if (!al) return fail(ctx, RXG_ERR_BAD_ARG, "peer push: slabs must be 16-byte aligned (batch_local * 4 bytes a multiple of 16)");
+    const int64_t cap0 = (int64_t)ctx->sm_count * 8;
+    if (!al) {
+        int64_t blocks = (n + 255) / 256;
+        if (blocks > cap0) blocks = cap0;
+        peer_push_scalar_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(local, d, n);
+        ctx->launches += 1;
+        return check_cuda(ctx, cudaGetLastError(), "peer_push_scalar_kernel");
+    }
     const int64_t n4 = n / 4;
     const int nt = (int)(n - 4 * n4);
     int64_t blocks = (n4 + 255) / 256;

@@ -571,3 +571,19 @@ def test_time_segmented_sweep_full_size(ctx):
     idx = [0, 31, 32, 40000, 65535]
     ref = lgssm.smooth_reference_schedule(y[:, :, idx].cpu().numpy(), **mod)
     assert rel_l2(r["mean"][:, :, idx].cpu().numpy(), ref["mean"]) < TOL_MEAN
+
+
+def test_large_state_d64_full_length(ctx):
+    """BASELINE configs[2] at its real length (d = 64, T = 1000): the 3xTF32 tensor-core recursion against the fp64
+    oracle over all 1000 steps (round 1 stopped at T = 300), per-chain covariance output included."""
+    mod = f32_model(lgssm.dense_model(64))
+    T, batch = 1000, 6
+    _, y = lgssm.generate_data(mod, T, batch, seed=64)
+    ref = lgssm.smooth_reference_schedule(y, **mod)
+    r = ctx.lgssm(dev(y), **_kw(mod), smooth=True, want_evidence=True)
+    em = rel_l2(r["mean"].cpu().numpy(), ref["mean"])
+    ec = rel_l2(r["cov"].cpu().numpy(), ref["cov"])
+    print("d=64 T=1000: mean relL2", em, "cov relF", ec)
+    assert em < TOL_MEAN and ec < TOL_COV
+    check(r, ref)
+    assert torch.equal(r["cov"][..., 0], r["cov"][..., batch - 1])
