@@ -21,12 +21,15 @@
 // the headline config -- inside the 126 MB L2 when the y lines are loaded evict_last in pass A, evict_first in pass B
 // and the 80 B/step of posterior stores are evict_first (createpolicy + .L2::cache_hint).  DRAM traffic per
 // (chain, step) then is 4 (m + d + d^2) = the algorithmic 96 B at d = m = 4 (checkpoint kernel: 114 B).
-// STATUS (B200, round 2): EXPERIMENTAL, not the default.  Measured 8.2 ms against 1.35 ms for lgssm_shared_kernel at
-// the headline config: with the 16-step segment held in registers the three fully unrolled loops make 31 K
-// instructions (500 KB of code) and the eight warps of a CTA sit at eight different places of it -- the kernel is
-// instruction-fetch bound (the same sensitivity showed on lgssm_shared_kernel when peer-store loops grew it from 3.4 K
-// to 11 K instructions: 1.35 -> 2.25 ms).  Kept selectable (RXG_OPT_SWEEP_VARIANT = 3) with its parity tests as the
-// record of the experiment; see DESIGN.md.
+// STATUS (B200, round 2): EXPERIMENTAL, not the default (RXG_OPT_SWEEP_VARIANT = 3 selects it; parity tests keep it honest).
+// Measured at the headline config: 1.96 ms (+ 0.28 ms for seg_tables_kernel) against 1.35 ms for lgssm_shared_kernel.
+// Two lessons recorded in DESIGN.md: (1) these sweeps are instruction-cache sensitive -- a first version with per-store
+// peer loops was 31 K instructions and took 8.2 ms, this one is 5.1 K (lgssm_shared_kernel: 3.4 K; the same effect took
+// that kernel from 1.35 to 2.25 ms when peer loops grew it to 11 K); (2) with y[T][m][batch] a CTA that owns 32 chains for
+// all T gathers 128-byte pieces 256 KB apart, and once the CTAs drift apart in time the DRAM pages and the output rows
+// are no longer shared between neighbouring CTAs -- the lock-step walk of lgssm_shared_kernel (all CTAs at the same t)
+// is what keeps its accesses row-coherent.  The L2 reuse the design aims at needs chain tiles that are wide in memory
+// (>= 4 K chains) AND time-parallel work inside them, i.e. a grouped three-phase schedule; that is the follow-up.
 #pragma once
 #include "rxg_lgssm_common.cuh"
 #include "rxg_lgssm_shared.cuh"

@@ -1,6 +1,11 @@
 import os
 import sys
 
+# Several contexts (= "ranks") with their own streams share one process in tests/test_peer_gather_gpu.py; with the default
+# 8 hardware work queues their streams can alias, and a kernel queued behind another rank's spinning barrier kernel would
+# never start.  Must be set before the CUDA context exists.  (Real multi-GPU jobs run one process per GPU.)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

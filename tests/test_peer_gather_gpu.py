@@ -32,6 +32,21 @@ def ranks(rx):
         c.close()
 
 
+def test_two_processes_cuda_ipc():
+    """The real multi-process protocol: handles exported, exchanged over torch.distributed (gloo), opened with
+    cudaIpcOpenMemHandle; the two ranks use cuda:0 and cuda:1 when there are two GPUs, else share cuda:0."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.path.join(ROOT, "tests") + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    port = 29500 + (os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "workers", "peer_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=env, cwd=ROOT)
+    print(r.stdout[-3000:], r.stderr[-3000:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("PEER_WORKER_OK") == 2
+
+
 @pytest.mark.parametrize("G", [2, 3])
 @pytest.mark.parametrize("variant", ["full", "replicate", "masked", "per_chain_path"])
 def test_virtual_ranks_fused_gather(rx, ranks, G, variant):
@@ -68,8 +83,8 @@ def test_virtual_ranks_fused_gather(rx, ranks, G, variant):
     assert rel_l2(rx.sharding.assemble_gathered(groups[0].cov).cpu().numpy(), ref["cov"]) < TOL_COV
 
 
-def test_virtual_ranks_large_state_and_generic_allgather(rx, ranks):
-    """d = 16 (tensor-core family: no in-kernel peer stores => slab push) and the generic rxg_peer_allgather_f32."""
+def test_virtual_ranks_large_state(rx, ranks):
+    """d = 16 (tensor-core family: no in-kernel peer stores => slab push)."""
     from rxinfer_jl_b200.sharding import PeerGroup
     mod = f32_model(lgssm.dense_model(16))
     T, b, G = 30, 64, 2
@@ -91,31 +106,23 @@ def test_virtual_ranks_large_state_and_generic_allgather(rx, ranks):
         for gr in groups:
             for r in range(G):
                 assert torch.equal(gr.mean[r], refs[r][1]["mean"]) and torch.equal(gr.cov[r], refs[r][1]["cov"])
-    # generic gather of an arbitrary array (here: an odd-sized one, exercising the scalar tail)
-    n = 4 * 1000 + 3
-    bufs = [rx.context.DeviceBuffer(c, 4 * G * n) for c in cs]
-    loc = [torch.randn(n, device="cuda") for _ in cs]
-    torch.cuda.synchronize()
-    for r, c in enumerate(cs):
-        c.peer_allgather(loc[r], [bf.ptr for bf in bufs], asynchronous=True)
-    for c in cs:
-        c.sync()
-    for bf in bufs:
-        t = bf.tensor(G, n)
-        for r in range(G):
-            assert torch.equal(t[r], loc[r])
 
 
-def test_two_processes_cuda_ipc():
-    """The real multi-process protocol: handles exported, exchanged over torch.distributed (gloo), opened with
-    cudaIpcOpenMemHandle; the two ranks use cuda:0 and cuda:1 when there are two GPUs, else share cuda:0."""
-    if not torch.cuda.is_available():
-        pytest.skip("no CUDA device")
-    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.path.join(ROOT, "tests") + os.pathsep + os.environ.get("PYTHONPATH", ""))
-    port = 29500 + (os.getpid() % 2000)
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), os.path.join(ROOT, "tests", "workers", "peer_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=env, cwd=ROOT)
-    print(r.stdout[-3000:], r.stderr[-3000:])
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert r.stdout.count("PEER_WORKER_OK") == 2
+def test_virtual_ranks_generic_allgather(rx, ranks):
+    """rxg_peer_allgather_f32 on arbitrary arrays: a 16-byte aligned slab (float4 path) and an odd-sized one (scalar path)."""
+    G = 2
+    cs = ranks[:G]
+    groups = rx.sharding.PeerGroup.local(cs, 4, 1, 32, with_cov=False)   # registers the group; keeps the flag buffers alive
+    assert len(groups) == G
+    for n in (4 * 1000, 4 * 1000 + 3):
+        bufs = [rx.context.DeviceBuffer(c, 4 * G * n) for c in cs]
+        loc = [torch.randn(n, device="cuda") for _ in cs]
+        torch.cuda.synchronize()
+        for r, c in enumerate(cs):
+            c.peer_allgather(loc[r], [bf.ptr for bf in bufs], asynchronous=True)
+        for c in cs:
+            c.sync()
+        for bf in bufs:
+            t = bf.tensor(G, n)
+            for r in range(G):
+                assert torch.equal(t[r], loc[r])
