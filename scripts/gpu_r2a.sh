@@ -5,6 +5,8 @@ mkdir -p gpurun_out
 timeout 2400 python -m pytest tests -m gpu -q -s 2>&1 | tail -60 > gpurun_out/r2a_pytest.txt
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/r2a_bench.json 2> gpurun_out/r2a_bench.err
 timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu --sweep-variant 3 > gpurun_out/r2a_bench_v3.json 2> gpurun_out/r2a_bench_v3.err
+timeout 600 python bench.py --config 2 --steps 5 --warmup 3 > gpurun_out/r2a_bench_cfg2.json 2> gpurun_out/r2a_bench_cfg2.err
+timeout 600 python bench.py --config 3 --steps 5 --warmup 3 > gpurun_out/r2a_bench_cfg3.json 2> gpurun_out/r2a_bench_cfg3.err
 
 tail -12 gpurun_out/r2a_pytest.txt; head -c 1500 gpurun_out/r2a_bench.json; echo; head -c 900 gpurun_out/r2a_bench_v3.json; tail -n 3 gpurun_out/r2a_bench.err; tail -n 3 gpurun_out/r2a_bench_v3.err
 python - <<'PY' > gpurun_out/r2a_hostfill.txt 2>&1
