@@ -59,8 +59,12 @@ enum rxg_flags {
     RXG_COV_SHARED_OUT  = 1u << 3, /* shared model only: write post_cov as [T][d][d] (one copy)  */
     RXG_PATH_PER_CHAIN  = 1u << 4, /* force the per-chain covariance recursion (no gain tables)  */
     RXG_TRANSITION_FIRST = 1u << 5, /* the prior sits one transition before the first datum      */
-    RXG_COV_REPLICATE   = 1u << 6  /* all-gather: covariances are chain independent (shared model,
+    RXG_COV_REPLICATE   = 1u << 6, /* all-gather: covariances are chain independent (shared model,
                                       no missing data) -- replicate them locally, gather only means */
+    RXG_MASK_SHARED     = 1u << 7  /* ymask is ONE pattern for all chains: a HOST array ymask[T] (like the model
+                                      matrices).  The covariances stay chain independent, so the call stays on the
+                                      gain-table path (a per-chain mask forces the per-chain covariance recursion,
+                                      ~2.7x slower at d = 4).  y at masked steps is ignored but must be finite.   */
 };
 
 /* Per-context options (rxg_set_option).  The RXG_* environment variables of the same name are read

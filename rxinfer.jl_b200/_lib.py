@@ -24,6 +24,7 @@ COV_SHARED_OUT = 1 << 3
 PATH_PER_CHAIN = 1 << 4
 TRANSITION_FIRST = 1 << 5
 COV_REPLICATE = 1 << 6
+MASK_SHARED = 1 << 7
 
 fp = POINTER(c_float)
 u8p = POINTER(c_uint8)

@@ -133,8 +133,17 @@ class Context:
             raise ValueError(f"y: expected [T, m, batch], got shape {tuple(y.shape)}")
         T, m, batch = y.shape
         self._io(y, "y", on_dev)
+        shared_mask = None
+        if mask is not None and getattr(mask, "ndim", 2) == 1:
+            # one missing-data pattern for every chain (RXG_MASK_SHARED): a host array [T]; the call stays on the gain-table path
+            shared_mask = np.ascontiguousarray(np.asarray(mask.cpu() if isinstance(mask, torch.Tensor) else mask, dtype=np.uint8))
+            if shared_mask.shape != (T,):
+                raise ValueError(f"shared mask: expected shape ({T},), got {shared_mask.shape}")
+            mask = None
         self._io(mask, "mask", on_dev, dtype=torch.uint8, shape=(T, batch))
         flags = L.PTR_DEVICE if on_dev else 0
+        if shared_mask is not None:
+            flags |= L.MASK_SHARED
         if per_chain_model:
             flags |= L.MODEL_PER_CHAIN
             d = A.shape[0]
@@ -172,6 +181,8 @@ class Context:
         status = out_status if out_status is not None else (mk(batch, dt=torch.int32) if want_status else None)
         fn = self.lib.rxg_lgssm_smooth_f32 if smooth else self.lib.rxg_lgssm_filter_f32
         mask_p = ctypes.cast(c_void_p(mask.data_ptr()), L.u8p) if mask is not None else ctypes.cast(c_void_p(None), L.u8p)
+        if shared_mask is not None:
+            mask_p = shared_mask.ctypes.data_as(L.u8p)
         st_p = ctypes.cast(c_void_p(status.data_ptr()), L.i32p) if status is not None else ctypes.cast(c_void_p(None), L.i32p)
         self._check(fn(self.h, d, m, T, batch, *ptrs, _fp(y), mask_p, _fp(mean), _fp(cov), _fp(nle), st_p, flags))
         return dict(mean=mean, cov=cov if (want_cov or need_cov) else None, neg_log_evidence=nle, status=status)

@@ -93,6 +93,20 @@ int end_bad_flag(rxg_ctx* ctx, bool sync_now) {
     if (rc != RXG_OK) return rc;
     return examine_bad_flag(ctx);
 }
+// one missing-data pattern for the whole batch (RXG_MASK_SHARED): a host array [T], staged like the model
+int stage_shared_mask(rxg_ctx* ctx, int T, const uint8_t* host_mask, LgssmCall& c) {
+    if (ctx->tmask_bytes < (size_t)T) {
+        if (ctx->d_tmask) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->d_tmask); ctx->d_tmask = nullptr; ctx->tmask_bytes = 0; }
+        RXG_CUDA(ctx, cudaMalloc(&ctx->d_tmask, ((size_t)T + 255) / 256 * 256));
+        ctx->tmask_bytes = ((size_t)T + 255) / 256 * 256;
+    }
+    RXG_CUDA(ctx, cudaMemcpyAsync(ctx->d_tmask, host_mask, (size_t)T, cudaMemcpyHostToDevice, ctx->stream));
+    int nobs = 0;
+    for (int t = 0; t < T; ++t) nobs += host_mask[t] != 0;
+    c.tmask = (const uint8_t*)ctx->d_tmask;
+    c.n_observed = nobs;
+    return RXG_OK;
+}
 void* workspace(rxg_ctx* ctx, size_t bytes) { return grow(ctx, &ctx->ws, &ctx->ws_bytes, bytes); }
 void* staging(rxg_ctx* ctx, size_t bytes) { return grow(ctx, &ctx->stage, &ctx->stage_bytes, bytes); }
 
@@ -172,6 +186,7 @@ int rxg_destroy(rxg_ctx* ctx) {
     if (ctx->stage) cudaFree(ctx->stage);
     if (ctx->d_bad) cudaFree(ctx->d_bad);
     for (int i = 0; i < 4; ++i) if (ctx->aux_buf[i]) cudaFree(ctx->aux_buf[i]);
+    if (ctx->d_tmask) cudaFree(ctx->d_tmask);
     if (ctx->h_bad) cudaFreeHost(ctx->h_bad);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->s_in) {
@@ -322,6 +337,13 @@ static int lgssm_entry(rxg_ctx* ctx, bool smooth, int d, int m, int T, int64_t b
     c.d = d; c.m = m; c.T = T; c.batch = batch;
     c.A = A; c.B = B; c.P = P; c.Q = Q; c.m0 = m0; c.S0 = S0; c.u = u;
     c.flags = flags; c.smooth = smooth;
+    if ((flags & RXG_MASK_SHARED) && ymask) {
+        if (per_chain_model || (flags & RXG_PATH_PER_CHAIN))
+            return fail(ctx, RXG_ERR_BAD_ARG, "lgssm: RXG_MASK_SHARED belongs to the shared-model gain-table path");
+        int rcm = stage_shared_mask(ctx, T, ymask, c);
+        if (rcm != RXG_OK) return rcm;
+        ymask = nullptr;
+    }
 
     if (flags & RXG_PTR_DEVICE) {
         if (!cov && (ymask || per_chain_model || (flags & RXG_PATH_PER_CHAIN)))

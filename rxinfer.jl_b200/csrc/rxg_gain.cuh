@@ -195,7 +195,10 @@ __device__ __forceinline__ BwdEl<D> bwd_combine(const BwdEl<D>& early, const Bwd
 template <int D, int M>
 __global__ void __cluster_dims__(GS_CTAS, 1, 1) __launch_bounds__(GS_THREADS, 1)
 gain_scan_kernel(const __grid_constant__ ModelF<D, M> mdl, GainWs ws, ScanWs sw, int T, int transition_first,
-                 float* __restrict__ cov_shared_out, int* __restrict__ bad_out) {
+                 float* __restrict__ cov_shared_out, int* __restrict__ bad_out, const uint8_t* __restrict__ tmask) {
+    // tmask[T] (or null): 1 = the datum of step t exists for EVERY chain, 0 = missing for every chain (RXG_MASK_SHARED).
+    // A missing step is a pure transition: scan element (A, P, 0), no gain, no evidence term -- the covariances stay
+    // chain independent, so the whole batch stays on this path instead of the per-chain covariance recursion.
     using TB = Tab<D, M>;
     cg::cluster_group cluster = cg::this_cluster();
     const int g = (int)cluster.block_rank() * GS_THREADS + (int)threadIdx.x;
@@ -249,17 +252,30 @@ gain_scan_kernel(const __grid_constant__ ModelF<D, M> mdl, GainWs ws, ScanWs sw,
                 if (k == 0) {
                     Mat<double, D, D> S = load_const<double, D, D>(mdl.S0);
                     if (transition_first) { Mat<double, D, D> AS = mul(A, S); S = sym_mul_nt_add(AS, A, P); }
-                    Mat<double, M, D> BS = mul(B, S);
-                    Mat<double, M, M> Sinn = sym_mul_nt_add(BS, B, Q);
-                    Chol<double, M> ch = cholesky<double, M, false>(Sinn, bad);
-                    Mat<double, D, M> V = solve_right_Lt(transpose(BS), ch.L);
                     FwdEl<D> first;
 #pragma unroll
                     for (int i = 0; i < D * D; ++i) { first.A.a[i] = 0.0; first.J.a[i] = 0.0; }
-                    first.C = sym_downdate(S, V);
+                    if (!tmask || tmask[0] != 0) {
+                        Mat<double, M, D> BS = mul(B, S);
+                        Mat<double, M, M> Sinn = sym_mul_nt_add(BS, B, Q);
+                        Chol<double, M> ch = cholesky<double, M, false>(Sinn, bad);
+                        Mat<double, D, M> V = solve_right_Lt(transpose(BS), ch.L);
+                        first.C = sym_downdate(S, V);
+                    } else {
+                        first.C = S;
+                    }
                     acc = first;
                 } else {
-                    acc = (k == k0) ? gen : fwd_combine<D, false>(acc, gen);
+                    const bool obs_k = !tmask || tmask[k] != 0;
+                    if (obs_k) {
+                        acc = (k == k0) ? gen : fwd_combine<D, false>(acc, gen);
+                    } else {
+                        FwdEl<D> miss;
+                        miss.A = A; miss.C = P;
+#pragma unroll
+                        for (int i = 0; i < D * D; ++i) miss.J.a[i] = 0.0;
+                        acc = (k == k0) ? miss : fwd_combine<D, false>(acc, miss);
+                    }
                 }
                 if (E > 1) fwd_store<D>(sw.fel, T, k, acc);
             }
@@ -312,12 +328,34 @@ gain_scan_kernel(const __grid_constant__ ModelF<D, M> mdl, GainWs ws, ScanWs sw,
             Sp = load_const<double, D, D>(mdl.S0);
             if (transition_first) { Mat<double, D, D> AS = mul(A, Sp); Sp = sym_mul_nt_add(AS, A, P); }
         }
+        const bool obs_t = !tmask || tmask[t] != 0;
         {
-            Mat<double, M, D> BS = mul(B, Sp);
-            Mat<double, M, M> Sinn = sym_mul_nt_add(BS, B, Q);
-            Chol<double, M> ch = cholesky<double, M, true>(Sinn, bad);
-            Mat<double, D, M> V = solve_right_Lt(transpose(BS), ch.L);
-            Mat<double, D, M> K = solve_right_L(V, ch.L);
+            Mat<double, D, M> K;
+            Mat<double, M, M> Li;
+            double cconst = 0.0;
+#pragma unroll
+            for (int i = 0; i < D * M; ++i) K.a[i] = 0.0;
+#pragma unroll
+            for (int i = 0; i < M * M; ++i) Li.a[i] = 0.0;
+            if (obs_t) {
+                Mat<double, M, D> BS = mul(B, Sp);
+                Mat<double, M, M> Sinn = sym_mul_nt_add(BS, B, Q);
+                Chol<double, M> ch = cholesky<double, M, true>(Sinn, bad);
+                Mat<double, D, M> V = solve_right_Lt(transpose(BS), ch.L);
+                K = solve_right_L(V, ch.L);
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                    Li(j, j) = ch.L(j, j);
+#pragma unroll
+                    for (int i = j + 1; i < M; ++i) {
+                        double sacc = 0.0;
+#pragma unroll
+                        for (int k = j; k < i; ++k) sacc -= ch.L(i, k) * Li(k, j);
+                        Li(i, j) = sacc * ch.L(i, i);
+                    }
+                }
+                cconst = M * RXG_HALF_LOG_2PI - ch.neg_half_logdet;
+            }
             Mat<double, D, D> IKB = identity<double, D>();
 #pragma unroll
             for (int i = 0; i < D; ++i)
@@ -326,25 +364,11 @@ gain_scan_kernel(const __grid_constant__ ModelF<D, M> mdl, GainWs ws, ScanWs sw,
 #pragma unroll
                     for (int k = 0; k < M; ++k) IKB(i, j) -= K(i, k) * B(k, j);
             Mat<double, D, D> F = (t > 0 || transition_first) ? mul(IKB, A) : IKB;
-            Mat<double, M, M> Li;
-#pragma unroll
-            for (int i = 0; i < M * M; ++i) Li.a[i] = 0.0;
-#pragma unroll
-            for (int j = 0; j < M; ++j) {
-                Li(j, j) = ch.L(j, j);
-#pragma unroll
-                for (int i = j + 1; i < M; ++i) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int k = j; k < i; ++k) s -= ch.L(i, k) * Li(k, j);
-                    Li(i, j) = s * ch.L(i, i);
-                }
-            }
             float* rec = ws.fwd + (size_t)t * TB::FWD_REC;
             store_f(rec + TB::F_OFF, F);
             store_f(rec + TB::K_OFF, K);
             store_f(rec + TB::LI_OFF, Li);
-            rec[TB::C_OFF] = (float)(M * RXG_HALF_LOG_2PI - ch.neg_half_logdet);
+            rec[TB::C_OFF] = (float)cconst;
             Vec<double, D> uu, gf;
 #pragma unroll
             for (int i = 0; i < D; ++i) uu(i) = (double)mdl.u[i];

@@ -48,6 +48,8 @@ struct rxg_ctx {
     int peer_n = 0, peer_rank = 0;
     int* peer_flags[RXG_MAX_PEERS] = {};     // peer_flags[g] = rank g's flag array as mapped here (own: cudaMalloc'ed)
     unsigned peer_epoch = 0;
+    void* d_tmask = nullptr;     // device copy of a shared missing-data pattern (RXG_MASK_SHARED)
+    size_t tmask_bytes = 0;
     // grow-only scratch of the general-shape front end (padded operands, shifted observations)
     void* aux_buf[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t aux_bytes[4] = {0, 0, 0, 0};
@@ -91,6 +93,8 @@ struct LgssmCall {
     const float* mean0_chain = nullptr;   // device [d][batch]: per-chain prior mean (streaming carry) or null
     const float* y;          // device
     const uint8_t* ymask;    // device or null
+    const uint8_t* tmask = nullptr;   // device [T] or null: missing-data pattern SHARED by all chains (RXG_MASK_SHARED)
+    int n_observed = -1;              // number of observed steps of tmask (-1: all T)
     float* mean;             // device
     float* cov;              // device
     float* nle;              // device or null
@@ -111,6 +115,7 @@ void host_broadcast_cov(float* cov, const float* tab, int64_t rows, int64_t batc
 int launch_replicate_cov(rxg_ctx* ctx, cudaStream_t st, const float* src, int64_t src_stride, float* dst, int64_t rows,
                          int64_t b, int G, int skip);
 int ensure_aux_stream(rxg_ctx* ctx);
+int stage_shared_mask(rxg_ctx* ctx, int T, const uint8_t* host_mask, LgssmCall& c);    // rxg_api.cu
 // rxg_lgssm_general.cu: any (d, m) in 1..64 (native families, embedding, generic per-chain kernel)
 int lgssm_dispatch(rxg_ctx* ctx, LgssmCall& c);
 // rxg_lgssm.cu: the register-resident families (d <= 6 shapes)

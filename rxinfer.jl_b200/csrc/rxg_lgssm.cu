@@ -209,7 +209,7 @@ lgssm_chain_kernel(const __grid_constant__ ModelF<D, M> mdl, PerChainPtrs pc,
 // Phase 1 (sequential in t): Riccati recursion for the predicted / filtered covariances.
 template <int D, int M>
 __global__ void gain_riccati_seq(const __grid_constant__ ModelF<D, M> mdl, GainWs ws, int T,
-                                 int transition_first, int* __restrict__ bad_out) {
+                                 int transition_first, int* __restrict__ bad_out, const uint8_t* __restrict__ tmask) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const Mat<double, D, D> A = load_const<double, D, D>(mdl.A), P = load_const<double, D, D>(mdl.P);
     const Mat<double, M, D> B = load_const<double, M, D>(mdl.B);
@@ -222,11 +222,13 @@ __global__ void gain_riccati_seq(const __grid_constant__ ModelF<D, M> mdl, GainW
             S = sym_mul_nt_add(AS, A, P);
         }
         store_d(ws.Sp + (size_t)t * D * D, S);
-        Mat<double, M, D> BS = mul(B, S);
-        Mat<double, M, M> Sinn = sym_mul_nt_add(BS, B, Q);
-        Chol<double, M> ch = cholesky<double, M, false>(Sinn, bad);
-        Mat<double, D, M> V = solve_right_Lt(transpose(BS), ch.L);
-        S = sym_downdate(S, V);
+        if (!tmask || tmask[t] != 0) {
+            Mat<double, M, D> BS = mul(B, S);
+            Mat<double, M, M> Sinn = sym_mul_nt_add(BS, B, Q);
+            Chol<double, M> ch = cholesky<double, M, false>(Sinn, bad);
+            Mat<double, D, M> V = solve_right_Lt(transpose(BS), ch.L);
+            S = sym_downdate(S, V);
+        }
         store_d(ws.Sf + (size_t)t * D * D, S);
     }
     if (bad) atomicOr(bad_out, 1);
@@ -235,7 +237,7 @@ __global__ void gain_riccati_seq(const __grid_constant__ ModelF<D, M> mdl, GainW
 // Phase 2 (parallel in t): gains, innovation factors, conditional covariances.
 template <int D, int M>
 __global__ void gain_tables(const __grid_constant__ ModelF<D, M> mdl, GainWs ws, int T,
-                            int transition_first, int* __restrict__ bad_out) {
+                            int transition_first, int* __restrict__ bad_out, const uint8_t* __restrict__ tmask) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     using TB = Tab<D, M>;
@@ -246,11 +248,32 @@ __global__ void gain_tables(const __grid_constant__ ModelF<D, M> mdl, GainWs ws,
     const Mat<double, D, D> Sp = load_d<D, D>(ws.Sp + (size_t)t * D * D);
     const Mat<double, D, D> Sf = load_d<D, D>(ws.Sf + (size_t)t * D * D);
     {
-        Mat<double, M, D> BS = mul(B, Sp);
-        Mat<double, M, M> Sinn = sym_mul_nt_add(BS, B, Q);
-        Chol<double, M> ch = cholesky<double, M, true>(Sinn, bad);
-        Mat<double, D, M> V = solve_right_Lt(transpose(BS), ch.L);
-        Mat<double, D, M> K = solve_right_L(V, ch.L);
+        Mat<double, D, M> K;
+        Mat<double, M, M> Li;
+        double cconst = 0.0;
+#pragma unroll
+        for (int i = 0; i < D * M; ++i) K.a[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < M * M; ++i) Li.a[i] = 0.0;
+        if (!tmask || tmask[t] != 0) {
+            Mat<double, M, D> BS = mul(B, Sp);
+            Mat<double, M, M> Sinn = sym_mul_nt_add(BS, B, Q);
+            Chol<double, M> ch = cholesky<double, M, true>(Sinn, bad);
+            Mat<double, D, M> V = solve_right_Lt(transpose(BS), ch.L);
+            K = solve_right_L(V, ch.L);
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                Li(j, j) = ch.L(j, j);
+#pragma unroll
+                for (int i = j + 1; i < M; ++i) {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int k = j; k < i; ++k) sacc -= ch.L(i, k) * Li(k, j);
+                    Li(i, j) = sacc * ch.L(i, i);
+                }
+            }
+            cconst = M * RXG_HALF_LOG_2PI - ch.neg_half_logdet;
+        }
         Mat<double, D, D> IKB = identity<double, D>();
 #pragma unroll
         for (int i = 0; i < D; ++i)
@@ -259,26 +282,11 @@ __global__ void gain_tables(const __grid_constant__ ModelF<D, M> mdl, GainWs ws,
 #pragma unroll
                 for (int k = 0; k < M; ++k) IKB(i, j) -= K(i, k) * B(k, j);
         Mat<double, D, D> F = (t > 0 || transition_first) ? mul(IKB, A) : IKB;
-        // L^-1 (lower, true diagonal)
-        Mat<double, M, M> Li;
-#pragma unroll
-        for (int i = 0; i < M * M; ++i) Li.a[i] = 0.0;
-#pragma unroll
-        for (int j = 0; j < M; ++j) {
-            Li(j, j) = ch.L(j, j);
-#pragma unroll
-            for (int i = j + 1; i < M; ++i) {
-                double s = 0.0;
-#pragma unroll
-                for (int k = j; k < i; ++k) s -= ch.L(i, k) * Li(k, j);
-                Li(i, j) = s * ch.L(i, i);
-            }
-        }
         float* rec = ws.fwd + (size_t)t * TB::FWD_REC;
         store_f(rec + TB::F_OFF, F);
         store_f(rec + TB::K_OFF, K);
         store_f(rec + TB::LI_OFF, Li);
-        rec[TB::C_OFF] = (float)(M * RXG_HALF_LOG_2PI - ch.neg_half_logdet);
+        rec[TB::C_OFF] = (float)cconst;
         Vec<double, D> uu, gf;
 #pragma unroll
         for (int i = 0; i < D; ++i) uu(i) = (double)mdl.u[i];
@@ -505,8 +513,8 @@ static int run_shared_family(rxg_ctx* ctx, LgssmCall& c) {
     float* cov_once = (cov_shared && c.cov && c.smooth) ? c.cov : (c.smooth ? c.cov_table : nullptr);
     if (ctx->opt[RXG_OPT_GAIN_SEQ] != 0) {
         // sequential Riccati recursion (cross-check of the scan; ~70x slower at T = 1000)
-        gain_riccati_seq<D, M><<<1, 32, 0, ctx->stream>>>(mdl, ws, c.T, tf, bad_flag(ctx));
-        gain_tables<D, M><<<(c.T + 63) / 64, 64, 0, ctx->stream>>>(mdl, ws, c.T, tf, bad_flag(ctx));
+        gain_riccati_seq<D, M><<<1, 32, 0, ctx->stream>>>(mdl, ws, c.T, tf, bad_flag(ctx), c.tmask);
+        gain_tables<D, M><<<(c.T + 63) / 64, 64, 0, ctx->stream>>>(mdl, ws, c.T, tf, bad_flag(ctx), c.tmask);
         ctx->launches += 2;
         if (c.smooth) {
             gain_smooth_seq<D, M><<<1, 32, 0, ctx->stream>>>(ws, c.T, cov_once);
@@ -514,7 +522,7 @@ static int run_shared_family(rxg_ctx* ctx, LgssmCall& c) {
         }
     } else {
         // time-parallel associative scans in one 8-CTA cluster
-        gain_scan_kernel<D, M><<<GS_CTAS, GS_THREADS, 0, ctx->stream>>>(mdl, ws, sw, c.T, tf, cov_once, bad_flag(ctx));
+        gain_scan_kernel<D, M><<<GS_CTAS, GS_THREADS, 0, ctx->stream>>>(mdl, ws, sw, c.T, tf, cov_once, bad_flag(ctx), c.tmask);
         ctx->launches += 1;
     }
     if (!c.smooth && cov_shared && c.cov) {

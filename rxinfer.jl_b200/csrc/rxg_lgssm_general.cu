@@ -56,6 +56,11 @@ __global__ void subblock_cov_kernel(const float* __restrict__ tab, float* __rest
     float* out = cov + row * batch;
     for (int64_t b = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; b < batch; b += (int64_t)gridDim.y * blockDim.x) out[b] = v;
 }
+// mask[t][b] = tmask[t]: a shared pattern expanded for the kernel families that only know per-chain masks
+__global__ void expand_mask_kernel(const uint8_t* __restrict__ tmask, uint8_t* __restrict__ mask, int T, int64_t batch) {
+    const int64_t n = (int64_t)T * batch;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) mask[i] = tmask[i / batch];
+}
 __global__ void add_const_kernel(float* __restrict__ v, int64_t n, float c) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) v[i] += c;
@@ -207,8 +212,9 @@ int embedded(rxg_ctx* ctx, LgssmCall& c, int D, int M) {
     }
     if (c.nle && !c.tables_only && M > m) {
         // each dummy observation contributes exactly 1/2 log 2 pi per step
+        const int nobs = c.n_observed >= 0 ? c.n_observed : T;        // dummy observations exist only at observed steps
         add_const_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, ctx->stream>>>(c.nle, batch,
-                                                                                   (float)(-(double)(M - m) * T * 0.91893853320467274178));
+                                                                                   (float)(-(double)(M - m) * nobs * 0.91893853320467274178));
         ctx->launches += 1;
     }
     c.fused_peer_stores = false;
@@ -224,8 +230,23 @@ bool lgssm_supported(int d, int m) { return d >= 1 && m >= 1 && d <= 64 && m <= 
 int lgssm_dispatch(rxg_ctx* ctx, LgssmCall& c) {
     if (!lgssm_supported(c.d, c.m))
         return fail(ctx, RXG_ERR_UNSUPPORTED, "lgssm: d and m must be in 1..64 (got d=%d, m=%d)", c.d, c.m);
-    const bool per_chain = (c.flags & (RXG_MODEL_PER_CHAIN | RXG_PATH_PER_CHAIN)) != 0 || c.ymask != nullptr;
     if (small_native(c.d, c.m)) return lgssm_dispatch_native(ctx, c);
+    int De = 0, Me = 0;
+    const bool emb_small = embedding_shape(c.d, c.m, &De, &Me) && small_native(De, Me);
+    if (c.tmask && !emb_small) {
+        // the large-state gain kernels have no missing-data variant: expand the shared pattern and take the generic kernel
+        if (!c.cov || (c.flags & RXG_COV_SHARED_OUT))
+            return fail(ctx, RXG_ERR_UNSUPPORTED, "lgssm (d=%d): a shared mask on the large-state family needs the per-chain covariance output", c.d);
+        uint8_t* mk = (uint8_t*)aux(ctx, 1, (size_t)c.T * c.batch);
+        if (!mk) return RXG_ERR_CUDA;
+        expand_mask_kernel<<<grid_for(ctx, (int64_t)c.T * c.batch), 256, 0, ctx->stream>>>(c.tmask, mk, c.T, c.batch);
+        ctx->launches += 1;
+        LgssmCall c2 = c;
+        c2.tmask = nullptr; c2.ymask = mk;
+        c.fused_peer_stores = false;
+        return lgssm_generic_chain(ctx, c2);
+    }
+    const bool per_chain = (c.flags & (RXG_MODEL_PER_CHAIN | RXG_PATH_PER_CHAIN)) != 0 || c.ymask != nullptr;
     if (per_chain) {
         if (c.tables_only) return fail(ctx, RXG_ERR_BAD_ARG, "lgssm: tables-only call on the per-chain path");
         c.fused_peer_stores = false;

@@ -942,23 +942,6 @@ static int run_large(rxg_ctx* ctx, LgssmCall& c) {
         ctx->launches += 1;
         return check_cuda(ctx, cudaGetLastError(), "lgssm_block_sweep");
     };
-    // Per-chain covariance output (the contract): T d^2 rows broadcast over the batch -- 67 GB at configs[2], pure HBM
-    // writes that depend on the gain tables only.  It runs on the low-priority side stream CONCURRENTLY with the mean
-    // sweeps (which are latency bound on a few SMs), instead of after them.
-    const bool bcast_side = c.cov && !(c.flags & RXG_COV_SHARED_OUT);
-    if (bcast_side) {
-        rc = ensure_aux_stream(ctx);
-        if (rc != RXG_OK) return rc;
-        RXG_CUDA(ctx, cudaEventRecord(ctx->ev_aux[0], ctx->stream));
-        RXG_CUDA(ctx, cudaStreamWaitEvent(ctx->s_aux, ctx->ev_aux[0], 0));
-        const int64_t rows = (int64_t)(T * DD);
-        dim3 grid((unsigned)rows, (unsigned)((c.batch + 4095) / 4096 > 16 ? 16 : (c.batch + 4095) / 4096));
-        broadcast_cov_kernel<<<grid, 256, 0, ctx->s_aux>>>(c.smooth ? w.ss : w.sf, c.cov, rows, c.batch);
-        ctx->launches += 1;
-        rc = check_cuda(ctx, cudaGetLastError(), "broadcast_cov_kernel");
-        if (rc != RXG_OK) return rc;
-        RXG_CUDA(ctx, cudaEventRecord(ctx->ev_aux[1], ctx->s_aux));
-    }
     if (ctx->profile) cudaEventRecord(ctx->ev[1], ctx->stream);
     if (c.nle) {
         // the evidence is a function of the FILTERED means: filter-mode sweep, then the (time-parallel) evidence
@@ -981,9 +964,23 @@ static int run_large(rxg_ctx* ctx, LgssmCall& c) {
         if (rc != RXG_OK) return rc;
     }
     if (ctx->profile) cudaEventRecord(ctx->ev[2], ctx->stream);
-    if (c.cov && (c.flags & RXG_COV_SHARED_OUT))
-        RXG_CUDA(ctx, cudaMemcpyAsync(c.cov, c.smooth ? w.ss : w.sf, T * DD * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-    if (bcast_side) RXG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_aux[1], 0));    // join the covariance broadcast
+    // Per-chain covariance output (the contract): T d^2 rows broadcast over the batch -- 67 GB at configs[2], pure HBM
+    // writes at the write roofline (8.9 ms).  Measured in round 2: running it on a side stream concurrently with the mean
+    // sweeps gains nothing (20.96 -> 21.0 ms): the broadcast streams through L2 and evicts the per-step gain records that
+    // all chain tiles of the latency-bound tcgen05 sweep share, which then slows from 5.5 to 14.3 ms.  Sequential it is.
+    if (c.cov) {
+        const float* tab = c.smooth ? w.ss : w.sf;
+        if (c.flags & RXG_COV_SHARED_OUT) {
+            RXG_CUDA(ctx, cudaMemcpyAsync(c.cov, tab, T * DD * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        } else {
+            const int64_t rows = (int64_t)(T * DD);
+            dim3 grid((unsigned)rows, (unsigned)((c.batch + 4095) / 4096 > 16 ? 16 : (c.batch + 4095) / 4096));
+            broadcast_cov_kernel<<<grid, 256, 0, ctx->stream>>>(tab, c.cov, rows, c.batch);
+            ctx->launches += 1;
+            rc = check_cuda(ctx, cudaGetLastError(), "broadcast_cov_kernel");
+            if (rc != RXG_OK) return rc;
+        }
+    }
     if (c.status) return fill_status_from_flag(ctx, c.status, c.batch);
     return RXG_OK;
 }

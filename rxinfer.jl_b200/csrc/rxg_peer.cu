@@ -45,7 +45,7 @@ __global__ void peer_barrier_kernel(PeerFlags pf, int n, int rank, int epoch, in
     }
 }
 
-struct PushDst { float* p[RXG_MAX_PEERS - 1]; int n; };
+struct PushDst { float* p[RXG_MAX_PEERS]; int n; };
 
 // dst[g][i] = src[i] for every peer g: one coalesced read of the local slab, n remote (NVLink) writes
 __global__ void __launch_bounds__(256) peer_push_kernel(const float4* __restrict__ src, PushDst d, int64_t n4,
@@ -250,11 +250,15 @@ int rxg_peer_allgather_f32(rxg_ctx* ctx, int64_t n_local, const float* local, fl
     float* own = gathered[r] + (int64_t)r * n_local;
     int rc = begin_bad_flag(ctx);
     if (rc != RXG_OK) return rc;
-    if (local && local != own) RXG_CUDA(ctx, cudaMemcpyAsync(own, local, (size_t)n_local * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-    float* dst[RXG_MAX_PEERS - 1];
+    // one kernel stores the local array into slab r of EVERY buffer, the own one included when `local` lives elsewhere
+    // (no cudaMemcpy: a device-to-device copy issued by the host may serialise with a peer's spinning barrier kernel
+    // when several ranks share one process)
+    const float* src = local ? local : own;
+    float* dst[RXG_MAX_PEERS];
     int nd = 0;
-    for (int g = 0; g < G; ++g) if (g != r) dst[nd++] = gathered[g] + (int64_t)r * n_local;
-    rc = peer_push(ctx, own, dst, nd, n_local);
+    for (int g = 0; g < G; ++g)
+        if (g != r || src != own) dst[nd++] = gathered[g] + (int64_t)r * n_local;
+    rc = peer_push(ctx, src, dst, nd, n_local);
     if (rc == RXG_OK) rc = peer_barrier(ctx);
     if (rc != RXG_OK) return rc;
     return end_bad_flag(ctx, !(flags & RXG_ASYNC));
@@ -272,7 +276,10 @@ int rxg_lgssm_smooth_gather_f32(rxg_ctx* ctx, int d, int m, int T, int64_t batch
     if (flags & RXG_COV_SHARED_OUT) return fail(ctx, RXG_ERR_BAD_ARG, "lgssm_smooth_gather: the gathered covariances are per chain");
     if (!lgssm_supported(d, m)) return fail(ctx, RXG_ERR_UNSUPPORTED, "lgssm_smooth_gather: (d=%d, m=%d) unsupported", d, m);
     const int G = ctx->peer_n, r = ctx->peer_rank;
-    const bool per_chain = (flags & (RXG_MODEL_PER_CHAIN | RXG_PATH_PER_CHAIN)) != 0 || ymask != nullptr;
+    const bool shared_mask = (flags & RXG_MASK_SHARED) && ymask;
+    const bool per_chain = (flags & (RXG_MODEL_PER_CHAIN | RXG_PATH_PER_CHAIN)) != 0 || (ymask != nullptr && !shared_mask);
+    if (shared_mask && (flags & (RXG_MODEL_PER_CHAIN | RXG_PATH_PER_CHAIN)))
+        return fail(ctx, RXG_ERR_BAD_ARG, "lgssm_smooth_gather: RXG_MASK_SHARED belongs to the shared-model gain-table path");
     const bool replicate = gathered_cov && (flags & RXG_COV_REPLICATE);
     if (replicate && per_chain)
         return fail(ctx, RXG_ERR_BAD_ARG, "lgssm_smooth_gather: RXG_COV_REPLICATE needs chain-independent covariances (shared model, no mask)");
@@ -287,10 +294,14 @@ int rxg_lgssm_smooth_gather_f32(rxg_ctx* ctx, int d, int m, int T, int64_t batch
     LgssmCall c;
     c.d = d; c.m = m; c.T = T; c.batch = batch_local;
     c.A = A; c.B = B; c.P = P; c.Q = Q; c.m0 = m0; c.S0 = S0; c.u = u;
-    c.y = y; c.ymask = ymask; c.nle = neg_log_evidence; c.status = status;
+    c.y = y; c.ymask = shared_mask ? nullptr : ymask; c.nle = neg_log_evidence; c.status = status;
+    if (shared_mask) {
+        int rcm = stage_shared_mask(ctx, T, ymask, c);
+        if (rcm != RXG_OK) return rcm;
+    }
     c.mean = gathered_mean[r] + r * slab_m;
     c.cov = gathered_cov ? gathered_cov[r] + r * slab_c : nullptr;
-    c.flags = flags & ~(unsigned)(RXG_COV_REPLICATE | RXG_ASYNC);
+    c.flags = flags & ~(unsigned)(RXG_COV_REPLICATE | RXG_ASYNC | RXG_MASK_SHARED);
     c.smooth = true;
     float* pm[RXG_MAX_PEERS - 1];
     float* pc[RXG_MAX_PEERS - 1];

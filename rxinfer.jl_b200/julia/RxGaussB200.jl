@@ -43,6 +43,7 @@ const RXG_COV_SHARED_OUT   = UInt32(1) << 3
 const RXG_PATH_PER_CHAIN   = UInt32(1) << 4
 const RXG_TRANSITION_FIRST = UInt32(1) << 5
 const RXG_COV_REPLICATE    = UInt32(1) << 6
+const RXG_MASK_SHARED      = UInt32(1) << 7
 
 const RXG_OPT_GAIN_SEQ, RXG_OPT_LARGE_SEQ, RXG_OPT_NO_UMMA, RXG_OPT_SWEEP_VARIANT, RXG_OPT_FORCE_CPT = 0, 1, 2, 3, 4
 const RXG_OPT_HOST_THREADS, RXG_OPT_HOST_COV_D2H, RXG_OPT_HOST_BCAST_MIN_MB, RXG_OPT_HOST_SLICES = 5, 6, 7, 8

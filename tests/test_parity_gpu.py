@@ -587,3 +587,30 @@ def test_large_state_d64_full_length(ctx):
     assert em < TOL_MEAN and ec < TOL_COV
     check(r, ref)
     assert torch.equal(r["cov"][..., 0], r["cov"][..., batch - 1])
+
+
+@pytest.mark.parametrize("d,m", [(4, 4), (2, 1), (5, 3), (16, 16)])
+def test_shared_missing_data_pattern_stays_on_gain_table_path(ctx, d, m):
+    """RXG_MASK_SHARED: one missing-data pattern for all chains (host array [T]).  The covariances stay chain independent,
+    so the gain tables handle it (missing step = pure transition) and the mean sweep is unchanged; result = the per-chain
+    mask path with the pattern broadcast = the oracle.  Time-parallel scan and sequential gain kernels, smoothing and
+    filtering with evidence, first / last step missing, T > 1024 (several steps per scan thread)."""
+    rng = np.random.default_rng(77 + d)
+    mod = _random_model(rng, d, m) if (d, m) != (4, 4) else f32_model(lgssm.notebook_model(4))
+    for T, batch in ((40, 70), (1300, 6)) if d <= 5 else ((24, 9),):
+        _, y = lgssm.generate_data(mod, T, batch, seed=5 + T)
+        tm = (rng.random(T) > 0.3).astype(np.uint8)
+        tm[0] = 0; tm[-1] = 0; tm[1] = 1
+        full = np.repeat(tm[:, None], batch, axis=1)
+        ref = lgssm.smooth_reference_schedule(y, **mod, mask=full)
+        for seq in (0, 1):
+            ctx.set_option("gain_seq", seq)
+            r = ctx.lgssm(dev(y), **_kw(mod), smooth=True, mask=tm, want_evidence=True)
+            check(r, ref)
+            f = ctx.lgssm(dev(y), **_kw(mod), smooth=False, mask=tm, want_evidence=True)
+            check(f, ref, smooth=False)
+        ctx.set_option("gain_seq", 0)
+        if d <= 5:
+            assert torch.equal(r["cov"][..., 0], r["cov"][..., batch - 1])        # still chain independent
+            rp = ctx.lgssm(dev(y), **_kw(mod), smooth=True, mask=dev(full, torch.uint8))
+            assert rel_l2(r["mean"].cpu().numpy(), rp["mean"].cpu().numpy()) < 2 * TOL_MEAN
