@@ -35,7 +35,7 @@ def timed(fn, warm=3, reps=5):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--which", default="per_chain,filter,hgf,rules,vmp,scaling_T,large,stream")
+    ap.add_argument("--which", default="per_chain,filter,hgf,rules,vmp,scaling_T,large,stream,round2")
     args = ap.parse_args()
     which = set(args.which.split(","))
     ctx = rx.Context(0)
@@ -83,6 +83,45 @@ def main():
             print(json.dumps({"what": "stream_mix_kernel (HBM yardstick)", "rows_read": nr, "rows_written": nw, "ms": ms,
                               "GBs": (nr + nw) * n * 4 / ms / 1e6, "frac_of_copy_peak": (nr + nw) * n * 4 / ms / 1e6 / peak}))
             del src, dst
+
+    if "round2" in which:
+        # round-2 additions: shared vs per-chain missing-data pattern, embedded shapes, the generic one-CTA-per-chain kernel,
+        # the IID Wishart VMP
+        y = torch.randn(T, 4, batch, device="cuda", generator=g) * 3.3
+        mean = torch.empty(T, 4, batch, device="cuda"); cov = torch.empty(T, 4, 4, batch, device="cuda")
+        tm = (np.random.default_rng(1).random(T) > 0.2).astype(np.uint8)
+        full = torch.as_tensor(np.repeat(tm[:, None], batch, axis=1), device="cuda")
+        for name, mk in (("shared pattern, RXG_MASK_SHARED (gain-table path)", tm), ("same pattern as a per-chain mask (per-chain covariance recursion)", full)):
+            ms = timed(lambda: ctx.lgssm(y, **kw, smooth=True, out_mean=mean, out_cov=cov, mask=mk))
+            print(json.dumps({"what": "lgssm smooth with 20 % missing steps: " + name, "d": 4, "T": T, "batch": batch, "ms": ms,
+                              "messages_per_s": 6 * T * batch / ms * 1e3, "frac_of_hbm_peak": 96 * T * batch / ms / 1e6 / peak}))
+        del y, mean, cov, full
+        rng = np.random.default_rng(5)
+        for d, m, b in ((5, 3, 65536), (6, 6, 65536), (12, 7, 16384), (16, 16, 16384)):
+            Aq, _ = np.linalg.qr(rng.standard_normal((d, d)))
+            md = {k: v.astype(np.float32) for k, v in dict(A=0.95 * Aq, B=rng.standard_normal((m, d)) / np.sqrt(d), P=0.2 * np.eye(d),
+                                                          Q=1.5 * np.eye(m), m0=np.zeros(d), S0=5.0 * np.eye(d)).items()}
+            y = torch.randn(T, m, b, device="cuda", generator=g)
+            mean = torch.empty(T, d, b, device="cuda"); cov = torch.empty(T, d, d, b, device="cuda")
+            ms = timed(lambda: ctx.lgssm(y, **md, smooth=True, out_mean=mean, out_cov=cov), warm=2, reps=3)
+            print(json.dumps({"what": "lgssm smooth, shared model, general shape" + (" (native)" if (d, m) in ((6, 6), (16, 16)) else " (embedded in the next native shape)"),
+                              "d": d, "m": m, "T": T, "batch": b, "ms": ms, "messages_per_s": 6 * T * b / ms * 1e3,
+                              "algorithmic_GBs": 4 * (m + d + d * d) * T * b / ms / 1e6}))
+            del y, mean, cov
+        for d, b in ((16, 2048), (64, 512)):
+            md = dense_model_f32(d)
+            y = torch.randn(T, d, b, device="cuda", generator=g) * 3.3
+            mk = (torch.rand(T, b, device="cuda", generator=g) > 0.2).to(torch.uint8)
+            mean = torch.empty(T, d, b, device="cuda"); cov = torch.empty(T, d, d, b, device="cuda")
+            ms = timed(lambda: ctx.lgssm(y, **md, smooth=True, out_mean=mean, out_cov=cov, mask=mk), warm=1, reps=2)
+            print(json.dumps({"what": "lgssm smooth, per-chain missing data, generic one-CTA-per-chain kernel (CUDA cores)", "d": d, "T": T,
+                              "batch": b, "ms": ms, "messages_per_s": 6 * T * b / ms * 1e3, "us_per_chain_step": ms * 1e3 / (T * b) * min(b, 148 * (2 if d <= 32 else 1))}))
+            del y, mk, mean, cov
+        yw = torch.randn(1500, 2, 32768, device="cuda", generator=g)
+        ms = timed(lambda: ctx.mv_iid_wishart_vmp(yw, iterations=10), warm=2, reps=3)
+        print(json.dumps({"what": "IID Wishart-precision VMP (mv_iid_precision model), 10 iterations", "d": 2, "N": 1500, "batch": 32768, "ms": ms,
+                          "datasets_per_s": 32768 / ms * 1e3, "GBs": yw.numel() * 4 / ms / 1e6}))
+        del yw
 
     if "large" in which:
         # BASELINE configs[2] (d = 64, T = 1000, batch = 4096) and the smaller tensor-core sizes; shared model.

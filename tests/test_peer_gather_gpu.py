@@ -18,6 +18,23 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+class _quiet_host:
+    """Virtual ranks share ONE process here: while rank 0's barrier kernel spins on the device waiting for rank 1, the host
+    must not run anything that synchronises the whole device before rank 1's work is queued -- in particular the cyclic
+    garbage collector freeing DeviceBuffers of an earlier test (cudaFree waits for every running kernel).  Real jobs run
+    one process per GPU and are not exposed to this."""
+
+    def __enter__(self):
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        gc.disable()
+
+    def __exit__(self, *a):
+        import gc
+        gc.enable()
+
+
 def _kw(mod):
     return dict(A=mod["A"], B=mod["B"], P=mod["P"], Q=mod["Q"], m0=mod["m0"], S0=mod["S0"])
 
@@ -68,10 +85,11 @@ def test_virtual_ranks_fused_gather(rx, ranks, G, variant):
         for gr in groups:
             gr.mean.zero_(); gr.cov.zero_()
         torch.cuda.synchronize()
-        for r, gr in enumerate(groups):
-            gr.smooth_gather(refs[r][0], mod, mask=refs[r][1], asynchronous=True, **kw)
-        for c in cs:
-            c.sync()
+        with _quiet_host():
+            for r, gr in enumerate(groups):
+                gr.smooth_gather(refs[r][0], mod, mask=refs[r][1], asynchronous=True, **kw)
+            for c in cs:
+                c.sync()
         for gr in groups:
             for r in range(G):
                 assert torch.equal(gr.mean[r], refs[r][2]["mean"]), (variant, rep, gr.rank, r)
@@ -99,10 +117,11 @@ def test_virtual_ranks_large_state(rx, ranks):
         for gr in groups:
             gr.mean.zero_(); gr.cov.zero_()
         torch.cuda.synchronize()
-        for r, gr in enumerate(groups):
-            gr.smooth_gather(refs[r][0], mod, replicate_cov=replicate, asynchronous=True)
-        for c in cs:
-            c.sync()
+        with _quiet_host():
+            for r, gr in enumerate(groups):
+                gr.smooth_gather(refs[r][0], mod, replicate_cov=replicate, asynchronous=True)
+            for c in cs:
+                c.sync()
         for gr in groups:
             for r in range(G):
                 assert torch.equal(gr.mean[r], refs[r][1]["mean"]) and torch.equal(gr.cov[r], refs[r][1]["cov"])
@@ -117,11 +136,12 @@ def test_virtual_ranks_generic_allgather(rx, ranks):
     for n in (4 * 1000, 4 * 1000 + 3):
         bufs = [rx.context.DeviceBuffer(c, 4 * G * n) for c in cs]
         loc = [torch.randn(n, device="cuda") for _ in cs]
-        torch.cuda.synchronize()
-        for r, c in enumerate(cs):
-            c.peer_allgather(loc[r], [bf.ptr for bf in bufs], asynchronous=True)
-        for c in cs:
-            c.sync()
+        ptrs = [bf.ptr for bf in bufs]
+        with _quiet_host():
+            for r, c in enumerate(cs):
+                c.peer_allgather(loc[r], ptrs, asynchronous=True)
+            for c in cs:
+                c.sync()
         for bf in bufs:
             t = bf.tensor(G, n)
             for r in range(G):
