@@ -69,9 +69,13 @@ int* bad_flag(rxg_ctx* ctx) {
     }
     return ctx->d_bad;
 }
+// a kernel, not cudaMemsetAsync: a host-issued device memset can serialise behind another stream's RUNNING kernel (the
+// spinning barrier of a peer rank that lives in the same process), a kernel launch on this stream cannot
+__global__ void clear_flag_kernel(int* f) { *f = 0; }
 int begin_bad_flag(rxg_ctx* ctx) {
     if (!bad_flag(ctx)) return RXG_ERR_CUDA;
-    return check_cuda(ctx, cudaMemsetAsync(ctx->d_bad, 0, 4, ctx->stream), "bad flag reset");
+    clear_flag_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_bad);
+    return check_cuda(ctx, cudaGetLastError(), "bad flag reset");
 }
 static int examine_bad_flag(rxg_ctx* ctx) {      // the stream has been synchronised
     if (!ctx->bad_pending) return RXG_OK;
