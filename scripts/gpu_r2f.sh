@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python scripts/debug_peer.py > gpurun_out/r2f_debug.txt 2>&1
-cat gpurun_out/r2f_debug.txt | tail -20
+timeout 900 python -m pytest tests/test_peer_gather_gpu.py -m gpu -q 2>&1 | tail -6 > gpurun_out/r2f_pytest.txt
+cat gpurun_out/r2f_pytest.txt
