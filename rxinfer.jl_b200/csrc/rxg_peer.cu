@@ -218,6 +218,13 @@ int rxg_peer_group(rxg_ctx* ctx, int nranks, int rank, void* const* flag_ptrs) {
         int rc0 = ensure_aux_stream(ctx);
         if (rc0 != RXG_OK) return rc0;
         if (!bad_flag(ctx)) return RXG_ERR_CUDA;
+        // CUDA loads a kernel's module at its FIRST launch (lazy loading), which may wait for running kernels; a rank
+        // whose peer is already spinning in the barrier must not hit that inside a gather: load the gather kernels now
+        cudaFuncAttributes fa;
+        RXG_CUDA(ctx, cudaFuncGetAttributes(&fa, peer_barrier_kernel));
+        RXG_CUDA(ctx, cudaFuncGetAttributes(&fa, peer_push_kernel));
+        RXG_CUDA(ctx, cudaFuncGetAttributes(&fa, peer_push_scalar_kernel));
+        RXG_CUDA(ctx, cudaFuncGetAttributes(&fa, replicate_cov_kernel));
     }
     ctx->peer_n = nranks;
     ctx->peer_rank = rank;

@@ -5,9 +5,9 @@ import sys
 # 8 hardware work queues their streams can alias, and a kernel queued behind another rank's spinning barrier kernel would
 # never start.  Must be set before the CUDA context exists.  (Real multi-GPU jobs run one process per GPU.)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-# Same single-process caveat (documented for CUDA lazy loading): the FIRST launch of a kernel loads its module, which can
-# wait for running kernels -- a deadlock if that running kernel is another virtual rank's barrier spinning for us.
-os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+# (Same single-process caveat for CUDA lazy loading: the FIRST launch of a kernel loads its module, which can wait for
+# running kernels; rxg_peer_group therefore loads the gather kernels up front, and the tests below run every sweep once
+# without a gather -- the reference result -- before the virtual ranks gather.)
 
 import pytest
 
