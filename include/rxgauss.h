@@ -283,6 +283,12 @@ int rxg_lgssm_vmp_gamma_f32(rxg_ctx*, int T, int64_t batch, int iterations, floa
                             float m0, float v0, float a0, float b0, float init_E_tau,
                             const float* y, float* post_mean, float* post_var, float* shape,
                             float* rate, unsigned flags);
+/* Same with the Bethe free energy after every iteration, free_energy[iterations][batch] (or NULL)
+ * [ref: free_energy = true, src/inference/batch.jl:184-189; definition src/model/plugins/reactivemp_free_energy.jl:84-126]. */
+int rxg_lgssm_vmp_gamma_fe_f32(rxg_ctx*, int T, int64_t batch, int iterations, float a, float v_proc,
+                               float m0, float v0, float a0, float b0, float init_E_tau, const float* y,
+                               float* post_mean, float* post_var, float* shape, float* rate,
+                               float* free_energy, unsigned flags);
 /* Hierarchical Gaussian Filter, streaming, `iters` VMP iterations per datum
  * [ref: test/models/statespace/hgf_tests.jl:10-69; loop src/inference/streaming.jl:349-407].
  * y[T][batch]; init = (m_z, v_z, m_x, v_x); out[T][4][batch] = (m_x, v_x, m_z, v_z).            */

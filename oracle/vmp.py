@@ -84,18 +84,34 @@ def two_node_gaussian(prior_mean=3.0, prior_var=1.0, y=0.0, obs_var=1.0):
 
 
 def lgssm_gamma_precision(y, A_scalar=1.0, prior=(0.0, 100.0), proc_var=1.0,
-                          gamma_prior=(1.0, 1.0), iterations=10, init_Etau=1.0):
+                          gamma_prior=(1.0, 1.0), iterations=10, init_Etau=1.0, return_free_energy=False):
     """Univariate smoother with an unknown SHARED observation precision tau ~ Gamma(a0, b0)
     (rules row 9): y[t] ~ N(x[t], 1/tau), x[t] ~ N(a x[t-1], v).
     Mean-field q(x) q(tau).  y[T, batch].  One VMP iteration = BP sweep given E[tau], then
-    tau update with shapes/rates adding over t: Gamma(a0 + T/2, b0 + 1/2 sum E[(y - x)^2])."""
+    tau update with shapes/rates adding over t: Gamma(a0 + T/2, b0 + 1/2 sum E[(y - x)^2]).
+
+    ``return_free_energy``: Bethe free energy after every iteration [iterations, batch], evaluated FROM ITS DEFINITION
+    (/root/reference/src/model/plugins/reactivemp_free_energy.jl:84-126; q(x) = the exact Gaussian chain posterior of the
+    sweep, dense T x T algebra): F = E_q[-log p(y, x, tau)] - H[q(x)] - H[q(tau)].  tests/test_oracle_goldens.py checks
+    the closed form the CUDA kernel uses (filter evidence + T/2 (log tau_old - E log tau) + (E tau - tau_old)(b - b0) +
+    KL(q(tau) || prior)) against it."""
+    from scipy.special import digamma, gammaln
     from .lgssm import smooth_reference_schedule
     y = np.asarray(y, dtype=np.float64)
     T, batch = y.shape
     Etau = np.full(batch, init_Etau, dtype=np.float64)
     a0, b0 = gamma_prior
-    hist = []
+    fes, fes_closed = [], []
+    # Gaussian chain prior over x[0..T-1]: precision J0 (tridiagonal), information vector h0
+    J0 = np.zeros((T, T)); h0 = np.zeros(T)
+    J0[0, 0] += 1.0 / prior[1]; h0[0] += prior[0] / prior[1]
+    for t in range(1, T):
+        J0[t, t] += 1.0 / proc_var; J0[t - 1, t - 1] += A_scalar ** 2 / proc_var
+        J0[t, t - 1] -= A_scalar / proc_var; J0[t - 1, t] -= A_scalar / proc_var
+    logdet_prior = -np.linalg.slogdet(J0)[1]                     # log det Sigma_prior
+    mu_prior = np.linalg.solve(J0, h0)
     for _ in range(iterations):
+        tau_old = Etau.copy()
         Q = (1.0 / Etau)[:, None, None]
         r = smooth_reference_schedule(
             y[:, None, :], np.array([[A_scalar]]), np.array([[1.0]]), np.array([[proc_var]]), Q,
@@ -104,8 +120,29 @@ def lgssm_gamma_precision(y, A_scalar=1.0, prior=(0.0, 100.0), proc_var=1.0,
         a = a0 + 0.5 * T
         b = b0 + 0.5 * ((y - mx) ** 2 + vx).sum(0)
         Etau = a / b
-        hist.append((mx, vx, a, b))
-    return dict(mean=mx, var=vx, shape=np.full(batch, a), rate=b, Etau=Etau)
+        if return_free_energy:
+            Elog = digamma(a) - np.log(b)
+            kl = (a - a0) * digamma(a) - gammaln(a) + gammaln(a0) + a0 * (np.log(b) - np.log(b0)) + a * (b0 - b) / b
+            fes_closed.append(r["neg_log_evidence"] + 0.5 * T * (np.log(tau_old) - Elog) + (Etau - tau_old) * (b - b0) + kl)
+            fe = np.zeros(batch)
+            for c in range(batch):
+                J = J0 + tau_old[c] * np.eye(T)                  # q(x) = N(mu, Sigma) under the E[tau] of the sweep
+                Sig = np.linalg.inv(J)
+                mu = Sig @ (h0 + tau_old[c] * y[:, c])
+                dmu = mu - mu_prior
+                E_prior = 0.5 * (T * np.log(2 * np.pi) + logdet_prior + np.trace(J0 @ Sig) + dmu @ J0 @ dmu)
+                Rt = (y[:, c] - mu) ** 2 + np.diag(Sig)
+                E_obs = 0.5 * (T * np.log(2 * np.pi) - T * Elog[c] + Etau[c] * Rt.sum())
+                H_x = 0.5 * (T * np.log(2 * np.pi * np.e) + np.linalg.slogdet(Sig)[1])
+                E_tau = -(a0 * np.log(b0) - gammaln(a0) + (a0 - 1) * Elog[c] - b0 * Etau[c])
+                H_tau = a - np.log(b[c]) + gammaln(a) + (1 - a) * digamma(a)
+                fe[c] = E_prior + E_obs + E_tau - H_x - H_tau
+            fes.append(fe)
+    out = dict(mean=mx, var=vx, shape=np.full(batch, a), rate=b, Etau=Etau)
+    if return_free_energy:
+        out["free_energy"] = np.stack(fes)
+        out["free_energy_closed_form"] = np.stack(fes_closed)
+    return out
 
 
 def stream_vmp_gamma(y, iterations=4, w=1.0, init_x=(0.0, 1e3), init_tau=(1.0, 1.0), return_free_energy=False):

@@ -245,15 +245,16 @@ class Context:
         return out, fe
 
     def lgssm_vmp_gamma(self, y, iterations=10, a=1.0, v_proc=1.0, prior=(0.0, 100.0), gamma_prior=(1.0, 1.0),
-                        init_E_tau=1.0):
+                        init_E_tau=1.0, want_free_energy=False):
         self._dev(y)
         T, batch = y.shape
         pm, pv = self.empty(T, batch), self.empty(T, batch)
         sh, rt = self.empty(batch), self.empty(batch)
-        self._check(self.lib.rxg_lgssm_vmp_gamma_f32(self.h, T, batch, iterations, a, v_proc, prior[0], prior[1],
-                                                     gamma_prior[0], gamma_prior[1], init_E_tau, _fp(y), _fp(pm),
-                                                     _fp(pv), _fp(sh), _fp(rt), L.PTR_DEVICE))
-        return dict(mean=pm, var=pv, shape=sh, rate=rt)
+        fe = self.empty(iterations, batch) if want_free_energy else None
+        self._check(self.lib.rxg_lgssm_vmp_gamma_fe_f32(self.h, T, batch, iterations, a, v_proc, prior[0], prior[1],
+                                                        gamma_prior[0], gamma_prior[1], init_E_tau, _fp(y), _fp(pm),
+                                                        _fp(pv), _fp(sh), _fp(rt), _fp(fe), L.PTR_DEVICE))
+        return dict(mean=pm, var=pv, shape=sh, rate=rt, free_energy=fe)
 
     # ------------------------------------------------------------------ per-rule kernels
     def _mat(self, M):

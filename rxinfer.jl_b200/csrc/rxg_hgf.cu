@@ -285,23 +285,37 @@ __global__ void k_gcv_z_prod(int64_t n, const float* m_yx, const float* V_yx, co
     m_z[i] = mz; v_z[i] = vz;
 }
 
-// ---- Gamma-precision VMP around a scalar smoother (d = m = 1), tau shared over time per chain
+__device__ __forceinline__ float digamma_f(float x) {      // psi(x), x > 0: recurrence up to x >= 6, then the asymptotic series
+    float r = 0.f;
+    while (x < 6.f) { r -= 1.f / x; x += 1.f; }
+    const float i = 1.f / x, i2 = i * i;
+    return r + logf(x) - 0.5f * i - i2 * (1.f / 12.f - i2 * (1.f / 120.f - i2 * (1.f / 252.f)));
+}
+// ---- Gamma-precision VMP around a scalar smoother (d = m = 1), tau shared over time per chain.
+// fe[iterations][batch] (optional): Bethe free energy after every iteration, with q(x) the exact chain posterior under the
+// E[tau] the sweep ran with and q(tau) the update that followed.  The Gaussian part collapses to the filter's evidence:
+//   F = NLE(tau_old) + T/2 (log tau_old - E log tau) + (E tau - tau_old)(b - b0) + KL(q(tau) || Gamma(a0, b0))
+// (E_q[-log p(x)] - H[q(x)] = -log Z(tau_old) - sum_t E_q[-log N(y_t; x_t, 1/tau_old)], sum_t E(y_t - x_t)^2 = 2 (b - b0);
+// checked against the dense evaluation of the definition in tests/test_oracle_goldens.py)
 __global__ void __launch_bounds__(128)
 vmp_gamma_kernel(const float* __restrict__ y, float* __restrict__ pm, float* __restrict__ pv,
                  float* __restrict__ shape, float* __restrict__ rate, int T, int64_t batch, int iterations,
-                 float a, float vproc, float m0, float v0, float a0, float b0, float init_Etau) {
+                 float a, float vproc, float m0, float v0, float a0, float b0, float init_Etau, float* __restrict__ fe) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
     float Etau = init_Etau, sh = a0, rt = b0;
     for (int it = 0; it < iterations; ++it) {
         const float q = 1.0f / Etau;       // NormalMeanPrecision(:out)(m_mu, q_tau): variance 1 / E[tau]
+        double nle = 0.0;
         float m = m0, v = v0;
         float ynext = __ldg(y + b);
         for (int t = 0; t < T; ++t) {
             const float yt = ynext;
             if (t + 1 < T) ynext = __ldg(y + (int64_t)(t + 1) * batch + b);
             if (t > 0) { m = a * m; v = __fmaf_rn(a * a, v, vproc); }
-            const float k = v / (v + q);
+            const float sinn = v + q;
+            const float k = v / sinn;
+            if (fe) { const float e = yt - m; nle += 0.5 * (double)(1.8378770664093453f + logf(sinn) + e * e / sinn); }
             m = __fmaf_rn(k, yt - m, m);
             v = __fmaf_rn(-k, v, v);
             pm[(int64_t)t * batch + b] = m;
@@ -322,9 +336,15 @@ vmp_gamma_kernel(const float* __restrict__ y, float* __restrict__ pm, float* __r
             res += (double)__fmaf_rn(d, d, vs);
         }
         // prod(Gamma(a0, b0), prod_t NormalMeanPrecision(:tau)(q_out = PointMass y_t, q_mu = q(x_t)))
+        const float tau_old = Etau;
         sh = a0 + 0.5f * (float)T;
         rt = b0 + 0.5f * (float)res;
         Etau = sh / rt;
+        if (fe) {
+            const float Elog = digamma_f(sh) - logf(rt);
+            const float kl = (sh - a0) * digamma_f(sh) - lgammaf(sh) + lgammaf(a0) + a0 * (logf(rt) - logf(b0)) + sh * (b0 - rt) / rt;
+            fe[(int64_t)it * batch + b] = (float)(nle + 0.5 * T * (double)(logf(tau_old) - Elog) + (double)(Etau - tau_old) * (0.5 * res) + (double)kl);
+        }
     }
     shape[b] = sh; rate[b] = rt;
 }
@@ -335,12 +355,6 @@ vmp_gamma_kernel(const float* __restrict__ y, float* __restrict__ pm, float* __r
 //   q(x_t)     = NormalMeanPrecision(:out)(q_mu = q(x_t_min)) x NormalMeanPrecision(:mu)(y, q_tau)
 //   q(tau)     = Gamma(a_p, b_p) x NormalMeanPrecision(:tau)(q_out = y, q_mu = q(x_t))
 // with the priors (m_p, v_p, a_p, b_p) autoupdated from the previous datum's q(x_t), q(tau).
-__device__ __forceinline__ float digamma_f(float x) {      // psi(x), x > 0: recurrence up to x >= 6, then the asymptotic series
-    float r = 0.f;
-    while (x < 6.f) { r -= 1.f / x; x += 1.f; }
-    const float i = 1.f / x, i2 = i * i;
-    return r + logf(x) - 0.5f * i - i2 * (1.f / 12.f - i2 * (1.f / 120.f - i2 * (1.f / 252.f)));
-}
 __global__ void __launch_bounds__(128)
 stream_vmp_gamma_kernel(const float* __restrict__ y, const float* __restrict__ prev, float* __restrict__ out,
                         float* __restrict__ fe, int T, int64_t batch, int iters, float w, float i_mx, float i_vx,
@@ -466,16 +480,25 @@ int rxg_rule_gcv_z_prod_f32(rxg_ctx* ctx, int64_t n, const float* m_yx, const fl
     RXG_GCV_EPILOGUE("k_gcv_z_prod")
 }
 
+int rxg_lgssm_vmp_gamma_fe_f32(rxg_ctx* ctx, int T, int64_t batch, int iterations, float a, float v_proc, float m0,
+                               float v0, float a0, float b0, float init_E_tau, const float* y, float* post_mean,
+                               float* post_var, float* shape, float* rate, float* free_energy, unsigned flags);
 int rxg_lgssm_vmp_gamma_f32(rxg_ctx* ctx, int T, int64_t batch, int iterations, float a, float v_proc, float m0,
                             float v0, float a0, float b0, float init_E_tau, const float* y, float* post_mean,
                             float* post_var, float* shape, float* rate, unsigned flags) {
+    return rxg_lgssm_vmp_gamma_fe_f32(ctx, T, batch, iterations, a, v_proc, m0, v0, a0, b0, init_E_tau, y, post_mean, post_var,
+                                      shape, rate, nullptr, flags);
+}
+int rxg_lgssm_vmp_gamma_fe_f32(rxg_ctx* ctx, int T, int64_t batch, int iterations, float a, float v_proc, float m0,
+                               float v0, float a0, float b0, float init_E_tau, const float* y, float* post_mean,
+                               float* post_var, float* shape, float* rate, float* free_energy, unsigned flags) {
     if (!ctx) return RXG_ERR_BAD_ARG;
     if (T < 1 || batch < 1 || iterations < 1 || !y || !post_mean || !post_var || !shape || !rate)
         return rxg::fail(ctx, RXG_ERR_BAD_ARG, "lgssm_vmp_gamma: bad argument");
     if (!(flags & RXG_PTR_DEVICE)) return rxg::fail(ctx, RXG_ERR_UNSUPPORTED, "lgssm_vmp_gamma takes device pointers");
     RXG_CUDA(ctx, cudaSetDevice(ctx->device));
     vmp_gamma_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, ctx->stream>>>(
-        y, post_mean, post_var, shape, rate, T, batch, iterations, a, v_proc, m0, v0, a0, b0, init_E_tau);
+        y, post_mean, post_var, shape, rate, T, batch, iterations, a, v_proc, m0, v0, a0, b0, init_E_tau, free_energy);
     ctx->launches += 1;
     int rc = rxg::check_cuda(ctx, cudaGetLastError(), "vmp_gamma_kernel");
     if (rc != RXG_OK) return rc;

@@ -170,9 +170,11 @@ def infer(*, model, iterations=None, free_energy=False, returnvars=None, options
                                             "τ": GammaShapeRate(out[:, 2], out[:, 3])})
         if isinstance(model, univariate_lgssm_gamma_precision):
             r = ctx.lgssm_vmp_gamma(y, iterations=iterations or 1, a=model.a, v_proc=model.v_proc, prior=model.x0,
-                                    gamma_prior=model.gamma_prior, init_E_tau=model.init_E_tau)
+                                    gamma_prior=model.gamma_prior, init_E_tau=model.init_E_tau,
+                                    want_free_energy=bool(free_energy))
             return InferenceResult(posteriors={"x": NormalMeanVariance(r["mean"], r["var"]),
-                                               "τ": GammaShapeRate(r["shape"], r["rate"])}, model=model)
+                                               "τ": GammaShapeRate(r["shape"], r["rate"])}, model=model,
+                                   free_energy=r["free_energy"])
         raise NotImplementedError(f"model pattern {type(model).__name__} is not on the batched hot path")
     except Exception as e:           # reference: catch_exception=true returns a partial result with .error
         if catch_exception:

@@ -183,6 +183,10 @@ lgssm_vmp_gamma(ctx, T, batch, its, a, vproc, m0, v0, a0, b0, Etau, y, pm, pv, s
     check(ctx, ccall((:rxg_lgssm_vmp_gamma_f32, LIB), Cint,
         (Ptr{Cvoid}, Cint, Int64, Cint, Cfloat, Cfloat, Cfloat, Cfloat, Cfloat, Cfloat, Cfloat, F32P, F32P, F32P, F32P, F32P, Cuint),
         ctx.handle, T, batch, its, a, vproc, m0, v0, a0, b0, Etau, y, pm, pv, sh, rt, fl))
+lgssm_vmp_gamma_fe(ctx, T, batch, its, a, vproc, m0, v0, a0, b0, Etau, y, pm, pv, sh, rt, fe, fl) =
+    check(ctx, ccall((:rxg_lgssm_vmp_gamma_fe_f32, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Int64, Cint, Cfloat, Cfloat, Cfloat, Cfloat, Cfloat, Cfloat, Cfloat, F32P, F32P, F32P, F32P, F32P, F32P, Cuint),
+        ctx.handle, T, batch, its, a, vproc, m0, v0, a0, b0, Etau, y, pm, pv, sh, rt, fe, fl))
 hgf_filter(ctx, T, batch, its, kappa, omega, zvar, yvar, init, y, out, fl) =
     check(ctx, ccall((:rxg_hgf_filter_f32, LIB), Cint,
         (Ptr{Cvoid}, Cint, Int64, Cint, Cfloat, Cfloat, Cfloat, Cfloat, F32P, F32P, F32P, Cuint), ctx.handle, T, batch, its, kappa, omega, zvar, yvar, init, y, out, fl))

@@ -95,6 +95,24 @@ def test_hgf_full_size_parity_report(ctx):
     assert rep["m_z"][0] < HGF_TOL["m_z"] and rep["v_z"][0] < HGF_TOL["v_z"]
 
 
+def test_vmp_gamma_precision_free_energy(ctx):
+    """rxg_lgssm_vmp_gamma_fe_f32: Bethe free energy per iteration against the oracle's evaluation of the definition
+    (dense q(x)); non-increasing over the iterations, as the reference asserts for its VMP models."""
+    rng = np.random.default_rng(14)
+    T, batch = 120, 33
+    x = np.cumsum(rng.standard_normal((T, batch)), axis=0)
+    y = (x + rng.standard_normal((T, batch)) / np.sqrt(rng.gamma(2.0, 1.0, batch) + 0.2)).astype(np.float32)
+    ref = vmp.lgssm_gamma_precision(y, iterations=7, return_free_energy=True)
+    r = ctx.lgssm_vmp_gamma(dev(y), iterations=7, want_free_energy=True)
+    fe = r["free_energy"].cpu().numpy()
+    assert fe.shape == (7, batch)
+    err = np.abs(fe - ref["free_energy"]) / np.abs(ref["free_energy"])
+    print("vmp gamma free energy rel err max", err.max())
+    assert err.max() < 2e-5
+    assert np.all(np.diff(fe, axis=0) < 1e-3 * np.abs(fe[:-1]))
+    assert rel_l2(r["mean"].cpu().numpy(), ref["mean"]) < 1e-5
+
+
 def test_vmp_gamma_precision(ctx):
     rng = np.random.default_rng(4)
     T, batch = 400, 70
