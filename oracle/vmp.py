@@ -218,3 +218,48 @@ def mv_iid_wishart(y, iterations=10, mu0=None, Lambda0=None, nu0=None, inv_scale
         EP = R.wishart_mean((df_acc, is_acc))
     return dict(m_mean=m.T.copy(), m_cov=np.moveaxis(Vm, 0, 2).copy(), df=df_acc, inv_scale=np.moveaxis(is_acc, 0, 2).copy(),
                 E_P=np.moveaxis(EP, 0, 2).copy())
+
+
+def ar_regression(series, order, iterations=15, gamma_prior=(1.0, 1.0), theta_prior_precision=1.0, init_gamma=(1.0, 1.0)):
+    """Mean-field VMP of the reference's autoregressive test model, message by message
+    (/root/reference/test/models/autoregressive/ar_tests.jl:7-36):
+
+        gamma ~ Gamma(shape = 1, rate = 1);  theta ~ MvNormal(mean = 0, precision = I)
+        y[i] ~ Normal(mean = dot(x[i], theta), precision = gamma),   x[i] = lags of the series (ar_ssm_data, :7-15)
+        q(gamma, theta) = q(gamma) q(theta);  init q(gamma) = GammaShapeRate(1, 1);  `iterations` sweeps
+
+    series[N, batch] -> dict(theta_mean[order, batch], theta_cov[order, order, batch], gamma_shape, gamma_rate[batch],
+    free_energy[iterations, batch]).  Per sweep: every Normal node sends, through the `dot` node with the PointMass x[i], the
+    backward message (xi, W) = (x_i E[gamma] y_i, E[gamma] x_i x_i') to theta (rules: NormalMeanPrecision(:mu)(q_out, q_tau),
+    dot(:in2)); q(theta) = prior x product of them; then NormalMeanPrecision(:tau)(q_out = y_i, q_mu = q(x_i'theta)) =
+    Gamma(3/2, 1/2 [(y_i - x_i'm)^2 + x_i' V x_i]) and q(gamma) = prior x product.  Bethe free energy of the fully factorised q:
+    E[-log p(y | theta, gamma)] + KL(q(theta) || p(theta)) + KL(q(gamma) || p(gamma))."""
+    from scipy.special import digamma, gammaln
+    s = np.asarray(series, dtype=np.float64)
+    N, batch = s.shape
+    p = order
+    n = N - p
+    # ar_ssm_data: inputs[k] = (s[k+p-1], ..., s[k]) reversed window, outputs[k] = s[k+p]
+    X = np.stack([s[p - 1 - j: N - 1 - j] for j in range(p)], axis=1)          # [n, p, batch]
+    Y = s[p:]                                                                  # [n, batch]
+    a0, b0 = gamma_prior
+    ga = np.full(batch, init_gamma[0]); gb = np.full(batch, init_gamma[1])
+    fes = []
+    for _ in range(iterations):
+        Eg = ga / gb
+        W = theta_prior_precision * np.eye(p)[:, :, None] + Eg * np.einsum("nib,njb->ijb", X, X)
+        xi = Eg * np.einsum("nib,nb->ib", X, Y)
+        V = np.linalg.inv(np.moveaxis(W, 2, 0))                                # [batch, p, p]
+        m = np.einsum("bij,jb->bi", V, xi)                                     # [batch, p]
+        pred = np.einsum("nib,bi->nb", X, m)
+        xVx = np.einsum("nib,bij,njb->nb", X, V, X)
+        res = ((Y - pred) ** 2 + xVx).sum(0)
+        ga = a0 + 0.5 * n + 0.0 * ga                                           # a0 + sum (3/2 - 1)
+        gb = b0 + 0.5 * res
+        Elog = digamma(ga) - np.log(gb); Egn = ga / gb
+        like = 0.5 * n * (np.log(2 * np.pi) - Elog) + 0.5 * Egn * res
+        klt = 0.5 * (theta_prior_precision * (np.trace(V, axis1=1, axis2=2) + (m ** 2).sum(1)) - p - p * np.log(theta_prior_precision)
+                     - np.linalg.slogdet(V)[1])
+        klg = (ga - a0) * digamma(ga) - gammaln(ga) + gammaln(a0) + a0 * (np.log(gb) - np.log(b0)) + ga * (b0 - gb) / gb
+        fes.append(like + klt + klg)
+    return dict(theta_mean=m.T.copy(), theta_cov=np.moveaxis(V, 0, 2).copy(), gamma_shape=ga, gamma_rate=gb, free_energy=np.stack(fes))

@@ -409,6 +409,19 @@ class Context:
                                                         ctypes.cast(c_void_p(st.data_ptr()), L.i32p), L.PTR_DEVICE))
         return dict(m_mean=mm, m_cov=mc, df=df, inv_scale=iS, status=st)
 
+    def ar_vmp(self, series, order, iterations=15, gamma_prior=(1.0, 1.0), theta_prior_precision=1.0, init_gamma=(1.0, 1.0),
+               want_free_energy=True):
+        """Fused VMP of the reference's autoregressive regression model (``rxg_ar_vmp_f32``); series[N, batch]."""
+        self._dev(series)
+        N, batch = series.shape
+        tm, tc = self.empty(order, batch), self.empty(order, order, batch)
+        gs, gr = self.empty(batch), self.empty(batch)
+        fe = self.empty(iterations, batch) if want_free_energy else None
+        self._check(self.lib.rxg_ar_vmp_f32(self.h, order, N, batch, iterations, gamma_prior[0], gamma_prior[1], theta_prior_precision,
+                                            init_gamma[0], init_gamma[1], _fp(series), _fp(tm), _fp(tc), _fp(gs), _fp(gr), _fp(fe),
+                                            L.PTR_DEVICE))
+        return dict(theta_mean=tm, theta_cov=tc, gamma_shape=gs, gamma_rate=gr, free_energy=fe)
+
     def prod_gamma(self, a1, b1, a2, b2):
         return self._six(self.lib.rxg_prod_gamma_f32, a1, b1, a2, b2)
 

@@ -147,6 +147,13 @@ __global__ void k_marginal(int64_t n, int k, PtrList pl, float* mu, float* S, in
     if (status) status[i] = bad ? RXG_ERR_NOT_SPD : RXG_OK;
 }
 
+__device__ __forceinline__ float digamma_rule(float x) {   // psi(x), x > 0: recurrence up to x >= 6, then the asymptotic series
+    float r = 0.f;
+    while (x < 6.f) { r -= 1.f / x; x += 1.f; }
+    const float i = 1.f / x, i2 = i * i;
+    return r + logf(x) - 0.5f * i - i2 * (1.f / 12.f - i2 * (1.f / 120.f - i2 * (1.f / 252.f)));
+}
+
 // ---- univariate / Gamma (rows 8-9)
 __global__ void k_normal_precision_tau(int64_t n, const float* mo, const float* vo, const float* mm, const float* vm,
                                        float* shape, float* rate) {
@@ -220,6 +227,144 @@ __global__ void k_wishart_mean(int64_t n, const float* df, const float* iS, floa
     for (int k = 0; k < D * D; ++k) S.a[k] *= nu;
     st_soa<D, D>(EL, n, i, S);
     if (status) status[i] = bad ? RXG_ERR_NOT_SPD : RXG_OK;
+}
+
+// Fused mean-field VMP of the reference's autoregressive regression model
+//   gamma ~ Gamma(a0, b0),  theta ~ MvNormal(0, I / w0),  y[i] ~ Normal(dot(x[i], theta), 1 / gamma),  q(gamma) q(theta)
+// with the regressors x[i] = (s[i-1], ..., s[i-p]) taken from the series itself
+// [ref: /root/reference/test/models/autoregressive/ar_tests.jl:17-36 (model, constraints, initialisation), :7-15 (lags)].
+// One thread = one series: sufficient statistics (sum x x', sum x y, sum y^2) in ONE coalesced pass over s[N][batch] with
+// a p-deep sliding window in registers (fp64 accumulators); every VMP iteration is then O(p^3):
+//   q(theta): Lambda = w0 I + E[gamma] Sxx,  xi = E[gamma] Sxy                  (dot(:in2) messages, product)
+//   q(gamma): Gamma(a0 + n/2, b0 + 1/2 [Syy - 2 m'Sxy + m'Sxx m + tr(Sxx V)])    (NormalMeanPrecision(:tau) messages)
+// Bethe free energy per iteration: E[-log p(y | theta, gamma)] + KL(q(theta) || p) + KL(q(gamma) || p).
+template <int PMAX>
+__global__ void __launch_bounds__(128)
+ar_vmp_kernel(const float* __restrict__ series, int N, int64_t batch, int p, int iters, float a0, float b0, float w0,
+              float init_a, float init_b, float* __restrict__ th_mean, float* __restrict__ th_cov,
+              float* __restrict__ g_shape, float* __restrict__ g_rate, float* __restrict__ fe) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    double Sxx[PMAX][PMAX], Sxy[PMAX], Syy = 0.0;
+#pragma unroll
+    for (int i = 0; i < PMAX; ++i) {
+        Sxy[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < PMAX; ++j) Sxx[i][j] = 0.0;
+    }
+    float win[PMAX];                                    // win[j] = s[k-1-j]
+#pragma unroll
+    for (int j = 0; j < PMAX; ++j) win[j] = (j < p) ? __ldg(series + (int64_t)(p - 1 - j) * batch + b) : 0.f;
+    for (int k = p; k < N; ++k) {
+        const float yk = __ldg(series + (int64_t)k * batch + b);
+        Syy += (double)yk * (double)yk;
+#pragma unroll
+        for (int i = 0; i < PMAX; ++i) {
+            Sxy[i] += (double)win[i] * (double)yk;
+#pragma unroll
+            for (int j = 0; j <= i; ++j) Sxx[i][j] += (double)win[i] * (double)win[j];
+        }
+#pragma unroll
+        for (int j = PMAX - 1; j > 0; --j) win[j] = (j < p) ? win[j - 1] : 0.f;
+        win[0] = yk;
+    }
+#pragma unroll
+    for (int i = 0; i < PMAX; ++i)
+#pragma unroll
+        for (int j = i + 1; j < PMAX; ++j) Sxx[i][j] = Sxx[j][i];
+    const int n = N - p;
+    double ga = (double)init_a, gb = (double)init_b;
+    double m[PMAX], V[PMAX][PMAX];
+    for (int it = 0; it < iters; ++it) {
+        const double Eg = ga / gb;
+        // Lambda = w0 I + Eg Sxx = L L' ; V = Lambda^-1 ; m = V (Eg Sxy)
+        double L[PMAX][PMAX];
+#pragma unroll
+        for (int i = 0; i < PMAX; ++i)
+#pragma unroll
+            for (int j = 0; j < PMAX; ++j) L[i][j] = (i < p && j < p) ? Eg * Sxx[i][j] + (i == j ? (double)w0 : 0.0) : (i == j ? 1.0 : 0.0);
+        double logdetL = 0.0;
+#pragma unroll
+        for (int j = 0; j < PMAX; ++j) {
+            double dj = L[j][j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) dj -= L[j][k] * L[j][k];
+            dj = sqrt(dj > 0.0 ? dj : 1e-300);
+            L[j][j] = dj;
+            logdetL += log(dj);
+#pragma unroll
+            for (int i = j + 1; i < PMAX; ++i) {
+                double sv = L[i][j];
+#pragma unroll
+                for (int k = 0; k < j; ++k) sv -= L[i][k] * L[j][k];
+                L[i][j] = sv / dj;
+            }
+        }
+        // Li = L^-1 (lower), V = Li' Li
+        double Li[PMAX][PMAX];
+#pragma unroll
+        for (int i = 0; i < PMAX; ++i)
+#pragma unroll
+            for (int j = 0; j < PMAX; ++j) Li[i][j] = 0.0;
+#pragma unroll
+        for (int j = 0; j < PMAX; ++j) {
+            Li[j][j] = 1.0 / L[j][j];
+#pragma unroll
+            for (int i = j + 1; i < PMAX; ++i) {
+                double sv = 0.0;
+#pragma unroll
+                for (int k = j; k < i; ++k) sv -= L[i][k] * Li[k][j];
+                Li[i][j] = sv / L[i][i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < PMAX; ++i)
+#pragma unroll
+            for (int j = 0; j < PMAX; ++j) {
+                double sv = 0.0;
+#pragma unroll
+                for (int k = 0; k < PMAX; ++k) sv += Li[k][i] * Li[k][j];
+                V[i][j] = sv;
+            }
+#pragma unroll
+        for (int i = 0; i < PMAX; ++i) {
+            double sv = 0.0;
+#pragma unroll
+            for (int j = 0; j < PMAX; ++j) sv += V[i][j] * ((j < p) ? Eg * Sxy[j] : 0.0);
+            m[i] = (i < p) ? sv : 0.0;
+        }
+        // residual: sum_i E(y_i - x_i' theta)^2
+        double res = Syy, trSV = 0.0, mm = 0.0, trV = 0.0;
+#pragma unroll
+        for (int i = 0; i < PMAX; ++i) {
+            if (i < p) {
+                res -= 2.0 * m[i] * Sxy[i];
+                mm += m[i] * m[i];
+                trV += V[i][i];
+#pragma unroll
+                for (int j = 0; j < PMAX; ++j)
+                    if (j < p) { res += m[i] * Sxx[i][j] * m[j]; trSV += Sxx[i][j] * V[j][i]; }
+            }
+        }
+        res += trSV;
+        ga = (double)a0 + 0.5 * n;
+        gb = (double)b0 + 0.5 * res;
+        if (fe) {
+            const float af = (float)ga;
+            const double dig = (double)digamma_rule(af);
+            const double Elog = dig - log(gb), Egn = ga / gb;
+            const double like = 0.5 * n * (1.8378770664093453 - Elog) + 0.5 * Egn * res;
+            // KL(N(m, V) || N(0, I / w0)) = 1/2 [w0 (tr V + m'm) - p - p log w0 - log det V],  log det V = -2 log det L
+            const double klt = 0.5 * ((double)w0 * (trV + mm) - p - p * log((double)w0) + 2.0 * logdetL);
+            const double klg = (ga - a0) * dig - lgamma(ga) + lgamma((double)a0) + a0 * (log(gb) - log((double)b0)) + ga * ((double)b0 - gb) / gb;
+            fe[(int64_t)it * batch + b] = (float)(like + klt + klg);
+        }
+    }
+    for (int i = 0; i < p; ++i) {
+        th_mean[(int64_t)i * batch + b] = (float)m[i];
+        for (int j = 0; j < p; ++j) th_cov[((int64_t)i * p + j) * batch + b] = (float)V[i][j];
+    }
+    g_shape[b] = (float)ga; g_rate[b] = (float)gb;
 }
 
 // Fused mean-field VMP of the multivariate IID model with unknown mean and precision
@@ -489,6 +634,25 @@ int rxg_mv_iid_wishart_vmp_f32(rxg_ctx* ctx, int d, int N, int64_t batch, int it
 #undef RXG_WISH
     }
     RXG_RULE_EPILOGUE(ctx, "mv_iid_wishart_vmp_kernel")
+}
+int rxg_ar_vmp_f32(rxg_ctx* ctx, int order, int N, int64_t batch, int iterations, float a0, float b0, float theta_prior_precision,
+                   float init_shape, float init_rate, const float* series, float* theta_mean, float* theta_cov,
+                   float* gamma_shape, float* gamma_rate, float* free_energy, unsigned flags) {
+    if (!ctx) return RXG_ERR_BAD_ARG;
+    if (!(flags & RXG_PTR_DEVICE)) return rxg::fail(ctx, RXG_ERR_UNSUPPORTED, "ar_vmp takes device pointers");
+    if (order < 1 || order > 8) return rxg::fail(ctx, RXG_ERR_UNSUPPORTED, "ar_vmp: order=%d unsupported (1-8)", order);
+    if (N <= order || batch < 1 || iterations < 1 || !series || !theta_mean || !theta_cov || !gamma_shape || !gamma_rate ||
+        !(a0 > 0.f) || !(b0 > 0.f) || !(theta_prior_precision > 0.f) || !(init_shape > 0.f) || !(init_rate > 0.f))
+        return rxg::fail(ctx, RXG_ERR_BAD_ARG, "ar_vmp: bad argument");
+    RXG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const unsigned grid = (unsigned)((batch + 127) / 128);
+    if (order <= 4)
+        ar_vmp_kernel<4><<<grid, 128, 0, ctx->stream>>>(series, N, batch, order, iterations, a0, b0, theta_prior_precision, init_shape,
+                                                        init_rate, theta_mean, theta_cov, gamma_shape, gamma_rate, free_energy);
+    else
+        ar_vmp_kernel<8><<<grid, 128, 0, ctx->stream>>>(series, N, batch, order, iterations, a0, b0, theta_prior_precision, init_shape,
+                                                        init_rate, theta_mean, theta_cov, gamma_shape, gamma_rate, free_energy);
+    RXG_RULE_EPILOGUE(ctx, "ar_vmp_kernel")
 }
 int rxg_prod_normal_f32(rxg_ctx* ctx, int64_t n, const float* m1, const float* v1, const float* m2, const float* v2,
                         float* m, float* v, unsigned flags) {

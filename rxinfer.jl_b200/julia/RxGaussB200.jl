@@ -205,6 +205,11 @@ mv_iid_wishart_vmp(ctx, d, N, batch, its, mu0, L0, nu0, iS0, EP0, y, mm, mc, df,
         (Ptr{Cvoid}, Cint, Cint, Int64, Cint, F32P, F32P, Cfloat, F32P, F32P, F32P, F32P, F32P, F32P, F32P, Ptr{Int32}, Cuint),
         ctx.handle, d, N, batch, its, mu0, L0, nu0, iS0, EP0, y, mm, mc, df, iS, st, fl))
 
+ar_vmp(ctx, order, N, batch, its, a0, b0, w0, ia, ib, series, tm, tc, gs, gr, fe, fl) =
+    check(ctx, ccall((:rxg_ar_vmp_f32, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Cint, Int64, Cint, Cfloat, Cfloat, Cfloat, Cfloat, Cfloat, F32P, F32P, F32P, F32P, F32P, F32P, Cuint),
+        ctx.handle, order, N, batch, its, a0, b0, w0, ia, ib, series, tm, tc, gs, gr, fe, fl))
+
 # ---- diagnostics
 selftest_umma(ctx, A, B, D, fl) = check(ctx, ccall((:rxg_selftest_umma_f32, LIB), Cint, (Ptr{Cvoid}, F32P, F32P, F32P, Cuint), ctx.handle, A, B, D, fl))
 selftest_umma_shape(ctx, n, k, A, B, D, fl) = check(ctx, ccall((:rxg_selftest_umma_shape_f32, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, F32P, F32P, F32P, Cuint), ctx.handle, n, k, A, B, D, fl))

@@ -173,3 +173,58 @@ def test_gpu_reproduces_reference_goldens(ctx):
         assert np.all(np.abs(fe - 1854.297647) < 0.01)                    # ulgssm_tests.jl:48
         m = r["mean"][:, 0, 5].cpu().numpy().astype(np.float64)
         assert np.linalg.norm(m - uref["mean"][:, 0, 0]) / np.linalg.norm(uref["mean"]) < 1e-5
+
+
+def _ar_reference_series():
+    """ar_tests.jl:53-57: rng = StableRNG(1234); for order in 1:5: series = randn(rng, 1_000)  (one stream, five draws)."""
+    from oracle.julia_rng import StableRNG
+    rng = StableRNG(1234)
+    return [rng.randn_vec(1000) for _ in range(5)]
+
+
+def _ar_reference_assertions(fe):
+    assert len(fe) == 15                                                            # :66-68
+    assert fe[-1] < fe[0]                                                           # :69
+    d = np.diff(fe)
+    assert np.all(d[np.abs(d) > 1e-3] < 0)                                          # :70
+
+
+def test_ar_reference_data_assertions():
+    """Autoregressive model (test/models/autoregressive/ar_tests.jl): the reference's own data stream regenerated
+    (StableRNG(1234) + Julia's ziggurat), its model run by the oracle for orders 1..5, its assertions verbatim; the
+    coefficient posterior also recovers an AR(0) series' zero coefficients within 4 sigma."""
+    from oracle import vmp
+    for order, series in zip(range(1, 6), _ar_reference_series()):
+        r = vmp.ar_regression(series[:, None], order, iterations=15)
+        _ar_reference_assertions(r["free_energy"][:, 0])
+        sd = np.sqrt(np.diag(r["theta_cov"][:, :, 0]))
+        assert np.all(np.abs(r["theta_mean"][:, 0]) < 4 * sd + 0.05)               # white noise: theta ~ 0
+        assert abs(r["gamma_shape"][0] / r["gamma_rate"][0] - 1.0) < 0.15           # unit-variance innovations
+
+
+@pytest.mark.gpu
+def test_gpu_ar_reference_data_assertions(ctx):
+    """Same stream and assertions on the CUDA path (rxg_ar_vmp_f32), and agreement with the oracle."""
+    import torch
+    from oracle import vmp
+    for order, series in zip(range(1, 6), _ar_reference_series()):
+        sb = np.repeat(series[:, None], 40, axis=1).astype(np.float32)
+        ref = vmp.ar_regression(sb[:, :1].astype(np.float64), order, iterations=15)
+        r = ctx.ar_vmp(torch.as_tensor(sb, device="cuda"), order, iterations=15)
+        fe = r["free_energy"].cpu().numpy()
+        for c in (0, 39):
+            _ar_reference_assertions(fe[:, c].astype(np.float64))
+        assert np.abs(fe[:, 0] - ref["free_energy"][:, 0]).max() / np.abs(ref["free_energy"]).max() < 1e-5
+        assert np.linalg.norm(r["theta_mean"][:, 0].cpu().numpy() - ref["theta_mean"][:, 0]) < 1e-5 * max(1.0, np.linalg.norm(ref["theta_mean"]))
+        assert np.linalg.norm(r["theta_cov"][:, :, 0].cpu().numpy() - ref["theta_cov"][:, :, 0]) / np.linalg.norm(ref["theta_cov"]) < 1e-4
+        assert abs(float(r["gamma_rate"][0]) - ref["gamma_rate"][0]) / ref["gamma_rate"][0] < 1e-5
+    # a genuinely autoregressive batch: coefficients recovered
+    rng = np.random.default_rng(2)
+    th = np.array([0.6, -0.3, 0.1])
+    s = np.zeros((3000, 64))
+    for k in range(3, 3000):
+        s[k] = th[0] * s[k - 1] + th[1] * s[k - 2] + th[2] * s[k - 3] + 0.5 * rng.standard_normal(64)
+    r = ctx.ar_vmp(torch.as_tensor(s.astype(np.float32), device="cuda"), 3, iterations=10)
+    est = r["theta_mean"].cpu().numpy()
+    assert np.abs(est - th[:, None]).max() < 0.08
+    assert np.abs((r["gamma_shape"] / r["gamma_rate"]).cpu().numpy() - 4.0).max() < 0.5
