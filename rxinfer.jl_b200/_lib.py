@@ -111,6 +111,13 @@ class RxGaussError(RuntimeError):
 
 
 _lib = None
+MISSING: list = []
+
+
+def _missing_entry(name):
+    def call(*a, **k):
+        raise ImportError(f"{LIB_PATH} does not export {name}: rebuild it (python rxinfer.jl_b200/build.py)")
+    return call
 
 
 def load():
@@ -124,7 +131,14 @@ def load():
             "(nvcc, sm_100a).  There is no CPU fallback for the hot path.")
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
-        fn = getattr(lib, name)          # AttributeError if the ABI and this table diverge
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            # a library older than this table (e.g. a stale build next to newer sources): everything it does export keeps
+            # working, the missing entry fails loudly when it is CALLED; tests/test_abi.py requires MISSING to be empty
+            MISSING.append(name)
+            setattr(lib, name, _missing_entry(name))
+            continue
         fn.restype = res
         fn.argtypes = args
     _lib = lib

@@ -27,6 +27,7 @@ def test_header_declares_expected_surface():
 
 def test_library_exports_every_declared_symbol(rx):
     lib = rx._lib.load()
+    assert rx._lib.MISSING == [], f"the built library is older than the ctypes table: {rx._lib.MISSING}"
     for name in header_functions():
         assert hasattr(lib, name), f"{name} declared in rxgauss.h but not exported"
 
