@@ -216,11 +216,12 @@ int rxg_mv_iid_wishart_vmp_f32(rxg_ctx*, int d, int N, int64_t batch, int iterat
  *   x[i] = (s[i-1], ..., s[i-order]) lags of the series itself, q(gamma) q(theta), q(gamma) initialised to
  *   Gamma(init_shape, init_rate) [ref: test/models/autoregressive/ar_tests.jl:7-36].  series[N][batch]; outputs
  *   theta_mean[order][batch], theta_cov[order][order][batch], gamma_shape / gamma_rate[batch], free_energy[iterations][batch]
- *   or NULL (Bethe free energy after every iteration; the reference asserts it to decrease, :70-71).  order <= 8.      */
+ *   or NULL (Bethe free energy after every iteration, in fp64: the reference asserts it to decrease, :69-70, and the
+ *   decreases are ~1e-5 on values of ~1.4e3).  order <= 8.                                                         */
 int rxg_ar_vmp_f32(rxg_ctx*, int order, int N, int64_t batch, int iterations, float a0, float b0,
                    float theta_prior_precision, float init_shape, float init_rate, const float* series,
                    float* theta_mean, float* theta_cov, float* gamma_shape, float* gamma_rate,
-                   float* free_energy, unsigned flags);
+                   double* free_energy, unsigned flags);
 /* prod(GammaShapeRate, GammaShapeRate) = (a1 + a2 - 1, b1 + b2)                                 */
 int rxg_prod_gamma_f32(rxg_ctx*, int64_t n, const float* a1, const float* b1, const float* a2,
                        const float* b2, float* a, float* b, unsigned flags);

@@ -416,9 +416,10 @@ class Context:
         N, batch = series.shape
         tm, tc = self.empty(order, batch), self.empty(order, order, batch)
         gs, gr = self.empty(batch), self.empty(batch)
-        fe = self.empty(iterations, batch) if want_free_energy else None
+        fe = self.empty(iterations, batch, dtype=torch.float64) if want_free_energy else None      # fp64 output (see the header)
+        fe_p = ctypes.cast(c_void_p(fe.data_ptr() if fe is not None else None), ctypes.POINTER(ctypes.c_double))
         self._check(self.lib.rxg_ar_vmp_f32(self.h, order, N, batch, iterations, gamma_prior[0], gamma_prior[1], theta_prior_precision,
-                                            init_gamma[0], init_gamma[1], _fp(series), _fp(tm), _fp(tc), _fp(gs), _fp(gr), _fp(fe),
+                                            init_gamma[0], init_gamma[1], _fp(series), _fp(tm), _fp(tc), _fp(gs), _fp(gr), fe_p,
                                             L.PTR_DEVICE))
         return dict(theta_mean=tm, theta_cov=tc, gamma_shape=gs, gamma_rate=gr, free_energy=fe)
 

@@ -207,7 +207,7 @@ mv_iid_wishart_vmp(ctx, d, N, batch, its, mu0, L0, nu0, iS0, EP0, y, mm, mc, df,
 
 ar_vmp(ctx, order, N, batch, its, a0, b0, w0, ia, ib, series, tm, tc, gs, gr, fe, fl) =
     check(ctx, ccall((:rxg_ar_vmp_f32, LIB), Cint,
-        (Ptr{Cvoid}, Cint, Cint, Int64, Cint, Cfloat, Cfloat, Cfloat, Cfloat, Cfloat, F32P, F32P, F32P, F32P, F32P, F32P, Cuint),
+        (Ptr{Cvoid}, Cint, Cint, Int64, Cint, Cfloat, Cfloat, Cfloat, Cfloat, Cfloat, F32P, F32P, F32P, F32P, F32P, Ptr{Float64}, Cuint),
         ctx.handle, order, N, batch, its, a0, b0, w0, ia, ib, series, tm, tc, gs, gr, fe, fl))
 
 # ---- diagnostics

@@ -214,7 +214,8 @@ def test_gpu_ar_reference_data_assertions(ctx):
         fe = r["free_energy"].cpu().numpy()
         for c in (0, 39):
             _ar_reference_assertions(fe[:, c].astype(np.float64))
-        assert np.abs(fe[:, 0] - ref["free_energy"][:, 0]).max() / np.abs(ref["free_energy"]).max() < 1e-5
+        # the series reaches the device in fp32 (the oracle gets the same rounded values): agreement to ~1e-9 relative
+        assert np.abs(fe[:, 0] - ref["free_energy"][:, 0]).max() / np.abs(ref["free_energy"]).max() < 1e-7
         assert np.linalg.norm(r["theta_mean"][:, 0].cpu().numpy() - ref["theta_mean"][:, 0]) < 1e-5 * max(1.0, np.linalg.norm(ref["theta_mean"]))
         assert np.linalg.norm(r["theta_cov"][:, :, 0].cpu().numpy() - ref["theta_cov"][:, :, 0]) / np.linalg.norm(ref["theta_cov"]) < 1e-4
         assert abs(float(r["gamma_rate"][0]) - ref["gamma_rate"][0]) / ref["gamma_rate"][0] < 1e-5
