@@ -79,7 +79,8 @@ typedef enum rxg_option {
     RXG_OPT_HOST_COV_D2H = 6,      /* 1: host-pointer calls copy the per-chain covariances over PCIe (no broadcast) */
     RXG_OPT_HOST_BCAST_MIN_MB = 7, /* below this covariance size the host broadcast is not used (default 64)        */
     RXG_OPT_HOST_SLICES = 8,       /* batch slices of the host-pointer pipeline (0 = auto)                          */
-    RXG_OPT_COUNT_ = 9
+    RXG_OPT_GATHER_MODE = 9,       /* rxg_lgssm_smooth_gather_f32: 0 auto, 1 peer stores fused into the sweep, 2 push after  */
+    RXG_OPT_COUNT_ = 10
 } rxg_option;
 
 #define RXG_MAX_PEERS 8            /* ranks of one peer group (one NVSwitch domain)                                 */

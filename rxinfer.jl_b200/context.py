@@ -65,7 +65,7 @@ class Context:
         return int(self.lib.rxg_host_fill_threads())
 
     OPTIONS = {"gain_seq": 0, "large_seq": 1, "no_umma": 2, "sweep_variant": 3, "force_cpt": 4, "host_threads": 5,
-               "host_cov_d2h": 6, "host_bcast_min_mb": 7, "host_slices": 8}
+               "host_cov_d2h": 6, "host_bcast_min_mb": 7, "host_slices": 8, "gather_mode": 9}
 
     def set_option(self, name: str, value: int):
         """``rxg_set_option``: per-context dispatch switches (cross-check kernels, host-pipeline tuning)."""

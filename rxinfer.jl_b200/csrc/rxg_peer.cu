@@ -319,9 +319,18 @@ int rxg_lgssm_smooth_gather_f32(rxg_ctx* ctx, int d, int m, int T, int64_t batch
             pc[np] = (gathered_cov && !replicate) ? gathered_cov[g] + r * slab_c : nullptr;
             ++np;
         }
-    for (int k = 0; k < np; ++k) { c.po.mean[k] = pm[k]; c.po.cov[k] = pc[k]; }
-    c.po.n_mean = np;
-    c.po.n_cov = (gathered_cov && !replicate) ? np : 0;
+    // Fused in-kernel peer stores or push-after-sweep.  Measured (B200, 65 536 chains per GPU): with replicated covariances
+    // only 4 mean rows per step go remote and the in-kernel stores run at 0.55 us per 256-byte store instruction -- at G = 2
+    // that hides under the sweep (2.63 ms vs 3.0 ms for sweep + push), at G = 8 it does not (15.4 ms; the means alone are
+    // 7.3 GB = 10.5 ms at the 700 GB/s peer_push_kernel reaches with wide stores from dedicated CTAs).  The full gather is
+    // NVLink bound either way (G = 8: fused 54.3 ms, sweep + ncclAllGather 55.8 ms, bound 47.7 ms) and stays fused.
+    const long long gmode = ctx->opt[RXG_OPT_GATHER_MODE];
+    const bool fuse = gmode == 1 || (gmode == 0 && (!replicate || G <= 2));
+    if (fuse) {
+        for (int k = 0; k < np; ++k) { c.po.mean[k] = pm[k]; c.po.cov[k] = pc[k]; }
+        c.po.n_mean = np;
+        c.po.n_cov = (gathered_cov && !replicate) ? np : 0;
+    }
     if (replicate && G > 1) {
         // the kernel family leaves the chain-independent covariance table in its workspace (no allocation here: a
         // device allocation may synchronise with a peer's spinning barrier when several ranks share one process)
@@ -335,7 +344,7 @@ int rxg_lgssm_smooth_gather_f32(rxg_ctx* ctx, int d, int m, int T, int64_t batch
         if (replicate) {
             // local broadcast fill of the other ranks' covariance slabs on the low-priority side stream
             const int64_t rows = (int64_t)T * d * d;
-            if (c.fused_peer_stores && c.cov_table) {      // the table exists as soon as the gain kernels are done: overlaps the whole sweep
+            if (c.cov_table) {      // the table exists as soon as the gain kernels are done (ev_tables): overlaps the whole sweep
                 RXG_CUDA(ctx, cudaStreamWaitEvent(ctx->s_aux, ctx->ev_aux[0], 0));
                 rc = launch_replicate_cov(ctx, ctx->s_aux, c.cov_table, 1, gathered_cov[r], rows, batch_local, G, r);
             } else {                        // other kernel families: replicate from the finished local slab

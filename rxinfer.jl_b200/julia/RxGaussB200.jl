@@ -46,7 +46,7 @@ const RXG_COV_REPLICATE    = UInt32(1) << 6
 const RXG_MASK_SHARED      = UInt32(1) << 7
 
 const RXG_OPT_GAIN_SEQ, RXG_OPT_LARGE_SEQ, RXG_OPT_NO_UMMA, RXG_OPT_SWEEP_VARIANT, RXG_OPT_FORCE_CPT = 0, 1, 2, 3, 4
-const RXG_OPT_HOST_THREADS, RXG_OPT_HOST_COV_D2H, RXG_OPT_HOST_BCAST_MIN_MB, RXG_OPT_HOST_SLICES = 5, 6, 7, 8
+const RXG_OPT_HOST_THREADS, RXG_OPT_HOST_COV_D2H, RXG_OPT_HOST_BCAST_MIN_MB, RXG_OPT_HOST_SLICES, RXG_OPT_GATHER_MODE = 5, 6, 7, 8, 9
 const RXG_MAX_PEERS = 8
 
 const F32P = Ptr{Float32}

@@ -35,7 +35,7 @@ def ctx(rx):
 
 
 _OPTION_DEFAULTS = {"gain_seq": 0, "large_seq": 0, "no_umma": 0, "sweep_variant": 0, "force_cpt": 0, "host_threads": 0,
-                    "host_cov_d2h": 0, "host_bcast_min_mb": 64, "host_slices": 0}
+                    "host_cov_d2h": 0, "host_bcast_min_mb": 64, "host_slices": 0, "gather_mode": 0}
 
 
 @pytest.fixture(autouse=True)
