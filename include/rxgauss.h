@@ -79,7 +79,7 @@ typedef enum rxg_option {
     RXG_OPT_HOST_COV_D2H = 6,      /* 1: host-pointer calls copy the per-chain covariances over PCIe (no broadcast) */
     RXG_OPT_HOST_BCAST_MIN_MB = 7, /* below this covariance size the host broadcast is not used (default 64)        */
     RXG_OPT_HOST_SLICES = 8,       /* batch slices of the host-pointer pipeline (0 = auto)                          */
-    RXG_OPT_GATHER_MODE = 9,       /* rxg_lgssm_smooth_gather_f32: 0 auto, 1 peer stores fused into the sweep, 2 push after  */
+    RXG_OPT_GATHER_MODE = 9,       /* rxg_lgssm_smooth_gather_f32: 0/1 peer stores fused into the sweep, 2 push after it  */
     RXG_OPT_COUNT_ = 10
 } rxg_option;
 
@@ -223,6 +223,22 @@ int rxg_ar_vmp_f32(rxg_ctx*, int order, int N, int64_t batch, int iterations, fl
                    float theta_prior_precision, float init_shape, float init_rate, const float* series,
                    float* theta_mean, float* theta_cov, float* gamma_shape, float* gamma_rate,
                    double* free_energy, unsigned flags);
+/* Fused structured VMP of the reference's LATENT autoregressive model, `batch` independent series, one launch:
+ *   gamma ~ Gamma(a0, b0); theta ~ N(0, I / w0); x0 ~ N(0, I / p0); x[t] ~ AR(x[t-1], theta, gamma) with
+ *   ARMeta(Multivariate | Univariate, order, ARsafe()); y[t] ~ Normal(dot(c, x[t]), 1 / tau), c = e1 (ReactiveMP.ar_unit);
+ *   q(x, x0) q(gamma) q(theta); q(gamma), q(theta) initialised to Gamma(init_shape, init_rate), N(0, I / init_theta_precision)
+ *   [ref: test/models/autoregressive/lar_tests.jl:52-122; free-energy pins :170 (AR(1): 518.9182342) and :201 (AR(5): 514.66086)].
+ *   The Univariate AR(1) node is the order = 1 case.  params (HOST, 8 floats, all > 0) = {tau, a0, b0, w0, p0, init_shape,
+ *   init_rate, init_theta_precision}.  y[T][batch]; outputs: x_mean[T][order][batch], x_cov[T][order][order][batch] of the
+ *   LAST iteration (KeepLast; either may be NULL), theta_mean[iterations][order][batch],
+ *   theta_cov[iterations][order][order][batch], gamma_shape / gamma_rate[iterations][batch] (KeepEach),
+ *   free_energy[iterations][batch] in fp64 or NULL, status[batch] or NULL.  Every iteration is a covariance-form filter + RTS
+ *   smoother over the companion-matrix state space in the exact limit of the AR node's deterministic coordinates (the
+ *   reference regularises them with a precision of 1e12), fp32 recursions, fp64 statistics / parameter updates / free energy.
+ *   order <= 6.  Device pointers.                                                                                   */
+int rxg_lar_vmp_f32(rxg_ctx*, int order, int T, int64_t batch, int iterations, const float* params, const float* y,
+                    float* x_mean, float* x_cov, float* theta_mean, float* theta_cov, float* gamma_shape,
+                    float* gamma_rate, double* free_energy, int32_t* status, unsigned flags);
 /* prod(GammaShapeRate, GammaShapeRate) = (a1 + a2 - 1, b1 + b2)                                 */
 int rxg_prod_gamma_f32(rxg_ctx*, int64_t n, const float* a1, const float* b1, const float* a2,
                        const float* b2, float* a, float* b, unsigned flags);

@@ -263,3 +263,164 @@ def ar_regression(series, order, iterations=15, gamma_prior=(1.0, 1.0), theta_pr
         klg = (ga - a0) * digamma(ga) - gammaln(ga) + gammaln(a0) + a0 * (np.log(gb) - np.log(b0)) + ga * (b0 - gb) / gb
         fes.append(like + klt + klg)
     return dict(theta_mean=m.T.copy(), theta_cov=np.moveaxis(V, 0, 2).copy(), gamma_shape=ga, gamma_rate=gb, free_energy=np.stack(fes))
+
+
+def latent_ar_reference_data(n=500, theta=None, gamma=5.0, tau=5.0, seed=123):
+    """/root/reference/test/models/autoregressive/lar_tests.jl:128-157 on the regenerated StableRNG stream:
+    states[1] = randn(rng, order); states[i] = [Normal(theta'states[i-1], 1/sqrt(gamma)); states[i-1][1:end-1]];
+    observations[i] ~ Normal(states[i][1], tau_std) with tau_std = sqrt(inv(gamma)) (sic, :137); the first 3*order
+    entries are dropped.  Returns (states[n, order], observations[n])."""
+    from .julia_rng import StableRNG
+    if theta is None:
+        theta = [0.10699399235785655, -0.5237303489793305, 0.3068897071844715, -0.17232255282458891, 0.13323964347539288]
+    theta = np.asarray(theta, dtype=np.float64)
+    p = len(theta)
+    rng = StableRNG(seed)
+    g_std = np.sqrt(1.0 / gamma)
+    t_std = np.sqrt(1.0 / gamma)
+    N = n + 3 * p
+    states = np.zeros((N, p)); obs = np.zeros(N)
+    states[0] = rng.randn_vec(p)
+    for i in range(1, N):
+        head = float(theta @ states[i - 1]) + g_std * rng.randn()
+        states[i] = np.concatenate([[head], states[i - 1][:-1]])
+        obs[i] = states[i][0] + t_std * rng.randn()
+    return states[3 * p:], obs[3 * p:]
+
+
+def latent_ar(y, order, tau, iterations=15, gamma_prior=(1.0, 1.0), init_gamma=(1.0, 1.0), schedule="x_theta_gamma",
+              literal_huge=None, theta_prior_precision=1.0, x0_prior_precision=1.0, init_theta_precision=1.0):
+    """Latent autoregressive model (/root/reference/test/models/autoregressive/lar_tests.jl:52-122):
+
+        gamma ~ Gamma(1, 1); theta ~ N(0, I); x0 ~ N(0, I)
+        x[t] ~ AR(x[t-1], theta, gamma)  (ARMeta(variate, order, ARsafe())),   y[t] ~ Normal(c'x[t], precision = tau), c = e1
+        q(x, x0, gamma, theta) = q(x, x0) q(gamma) q(theta); init q(gamma) = Gamma(1, 1), q(theta) = N(0, I)
+
+    y[T, batch] -> dict(x_mean[T, order, batch], x_cov[T, order, order, batch], theta_mean/cov per iteration, gamma per
+    iteration, free_energy[iterations, batch]).  The AR node (ReactiveMP `AR`, rules restated from the published
+    algorithm: the reference repo only holds the call sites and the free-energy pins :170, :201) is
+        f(y, x, theta, gamma) = N(y1 | theta'x, 1/gamma) * prod_{i>1} delta(y_i - x_{i-1});
+    ReactiveMP regularises the deltas with precision `huge` = 1e12 (`ARPrecisionMatrix`); this restatement works in
+    the exact limit on u = (y1, x) (order + 1 coordinates; y = u[:order], x = u[1:]) and `literal_huge` switches to the
+    regularised 2*order-dimensional form for the cross-check.  Rules:
+        AR(:y)(m_x, q_theta, q_gamma):  D = W_x + E[gamma] V_theta, my = A D^-1 xi_x, Vy = A D^-1 A' + diag(1/E[gamma], 0...)
+        AR(:x)(m_y, q_theta, q_gamma):  W = A'(Vy + V)^-1 A + E[gamma] V_theta, xi = A'(Vy + V)^-1 my   (A = companion(E theta))
+        marginal q(y, x):               precision S_y'W_y S_y + S_x'(W_x + E[gamma] V_theta)S_x + E[gamma] a a', a = (1, -E theta)
+        AR(:theta)(q_yx, q_gamma):      (xi, W) = E[gamma] (V_y1x + m_x m_y1,  V_x + m_x m_x')
+        AR(:gamma)(q_yx, q_theta):      Gamma(3/2, B/2), B = E[(y1 - theta'x)^2]
+    Bethe free energy: the AR node's average energy carries the reference's entropy correction (the degenerate
+    coordinates of q(y, x) are dropped: H[q(y, x)] -> H[q(y1, x)]); deterministic `dot` / `*` nodes contribute -H[q(x_t)];
+    summed over the graph:
+        F = KL(q(theta)||p) + KL(q(gamma)||p) + E[-log p(x0)] + sum_t (U_AR,t - H[q(y1, x)_t]) + sum_{t<T} H[q(x_t)] + sum_t U_obs,t."""
+    from scipy.special import digamma, gammaln
+    y = np.asarray(y, dtype=np.float64)
+    T, Bn = y.shape
+    p = order
+    I = np.eye(p)
+    c = np.zeros(p); c[0] = 1.0
+    ccT = np.outer(c, c)
+    a0, b0 = gamma_prior
+    mth = np.zeros((Bn, p)); Vth = np.tile(I / init_theta_precision, (Bn, 1, 1))
+    ga = np.full(Bn, init_gamma[0]); gb = np.full(Bn, init_gamma[1])
+    w0, p0 = theta_prior_precision, x0_prior_precision
+    hist = dict(theta_mean=[], theta_cov=[], gamma_shape=[], gamma_rate=[], free_energy=[])
+    inv = np.linalg.inv
+    for _ in range(iterations):
+        Eg = ga / gb
+        A = np.zeros((Bn, p, p)); A[:, 0, :] = mth
+        for i in range(1, p):
+            A[:, i, i - 1] = 1.0
+        AT = np.swapaxes(A, 1, 2)
+        V = np.zeros((Bn, p, p)); V[:, 0, 0] = 1.0 / Eg
+        gV = Eg[:, None, None] * Vth
+        # ---- forward messages (xi, W) on x_0 .. x_T, observation included
+        Wf = np.zeros((T + 1, Bn, p, p)); xf = np.zeros((T + 1, Bn, p))
+        Wf[0] = p0 * I
+        for t in range(1, T + 1):
+            Dinv = inv(Wf[t - 1] + gV)
+            C = A @ Dinv
+            my = np.einsum("bij,bj->bi", C, xf[t - 1])
+            Vy = C @ AT + V
+            Wy = inv(Vy)
+            Wf[t] = Wy + tau * ccT
+            xf[t] = np.einsum("bij,bj->bi", Wy, my) + tau * y[t - 1][:, None] * c
+        # ---- backward messages into AR_t's y interface, marginals q(u_t), u = (y1, x)
+        Wb = np.tile(tau * ccT, (Bn, 1, 1)); xb = tau * y[T - 1][:, None] * c
+        mu = np.zeros((T + 1, Bn, p + 1)); Su = np.zeros((T + 1, Bn, p + 1, p + 1))
+        a = np.concatenate([np.ones((Bn, 1)), -mth], axis=1)
+        for t in range(T, 0, -1):
+            if literal_huge is None:
+                L = Eg[:, None, None] * np.einsum("bi,bj->bij", a, a)
+                L[:, :p, :p] += Wb
+                L[:, 1:, 1:] += Wf[t - 1] + gV
+                eta = np.zeros((Bn, p + 1)); eta[:, :p] += xb; eta[:, 1:] += xf[t - 1]
+                S = inv(L)
+                mu[t] = np.einsum("bij,bj->bi", S, eta); Su[t] = S
+            else:
+                mW = np.zeros((Bn, p, p)); mW[:, 0, 0] = Eg
+                for i in range(1, p):
+                    mW[:, i, i] = literal_huge
+                W = np.zeros((Bn, 2 * p, 2 * p))
+                W[:, :p, :p] = Wb + mW
+                W[:, :p, p:] = -mW @ A
+                W[:, p:, :p] = -AT @ mW
+                W[:, p:, p:] = Wf[t - 1] + gV + AT @ mW @ A
+                eta = np.concatenate([xb, xf[t - 1]], axis=1)
+                S2 = inv(W); m2 = np.einsum("bij,bj->bi", S2, eta)
+                idx = [0] + list(range(p, 2 * p))
+                mu[t] = m2[:, idx]; Su[t] = S2[:, idx][:, :, idx]
+            if t > 1:
+                M = inv(I + Wb @ V)
+                AM = AT @ M
+                Wx = AM @ Wb @ A + gV
+                xx = np.einsum("bij,bj->bi", AM, xb)
+                Wb = Wx + tau * ccT
+                xb = xx + tau * y[t - 2][:, None] * c
+        my1 = mu[1:, :, 0]; mx = mu[1:, :, 1:]
+        Vy1 = Su[1:, :, 0, 0]; Vy1x = Su[1:, :, 0, 1:]; Vx = Su[1:, :, 1:, 1:]
+        Cx = Vx + np.einsum("tbi,tbj->tbij", mx, mx)
+        Lx = Vy1x + mx * my1[:, :, None]
+        Rx = Vy1 + my1 ** 2
+
+        def theta_update(Eg_):
+            W = w0 * I + Eg_[:, None, None] * Cx.sum(0)
+            xi = Eg_[:, None] * Lx.sum(0)
+            Vn = inv(W)
+            return np.einsum("bij,bj->bi", Vn, xi), Vn
+
+        def gamma_update(mth_, Vth_):
+            Bt = (Rx - 2 * np.einsum("bi,tbi->tb", mth_, Lx) + np.einsum("bi,tbij,bj->tb", mth_, Cx, mth_)
+                  + np.einsum("bij,tbji->tb", Vth_, Cx))
+            return np.full(Bn, a0 + 0.5 * T), b0 + 0.5 * Bt.sum(0)
+
+        if schedule == "x_theta_gamma":
+            mth, Vth = theta_update(Eg)
+            ga, gb = gamma_update(mth, Vth)
+        elif schedule == "x_gamma_theta":
+            ga, gb = gamma_update(mth, Vth)
+            mth, Vth = theta_update(ga / gb)
+        else:                                            # "jacobi": both from the previous iteration's marginals
+            mth_n, Vth_n = theta_update(Eg)
+            ga, gb = gamma_update(mth, Vth)
+            mth, Vth = mth_n, Vth_n
+        # ---- Bethe free energy with the new q(theta), q(gamma) and the q(u_t) just computed
+        Egn = ga / gb; Elog = digamma(ga) - np.log(gb)
+        Bt = (Rx - 2 * np.einsum("bi,tbi->tb", mth, Lx) + np.einsum("bi,tbij,bj->tb", mth, Cx, mth)
+              + np.einsum("bij,tbji->tb", Vth, Cx))
+        U_ar = 0.5 * (np.log(2 * np.pi) - Elog[None] + Egn[None] * Bt)
+        H_u = 0.5 * ((p + 1) * (1 + np.log(2 * np.pi)) + np.linalg.slogdet(Su[1:])[1])
+        # q(x_t) = marginal of the y block of q(y, x)_t: y = u[:p]
+        mxt = mu[1:, :, :p]; Vxt = Su[1:, :, :p, :p]
+        H_x = 0.5 * (p * (1 + np.log(2 * np.pi)) + np.linalg.slogdet(Vxt)[1])
+        U_obs = 0.5 * (np.log(2 * np.pi) - np.log(tau) + tau * ((y - mxt[:, :, 0]) ** 2 + Vxt[:, :, 0, 0]))
+        m0 = mu[1, :, 1:]; V0 = Su[1, :, 1:, 1:]
+        U_x0 = 0.5 * (p * np.log(2 * np.pi) - p * np.log(p0) + p0 * (np.trace(V0, axis1=1, axis2=2) + (m0 ** 2).sum(1)))
+        kl_t = 0.5 * (w0 * (np.trace(Vth, axis1=1, axis2=2) + (mth ** 2).sum(1)) - p - p * np.log(w0) - np.linalg.slogdet(Vth)[1])
+        kl_g = (ga - a0) * digamma(ga) - gammaln(ga) + gammaln(a0) + a0 * (np.log(gb) - np.log(b0)) + ga * (b0 - gb) / gb
+        fe = kl_t + kl_g + U_x0 + (U_ar - H_u).sum(0) + H_x[:-1].sum(0) + U_obs.sum(0)
+        hist["theta_mean"].append(mth.T.copy()); hist["theta_cov"].append(np.moveaxis(Vth, 0, 2).copy())
+        hist["gamma_shape"].append(ga.copy()); hist["gamma_rate"].append(gb.copy()); hist["free_energy"].append(fe)
+    out = {k: np.stack(v) for k, v in hist.items()}
+    out["x_mean"] = np.moveaxis(mxt, 1, 2).copy()                    # [T, order, batch]
+    out["x_cov"] = np.moveaxis(Vxt, 1, 3).copy()                     # [T, order, order, batch]
+    return out

@@ -67,6 +67,7 @@ SIGNATURES = {
     "rxg_wishart_mean_f32": (c_int, [c_void_p, c_int64, c_int, fp, fp, fp, i32p, c_uint]),
     "rxg_mv_iid_wishart_vmp_f32": (c_int, [c_void_p, c_int, c_int, c_int64, c_int, fp, fp, c_float, fp, fp, fp, fp, fp, fp, fp, i32p, c_uint]),
     "rxg_ar_vmp_f32": (c_int, [c_void_p, c_int, c_int, c_int64, c_int, c_float, c_float, c_float, c_float, c_float, fp, fp, fp, fp, fp, POINTER(c_double), c_uint]),
+    "rxg_lar_vmp_f32": (c_int, [c_void_p, c_int, c_int, c_int64, c_int, fp, fp, fp, fp, fp, fp, fp, fp, POINTER(c_double), i32p, c_uint]),
     "rxg_prod_gamma_f32": (c_int, [c_void_p, c_int64, fp, fp, fp, fp, fp, fp, c_uint]),
     "rxg_prod_normal_f32": (c_int, [c_void_p, c_int64, fp, fp, fp, fp, fp, fp, c_uint]),
     "rxg_rule_gcv_out_f32": (c_int, [c_void_p, c_int64, fp, fp, fp, fp, c_float, c_float, fp, fp, c_uint]),

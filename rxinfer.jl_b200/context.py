@@ -423,6 +423,30 @@ class Context:
                                             L.PTR_DEVICE))
         return dict(theta_mean=tm, theta_cov=tc, gamma_shape=gs, gamma_rate=gr, free_energy=fe)
 
+    def lar_vmp(self, y, order, tau, iterations=15, gamma_prior=(1.0, 1.0), theta_prior_precision=1.0, x0_prior_precision=1.0,
+                init_gamma=(1.0, 1.0), init_theta_precision=1.0, want_states=True, want_free_energy=True):
+        """Fused structured VMP of the reference's latent autoregressive model (``rxg_lar_vmp_f32``,
+        /root/reference/test/models/autoregressive/lar_tests.jl); y[T, batch] on the device.  Returns the KeepLast
+        state posteriors and the KeepEach parameter posteriors / free energy, as the reference's ``returnvars``."""
+        self._dev(y)
+        if y.dim() != 2:
+            raise ValueError("lar_vmp: y must be [T, batch]")
+        T, batch = y.shape
+        iters = int(iterations)
+        prm = (ctypes.c_float * 8)(float(tau), float(gamma_prior[0]), float(gamma_prior[1]), float(theta_prior_precision),
+                                   float(x0_prior_precision), float(init_gamma[0]), float(init_gamma[1]), float(init_theta_precision))
+        xm = self.empty(T, order, batch) if want_states else None
+        xc = self.empty(T, order, order, batch) if want_states else None
+        tm, tc = self.empty(iters, order, batch), self.empty(iters, order, order, batch)
+        gs, gr = self.empty(iters, batch), self.empty(iters, batch)
+        fe = self.empty(iters, batch, dtype=torch.float64) if want_free_energy else None
+        st = self.empty(batch, dtype=torch.int32)
+        fe_p = ctypes.cast(c_void_p(fe.data_ptr() if fe is not None else None), ctypes.POINTER(ctypes.c_double))
+        self._check(self.lib.rxg_lar_vmp_f32(self.h, int(order), T, batch, iters, ctypes.cast(prm, L.fp), _fp(y), _fp(xm), _fp(xc),
+                                             _fp(tm), _fp(tc), _fp(gs), _fp(gr), fe_p,
+                                             ctypes.cast(c_void_p(st.data_ptr()), L.i32p), L.PTR_DEVICE))
+        return dict(x_mean=xm, x_cov=xc, theta_mean=tm, theta_cov=tc, gamma_shape=gs, gamma_rate=gr, free_energy=fe, status=st)
+
     def prod_gamma(self, a1, b1, a2, b2):
         return self._six(self.lib.rxg_prod_gamma_f32, a1, b1, a2, b2)
 

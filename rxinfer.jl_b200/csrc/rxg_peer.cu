@@ -319,13 +319,13 @@ int rxg_lgssm_smooth_gather_f32(rxg_ctx* ctx, int d, int m, int T, int64_t batch
             pc[np] = (gathered_cov && !replicate) ? gathered_cov[g] + r * slab_c : nullptr;
             ++np;
         }
-    // Fused in-kernel peer stores or push-after-sweep.  Measured (B200, 65 536 chains per GPU): with replicated covariances
-    // only 4 mean rows per step go remote and the in-kernel stores run at 0.55 us per 256-byte store instruction -- at G = 2
-    // that hides under the sweep (2.63 ms vs 3.0 ms for sweep + push), at G = 8 it does not (15.4 ms; the means alone are
-    // 7.3 GB = 10.5 ms at the 700 GB/s peer_push_kernel reaches with wide stores from dedicated CTAs).  The full gather is
-    // NVLink bound either way (G = 8: fused 54.3 ms, sweep + ncclAllGather 55.8 ms, bound 47.7 ms) and stays fused.
+    // Fused in-kernel peer stores (default) or push-after-sweep (RXG_OPT_GATHER_MODE = 2, kept for comparison).  Measured
+    // (B200, 65 536 chains per GPU, profiles/r2_bench_{2,8}gpu*.json): replicated covariances G = 2: fused 2.64 ms, push
+    // 3.61 ms; G = 8: fused 15.4 ms, push 16.4 ms (the 7.3 GB of means leave at ~480 GB/s either way while the local
+    // covariance replication writes 29 GB into the same HBM).  Full gather G = 2: 7.84 vs 8.98 ms; G = 8: 54.3 ms fused vs
+    // 55.8 ms sweep + ncclAllGather (NVLink bound: 47.7 ms).
     const long long gmode = ctx->opt[RXG_OPT_GATHER_MODE];
-    const bool fuse = gmode == 1 || (gmode == 0 && (!replicate || G <= 2));
+    const bool fuse = gmode != 2;
     if (fuse) {
         for (int k = 0; k < np; ++k) { c.po.mean[k] = pm[k]; c.po.cov[k] = pc[k]; }
         c.po.n_mean = np;

@@ -210,6 +210,11 @@ ar_vmp(ctx, order, N, batch, its, a0, b0, w0, ia, ib, series, tm, tc, gs, gr, fe
         (Ptr{Cvoid}, Cint, Cint, Int64, Cint, Cfloat, Cfloat, Cfloat, Cfloat, Cfloat, F32P, F32P, F32P, F32P, F32P, Ptr{Float64}, Cuint),
         ctx.handle, order, N, batch, its, a0, b0, w0, ia, ib, series, tm, tc, gs, gr, fe, fl))
 
+lar_vmp(ctx, order, T, batch, its, params, y, xm, xc, tm, tc, gs, gr, fe, st, fl) =
+    check(ctx, ccall((:rxg_lar_vmp_f32, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Cint, Int64, Cint, F32P, F32P, F32P, F32P, F32P, F32P, F32P, F32P, Ptr{Float64}, Ptr{Int32}, Cuint),
+        ctx.handle, order, T, batch, its, params, y, xm, xc, tm, tc, gs, gr, fe, st, fl))
+
 # ---- diagnostics
 selftest_umma(ctx, A, B, D, fl) = check(ctx, ccall((:rxg_selftest_umma_f32, LIB), Cint, (Ptr{Cvoid}, F32P, F32P, F32P, Cuint), ctx.handle, A, B, D, fl))
 selftest_umma_shape(ctx, n, k, A, B, D, fl) = check(ctx, ccall((:rxg_selftest_umma_shape_f32, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, F32P, F32P, F32P, Cuint), ctx.handle, n, k, A, B, D, fl))

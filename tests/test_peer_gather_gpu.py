@@ -65,7 +65,7 @@ def test_two_processes_cuda_ipc():
 
 
 @pytest.mark.parametrize("G", [2, 3])
-@pytest.mark.parametrize("variant", ["full", "replicate", "masked", "per_chain_path"])
+@pytest.mark.parametrize("variant", ["full", "replicate", "masked", "per_chain_path", "full_push", "replicate_push"])
 def test_virtual_ranks_fused_gather(rx, ranks, G, variant):
     from rxinfer_jl_b200.sharding import PeerGroup
     mod = f32_model(lgssm.notebook_model(4))
@@ -74,6 +74,10 @@ def test_virtual_ranks_fused_gather(rx, ranks, G, variant):
     rng = np.random.default_rng(5)
     mask = (rng.random((T, G * b)) > 0.25).astype(np.uint8) if variant == "masked" else None
     cs = ranks[:G]
+    push = variant.endswith("_push")                        # RXG_OPT_GATHER_MODE = 2: plain sweep, then peer_push_kernel
+    variant = variant[:-5] if push else variant
+    for c in cs:                                            # (module-scoped contexts: set it every time)
+        c.set_option("gather_mode", 2 if push else 0)
     groups = PeerGroup.local(cs, T, 4, b)
     kw = dict(replicate_cov=(variant == "replicate"), force_per_chain_path=(variant == "per_chain_path"))
     refs = []
