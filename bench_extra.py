@@ -122,6 +122,13 @@ def main():
         print(json.dumps({"what": "IID Wishart-precision VMP (mv_iid_precision model), 10 iterations", "d": 2, "N": 1500, "batch": 32768, "ms": ms,
                           "datasets_per_s": 32768 / ms * 1e3, "GBs": yw.numel() * 4 / ms / 1e6}))
         del yw
+        # latent AR (lar_tests.jl model): T = 500, 15 structured-VMP iterations = 15 filter + RTS passes per series
+        for order, bl in ((1, 65536), (5, 16384)):
+            yl = torch.randn(500, bl, device="cuda", generator=g)
+            ms = timed(lambda: ctx.lar_vmp(yl, order, 5.0, iterations=15), warm=1, reps=3)
+            print(json.dumps({"what": "latent AR structured VMP (lar_tests.jl model), 15 iterations", "order": order, "T": 500, "batch": bl,
+                              "ms": ms, "series_per_s": bl / ms * 1e3, "chain_steps_per_s": 2 * 15 * 500 * bl / ms * 1e3}))
+            del yl
 
     if "large" in which:
         # BASELINE configs[2] (d = 64, T = 1000, batch = 4096) and the smaller tensor-core sizes; shared model.

@@ -25,6 +25,11 @@ Pin status:
   * HGF / GCV: PINNED -- the data stream of test/models/statespace/hgf_tests.jl:94-102 is regenerated
     (oracle/julia_rng.py) and the reference test runs verbatim: coverage / variance assertions (:121-133) and the
     free-energy pin 1.009879989585 +- 0.01 (:118; the oracle gives 1.0098705, see oracle/hgf.py).
+  * Latent autoregressive model (AR node, structured VMP; oracle/vmp.py::latent_ar): PINNED -- the data of
+    test/models/autoregressive/lar_tests.jl:128-157 is regenerated (StableRNG(123)) and the reference's free-energy pins are
+    reproduced: Univariate AR(1) 518.918234267 vs 518.9182342 (:170, every printed digit), Multivariate AR(5) 514.65389 vs
+    514.66086 +- 0.01 (:201, inside the reference's tolerance; residual 0.007 unexplained); all other assertions verbatim.
+  * Autoregressive regression model (ar_tests.jl): the reference's assertions on its regenerated data (no absolute pin there).
   * Streaming mean-field Gamma model (test/inference/inference_tests.jl:752-860): rules pinned as above; the test's
     own assertion (free energy non-increasing over the iterations, :846) holds for oracle/vmp.py::stream_vmp_gamma.
 """

@@ -75,6 +75,21 @@ class kalman_gamma_streaming:
 
 
 @dataclass
+class latent_autoregressive:
+    """``lar_model`` with ``lar_constraints`` / ``lar_init_marginals``
+    (/root/reference/test/models/autoregressive/lar_tests.jl:52-122): gamma ~ Gamma, theta ~ N(0, I / w0), x0 ~ N(0, I / p0),
+    x[t] ~ AR(x[t-1], theta, gamma) with ARMeta(variate, order, ARsafe()), y[t] ~ Normal(dot(c, x[t]), 1 / tau), c = e1,
+    q(x, x0) q(gamma) q(theta).  The Univariate case is order = 1."""
+    order: int
+    tau: float
+    gamma_prior: tuple = (1.0, 1.0)
+    theta_prior_precision: float = 1.0
+    x0_prior_precision: float = 1.0
+    init_gamma: tuple = (1.0, 1.0)          # q(gamma) of the @initialization
+    init_theta_precision: float = 1.0       # q(theta) = N(0, I / init_theta_precision)
+
+
+@dataclass
 class InferenceResult:
     """``InferenceResult`` (/root/reference/src/inference/batch.jl:18-24)."""
     posteriors: dict
@@ -175,6 +190,17 @@ def infer(*, model, iterations=None, free_energy=False, returnvars=None, options
             return InferenceResult(posteriors={"x": NormalMeanVariance(r["mean"], r["var"]),
                                                "τ": GammaShapeRate(r["shape"], r["rate"])}, model=model,
                                    free_energy=r["free_energy"])
+        if isinstance(model, latent_autoregressive):
+            yy = y[:, 0] if y.dim() == 3 else y
+            r = ctx.lar_vmp(yy.contiguous(), model.order, model.tau, iterations=iterations or 1, gamma_prior=model.gamma_prior,
+                            theta_prior_precision=model.theta_prior_precision, x0_prior_precision=model.x0_prior_precision,
+                            init_gamma=model.init_gamma, init_theta_precision=model.init_theta_precision,
+                            want_free_energy=bool(free_energy))
+            # returnvars of the reference's call: x = KeepLast(), gamma / theta = KeepEach() (leading iteration axis)
+            return InferenceResult(posteriors={"x": MvNormalMeanCovariance(r["x_mean"], r["x_cov"]),
+                                               "γ": GammaShapeRate(r["gamma_shape"], r["gamma_rate"]),
+                                               "θ": MvNormalMeanCovariance(r["theta_mean"], r["theta_cov"])},
+                                   model=model, free_energy=r["free_energy"])
         raise NotImplementedError(f"model pattern {type(model).__name__} is not on the batched hot path")
     except Exception as e:           # reference: catch_exception=true returns a partial result with .error
         if catch_exception:

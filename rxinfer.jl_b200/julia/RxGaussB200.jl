@@ -588,6 +588,28 @@ function mv_iid_wishart(ctx::Context, y::Array{Float32, 3}; iterations = 10)
     return download(mm), download(mc), download(df), download(iS)
 end
 
+"""Fused structured VMP of the latent autoregressive model (lar_tests.jl:52-122); `y[batch, T]`.  Returns the reference's
+`returnvars` as host arrays: x (KeepLast: mean `[batch, order, T]`, cov `[batch, order, order, T]`), θ and γ (KeepEach: trailing
+iteration axis) and the Bethe free energy `[batch, iterations]` (Float64)."""
+function latent_ar(ctx::Context, y::Matrix{Float32}, order::Integer, τ::Real; iterations = 15, gamma_prior = (1f0, 1f0),
+                   theta_prior_precision = 1f0, x0_prior_precision = 1f0, init_gamma = (1f0, 1f0), init_theta_precision = 1f0)
+    batch, T = size(y)
+    dy = upload(ctx, y)
+    xm, xc = DeviceArray(ctx, batch, order, T), DeviceArray(ctx, batch, order, order, T)
+    tm, tc = DeviceArray(ctx, batch, order, iterations), DeviceArray(ctx, batch, order, order, iterations)
+    gs, gr = DeviceArray(ctx, batch, iterations), DeviceArray(ctx, batch, iterations)
+    fe = Lib.device_alloc(ctx, 8 * batch * iterations)
+    params = Float32[τ, gamma_prior[1], gamma_prior[2], theta_prior_precision, x0_prior_precision, init_gamma[1], init_gamma[2],
+                     init_theta_precision]
+    GC.@preserve params Lib.lar_vmp(ctx, order, T, batch, iterations, pointer(params), dy.ptr, xm.ptr, xc.ptr, tm.ptr, tc.ptr, gs.ptr,
+                                    gr.ptr, Ptr{Float64}(fe), Ptr{Int32}(C_NULL), RXG_PTR_DEVICE)
+    fe_host = Array{Float64}(undef, batch, iterations)
+    GC.@preserve fe_host Lib.memcpy_d2h(ctx, pointer(fe_host), fe, 8 * batch * iterations)
+    Lib.device_free(ctx, fe)
+    return (x_mean = download(xm), x_cov = download(xc), θ_mean = download(tm), θ_cov = download(tc), γ_shape = download(gs),
+            γ_rate = download(gr), free_energy = fe_host)
+end
+
 # ---------------------------------------------------------------------------------------------- 4. pattern recogniser + infer_batched
 # Keyword arguments of `infer` that the fused path cannot honour: their presence routes the call to stock RxInfer
 # (SURVEY.md appendix C) -- never silently ignored.
