@@ -172,14 +172,16 @@ def main():
                           "sweeps_per_s": 10 / ms * 1e3}))
 
     if "rules" in which:
-        n, d = 1 << 22, 4
+      for n, d in ((1 << 22, 4), (1 << 16, 16), (1 << 14, 64)):       # d = 16 / 64: csrc/rxg_rules_large.cu (configs[2] message size)
         mu = torch.randn(d, n, device="cuda", generator=g)
         X = torch.randn(d, d, n, device="cuda", generator=g)
-        S = torch.einsum("ikn,jkn->ijn", X, X).contiguous() + 4 * torch.eye(d, device="cuda")[:, :, None]
+        S = torch.einsum("ikn,jkn->ijn", X, X).contiguous() + d * torch.eye(d, device="cuda")[:, :, None]
         S = S.contiguous()
-        A = np.asarray(mod["A"])
+        del X
+        A = np.asarray(mod["A"]) if d == 4 else np.asarray(dense_model_f32(d)["A"])
+        Pm = np.asarray(mod["P"]) if d == 4 else np.eye(d, dtype=np.float32)
         rows = []
-        rows.append(("MvNormalMeanCovariance(:out)  (mu, S + Sigma)", timed(lambda: ctx.rule_add_cov(mu, S, mod["P"])), 2 * (d + d * d) * 4))
+        rows.append(("MvNormalMeanCovariance(:out)  (mu, S + Sigma)", timed(lambda: ctx.rule_add_cov(mu, S, Pm)), 2 * (d + d * d) * 4))
         rows.append(("*(:out)  (A mu, A S A')", timed(lambda: ctx.rule_mul_out(A, mu, S)), 2 * (d + d * d) * 4))
         rows.append(("*(:in)   cholinv + A' W A", timed(lambda: ctx.rule_mul_in(A, mu, S)), 2 * (d + d * d) * 4 + 4))
         mu2, S2 = (mu * 0.5).contiguous(), (S * 2.0).contiguous()          # distinct operands: 2 reads + 1 write per message

@@ -123,7 +123,10 @@ int rxg_profile_last_ms(rxg_ctx* ctx, float* main_kernel_ms, float* gain_kernels
  * shared by all n messages, else it is [r][c][n].
  * The reference reaches these through ReactiveMP.rule(...) dispatched from the edge pipelines
  * wired in activate_rmp_factornode! [ref: src/model/plugins/reactivemp_inference.jl:509-540];
- * callable directly as @call_rule [ref: test/inference/inference_tests.jl:547-585].            */
+ * callable directly as @call_rule [ref: test/inference/inference_tests.jl:547-585].
+ * State sizes: any 1 <= d <= 64 (d_out, d_in <= 64 for the multiplication rules).  d in {1..6, 8} (and the rectangular
+ * shapes 1x2, 1x4, 2x4) run register resident, one thread per message; every other size runs on the shared-memory /
+ * left-GEMM kernels of csrc/rxg_rules_large.cu, where the multiplication rules need M_shared != 0.                  */
 
 /* @rule MvNormalMeanCovariance(:out)(m_mu, q_Sigma) -> (mu, S + Sigma)  (upstream
  * rules/mv_normal_mean_covariance/out.jl)  [ref: alias src/model/graphppl.jl:372-376;

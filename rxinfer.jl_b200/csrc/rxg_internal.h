@@ -123,6 +123,19 @@ int lgssm_dispatch_native(rxg_ctx* ctx, LgssmCall& c);
 // status[i] = RXG_ERR_NOT_SPD if the ctx's gain-table failure flag is set on the device, else RXG_OK
 int fill_status_from_flag(rxg_ctx* ctx, int32_t* status, int64_t n);
 bool lgssm_supported(int d, int m);
+// rxg_rules_large.cu: Gaussian rule kernels for state sizes without a register-resident instantiation (d up to 64)
+bool rules_small(int d);
+bool rules_small2(int dout, int din);
+int rules_large_add_cov(rxg_ctx* ctx, int64_t n, int d, const float* mu_in, const float* S_in, const float* Sigma, int shared,
+                        float* mu_out, float* S_out);
+int rules_large_pair_axpy(rxg_ctx* ctx, int64_t n, int d, const float* v1, const float* M1, const float* v2, const float* M2,
+                          float sv, float* vo, float* Mo);
+int rules_large_mul_out(rxg_ctx* ctx, int64_t n, int dout, int din, const float* A, const float* mu_in, const float* S_in,
+                        float* mu_out, float* S_out);
+int rules_large_mul_in(rxg_ctx* ctx, int64_t n, int dout, int din, const float* A, const float* mu_out, const float* S_out,
+                       float* xi_in, float* W_in, int32_t* status);
+int rules_large_convert(rxg_ctx* ctx, int64_t n, int d, int k, const float* const* v_list, const float* const* M_list,
+                        float* vo, float* Mo, int32_t* status);
 // rxg_lgssm_large.cu
 int lgssm_large_dispatch(rxg_ctx* ctx, LgssmCall& c);
 bool lgssm_large_supported(int d, int m);

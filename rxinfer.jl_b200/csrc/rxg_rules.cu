@@ -467,6 +467,15 @@ static inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / 
     if (!(flags & RXG_ASYNC)) RXG_CUDA((ctx), cudaStreamSynchronize((ctx)->stream));  \
     return RXG_OK;
 
+// state sizes without a register-resident instantiation go to csrc/rxg_rules_large.cu (any d <= 64)
+#define RXG_LARGE_D(ctx, d, CALL, what)                                                                   \
+    if (!rxg::rules_small(d)) {                                                                           \
+        if ((d) < 1 || (d) > 64) return rxg::fail((ctx), RXG_ERR_UNSUPPORTED, "rule kernels: d=%d unsupported (1-64)", (d)); \
+        { int _rc = (CALL); if (_rc != RXG_OK) return _rc; }                                              \
+        (ctx)->launches -= 1;                                                                             \
+        RXG_RULE_EPILOGUE(ctx, what)                                                                      \
+    }
+
 #define RXG_DISPATCH_D(d, CALL)                                                        \
     switch (d) {                                                                       \
         case 1: { constexpr int D = 1; CALL; } break;                                  \
@@ -499,6 +508,7 @@ int rxg_rule_mvnormal_meancov_out_f32(rxg_ctx* ctx, int64_t n, int d, const floa
                                       const float* Sigma, int M_shared, float* mu_out, float* S_out,
                                       unsigned flags) {
     RXG_RULE_PROLOGUE(ctx, n)
+    RXG_LARGE_D(ctx, d, rxg::rules_large_add_cov(ctx, n, d, mu_in, S_in, Sigma, M_shared, mu_out, S_out), "rules_large_add_cov")
     RXG_DISPATCH_D(d, (k_add_cov<D><<<nblk(n, 128), 128, 0, ctx->stream>>>(n, mu_in, S_in, Sigma, M_shared, mu_out, S_out)))
     RXG_RULE_EPILOGUE(ctx, "k_add_cov")
 }
@@ -510,12 +520,20 @@ int rxg_rule_mvnormal_meancov_mean_f32(rxg_ctx* ctx, int64_t n, int d, const flo
 int rxg_rule_mvnormal_meancov_mean_data_f32(rxg_ctx* ctx, int64_t n, int d, const float* y, const float* Sigma,
                                             int M_shared, float* mu_out, float* S_out, unsigned flags) {
     RXG_RULE_PROLOGUE(ctx, n)
+    RXG_LARGE_D(ctx, d, rxg::rules_large_add_cov(ctx, n, d, y, nullptr, Sigma, M_shared, mu_out, S_out), "rules_large_from_data")
     RXG_DISPATCH_D(d, (k_from_data<D><<<nblk(n, 128), 128, 0, ctx->stream>>>(n, y, Sigma, M_shared, mu_out, S_out)))
     RXG_RULE_EPILOGUE(ctx, "k_from_data")
 }
 int rxg_rule_mul_out_f32(rxg_ctx* ctx, int64_t n, int d_out, int d_in, const float* A, int M_shared,
                          const float* mu_in, const float* S_in, float* mu_out, float* S_out, unsigned flags) {
     RXG_RULE_PROLOGUE(ctx, n)
+    if (!rxg::rules_small2(d_out, d_in)) {
+        if (d_out < 1 || d_out > 64 || d_in < 1 || d_in > 64) return rxg::fail(ctx, RXG_ERR_UNSUPPORTED, "mul_out: A is %dx%d, unsupported (1-64)", d_out, d_in);
+        if (!M_shared) return rxg::fail(ctx, RXG_ERR_UNSUPPORTED, "mul_out: a per-message A needs one of the register-resident shapes (A %dx%d)", d_out, d_in);
+        { int _rc = rxg::rules_large_mul_out(ctx, n, d_out, d_in, A, mu_in, S_in, mu_out, S_out); if (_rc != RXG_OK) return _rc; }
+        ctx->launches -= 1;
+        RXG_RULE_EPILOGUE(ctx, "rules_large_mul_out")
+    }
     RXG_DISPATCH_DODI(d_out, d_in, (k_mul_out<DO, DI><<<nblk(n, 128), 128, 0, ctx->stream>>>(n, A, M_shared, mu_in, S_in, mu_out, S_out)))
     RXG_RULE_EPILOGUE(ctx, "k_mul_out")
 }
@@ -523,30 +541,41 @@ int rxg_rule_mul_in_f32(rxg_ctx* ctx, int64_t n, int d_out, int d_in, const floa
                         const float* mu_out, const float* S_out, float* xi_in, float* W_in, int32_t* status,
                         unsigned flags) {
     RXG_RULE_PROLOGUE(ctx, n)
+    if (!rxg::rules_small2(d_out, d_in)) {
+        if (d_out < 1 || d_out > 64 || d_in < 1 || d_in > 64) return rxg::fail(ctx, RXG_ERR_UNSUPPORTED, "mul_in: A is %dx%d, unsupported (1-64)", d_out, d_in);
+        if (!M_shared) return rxg::fail(ctx, RXG_ERR_UNSUPPORTED, "mul_in: a per-message A needs one of the register-resident shapes (A %dx%d)", d_out, d_in);
+        { int _rc = rxg::rules_large_mul_in(ctx, n, d_out, d_in, A, mu_out, S_out, xi_in, W_in, status); if (_rc != RXG_OK) return _rc; }
+        ctx->launches -= 1;
+        RXG_RULE_EPILOGUE(ctx, "rules_large_mul_in")
+    }
     RXG_DISPATCH_DODI(d_out, d_in, (k_mul_in<DO, DI><<<nblk(n, 128), 128, 0, ctx->stream>>>(n, A, M_shared, mu_out, S_out, xi_in, W_in, status)))
     RXG_RULE_EPILOGUE(ctx, "k_mul_in")
 }
 int rxg_rule_add_out_f32(rxg_ctx* ctx, int64_t n, int d, const float* mu1, const float* S1, const float* mu2,
                          const float* S2, float* mu_out, float* S_out, unsigned flags) {
     RXG_RULE_PROLOGUE(ctx, n)
+    RXG_LARGE_D(ctx, d, rxg::rules_large_pair_axpy(ctx, n, d, mu1, S1, mu2, S2, 1.0f, mu_out, S_out), "rules_large_add_out")
     RXG_DISPATCH_D(d, (k_pair_axpy<D><<<nblk(n, 128), 128, 0, ctx->stream>>>(n, mu1, S1, mu2, S2, 1.0f, mu_out, S_out)))
     RXG_RULE_EPILOGUE(ctx, "k_pair_axpy(add_out)")
 }
 int rxg_rule_add_in_f32(rxg_ctx* ctx, int64_t n, int d, const float* mu_out, const float* S_out,
                         const float* mu_other, const float* S_other, float* mu_in, float* S_in, unsigned flags) {
     RXG_RULE_PROLOGUE(ctx, n)
+    RXG_LARGE_D(ctx, d, rxg::rules_large_pair_axpy(ctx, n, d, mu_out, S_out, mu_other, S_other, -1.0f, mu_in, S_in), "rules_large_add_in")
     RXG_DISPATCH_D(d, (k_pair_axpy<D><<<nblk(n, 128), 128, 0, ctx->stream>>>(n, mu_out, S_out, mu_other, S_other, -1.0f, mu_in, S_in)))
     RXG_RULE_EPILOGUE(ctx, "k_pair_axpy(add_in)")
 }
 int rxg_prod_gaussian_f32(rxg_ctx* ctx, int64_t n, int d, const float* xi1, const float* W1, const float* xi2,
                           const float* W2, float* xi, float* W, unsigned flags) {
     RXG_RULE_PROLOGUE(ctx, n)
+    RXG_LARGE_D(ctx, d, rxg::rules_large_pair_axpy(ctx, n, d, xi1, W1, xi2, W2, 1.0f, xi, W), "rules_large_prod")
     RXG_DISPATCH_D(d, (k_pair_axpy<D><<<nblk(n, 128), 128, 0, ctx->stream>>>(n, xi1, W1, xi2, W2, 1.0f, xi, W)))
     RXG_RULE_EPILOGUE(ctx, "k_pair_axpy(prod)")
 }
 int rxg_meancov_to_wmp_f32(rxg_ctx* ctx, int64_t n, int d, const float* mu, const float* S, float* xi, float* W,
                            int32_t* status, unsigned flags) {
     RXG_RULE_PROLOGUE(ctx, n)
+    RXG_LARGE_D(ctx, d, rxg::rules_large_convert(ctx, n, d, 1, &mu, &S, xi, W, status), "rules_large_convert")
     RXG_DISPATCH_D(d, (k_convert<D><<<nblk(n, 128), 128, 0, ctx->stream>>>(n, mu, S, xi, W, status)))
     RXG_RULE_EPILOGUE(ctx, "k_convert")
 }
@@ -558,6 +587,7 @@ int rxg_marginal_gaussian_f32(rxg_ctx* ctx, int64_t n, int d, int k, const float
                               const float* const* W_list, float* mu, float* S, int32_t* status, unsigned flags) {
     RXG_RULE_PROLOGUE(ctx, n)
     if (k < 1 || k > 8) return rxg::fail(ctx, RXG_ERR_BAD_ARG, "marginal: k=%d must be in 1..8", k);
+    RXG_LARGE_D(ctx, d, rxg::rules_large_convert(ctx, n, d, k, xi_list, W_list, mu, S, status), "rules_large_marginal")
     PtrList pl = {};
     for (int q = 0; q < k; ++q) { pl.xi[q] = xi_list[q]; pl.W[q] = W_list[q]; }
     RXG_DISPATCH_D(d, (k_marginal<D><<<nblk(n, 128), 128, 0, ctx->stream>>>(n, k, pl, mu, S, status)))

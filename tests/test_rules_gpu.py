@@ -36,10 +36,12 @@ def r32(a):
     return a.astype(np.float32).astype(np.float64)
 
 
-@pytest.mark.parametrize("d", [1, 2, 3, 4, 6, 8])
+@pytest.mark.parametrize("d", [1, 2, 3, 4, 6, 8, 7, 16, 33, 64])
 def test_gaussian_rules(ctx, d):
+    """d = 7, 16, 33, 64: no register-resident instantiation -- csrc/rxg_rules_large.cu (element-wise pass, left-GEMM with the
+    shared matrix, warp-per-message cholinv); same entry points, same tolerances."""
     rng = np.random.default_rng(d)
-    n = 1000 + d                                        # ragged vs block size
+    n = (1000 if d <= 8 else 301) + d                   # ragged vs block size / vs the 8 messages per CTA of the large path
     mu, S = r32(rng.standard_normal((n, d))), r32(spd(rng, n, d))
     mu2, S2 = r32(rng.standard_normal((n, d))), r32(spd(rng, n, d))
     Sig = r32(spd(rng, 1, d)[0])
@@ -90,15 +92,34 @@ def test_non_spd_is_reported_per_message(ctx, rx):
     assert st.cpu().tolist() == [0, rx._lib.RXG_ERR_NOT_SPD]
 
 
-def test_rectangular_multiplication(ctx):
+def test_large_d_rules_report_non_spd_and_refuse_per_message_matrices(ctx, rx):
+    rng = np.random.default_rng(3)
+    d, n = 24, 19
+    S = spd(rng, n, d)
+    S[5] = -S[5]                                                            # one indefinite message
+    S[11, 3, 3] = -1.0
+    xi, W, st = ctx.meancov_to_wmp(soa_v(np.zeros((n, d))), soa_m(S))
+    want = [0] * n; want[5] = rx._lib.RXG_ERR_NOT_SPD; want[11] = rx._lib.RXG_ERR_NOT_SPD
+    assert st.cpu().tolist() == want
+    ok = [i for i in range(n) if i not in (5, 11)]
+    assert rel_l2(back_m(W)[ok], np.linalg.inv(r32(S)[ok])) < 1e-4
+    with pytest.raises(rx.RxGaussError):                                    # per-message A only on the register-resident shapes
+        ctx.rule_mul_out(soa_m(rng.standard_normal((n, d, d))), soa_v(np.zeros((n, d))), soa_m(S))
+    with pytest.raises(rx.RxGaussError):
+        ctx.meancov_to_wmp(soa_v(np.zeros((n, 65))), soa_m(np.tile(np.eye(65), (n, 1, 1))))
+
+
+@pytest.mark.parametrize("shape", [(2, 4), (3, 5), (16, 64), (64, 16), (20, 20)])
+def test_rectangular_multiplication(ctx, shape):
     rng = np.random.default_rng(0)
     n = 257
-    B = r32(rng.standard_normal((2, 4)))
-    mu, S = r32(rng.standard_normal((n, 4))), r32(spd(rng, n, 4))
+    do, di = shape
+    B = r32(rng.standard_normal((do, di)))
+    mu, S = r32(rng.standard_normal((n, di))), r32(spd(rng, n, di))
     mo, So = ctx.rule_mul_out(B, soa_v(mu), soa_m(S))
     ref = R.multiplication_out(B, (mu, S))
     assert rel_l2(back_v(mo), ref[0]) < TOL and rel_l2(back_m(So), ref[1]) < TOL
-    my, Sy = r32(rng.standard_normal((n, 2))), r32(spd(rng, n, 2))
+    my, Sy = r32(rng.standard_normal((n, do))), r32(spd(rng, n, do))
     xi, W, _ = ctx.rule_mul_in(B, soa_v(my), soa_m(Sy))
     ref = R.multiplication_in(R.meancov_to_wmp(my, Sy), B)
     assert rel_l2(back_v(xi), ref[0]) < 5 * TOL and rel_l2(back_m(W), ref[1]) < 5 * TOL
