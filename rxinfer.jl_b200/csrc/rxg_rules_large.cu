@@ -20,7 +20,7 @@
 
 namespace rxg {
 
-constexpr int RL_MSGS = 8;          // messages (= warps) per CTA of k_cholinv_warp
+constexpr int RL_MSGS = 8;          // messages (= warps) per CTA of k_cholinv_warp (6 at d > 57, see cholinv_warp)
 
 // o[r][i] = (a ? a[r][i] : 0) + sb * (b ? (b_bcast ? b[r] : b[r][i]) : 0)
 __global__ void __launch_bounds__(256)
@@ -34,41 +34,70 @@ k_ew(int64_t rows, int64_t n, const float* __restrict__ a, const float* __restri
     }
 }
 
-// Y = op(A) X per batch slice (blockIdx.y): op(A) is M x K; transA = 0: A stored M x K row-major; 1: A stored K x M row-major
+// Y = op(A) X per batch slice (blockIdx.y): op(A) is M x K; transA = 0: A stored M x K row-major; 1: A stored K x M row-major.
+// A is staged per CTA (coalesced global reads; shared-memory row stride MMAX + 4 keeps the float4 reads aligned and the
+// transposing stores at 4-way instead of 32-way bank conflicts).  One thread = LG_NC columns (j, j + 128): every float4 of A'
+// read from shared memory feeds 4 * LG_NC FMAs -- with one column per thread the broadcast LDS.128 stream (16 per row at
+// M = 64, one shared-memory pipe for the four schedulers) costs as many cycles as the 64 FMAs it feeds.
+constexpr int LG_NC = 2;
 template <int MMAX>
 __global__ void __launch_bounds__(128)
 k_left_gemm(int M, int K, int64_t N, const float* __restrict__ A, int transA, const float* __restrict__ X,
             float* __restrict__ Y, int64_t x_slice, int64_t y_slice) {
-    extern __shared__ __align__(16) float At[];                      // [K][MMAX]: At[k][m] = op(A)(m, k), zero padded
-    for (int idx = threadIdx.x; idx < K * MMAX; idx += blockDim.x) {
-        const int k = idx / MMAX, m = idx % MMAX;
-        At[idx] = (m < M) ? (transA ? __ldg(A + (int64_t)k * M + m) : __ldg(A + (int64_t)m * K + k)) : 0.f;
+    extern __shared__ __align__(16) float At[];                      // [K][LDA]: At[k][m] = op(A)(m, k), zero padded
+    constexpr int LDA = MMAX + 4;
+    for (int idx = threadIdx.x; idx < K * LDA; idx += blockDim.x) At[idx] = 0.f;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < M * K; idx += blockDim.x) {
+        const int m = transA ? idx % M : idx / K, k = transA ? idx / M : idx % K;      // idx walks A as it lies in memory
+        At[k * LDA + m] = __ldg(A + idx);
     }
     __syncthreads();
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= N) return;
     X += (int64_t)blockIdx.y * x_slice;
     Y += (int64_t)blockIdx.y * y_slice;
-    float acc[MMAX];
+    int64_t j[LG_NC];
+    bool on[LG_NC];
 #pragma unroll
-    for (int m = 0; m < MMAX; ++m) acc[m] = 0.f;
-    float xn = __ldg(X + j);
+    for (int c = 0; c < LG_NC; ++c) {
+        j[c] = ((int64_t)blockIdx.x * LG_NC + c) * blockDim.x + threadIdx.x;
+        on[c] = j[c] < N;
+        if (!on[c]) j[c] = N - 1;                                     // clamp: loads stay in bounds, the store is skipped
+    }
+    float acc[LG_NC][MMAX];
+#pragma unroll
+    for (int c = 0; c < LG_NC; ++c)
+#pragma unroll
+        for (int m = 0; m < MMAX; ++m) acc[c][m] = 0.f;
+    float xn[LG_NC];
+#pragma unroll
+    for (int c = 0; c < LG_NC; ++c) xn[c] = __ldg(X + j[c]);
     for (int k = 0; k < K; ++k) {
-        const float x = xn;
-        if (k + 1 < K) xn = __ldg(X + (int64_t)(k + 1) * N + j);        // next row in flight under this row's FMAs
-        const float4* a4 = reinterpret_cast<const float4*>(At + k * MMAX);
+        float x[LG_NC];
+#pragma unroll
+        for (int c = 0; c < LG_NC; ++c) {
+            x[c] = xn[c];
+            if (k + 1 < K) xn[c] = __ldg(X + (int64_t)(k + 1) * N + j[c]);   // next row in flight under this row's FMAs
+        }
+        const float4* a4 = reinterpret_cast<const float4*>(At + k * LDA);
 #pragma unroll
         for (int q = 0; q < MMAX / 4; ++q) {
             const float4 a = a4[q];
-            acc[4 * q + 0] = __fmaf_rn(a.x, x, acc[4 * q + 0]);
-            acc[4 * q + 1] = __fmaf_rn(a.y, x, acc[4 * q + 1]);
-            acc[4 * q + 2] = __fmaf_rn(a.z, x, acc[4 * q + 2]);
-            acc[4 * q + 3] = __fmaf_rn(a.w, x, acc[4 * q + 3]);
+#pragma unroll
+            for (int c = 0; c < LG_NC; ++c) {
+                acc[c][4 * q + 0] = __fmaf_rn(a.x, x[c], acc[c][4 * q + 0]);
+                acc[c][4 * q + 1] = __fmaf_rn(a.y, x[c], acc[c][4 * q + 1]);
+                acc[c][4 * q + 2] = __fmaf_rn(a.z, x[c], acc[c][4 * q + 2]);
+                acc[c][4 * q + 3] = __fmaf_rn(a.w, x[c], acc[c][4 * q + 3]);
+            }
         }
     }
 #pragma unroll
-    for (int m = 0; m < MMAX; ++m)
-        if (m < M) Y[(int64_t)m * N + j] = acc[m];
+    for (int c = 0; c < LG_NC; ++c)
+        if (on[c]) {
+#pragma unroll
+            for (int m = 0; m < MMAX; ++m)
+                if (m < M) Y[(int64_t)m * N + j[c]] = acc[c][m];
+        }
 }
 
 struct RuleList { const float* v[8]; const float* M[8]; };
@@ -82,10 +111,11 @@ k_cholinv_warp(int64_t n, int d, int k, RuleList in, float* __restrict__ vo, flo
     const int ld = d + 1;
     const int per = d * ld + 3 * d;                                   // matrix, reciprocal diagonal, v, result
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t i0 = (int64_t)blockIdx.x * RL_MSGS;
+    const int nm = blockDim.x >> 5;                                   // messages (= warps) of this CTA: 8, or 6 when 8 would not leave room for two CTAs per SM
+    const int64_t i0 = (int64_t)blockIdx.x * nm;
     // ---- cooperative load (+ sum over the k inputs): 8 consecutive messages per (row, col) = one 32-byte sector
-    for (int e = threadIdx.x; e < d * d * RL_MSGS; e += blockDim.x) {
-        const int msg = e % RL_MSGS, el = e / RL_MSGS;
+    for (int e = threadIdx.x; e < d * d * nm; e += blockDim.x) {
+        const int msg = e % nm, el = e / nm;
         const int64_t i = i0 + msg;
         if (i < n) {
             float s = 0.f;
@@ -93,8 +123,8 @@ k_cholinv_warp(int64_t n, int d, int k, RuleList in, float* __restrict__ vo, flo
             sm[msg * per + (el / d) * ld + (el % d)] = s;
         }
     }
-    for (int e = threadIdx.x; e < d * RL_MSGS; e += blockDim.x) {
-        const int msg = e % RL_MSGS, el = e / RL_MSGS;
+    for (int e = threadIdx.x; e < d * nm; e += blockDim.x) {
+        const int msg = e % nm, el = e / nm;
         const int64_t i = i0 + msg;
         if (i < n) {
             float s = 0.f;
@@ -173,14 +203,14 @@ k_cholinv_warp(int64_t n, int d, int k, RuleList in, float* __restrict__ vo, flo
     }
     __syncthreads();
     if (Mo)
-        for (int e = threadIdx.x; e < d * d * RL_MSGS; e += blockDim.x) {
-            const int msg = e % RL_MSGS, el = e / RL_MSGS;
+        for (int e = threadIdx.x; e < d * d * nm; e += blockDim.x) {
+            const int msg = e % nm, el = e / nm;
             const int64_t ii = i0 + msg;
             if (ii < n) Mo[(int64_t)el * n + ii] = sm[msg * per + (el / d) * ld + (el % d)];
         }
     if (vo)
-        for (int e = threadIdx.x; e < d * RL_MSGS; e += blockDim.x) {
-            const int msg = e % RL_MSGS, el = e / RL_MSGS;
+        for (int e = threadIdx.x; e < d * nm; e += blockDim.x) {
+            const int msg = e % nm, el = e / nm;
             const int64_t ii = i0 + msg;
             if (ii < n) vo[(int64_t)el * n + ii] = sm[msg * per + d * ld + 2 * d + el];
         }
@@ -207,9 +237,9 @@ static int ew(rxg_ctx* ctx, int64_t rows, int64_t n, const float* a, const float
 }
 static int left_gemm(rxg_ctx* ctx, int M, int K, int64_t N, const float* A, int transA, const float* X, float* Y, int slices,
                      int64_t x_slice, int64_t y_slice) {
-    const dim3 grid((unsigned)((N + 127) / 128), (unsigned)slices);
+    const dim3 grid((unsigned)((N + 128 * LG_NC - 1) / (128 * LG_NC)), (unsigned)slices);
     const int mmax = M <= 16 ? 16 : (M <= 32 ? 32 : 64);
-    const size_t smem = (size_t)K * mmax * sizeof(float);
+    const size_t smem = (size_t)K * (mmax + 4) * sizeof(float);
     if (mmax == 16) k_left_gemm<16><<<grid, 128, smem, ctx->stream>>>(M, K, N, A, transA, X, Y, x_slice, y_slice);
     else if (mmax == 32) k_left_gemm<32><<<grid, 128, smem, ctx->stream>>>(M, K, N, A, transA, X, Y, x_slice, y_slice);
     else k_left_gemm<64><<<grid, 128, smem, ctx->stream>>>(M, K, N, A, transA, X, Y, x_slice, y_slice);
@@ -217,7 +247,11 @@ static int left_gemm(rxg_ctx* ctx, int M, int K, int64_t N, const float* A, int 
     return check_cuda(ctx, cudaGetLastError(), "k_left_gemm");
 }
 static int cholinv_warp(rxg_ctx* ctx, int64_t n, int d, int k, const RuleList& in, float* vo, float* Mo, int32_t* status) {
-    const size_t smem = (size_t)RL_MSGS * ((size_t)d * (d + 1) + 3 * d) * sizeof(float);
+    // 8 messages per CTA (one 32-byte sector per element) unless that leaves room for only one CTA per SM (d > 57): then 6,
+    // so that two CTAs = 12 warps share an SM -- the kernel is latency bound
+    const size_t per_msg = ((size_t)d * (d + 1) + 3 * d) * sizeof(float);
+    const int nm = (RL_MSGS * per_msg > 113 * 1024) ? 6 : RL_MSGS;
+    const size_t smem = nm * per_msg;
     static size_t attr_set[64] = {};                         // per device: largest dynamic shared memory opted in so far
     if (smem > 48 * 1024 && attr_set[ctx->device & 63] < smem) {
         int rc = check_cuda(ctx, cudaFuncSetAttribute(k_cholinv_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
@@ -225,7 +259,7 @@ static int cholinv_warp(rxg_ctx* ctx, int64_t n, int d, int k, const RuleList& i
         if (rc != RXG_OK) return rc;
         attr_set[ctx->device & 63] = smem;
     }
-    k_cholinv_warp<<<(unsigned)((n + RL_MSGS - 1) / RL_MSGS), 32 * RL_MSGS, smem, ctx->stream>>>(n, d, k, in, vo, Mo, status);
+    k_cholinv_warp<<<(unsigned)((n + nm - 1) / nm), 32 * nm, smem, ctx->stream>>>(n, d, k, in, vo, Mo, status);
     ctx->launches += 1;
     return check_cuda(ctx, cudaGetLastError(), "k_cholinv_warp");
 }

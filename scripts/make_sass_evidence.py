@@ -41,7 +41,8 @@ def main():
     names = demangle([r[1] for r in rows])
     keep = re.compile(r"lgssm_shared_kernel<4, 4, 2, 4, true, false, false, true|lgssm_seg_kernel<4, 4|lgssm_umma_sweep|umma_ky_kernel|"
                       r"umma_selftest|hgf_filter_kernel|gain_scan_kernel<4, 4>|lgssm_chain_kernel<4, 4|lgssm_generic_chain_kernel|"
-                      r"peer_|replicate_cov|large_gain_tables<64|large_fwd_doubling<64|broadcast_cov|mv_iid_wishart_vmp_kernel<2>|seg_tables_kernel<4, 4>")
+                      r"peer_|replicate_cov|large_gain_tables<64|large_fwd_doubling<64|broadcast_cov|mv_iid_wishart_vmp_kernel<2>|seg_tables_kernel<4, 4>|"
+                      r"lar_vmp_kernel<[15]>|k_left_gemm<64>|k_cholinv_warp|k_ew")
     with open(os.path.join(OUT, "r2_sass_summary.txt"), "w") as f:
         f.write("# SASS instruction counts per kernel (cuobjdump -sass of rxinfer.jl_b200/build/*.o, sm_100a); made by scripts/make_sass_evidence.py\n")
         f.write("# UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit, UBLKCP = cp.async.bulk (TMA bulk), LDGSTS = cp.async\n")
