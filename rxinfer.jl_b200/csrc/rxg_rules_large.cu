@@ -252,12 +252,10 @@ static int cholinv_warp(rxg_ctx* ctx, int64_t n, int d, int k, const RuleList& i
     const size_t per_msg = ((size_t)d * (d + 1) + 3 * d) * sizeof(float);
     const int nm = (RL_MSGS * per_msg > 113 * 1024) ? 6 : RL_MSGS;
     const size_t smem = nm * per_msg;
-    static size_t attr_set[64] = {};                         // per device: largest dynamic shared memory opted in so far
-    if (smem > 48 * 1024 && attr_set[ctx->device & 63] < smem) {
+    if (smem > 48 * 1024) {   // per-device function attribute: set on every call (microseconds), no per-process "done" flag
         int rc = check_cuda(ctx, cudaFuncSetAttribute(k_cholinv_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                             "cudaFuncSetAttribute(k_cholinv_warp)");
         if (rc != RXG_OK) return rc;
-        attr_set[ctx->device & 63] = smem;
     }
     k_cholinv_warp<<<(unsigned)((n + nm - 1) / nm), 32 * nm, smem, ctx->stream>>>(n, d, k, in, vo, Mo, status);
     ctx->launches += 1;
