@@ -10,11 +10,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CDIR = os.path.join(ROOT, "tests", "c")
 
 
-def _build():
+def _build(target="abi_host"):
     import rxinfer_jl_b200 as rx
     rx._lib.load()                                           # the library must exist (built by __graft_entry__.build())
-    subprocess.check_call(["make", "-s", "-C", CDIR, "abi_host"])
-    return os.path.join(CDIR, "abi_host")
+    subprocess.check_call(["make", "-s", "-C", CDIR, target])
+    return os.path.join(CDIR, target)
 
 
 def test_header_is_plain_c_and_cxx():
@@ -32,6 +32,11 @@ def test_c_host_links_and_fails_loudly_without_gpu():
         pytest.skip("GPU present: covered by the gpu test")
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 2 and "no CPU fallback" in (r.stderr + r.stdout) or "no CUDA device" in (r.stderr + r.stdout)
+    exe2 = _build("abi_host_entries")                        # second program: the round-2 entries through device buffers
+    ldd = subprocess.run(["ldd", exe2], capture_output=True, text=True).stdout
+    assert "librxgauss.so" in ldd and "python" not in ldd and "torch" not in ldd and "libcudart" not in ldd
+    r = subprocess.run([exe2], capture_output=True, text=True)
+    assert r.returncode == 2 and "no CPU fallback" in (r.stderr + r.stdout)
 
 
 @pytest.mark.gpu
@@ -44,3 +49,18 @@ def test_c_host_parity_on_gpu():
     print(r.stdout, r.stderr)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "mean relL2" in r.stdout
+
+
+@pytest.mark.gpu
+def test_c_host_round2_entries_on_gpu():
+    """tests/c/abi_host_entries.c: rule kernels (register-resident and shared-memory families), general-shape filter /
+    smoother, AR / latent-AR / Gamma-precision VMP and the HGF with its free energy from a plain-C host that owns no CUDA
+    runtime (rxg_device_alloc + rxg_memcpy_*), checked through self-consistency properties."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    exe = _build("abi_host_entries")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all properties hold" in r.stdout
